@@ -1,0 +1,184 @@
+/* rtgpu.h — C ABI of the B200 wavefront renderer (librtgpu.so).
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b): what a Rust `extern "C"` block + build.rs/nvcc in
+ * rustracer-core would bind to replace the body of `renderer::render` (rustracer-core/src/renderer.rs:22-143)
+ * and the `Primitive` aggregate calls `BVH::intersect` / `BVH::intersect_p`
+ * (rustracer-core/src/bvh/mod.rs:366-501).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Call order (mirrors `RealApi::world_end`, rustracer-core/src/api.rs:992-1010):
+ *   rtgpu_create -> rtgpu_upload_scene -> rtgpu_render -> rtgpu_read_film | rtgpu_resolve_film -> rtgpu_destroy
+ * Every function returns 0 on success or a negative rtgpu_status; rtgpu_last_error() gives the text.
+ * One context per GPU; calls on one context are serialised by the caller and block until finished.
+ *
+ * All scene arrays are HOST pointers owned by the caller; rtgpu_upload_scene copies them.
+ * The host side that fills them (same SAH BVH as the reference, flattened) lives in
+ * rustracer_b200/csrc/host and is exported through include/rthost.h.
+ */
+#ifndef RTGPU_H
+#define RTGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtgpu_ctx rtgpu_ctx;
+
+enum rtgpu_status {
+  RTGPU_OK = 0, RTGPU_ERR_CUDA = -1, RTGPU_ERR_ARG = -2, RTGPU_ERR_NO_SCENE = -3, RTGPU_ERR_OOM = -4,
+  RTGPU_ERR_QUEUE_OVERFLOW = -5, RTGPU_ERR_UNSUPPORTED = -6
+};
+
+/* Ray as `Ray {o, d, t_max}` (rustracer-core/src/ray.rs:9-15); d need not be unit (Q6). 32 B. */
+typedef struct rtgpu_ray { float ox, oy, oz, tmax, dx, dy, dz; uint32_t tag; } rtgpu_ray;
+/* Closest hit: t, prim = prim_number in Shape-directive order (bvh/mod.rs:92) or -1, and for triangles the
+ * barycentrics b1,b2 of mesh.rs:296-299 (quadrics: u,v). 16 B. */
+typedef struct rtgpu_hit { float t; int32_t prim; float b1, b2; } rtgpu_hit;
+
+enum { RTGPU_PRIM_TRIANGLE = 0, RTGPU_PRIM_SPHERE = 1, RTGPU_PRIM_DISK = 2, RTGPU_PRIM_CYLINDER = 3 };
+enum { RTGPU_PRIMFLAG_FLIP = 1 /* reverse_orientation ^ swaps_handedness */, RTGPU_PRIMFLAG_HAS_N = 2, RTGPU_PRIMFLAG_HAS_S = 4,
+       RTGPU_PRIMFLAG_HAS_UV = 8, RTGPU_PRIMFLAG_REVERSE = 16 /* reverse_orientation alone (sphere.rs:300-302) */ };
+
+/* Sphere / Disk / Cylinder with the derived constants the reference computes at construction
+ * (shapes/sphere.rs:30-51, disk.rs:25-45, cylinder.rs:26-46).  176 B. */
+typedef struct rtgpu_quadric {
+  float o2w[16], w2o[16];      /* object_to_world.m and .m_inv */
+  float radius, z_min, z_max, theta_min, theta_max, phi_max;
+  float height, inner_radius;
+  float area;
+  uint32_t kind, flags, pad;
+} rtgpu_quadric;
+
+enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MAT_GLASS = 3, RTGPU_MAT_MIRROR = 4, RTGPU_MAT_NONE = 5 };
+/* Material constants after texture evaluation and after the host-side scalar prep the reference does with
+ * libm at shading time (roughness_to_alpha: microfacet.rs:485-493; OrenNayar A/B: oren_nayar.rs:17-26). 96 B. */
+typedef struct rtgpu_material {
+  uint32_t type;
+  float kd[3], ks[3], kr[3], kt[3], eta_rgb[3], k_rgb[3];
+  float oren_a, oren_b; uint32_t use_oren_nayar;
+  float alpha_u, alpha_v;      /* after optional remap */
+  float eta;                   /* glass index */
+  uint32_t glass_specular;     /* uroughness == 0 && vroughness == 0 (glass.rs:68) */
+} rtgpu_material;
+
+enum { RTGPU_LIGHT_POINT = 0, RTGPU_LIGHT_DISTANT = 1, RTGPU_LIGHT_INFINITE = 2, RTGPU_LIGHT_AREA = 3 };
+/* Light table row in `Scene::lights` order (api.rs:905-911,963); the row index is the light id. */
+typedef struct rtgpu_light {
+  uint32_t kind;
+  float pos[3];                /* point */
+  float dir[3];                /* distant, normalised (distant.rs:24-33) */
+  float I[3];                  /* point I ; distant L ; area L_emit */
+  uint32_t prim_slot;          /* area: index into the ordered primitive arrays */
+  uint32_t two_sided, n_samples;
+  float area;                  /* area: Shape::area() */
+  float world_radius;          /* distant / infinite: Scene bounding-sphere radius (scene.rs:36-41) */
+  float l2w[9], w2l[9];        /* infinite: upper 3x3 of light_to_world.m and .m_inv (vectors only) */
+  uint32_t env_w, env_h;       /* infinite: map size (1x1 for a constant) */
+  uint32_t env_texels;         /* offset (in floats) into env_data: 3*w*h RGB texels already * L*scale */
+  uint32_t env_func, env_cdf, env_func_int;      /* Distribution2D conditional rows: (2w)x(2h), (2w+1)x(2h), 2h */
+  uint32_t env_mfunc, env_mcdf; float env_mfunc_int; /* marginal: 2h, 2h+1 */
+} rtgpu_light;
+
+/* Flattened scene (SoA, host pointers). */
+typedef struct rtgpu_scene_desc {
+  /* LinearBVHNode (bvh/mod.rs:582-598) as two float4 per node:
+   *   lo = {min.x, min.y, min.z, bits(offset)}   offset = primitives_offset (leaf) | second_child_offset (interior)
+   *   hi = {max.x, max.y, max.z, bits((n_prims << 2) | axis)}   n_prims == 0 for interior nodes */
+  uint32_t n_nodes; const float* node_lo; const float* node_hi;
+  /* primitives in `ordered_prims` order (bvh/mod.rs:120).  prim_geom: 3 float4 per slot —
+   *   triangle: {v0.xyz, bits(0)}, {v1.xyz, 0}, {v2.xyz, 0}  world space (mesh.rs:61)
+   *   quadric : {0,0,0, bits(kind | quadric_index << 2)}, 0, 0 */
+  uint32_t n_prims; const float* prim_geom;
+  const uint32_t* prim_info;   /* 4 per slot: prim_number, material row, light row or 0xffffffff, RTGPU_PRIMFLAG_* */
+  const float* tri_n;          /* 9 per slot (n0,n1,n2) or NULL when no mesh has normals */
+  const float* tri_s;          /* 9 per slot or NULL */
+  const float* tri_uv;         /* 6 per slot or NULL */
+  uint32_t n_quadrics;  const rtgpu_quadric* quadrics;
+  uint32_t n_materials; const rtgpu_material* materials;
+  uint32_t n_lights;    const rtgpu_light* lights;
+  uint32_t n_env_floats; const float* env_data;
+  float world_lo[3], world_hi[3];  /* nodes[0].bounds */
+} rtgpu_scene_desc;
+
+enum { RTGPU_INTEGRATOR_PATH = 0, RTGPU_INTEGRATOR_WHITTED = 1, RTGPU_INTEGRATOR_DIRECT = 2, RTGPU_INTEGRATOR_AO = 3, RTGPU_INTEGRATOR_NORMAL = 4 };
+
+/* Everything `renderer::render` reads from integrator, camera, film and sampler. */
+typedef struct rtgpu_render_desc {
+  int32_t integrator;          /* RTGPU_INTEGRATOR_* */
+  int32_t max_depth;           /* as u8 in the reference (path.rs:42) */
+  float rr_threshold;
+  int32_t light_strategy;      /* 0 uniform, 1 spatial (path.rs:86-94; uniform is forced when n_lights == 1) */
+  int32_t direct_strategy;     /* 0 all, 1 one */
+  int32_t ao_samples;
+  int32_t xres, yres;
+  int32_t cropped[4];          /* Film::cropped_pixel_bounds x0,y0,x1,y1 (film.rs:66-75) */
+  int32_t sample_bounds[4];    /* Film::get_sample_bounds (film.rs:249-257) */
+  int32_t pixel_bounds[4];     /* SamplerIntegrator::pixel_bounds (integrator/mod.rs:35) */
+  int32_t spp;                 /* already rounded up to a power of two (zerotwosequence.rs:32) */
+  int32_t sampler_dims;
+  float raster_to_camera[16], camera_to_world[16];   /* .m of each (camera.rs:38-60) */
+  float lens_radius, focal_distance;
+  float filter_radius[2]; float filter_table[256];    /* film.rs:92-102 */
+  float max_sample_luminance, scale;
+  /* work partition (multi-GPU): 16x16 tiles t with t % tile_world == tile_rank, samples [sample_begin, sample_end) */
+  int32_t tile_rank, tile_world;
+  int32_t sample_begin, sample_end;
+  uint64_t seed;
+  int32_t clear_film;          /* 1 = zero the film first */
+  int32_t wave_paths;          /* 0 = default; paths in flight per wave */
+} rtgpu_render_desc;
+
+/* The counters the reference reports plus device timings (CUDA events, milliseconds). */
+typedef struct rtgpu_stats {
+  uint64_t camera_rays, regular_rays, shadow_rays;
+  uint64_t waves, kernel_launches;
+  float ms_total, ms_closest, ms_anyhit, ms_shade, ms_other;
+  uint64_t closest_launches, anyhit_launches;
+} rtgpu_stats;
+
+int rtgpu_create(int device, rtgpu_ctx** out);
+int rtgpu_destroy(rtgpu_ctx* ctx);
+const char* rtgpu_last_error(rtgpu_ctx* ctx);
+
+int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* scene);
+
+/* == BVH::intersect / BVH::intersect_p over a batch; host buffers, H2D + kernel + D2H inside. */
+int rtgpu_intersect(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits);
+int rtgpu_occluded(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, uint8_t* occluded);
+/* Same, device-resident buffers (device pointers), asynchronous on the context's stream; elapsed_ms (may be NULL)
+ * is the CUDA-event time of the kernel alone and forces a synchronise. */
+int rtgpu_intersect_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, float* elapsed_ms);
+int rtgpu_occluded_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, float* elapsed_ms);
+
+/* == PerspectiveCamera::generate_ray_differential's ray (camera.rs:150-202) for explicit camera samples
+ * {p_film.x, p_film.y, p_lens.x, p_lens.y}; host buffers.  Used by the parity tests. */
+int rtgpu_generate_rays(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const float* samples, size_t n, rtgpu_ray* rays);
+
+/* == renderer::render: accumulate into the device film. */
+int rtgpu_render(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, rtgpu_stats* stats);
+/* Radiance `li()` of individual samples {x, y, sample_index} (no film); host buffers; rgb = 3 floats each. */
+int rtgpu_li_samples(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const int32_t* pixels, size_t n, float* rgb);
+
+/* Film accumulators X,Y,Z,weight per cropped pixel (film.rs:38-43), row-major; host buffer of 4*W*H floats. */
+int rtgpu_read_film(rtgpu_ctx* ctx, float* xyzw);
+/* == Film::write_image arithmetic (film.rs:196-234): RGB = max(0, XYZ->RGB / weight) * scale; 3*W*H floats. */
+int rtgpu_resolve_film(rtgpu_ctx* ctx, float* rgb);
+/* Device pointer + length (floats) of the raw accumulator (R,G,B,weight sums) so the host can run the film
+ * reduce (NCCL via its own communicator, or rtgpu_reduce_film below). */
+int rtgpu_film_device_ptr(rtgpu_ctx* ctx, void** d_ptr, size_t* n_floats);
+/* Single-process multi-GPU: sum the films of ctxs[0..n) into ctxs[root] with peer copies + an add kernel. */
+int rtgpu_reduce_film(rtgpu_ctx** ctxs, int n, int root);
+
+/* device memory helpers so FFI callers need no CUDA runtime binding */
+int rtgpu_malloc(rtgpu_ctx* ctx, size_t bytes, void** d_ptr);
+int rtgpu_free(rtgpu_ctx* ctx, void* d_ptr);
+int rtgpu_memcpy_h2d(rtgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int rtgpu_memcpy_d2h(rtgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int rtgpu_synchronize(rtgpu_ctx* ctx);
+/* number of kernels launched by this context since creation (the bench's gpu_launches claim) */
+uint64_t rtgpu_launch_count(rtgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,185 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (rustracer_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class orc_stats(C.Structure):
+    _fields_ = [("camera_rays", C.c_uint64), ("regular_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("tri_hits", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64), ("seconds_tiles", C.c_double),
+                ("seconds_total", C.c_double), ("threads", C.c_int32)]
+
+
+def build(native=False, quiet=True):
+    """Compile the oracle with g++ (no FMA contraction).  native=True adds -march=native (GPU-box baseline)."""
+    target = "native" if native else "all"
+    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL if quiet else None)
+    return os.path.join(_HERE, "_build", "liboracle_native.so" if native else "liboracle.so")
+
+
+def lib(native=False):
+    global _lib
+    if _lib is not None and not native:
+        return _lib
+    path = os.path.join(_HERE, "_build", "liboracle_native.so" if native else "liboracle.so")
+    if not os.path.exists(path):
+        build(native=native)
+    l = C.CDLL(path)
+    PF = C.POINTER(C.c_float)
+    l.orc_scene_create.restype = C.c_void_p
+    l.orc_scene_create.argtypes = [C.c_void_p]
+    l.orc_scene_destroy.argtypes = [C.c_void_p]
+    l.orc_scene_error.argtypes = [C.c_void_p]
+    l.orc_scene_error.restype = C.c_char_p
+    l.orc_scene_build_seconds.argtypes = [C.c_void_p]
+    l.orc_scene_build_seconds.restype = C.c_double
+    l.orc_bvh_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    l.orc_bvh_export.argtypes = [C.c_void_p, PF, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    l.orc_prim_world_vertices.argtypes = [C.c_void_p, PF]
+    l.orc_intersect.argtypes = [C.c_void_p, PF, C.c_uint64, PF, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), PF, C.c_int]
+    l.orc_occluded.argtypes = [C.c_void_p, PF, C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
+    l.orc_intersect_full.argtypes = [C.c_void_p, PF, C.c_uint64, PF]
+    l.orc_camera_rays.argtypes = [C.c_void_p, PF, C.c_uint64, PF]
+    l.orc_film_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, PF, PF, C.POINTER(orc_stats)]
+    l.orc_li_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, PF, PF]
+    l.orc_find_interval_le.argtypes = [PF, C.c_uint64, C.c_float]
+    l.orc_find_interval_le.restype = C.c_uint64
+    l.orc_distribution1d_sample_discrete.argtypes = [PF, C.c_uint64, C.c_float, PF]
+    l.orc_distribution1d_sample_discrete.restype = C.c_uint64
+    l.orc_distribution1d_sample_continuous.argtypes = [PF, C.c_uint64, C.c_float, PF, C.POINTER(C.c_uint64)]
+    l.orc_distribution1d_sample_continuous.restype = C.c_float
+    l.orc_next_float_up.argtypes = [C.c_float]
+    l.orc_next_float_up.restype = C.c_float
+    l.orc_next_float_down.argtypes = [C.c_float]
+    l.orc_next_float_down.restype = C.c_float
+    l.orc_gamma.argtypes = [C.c_uint32]
+    l.orc_gamma.restype = C.c_float
+    l.orc_radical_inverse.argtypes = [C.c_uint32, C.c_uint64]
+    l.orc_radical_inverse.restype = C.c_float
+    l.orc_pcg32_sequence.argtypes = [C.c_uint64, C.POINTER(C.c_uint32), C.c_uint64]
+    l.orc_matrix_inverse.argtypes = [PF, PF]
+    l.orc_zerotwo_camera_samples.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, PF]
+    l.orc_counter_draws.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, PF]
+    l.orc_fr_dielectric.argtypes = [C.c_float] * 3
+    l.orc_fr_dielectric.restype = C.c_float
+    l.orc_roughness_to_alpha.argtypes = [C.c_float]
+    l.orc_roughness_to_alpha.restype = C.c_float
+    l.orc_selftest.argtypes = [C.c_uint64, C.c_char_p, C.c_int]
+    if not native:
+        _lib = l
+    return l
+
+
+def _pf(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class OracleScene:
+    """CPU restatement of rustracer's Scene + BVH + integrators built from an `rt_scene` pointer."""
+
+    def __init__(self, rt_scene_ptr, native=False):
+        self._l = lib(native)
+        self._h = C.c_void_p(self._l.orc_scene_create(C.cast(rt_scene_ptr, C.c_void_p)))
+        err = self._l.orc_scene_error(self._h)
+        if err:
+            raise RuntimeError(err.decode())
+        n, p, li = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._l.orc_bvh_info(self._h, C.byref(n), C.byref(p), C.byref(li))
+        self.n_nodes, self.n_prims, self.n_lights = n.value, p.value, li.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._l.orc_scene_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def build_seconds(self):
+        return self._l.orc_scene_build_seconds(self._h)
+
+    def bvh(self):
+        bounds = np.zeros((self.n_nodes, 6), np.float32)
+        meta = np.zeros((self.n_nodes, 3), np.int64)
+        ordered = np.zeros(self.n_prims, np.int32)
+        self._l.orc_bvh_export(self._h, _pf(bounds), meta.ctypes.data_as(C.POINTER(C.c_int64)), ordered.ctypes.data_as(C.POINTER(C.c_int32)))
+        return bounds, meta, ordered
+
+    def prim_world_vertices(self):
+        out = np.zeros((self.n_prims, 9), np.float32)
+        self._l.orc_prim_world_vertices(self._h, _pf(out))
+        return out
+
+    def intersect(self, rays, threads=0, stats=True):
+        """rays: (n, 8) float32 {o, tmax, d, tag}. Returns dict(t, prim, b1, b2, nodes, prims, edge)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        hits = np.zeros((n, 4), np.float32)
+        nodes = np.zeros(n, np.uint32)
+        prims = np.zeros(n, np.uint32)
+        edge = np.zeros(n, np.float32)
+        self._l.orc_intersect(self._h, _pf(rays), n, _pf(hits), nodes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                              prims.ctypes.data_as(C.POINTER(C.c_uint32)), _pf(edge), threads)
+        return dict(t=hits[:, 0].copy(), prim=hits[:, 1].copy().view(np.int32), b1=hits[:, 2].copy(), b2=hits[:, 3].copy(),
+                    nodes=nodes, prims=prims, edge=edge)
+
+    def occluded(self, rays, threads=0):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        out = np.zeros(n, np.uint8)
+        nodes = np.zeros(n, np.uint32)
+        prims = np.zeros(n, np.uint32)
+        self._l.orc_occluded(self._h, _pf(rays), n, out.ctypes.data_as(C.POINTER(C.c_uint8)), nodes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                             prims.ctypes.data_as(C.POINTER(C.c_uint32)), threads)
+        return dict(occluded=out, nodes=nodes, prims=prims)
+
+    def intersect_full(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros((rays.shape[0], 24), np.float32)
+        self._l.orc_intersect_full(self._h, _pf(rays), rays.shape[0], _pf(out))
+        return out
+
+    def camera_rays(self, samples):
+        samples = np.ascontiguousarray(samples, np.float32)
+        out = np.zeros((samples.shape[0], 8), np.float32)
+        self._l.orc_camera_rays(self._h, _pf(samples), samples.shape[0], _pf(out))
+        return out
+
+    def film_bounds(self):
+        c = (C.c_int32 * 4)()
+        s = (C.c_int32 * 4)()
+        self._l.orc_film_bounds(self._h, c, s)
+        return list(c), list(s)
+
+    def render(self, integrator=None, sampler=None, sampler_kind=0, seed=0, threads=0, tile_stride=1):
+        """Returns (film_xyzw (H,W,4), rgb (H,W,3), stats). sampler_kind 0 = ZeroTwoSequence, 1 = counter sampler."""
+        c, _ = self.film_bounds()
+        w, h = c[2] - c[0], c[3] - c[1]
+        film = np.zeros((h, w, 4), np.float32)
+        rgb = np.zeros((h, w, 3), np.float32)
+        st = orc_stats()
+        ip = C.cast(C.byref(integrator), C.c_void_p) if integrator is not None else None
+        sp = C.cast(C.byref(sampler), C.c_void_p) if sampler is not None else None
+        self._l.orc_render(self._h, ip, sp, sampler_kind, seed, threads, tile_stride, _pf(film), _pf(rgb), C.byref(st))
+        return film, rgb, st
+
+    def li_samples(self, pixels, integrator=None, sampler=None, seed=0):
+        pixels = np.ascontiguousarray(pixels, np.int32)
+        n = pixels.shape[0]
+        out = np.zeros((n, 3), np.float32)
+        pf = np.zeros((n, 2), np.float32)
+        ip = C.cast(C.byref(integrator), C.c_void_p) if integrator is not None else None
+        sp = C.cast(C.byref(sampler), C.c_void_p) if sampler is not None else None
+        self._l.orc_li_samples(self._h, ip, sp, seed, pixels.ctypes.data_as(C.POINTER(C.c_int32)), n, _pf(out), _pf(pf))
+        return out, pf

@@ -1,0 +1,144 @@
+// C ABI of the host side (include/rthost.h).
+#include "../../../include/rthost.h"
+#include "pbrt_frontend.hpp"
+#include "scene_build.hpp"
+#include <cstdio>
+#include <string>
+
+using namespace rth;
+
+struct rth_scene {
+  std::unique_ptr<ParsedScene> parsed;
+  FlatScene flat;
+  bool flattened = false;
+};
+
+static thread_local std::string g_error;
+
+template <class F> static int guarded(F f) {
+  try { f(); g_error.clear(); return 0; }
+  catch (const std::exception& e) { g_error = e.what(); return -1; }
+  catch (...) { g_error = "unknown error"; return -1; }
+}
+
+extern "C" {
+
+const char* rth_last_error(void) { return g_error.c_str(); }
+
+int rth_parse_file(const char* path, rth_scene** out) {
+  *out = nullptr;
+  return guarded([&] { auto s = new rth_scene(); try { s->parsed = parse_scene_file(path, FrontendOptions()); } catch (...) { delete s; throw; } *out = s; });
+}
+int rth_parse_string(const char* text, const char* search_dir, rth_scene** out) {
+  *out = nullptr;
+  return guarded([&] {
+    FrontendOptions opt; if (search_dir) opt.search_dir = search_dir;
+    auto s = new rth_scene(); try { s->parsed = parse_scene_text(text, opt); } catch (...) { delete s; throw; } *out = s;
+  });
+}
+void rth_scene_free(rth_scene* s) { delete s; }
+rt_scene* rth_scene_ir(rth_scene* s) { return &s->parsed->store.view; }
+int rth_n_warnings(rth_scene* s) { return (int)s->parsed->store.warnings.size(); }
+const char* rth_warning(rth_scene* s, int i) { return s->parsed->store.warnings.at((size_t)i).c_str(); }
+const char* rth_film_filename(rth_scene* s) { return s->parsed->film_filename.c_str(); }
+const char* rth_integrator_name(rth_scene* s) { return s->parsed->integrator_name.c_str(); }
+
+int rth_flatten(rth_scene* s, int threads) {
+  return guarded([&] { s->flat = FlatScene(); flatten_scene(s->parsed->store.view, threads, s->flat); s->flattened = true; });
+}
+const rtgpu_scene_desc* rth_scene_desc(rth_scene* s) { return s->flattened ? &s->flat.desc : nullptr; }
+double rth_bvh_build_seconds(rth_scene* s) { return s->flat.bvh.build_seconds; }
+uint64_t rth_n_triangles(rth_scene* s) { return s->flat.n_triangles; }
+const uint32_t* rth_slot_of_prim(rth_scene* s) { return s->flattened ? s->flat.slot_of_prim.data() : nullptr; }
+int rth_render_desc(rth_scene* s, rtgpu_render_desc* out) { return guarded([&] { make_render_desc(s->parsed->store.view, *out); }); }
+
+int rth_tokenize(const char* text, char* out, size_t out_len) {
+  int count = -1;
+  int rc = guarded([&] {
+    std::vector<Token> toks = tokenize(text);
+    std::string s;
+    for (const Token& t : toks) {
+      if (t.kind == Tok::STR) s += "STR:" + t.str;
+      else if (t.kind == Tok::NUMBER) { char b[64]; std::snprintf(b, sizeof b, "NUMBER:%.9g", (double)t.num); s += b; }
+      else s += tok_name(t.kind);
+      s += "\n";
+    }
+    if (out && out_len) std::snprintf(out, out_len, "%s", s.c_str());
+    count = (int)toks.size();
+  });
+  return rc == 0 ? count : -1;
+}
+int rth_param_header(const char* s, int* type_out, char* name_out, size_t name_len) {
+  ParamType t; std::string n;
+  if (!parse_param_header(s, t, n)) return -1;
+  *type_out = (int)t;
+  std::snprintf(name_out, name_len, "%s", n.c_str());
+  return 0;
+}
+
+// ---- image output -------------------------------------------------------------------------------
+static uint32_t crc32_of(const unsigned char* d, size_t n, uint32_t crc = 0) {
+  static uint32_t table[256]; static bool init = false;
+  if (!init) { for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1; table[i] = c; } init = true; }
+  crc = ~crc;
+  for (size_t i = 0; i < n; i++) crc = table[(crc ^ d[i]) & 0xff] ^ (crc >> 8);
+  return ~crc;
+}
+static void png_chunk(FILE* f, const char* type, const std::vector<unsigned char>& data) {
+  unsigned char len[4] = {(unsigned char)(data.size() >> 24), (unsigned char)(data.size() >> 16), (unsigned char)(data.size() >> 8), (unsigned char)data.size()};
+  std::fwrite(len, 1, 4, f);
+  std::vector<unsigned char> buf(type, type + 4);
+  buf.insert(buf.end(), data.begin(), data.end());
+  std::fwrite(buf.data(), 1, buf.size(), f);
+  uint32_t c = crc32_of(buf.data(), buf.size());
+  unsigned char cb[4] = {(unsigned char)(c >> 24), (unsigned char)(c >> 16), (unsigned char)(c >> 8), (unsigned char)c};
+  std::fwrite(cb, 1, 4, f);
+}
+static float gamma_correct(float v) { return v <= 0.0031308f ? 12.92f * v : 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f; }   // spectrum.rs:387-393
+
+int rth_write_image(const char* path, const float* rgb, int width, int height) {
+  return guarded([&] {
+    std::string p(path);
+    auto ends = [&](const char* e) { size_t L = std::strlen(e); return p.size() >= L && p.compare(p.size() - L, L, e) == 0; };
+    FILE* f = std::fopen(path, "wb");
+    if (!f) throw std::runtime_error("Failed to save image file " + p);
+    if (ends(".pfm")) {
+      std::fprintf(f, "PF\n%d %d\n-1.0\n", width, height);
+      for (int y = height - 1; y >= 0; y--) std::fwrite(rgb + (size_t)y * width * 3, sizeof(float), (size_t)width * 3, f);
+    } else if (ends(".png")) {                                        // imageio.rs:52-73
+      static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+      std::fwrite(sig, 1, 8, f);
+      std::vector<unsigned char> ihdr = {(unsigned char)(width >> 24), (unsigned char)(width >> 16), (unsigned char)(width >> 8), (unsigned char)width,
+                                         (unsigned char)(height >> 24), (unsigned char)(height >> 16), (unsigned char)(height >> 8), (unsigned char)height, 8, 2, 0, 0, 0};
+      png_chunk(f, "IHDR", ihdr);
+      std::vector<unsigned char> raw; raw.reserve((size_t)height * ((size_t)width * 3 + 1));
+      for (int y = 0; y < height; y++) {
+        raw.push_back(0);
+        for (int x = 0; x < width * 3; x++) {
+          float v = 255.0f * gamma_correct(rgb[(size_t)y * width * 3 + x]) + 0.5f;
+          v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+          raw.push_back((v == v) ? (unsigned char)v : 0);
+        }
+      }
+      std::vector<unsigned char> z = {0x78, 0x01};                    // zlib header, stored (uncompressed) deflate blocks
+      uint32_t a = 1, b = 0;
+      for (unsigned char c : raw) { a = (a + c) % 65521; b = (b + a) % 65521; }
+      size_t pos = 0;
+      while (pos < raw.size() || raw.empty()) {
+        size_t n = std::min<size_t>(65535, raw.size() - pos);
+        bool last = pos + n >= raw.size();
+        z.push_back(last ? 1 : 0); z.push_back((unsigned char)n); z.push_back((unsigned char)(n >> 8)); z.push_back((unsigned char)~n); z.push_back((unsigned char)(~n >> 8));
+        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
+        pos += n;
+        if (last) break;
+      }
+      uint32_t ad = (b << 16) | a;
+      z.push_back((unsigned char)(ad >> 24)); z.push_back((unsigned char)(ad >> 16)); z.push_back((unsigned char)(ad >> 8)); z.push_back((unsigned char)ad);
+      png_chunk(f, "IDAT", z);
+      png_chunk(f, "IEND", {});
+    } else { std::fclose(f); throw std::runtime_error("Unsupported file format"); }   // imageio.rs:47-49 (.exr is out of scope here)
+    std::fclose(f);
+  });
+}
+
+}  // extern "C"

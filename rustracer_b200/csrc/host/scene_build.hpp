@@ -1,0 +1,34 @@
+// rt_scene -> rtgpu_scene_desc + rtgpu_render_desc (host, product code).
+// This is the "flatten LinearBVHNode, triangle, sphere, disc and cylinder data into SoA device arrays" step of
+// the north star, plus the host-side constants the reference computes at object construction
+// (Sphere::new, Disk::new, Film::new, PerspectiveCamera::new, InfiniteAreaLight::new, Scene::new ...).
+#pragma once
+#include <string>
+#include <vector>
+#include "bvh_builder.hpp"
+#include "../../../include/rtgpu.h"
+
+namespace rth {
+
+struct FlatScene {
+  FlatBvh bvh;
+  std::vector<float> prim_geom;          // 12 floats per slot
+  std::vector<uint32_t> prim_info;       // 4 per slot
+  std::vector<float> tri_n, tri_s, tri_uv;
+  std::vector<rtgpu_quadric> quadrics;
+  std::vector<rtgpu_material> materials;
+  std::vector<rtgpu_light> lights;
+  std::vector<float> env_data;
+  std::vector<uint32_t> slot_of_prim;    // prim_number -> slot
+  rtgpu_scene_desc desc{};
+  rtgpu_render_desc render{};
+  size_t n_triangles = 0;
+  std::string error;
+};
+
+// threads: BVH build threads (<= 0: all).  Throws std::runtime_error on unsupported input.
+void flatten_scene(const rt_scene& in, int threads, FlatScene& out);
+// Film / camera / integrator / sampler part only (no geometry): fills out.render from `in`.
+void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd);
+
+}  // namespace rth

@@ -1,0 +1,312 @@
+"""Synthetic scenes for the benchmark configs of SURVEY.md §8(d) (C1..C5), written as PBRT text + binary PLY
+that obey the subset rustracer's front end accepts: `Sampler "02sequence"`, box filter,
+`trianglemesh` / `plymesh` / `sphere` / `disk`, matte / plastic / metal / glass / mirror.
+
+Everything is seeded with PCG32 (rustracer-core/src/rng.rs) so the same files are produced everywhere.
+"""
+import os
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------
+# PCG32 (rng.rs:5-52), vectorised over independent streams
+
+
+class PCG32:
+    MULT = np.uint64(0x5851F42D4C957F2D)
+
+    def __init__(self, seeds):
+        """One generator per entry of `seeds` (== RNG::set_sequence(seed))."""
+        old = np.seterr(over="ignore")
+        try:
+            seeds = np.atleast_1d(np.asarray(seeds, dtype=np.uint64))
+            self.state = np.zeros_like(seeds)
+            self.inc = (seeds << np.uint64(1)) | np.uint64(1)
+            self.u32()
+            self.state = self.state + np.uint64(0x853C49E6748FEA9B)
+            self.u32()
+        finally:
+            np.seterr(**old)
+
+    def u32(self):
+        old = np.seterr(over="ignore")
+        try:
+            s = self.state
+            self.state = s * self.MULT + self.inc
+            xorshifted = (((s >> np.uint64(18)) ^ s) >> np.uint64(27)).astype(np.uint32)
+            rot = (s >> np.uint64(59)).astype(np.uint32)
+            return (xorshifted >> rot) | (xorshifted << ((~rot + np.uint32(1)) & np.uint32(31)))
+        finally:
+            np.seterr(**old)
+
+    def f32(self):
+        return np.minimum(self.u32().astype(np.float32) * np.float32(2.3283064365386963e-10), np.float32(0.99999994))
+
+
+def uniform_sample_sphere(u0, u1):
+    """sampling/mod.rs:14-20 in float32."""
+    z = np.float32(1.0) - np.float32(2.0) * u0
+    r = np.sqrt(np.maximum(np.float32(1.0) - z * z, np.float32(0.0)))
+    phi = np.float32(2.0 * np.pi) * u1
+    return np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=-1).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry
+
+
+def icosphere(level):
+    """Unit icosphere: (V,3) float64 vertices, (F,3) int32 faces; 20*4**level faces."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+                  [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    for _ in range(level):
+        e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], axis=0)
+        e_sorted = np.sort(e, axis=1)
+        key = e_sorted[:, 0] * (len(v) + 1) + e_sorted[:, 1]
+        uniq, inv = np.unique(key, return_inverse=True)
+        first = np.zeros(len(uniq), dtype=np.int64)
+        first[inv[::-1]] = np.arange(len(key))[::-1]
+        mid = v[e_sorted[first, 0]] + v[e_sorted[first, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        mid_idx = len(v) + inv
+        v = np.concatenate([v, mid], axis=0)
+        n = len(f)
+        a, b, c = mid_idx[:n], mid_idx[n:2 * n], mid_idx[2 * n:]
+        f = np.concatenate([np.stack([f[:, 0], a, c], 1), np.stack([f[:, 1], b, a], 1), np.stack([f[:, 2], c, b], 1), np.stack([a, b, c], 1)], axis=0)
+    return v, f.astype(np.int32)
+
+
+def write_ply(path, verts, faces):
+    """binary_little_endian PLY: float x y z, `list uchar int vertex_indices` (what plymesh.rs accepts)."""
+    verts = np.ascontiguousarray(verts, dtype="<f4")
+    faces = np.ascontiguousarray(faces, dtype="<i4")
+    hdr = ("ply\nformat binary_little_endian 1.0\ncomment rustracer_b200 synthetic\n"
+           f"element vertex {len(verts)}\nproperty float x\nproperty float y\nproperty float z\n"
+           f"element face {len(faces)}\nproperty list uchar int vertex_indices\nend_header\n")
+    rec = np.zeros(len(faces), dtype=[("n", "u1"), ("i", "<i4", (3,))])
+    rec["n"] = 3
+    rec["i"] = faces
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        f.write(verts.tobytes())
+        f.write(rec.tobytes())
+
+
+def sphere_field(n_spheres, level, seed, extent, rmin, rmax, grid=None):
+    """n_spheres icospheres: centres jittered on a grid (grid=(nx,ny): XZ plane, resting on y=0) or uniform in a
+    cube of half-size `extent`.  Returns verts (float32), faces (int32), centres, radii."""
+    rng = PCG32([seed])
+    base_v, base_f = icosphere(level)
+    centres = np.zeros((n_spheres, 3), np.float32)
+    radii = np.zeros(n_spheres, np.float32)
+    for i in range(n_spheres):
+        r = np.float32(rmin) + np.float32(rmax - rmin) * rng.f32()[0]
+        if grid is not None:
+            nx, ny = grid
+            gx, gz = i % nx, i // nx
+            cell = np.float32(2.0 * extent / max(nx, ny))
+            jx = (rng.f32()[0] - np.float32(0.5)) * cell * np.float32(0.4)
+            jz = (rng.f32()[0] - np.float32(0.5)) * cell * np.float32(0.4)
+            centres[i] = [(gx + 0.5) * cell - extent + jx, r, (gz + 0.5) * cell - extent + jz]
+        else:
+            centres[i] = [(rng.f32()[0] * 2 - 1) * extent, (rng.f32()[0] * 2 - 1) * extent, (rng.f32()[0] * 2 - 1) * extent]
+        radii[i] = r
+    nv = len(base_v)
+    verts = (base_v[None, :, :] * radii[:, None, None].astype(np.float64) + centres[:, None, :].astype(np.float64)).reshape(-1, 3).astype(np.float32)
+    faces = (base_f[None, :, :].astype(np.int64) + (np.arange(n_spheres, dtype=np.int64) * nv)[:, None, None]).reshape(-1, 3).astype(np.int32)
+    return verts, faces, centres, radii
+
+
+# ------------------------------------------------------------------------------------------------
+# pbrt text helpers
+
+
+def _fmt(a):
+    return " ".join(repr(float(np.float32(x))) for x in np.asarray(a).ravel())
+
+
+def _mesh(P, idx):
+    return f'Shape "trianglemesh" "integer indices" [{" ".join(str(int(i)) for i in np.asarray(idx).ravel())}] "point P" [{_fmt(P)}]\n'
+
+
+def _quad(p0, p1, p2, p3):
+    return _mesh([p0, p1, p2, p3], [0, 1, 2, 0, 2, 3])
+
+
+def _box(lo, hi, rot_y_deg=0.0, centre=None):
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    c = np.array([[lo[0], lo[1], lo[2]], [hi[0], lo[1], lo[2]], [hi[0], hi[1], lo[2]], [lo[0], hi[1], lo[2]],
+                  [lo[0], lo[1], hi[2]], [hi[0], lo[1], hi[2]], [hi[0], hi[1], hi[2]], [lo[0], hi[1], hi[2]]])
+    if rot_y_deg:
+        ctr = (lo + hi) / 2 if centre is None else np.asarray(centre, float)
+        a = np.deg2rad(rot_y_deg)
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        c = (c - ctr) @ R.T + ctr
+    idx = [0, 2, 1, 0, 3, 2, 4, 5, 6, 4, 6, 7, 0, 1, 5, 0, 5, 4, 2, 3, 7, 2, 7, 6, 1, 2, 6, 1, 6, 5, 3, 0, 4, 3, 4, 7]
+    return _mesh(c, idx)
+
+
+def header(xres, yres, spp, integrator, fov, look, crop=None, extra_film=""):
+    eye, at, up = look
+    cropw = "" if crop is None else f' "float cropwindow" [{_fmt(crop)}]'
+    return (f"LookAt {_fmt(eye)}  {_fmt(at)}  {_fmt(up)}\n"
+            f'Camera "perspective" "float fov" [{fov}]\n'
+            f'Film "image" "integer xresolution" [{xres}] "integer yresolution" [{yres}] "string filename" "out.png"{cropw}{extra_film}\n'
+            f'Sampler "02sequence" "integer pixelsamples" [{spp}]\n'
+            'PixelFilter "box"\n'
+            f"{integrator}\n")
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: Cornell box
+
+
+def cornell_box(xres=512, yres=512, spp=16, integrator=None, crop=None):
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "uniform"'
+    s = header(xres, yres, spp, integrator, 39, ([278, 273, -800], [278, 273, 0], [0, 1, 0]), crop)
+    s += "WorldBegin\n"
+    white, red, green = "0.73 0.73 0.73", "0.65 0.05 0.05", "0.12 0.45 0.15"
+    s += f'Material "matte" "rgb Kd" [{white}]\n'
+    s += _quad([0, 0, 0], [556, 0, 0], [556, 0, 559.2], [0, 0, 559.2])              # floor
+    s += _quad([0, 548.8, 0], [0, 548.8, 559.2], [556, 548.8, 559.2], [556, 548.8, 0])  # ceiling
+    s += _quad([0, 0, 559.2], [556, 0, 559.2], [556, 548.8, 559.2], [0, 548.8, 559.2])  # back
+    s += f'Material "matte" "rgb Kd" [{green}]\n'
+    s += _quad([0, 0, 0], [0, 0, 559.2], [0, 548.8, 559.2], [0, 548.8, 0])             # right (x=0)
+    s += f'Material "matte" "rgb Kd" [{red}]\n'
+    s += _quad([556, 0, 0], [556, 548.8, 0], [556, 548.8, 559.2], [556, 0, 559.2])     # left (x=556)
+    s += f'Material "matte" "rgb Kd" [{white}]\n'
+    s += _box([130, 0, 65], [295, 165, 230], rot_y_deg=-18)                           # short box
+    s += _box([265, 0, 295], [430, 330, 460], rot_y_deg=15)                           # tall box
+    s += "AttributeBegin\n"
+    s += 'AreaLightSource "diffuse" "rgb L" [17 12 4]\n'
+    s += 'Material "matte" "rgb Kd" [0 0 0]\n'
+    # ceiling light, facing down (normal = -y)
+    s += _quad([213, 548.7, 227], [343, 548.7, 227], [343, 548.7, 332], [213, 548.7, 332])
+    s += "AttributeEnd\nWorldEnd\n"
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# C2: balls (64 spheres + ground disk)
+
+_MATERIALS = [
+    'Material "matte" "rgb Kd" [{c}]',
+    'Material "plastic" "rgb Kd" [{c}] "rgb Ks" [0.3 0.3 0.3] "float roughness" [0.05]',
+    'Material "metal" "float roughness" [0.02]',
+    'Material "glass" "float index" [1.5]',
+    'Material "mirror" "rgb Kr" [0.9 0.9 0.9]',
+]
+
+
+def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None):
+    if integrator is None:
+        integrator = 'Integrator "whitted" "integer maxdepth" [5]'
+    s = header(xres, yres, spp, integrator, 40, ([0, 7.5, -13], [0, 0.3, 0], [0, 1, 0]), crop)
+    s += "WorldBegin\n"
+    s += 'LightSource "point" "rgb I" [220 220 220] "point from" [-6 9 -6]\n'
+    s += 'LightSource "point" "rgb I" [120 110 100] "point from" [7 6 -3]\n'
+    s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [12 12 12]\nTranslate 0 6 2\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "sphere" "float radius" [0.6]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "matte" "rgb Kd" [0.55 0.55 0.5]\nRotate -90 1 0 0\nShape "disk" "float radius" [20]\nAttributeEnd\n'
+    rng = PCG32([2])
+    n = n_side * n_side
+    for i in range(n):
+        r = np.float32(0.3) + np.float32(0.2) * rng.f32()[0]
+        gx, gz = i % n_side, i // n_side
+        x = (gx - (n_side - 1) / 2) * 1.25 + float(rng.f32()[0] - 0.5) * 0.3
+        z = (gz - (n_side - 1) / 2) * 1.25 + float(rng.f32()[0] - 0.5) * 0.3
+        col = f"{0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f}"
+        s += "AttributeBegin\n" + _MATERIALS[i % 5].format(c=col) + f"\nTranslate {x:.5f} {float(r):.5f} {z:.5f}\n"
+        s += f'Shape "sphere" "float radius" [{float(r):.5f}]\nAttributeEnd\n'
+    s += "WorldEnd\n"
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# C3 / C5: icosphere fields written as PLY; C4: ray-batch field
+
+
+def sphere_field_scene(out_dir, name, n_spheres, level, seed, xres, yres, spp, integrator, grid, materials_cycle=False, n_area_lights=1,
+                       env=True, crop=None):
+    """Writes <out_dir>/<name>*.ply and returns the pbrt text (the scene must be parsed with search_dir=out_dir)."""
+    os.makedirs(out_dir, exist_ok=True)
+    extent = 2.2 * max(grid)
+    verts, faces, centres, radii = sphere_field(n_spheres, level, seed, extent, 0.7, 1.3, grid=grid)
+    s = header(xres, yres, spp, integrator, 38, ([0, 0.9 * extent, -2.1 * extent], [0, 0.8, -0.1 * extent], [0, 1, 0]), crop)
+    s += "WorldBegin\n"
+    if env:
+        s += 'LightSource "infinite" "rgb L" [0.35 0.4 0.5]\n'
+    nv = len(verts) // n_spheres
+    nf = len(faces) // n_spheres
+    groups = 5 if materials_cycle else 1
+    for g in range(groups):
+        sel = np.arange(g, n_spheres, groups)
+        if len(sel) == 0:
+            continue
+        v = verts.reshape(n_spheres, nv, 3)[sel].reshape(-1, 3)
+        f = (faces.reshape(n_spheres, nf, 3)[sel] - (sel * nv)[:, None, None] + (np.arange(len(sel)) * nv)[:, None, None]).reshape(-1, 3)
+        fn = f"{name}_{g}.ply"
+        write_ply(os.path.join(out_dir, fn), v, f)
+        mat = _MATERIALS[g % 5].format(c="0.6 0.55 0.5") if materials_cycle else 'Material "matte" "rgb Kd" [0.6 0.55 0.5]'
+        s += f'AttributeBegin\n{mat}\nShape "plymesh" "string filename" "{fn}"\nAttributeEnd\n'
+    e = 1.6 * extent
+    s += 'Material "matte" "rgb Kd" [0.5 0.5 0.5]\n' + _quad([-e, 0, -e], [e, 0, -e], [e, 0, e], [-e, 0, e])
+    for k in range(n_area_lights):
+        cx = (k - (n_area_lights - 1) / 2) * extent * 0.8
+        h = 2.2 * extent * 0.5 + 3.0
+        q = extent * 0.25
+        s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [30 28 25]\nMaterial "matte" "rgb Kd" [0 0 0]\n'
+        s += _quad([cx - q, h, -q], [cx + q, h, -q], [cx + q, h, q], [cx - q, h, q]) + "AttributeEnd\n"
+    s += "WorldEnd\n"
+    return s
+
+
+def c3_scene(out_dir, integrator=None, level=5, xres=1920, yres=1080, spp=256, crop=None):
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "spatial"'
+    return sphere_field_scene(out_dir, "c3", 49, level, 3, xres, yres, spp, integrator, grid=(7, 7), crop=crop)
+
+
+def c5_scene(out_dir, integrator=None, level=5, xres=3840, yres=2160, spp=1024, n_spheres=244, crop=None):
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "spatial"'
+    return sphere_field_scene(out_dir, "c5", n_spheres, level, 6, xres, yres, spp, integrator, grid=(16, 16), materials_cycle=True,
+                              n_area_lights=4, crop=crop)
+
+
+def c4_scene(out_dir, n_spheres=489, level=5, seed=4):
+    """Ray-batch field: n_spheres level-`level` icospheres uniformly placed in a cube (489 x 20480 = 10 014 720 tris)."""
+    os.makedirs(out_dir, exist_ok=True)
+    verts, faces, _, _ = sphere_field(n_spheres, level, seed, 30.0, 1.5, 3.5, grid=None)
+    write_ply(os.path.join(out_dir, "c4.ply"), verts, faces)
+    s = header(64, 64, 1, 'Integrator "path"', 40, ([0, 0, -120], [0, 0, 0], [0, 1, 0]))
+    s += 'WorldBegin\nMaterial "matte"\nShape "plymesh" "string filename" "c4.ply"\nWorldEnd\n'
+    return s
+
+
+def ray_batch(n, world_lo, world_hi, seed=5, any_hit=False, first=0):
+    """ray i uses PCG32 stream (seed*2^32 + i): origin uniform in the world bounds grown 5 %,
+    direction uniform on the sphere (closest-hit, t_max = inf) or the segment to a second uniform point
+    (any-hit, d = p1 - p0, t_max = 1 - 1e-4).  Returns (n, 8) float32 {o, tmax, d, tag}."""
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    rng = PCG32((np.uint64(seed) << np.uint64(32)) + idx)
+    lo = np.asarray(world_lo, np.float32)
+    hi = np.asarray(world_hi, np.float32)
+    c, h = (lo + hi) * np.float32(0.5), (hi - lo) * np.float32(0.5 * 1.05)
+    rays = np.zeros((n, 8), np.float32)
+    for k in range(3):
+        rays[:, k] = c[k] + (rng.f32() * np.float32(2) - np.float32(1)) * h[k]
+    if any_hit:
+        for k in range(3):
+            p1 = c[k] + (rng.f32() * np.float32(2) - np.float32(1)) * h[k]
+            rays[:, 4 + k] = p1 - rays[:, k]
+        rays[:, 3] = np.float32(1.0 - 1e-4)
+    else:
+        rays[:, 4:7] = uniform_sample_sphere(rng.f32(), rng.f32())
+        rays[:, 3] = np.inf
+    rays[:, 7] = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+    return rays
