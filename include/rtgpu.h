@@ -149,6 +149,12 @@ int rtgpu_occluded(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, uint8_t* occ
  * is the CUDA-event time of the kernel alone and forces a synchronise. */
 int rtgpu_intersect_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, float* elapsed_ms);
 int rtgpu_occluded_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, float* elapsed_ms);
+/* Same walks, additionally writing per ray {BVH nodes visited, primitives tested} (2 x uint32 per ray, device
+ * pointer): the N and T of the roofline's algorithmic bytes per ray; equal to the oracle's counts. */
+int rtgpu_intersect_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, uint32_t* d_stats);
+int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, uint32_t* d_stats);
+/* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1). */
+int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);
 
 /* == PerspectiveCamera::generate_ray_differential's ray (camera.rs:150-202) for explicit camera samples
  * {p_film.x, p_film.y, p_lens.x, p_lens.y}; host buffers.  Used by the parity tests. */

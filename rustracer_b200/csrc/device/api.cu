@@ -1,0 +1,368 @@
+// librtgpu.so — context, scene upload and the batched BVH::intersect / BVH::intersect_p entry points
+// (include/rtgpu.h).  Hand-written CUDA for sm_100a; compiled with -fmad=false.
+#include "context.hpp"
+#include <cstring>
+#include <new>
+
+using namespace rt;
+
+namespace rt {
+
+// ---------------------------------------------------------------------------------------------------------
+// Ray binning: incoherent batches are reordered by (origin cell Morton code, direction octant) so that the
+// 32 rays of a warp start in the same part of the tree.  Results are written back through the permutation,
+// so the caller sees the original order; per-ray results do not depend on the order.
+constexpr int kCellBits = 5;                       // 32^3 origin cells
+constexpr int kSortBins = 1 << (3 * kCellBits + 3);
+
+RT_DEV uint32_t spread3(uint32_t v) {              // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+RT_DEV uint32_t ray_sort_key(const float4 a, const float4 b, const float* lo, const float* inv_ext) {
+  const float cells = (float)(1 << kCellBits);
+  int cx = min(max(__float2int_rd((a.x - lo[0]) * inv_ext[0] * cells), 0), (1 << kCellBits) - 1);
+  int cy = min(max(__float2int_rd((a.y - lo[1]) * inv_ext[1] * cells), 0), (1 << kCellBits) - 1);
+  int cz = min(max(__float2int_rd((a.z - lo[2]) * inv_ext[2] * cells), 0), (1 << kCellBits) - 1);
+  uint32_t morton = spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
+  uint32_t oct = (b.x < 0.0f ? 1u : 0u) | (b.y < 0.0f ? 2u : 0u) | (b.z < 0.0f ? 4u : 0u);
+  return (morton << 3) | oct;
+}
+
+struct SortParams { float lo[3], inv_ext[3]; };
+
+__global__ void __launch_bounds__(256) k_sort_hist(const float4* __restrict__ rays, uint32_t n, SortParams sp, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+  uint32_t k = ray_sort_key(a, b, sp.lo, sp.inv_ext);
+  keys[i] = k;
+  atomicAdd(&hist[k], 1u);
+}
+// exclusive scan of kSortBins counters by one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t partial[1024];
+  constexpr int per = kSortBins / 1024;
+  uint32_t base = threadIdx.x * per, sum = 0;
+  for (int i = 0; i < per; i++) sum += hist[base + i];
+  partial[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t v = threadIdx.x >= off ? partial[threadIdx.x - off] : 0;
+    __syncthreads();
+    partial[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = partial[threadIdx.x] - sum;
+  for (int i = 0; i < per; i++) { uint32_t c = hist[base + i]; hist[base + i] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ offsets, uint32_t* __restrict__ perm) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t pos = atomicAdd(&offsets[keys[i]], 1u);
+  perm[pos] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched traversal kernels.  One thread per ray.  PERM: gather rays / scatter results through `perm`.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_closest_batch(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
+                                                        HitRec* __restrict__ hits, int to_prim_number, uint2* __restrict__ stats) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = perm ? perm[i] : i;
+  const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
+  Ray ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
+  HitRec h; TravStats st; st.nodes = 0; st.prims = 0;
+  bvh_traverse<false, STATS>(sc, ray, h, &st);
+  if (to_prim_number) h.slot = h.slot == kMiss ? kMiss : sc.info[h.slot].x;
+  hits[r] = h;
+  if (STATS) stats[r] = make_uint2(st.nodes, st.prims);
+}
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_anyhit_batch(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
+                                                       uint8_t* __restrict__ occluded, uint2* __restrict__ stats) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = perm ? perm[i] : i;
+  const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
+  Ray ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
+  HitRec h; TravStats st; st.nodes = 0; st.prims = 0;
+  bool occ = bvh_traverse<true, STATS>(sc, ray, h, &st);
+  occluded[r] = occ ? 1 : 0;
+  if (STATS) stats[r] = make_uint2(st.nodes, st.prims);
+}
+
+static int ensure_sort_scratch(rtgpu_ctx* ctx, size_t n, uint32_t** keys, uint32_t** perm, uint32_t** hist) {
+  // layout in one allocation: hist[kSortBins] | keys[n] | perm[n]
+  size_t need = (size_t)kSortBins * 4 + n * 8;
+  if (ctx->scratch_n < need) {
+    if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
+    ctx->scratch_rays = nullptr; ctx->scratch_n = 0;
+    RT_CUDA(ctx, cudaMalloc(&ctx->scratch_rays, need));
+    ctx->scratch_n = need;
+  }
+  *hist = (uint32_t*)ctx->scratch_rays; *keys = *hist + kSortBins; *perm = *keys + n;
+  return 0;
+}
+
+static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_t** perm_out) {
+  *perm_out = nullptr;
+  if (!ctx->sort_rays || n < 4096) return 0;
+  uint32_t *keys, *perm, *hist;
+  int rc = ensure_sort_scratch(ctx, n, &keys, &perm, &hist); if (rc) return rc;
+  SortParams sp;
+  for (int k = 0; k < 3; k++) {
+    float ext = ctx->scene.world_hi[k] - ctx->scene.world_lo[k];
+    // rays may start outside the world bounds: bin over the bounds grown by 10 %
+    sp.lo[k] = ctx->scene.world_lo[k] - 0.1f * ext;
+    sp.inv_ext[k] = ext > 0.0f ? 1.0f / (1.2f * ext) : 0.0f;
+  }
+  RT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)kSortBins * 4, ctx->stream));
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  k_sort_hist<<<blocks, 256, 0, ctx->stream>>>((const float4*)d_rays, (uint32_t)n, sp, keys, hist);
+  k_sort_scan<<<1, 1024, 0, ctx->stream>>>(hist);
+  k_sort_scatter<<<blocks, 256, 0, ctx->stream>>>(keys, (uint32_t)n, hist, perm);
+  ctx->launches += 3;
+  RT_CUDA(ctx, cudaGetLastError());
+  *perm_out = perm;
+  return 0;
+}
+
+}  // namespace rt
+
+template <class T> static int upload(rtgpu_ctx* ctx, const T* host, size_t count, const T** dev) {
+  *dev = nullptr;
+  if (count == 0 || host == nullptr) return 0;
+  void* p = nullptr;
+  RT_CUDA(ctx, cudaMalloc(&p, count * sizeof(T)));
+  ctx->scene_allocs.push_back(p);
+  RT_CUDA(ctx, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *dev = (const T*)p;
+  return 0;
+}
+
+static void free_scene(rtgpu_ctx* ctx) {
+  for (void* p : ctx->scene_allocs) cudaFree(p);
+  ctx->scene_allocs.clear();
+  ctx->has_scene = false;
+  std::memset(&ctx->scene, 0, sizeof(ctx->scene));
+  rt::free_lightgrid(ctx);
+}
+
+extern "C" {
+
+int rtgpu_create(int device, rtgpu_ctx** out) {
+  if (!out) return RTGPU_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return RTGPU_ERR_CUDA;   // no CPU fallback exists
+  if (device < 0 || device >= count) return RTGPU_ERR_ARG;
+  rtgpu_ctx* ctx = new (std::nothrow) rtgpu_ctx();
+  if (!ctx) return RTGPU_ERR_OOM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx; return RTGPU_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // traversal stacks live in local memory; prefer L1 over shared memory for the traversal kernels
+  *out = ctx;
+  return RTGPU_OK;
+}
+
+int rtgpu_destroy(rtgpu_ctx* ctx) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_scene(ctx);
+  rt::free_wave_buffers(ctx);
+  if (ctx->film) cudaFree(ctx->film);
+  if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
+  if (ctx->scratch_hits) cudaFree(ctx->scratch_hits);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return RTGPU_OK;
+}
+
+const char* rtgpu_last_error(rtgpu_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+uint64_t rtgpu_launch_count(rtgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return RTGPU_ERR_ARG;
+  if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
+  return fail(ctx, RTGPU_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
+  if (!ctx || !s) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  free_scene(ctx);
+  if (s->n_nodes > 0 && (!s->node_lo || !s->node_hi)) return fail(ctx, RTGPU_ERR_ARG, "node arrays missing");
+  if (s->n_prims > 0 && (!s->prim_geom || !s->prim_info)) return fail(ctx, RTGPU_ERR_ARG, "primitive arrays missing");
+  DScene& d = ctx->scene;
+  // interleave node_lo / node_hi into one 32-byte record per node (one DRAM sector per node visit)
+  {
+    std::vector<float> inter((size_t)s->n_nodes * 8);
+    for (size_t i = 0; i < s->n_nodes; i++) {
+      std::memcpy(&inter[i * 8], &s->node_lo[i * 4], 16);
+      std::memcpy(&inter[i * 8 + 4], &s->node_hi[i * 4], 16);
+    }
+    const float* p = nullptr;
+    int rc = upload(ctx, inter.data(), inter.size(), &p); if (rc) return rc;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `inter` dies at scope end
+    d.nodes = (const float4*)p;
+  }
+  int rc;
+  const float* pf = nullptr; const uint32_t* pu = nullptr;
+  if ((rc = upload(ctx, s->prim_geom, (size_t)s->n_prims * 12, &pf))) return rc; d.geom = (const float4*)pf;
+  if ((rc = upload(ctx, s->prim_info, (size_t)s->n_prims * 4, &pu))) return rc; d.info = (const uint4*)pu;
+  if ((rc = upload(ctx, s->tri_n, s->tri_n ? (size_t)s->n_prims * 9 : 0, &d.tri_n))) return rc;
+  if ((rc = upload(ctx, s->tri_s, s->tri_s ? (size_t)s->n_prims * 9 : 0, &d.tri_s))) return rc;
+  if ((rc = upload(ctx, s->tri_uv, s->tri_uv ? (size_t)s->n_prims * 6 : 0, &d.tri_uv))) return rc;
+  if ((rc = upload(ctx, s->quadrics, (size_t)s->n_quadrics, &d.quadrics))) return rc;
+  if ((rc = upload(ctx, s->materials, (size_t)s->n_materials, &d.materials))) return rc;
+  if ((rc = upload(ctx, s->lights, (size_t)s->n_lights, &d.lights))) return rc;
+  if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
+  d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;
+  for (int i = 0; i < 3; i++) { d.world_lo[i] = s->world_lo[i]; d.world_hi[i] = s->world_hi[i]; }
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->has_scene = true;
+  return RTGPU_OK;
+}
+
+int rtgpu_malloc(rtgpu_ctx* ctx, size_t bytes, void** d_ptr) {
+  if (!ctx || !d_ptr) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+  return RTGPU_OK;
+}
+int rtgpu_free(rtgpu_ctx* ctx, void* d_ptr) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaFree(d_ptr));
+  return RTGPU_OK;
+}
+int rtgpu_memcpy_h2d(rtgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RTGPU_OK;
+}
+int rtgpu_memcpy_d2h(rtgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RTGPU_OK;
+}
+int rtgpu_synchronize(rtgpu_ctx* ctx) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RTGPU_OK;
+}
+
+static int run_closest(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, uint32_t* d_stats, float* elapsed_ms) {
+  if (!ctx->has_scene) return fail(ctx, RTGPU_ERR_NO_SCENE, "no scene uploaded");
+  if (n == 0) { if (elapsed_ms) *elapsed_ms = 0; return RTGPU_OK; }
+  if (n > 0xfffffff0ull) return fail(ctx, RTGPU_ERR_ARG, "batch too large (max 2^32-16 rays)");
+  cudaSetDevice(ctx->device);
+  if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  uint32_t* perm = nullptr;
+  int rc = build_perm(ctx, d_rays, n, &perm); if (rc) return rc;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (d_stats) k_closest_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, (uint2*)d_stats);
+  else k_closest_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, nullptr);
+  ctx->launches += 1;
+  RT_CUDA(ctx, cudaGetLastError());
+  if (elapsed_ms) {
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    RT_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  }
+  return RTGPU_OK;
+}
+static int run_anyhit(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occ, uint32_t* d_stats, float* elapsed_ms) {
+  if (!ctx->has_scene) return fail(ctx, RTGPU_ERR_NO_SCENE, "no scene uploaded");
+  if (n == 0) { if (elapsed_ms) *elapsed_ms = 0; return RTGPU_OK; }
+  if (n > 0xfffffff0ull) return fail(ctx, RTGPU_ERR_ARG, "batch too large (max 2^32-16 rays)");
+  cudaSetDevice(ctx->device);
+  if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  uint32_t* perm = nullptr;
+  int rc = build_perm(ctx, d_rays, n, &perm); if (rc) return rc;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (d_stats) k_anyhit_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, (uint2*)d_stats);
+  else k_anyhit_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, nullptr);
+  ctx->launches += 1;
+  RT_CUDA(ctx, cudaGetLastError());
+  if (elapsed_ms) {
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    RT_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  }
+  return RTGPU_OK;
+}
+
+int rtgpu_intersect_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, float* elapsed_ms) {
+  if (!ctx || (n && (!d_rays || !d_hits))) return RTGPU_ERR_ARG;
+  return run_closest(ctx, d_rays, n, d_hits, nullptr, elapsed_ms);
+}
+int rtgpu_occluded_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, float* elapsed_ms) {
+  if (!ctx || (n && (!d_rays || !d_occluded))) return RTGPU_ERR_ARG;
+  return run_anyhit(ctx, d_rays, n, d_occluded, nullptr, elapsed_ms);
+}
+// Same as the _device calls plus per-ray {nodes visited, primitives tested} (2 x uint32 each): the N and T of
+// the roofline's algorithmic bytes.  d_stats must hold 2*n uint32.
+int rtgpu_intersect_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, uint32_t* d_stats) {
+  if (!ctx || (n && (!d_rays || !d_hits || !d_stats))) return RTGPU_ERR_ARG;
+  return run_closest(ctx, d_rays, n, d_hits, d_stats, nullptr);
+}
+int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, uint32_t* d_stats) {
+  if (!ctx || (n && (!d_rays || !d_occluded || !d_stats))) return RTGPU_ERR_ARG;
+  return run_anyhit(ctx, d_rays, n, d_occluded, d_stats, nullptr);
+}
+
+// Host-buffer variants: H2D + kernel + D2H inside, chunked so any batch size fits.
+static int host_batch(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits, uint8_t* occluded) {
+  if (!ctx->has_scene) return fail(ctx, RTGPU_ERR_NO_SCENE, "no scene uploaded");
+  cudaSetDevice(ctx->device);
+  const size_t chunk = (size_t)1 << 24;   // 16 Mi rays: 512 MiB of rays + 256 MiB of hits per chunk
+  void *d_rays = nullptr, *d_out = nullptr;
+  size_t cap = n < chunk ? n : chunk;
+  if (cap == 0) return RTGPU_OK;
+  RT_CUDA(ctx, cudaMalloc(&d_rays, cap * sizeof(rtgpu_ray)));
+  cudaError_t e = cudaMalloc(&d_out, cap * (hits ? sizeof(rtgpu_hit) : 1));
+  if (e != cudaSuccess) { cudaFree(d_rays); return check_cuda(ctx, e, "cudaMalloc"); }
+  int rc = RTGPU_OK;
+  for (size_t first = 0; first < n && rc == RTGPU_OK; first += cap) {
+    size_t m = n - first < cap ? n - first : cap;
+    e = cudaMemcpyAsync(d_rays, rays + first, m * sizeof(rtgpu_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { rc = check_cuda(ctx, e, "cudaMemcpyAsync h2d"); break; }
+    if (hits) rc = run_closest(ctx, (const rtgpu_ray*)d_rays, m, (rtgpu_hit*)d_out, nullptr, nullptr);
+    else rc = run_anyhit(ctx, (const rtgpu_ray*)d_rays, m, (uint8_t*)d_out, nullptr, nullptr);
+    if (rc) break;
+    if (hits) e = cudaMemcpyAsync(hits + first, d_out, m * sizeof(rtgpu_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    else e = cudaMemcpyAsync(occluded + first, d_out, m, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = check_cuda(ctx, e, "cudaMemcpyAsync d2h");
+  }
+  cudaFree(d_rays); cudaFree(d_out);
+  return rc;
+}
+int rtgpu_intersect(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits) {
+  if (!ctx || (n && (!rays || !hits))) return RTGPU_ERR_ARG;
+  return host_batch(ctx, rays, n, hits, nullptr);
+}
+int rtgpu_occluded(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, uint8_t* occluded) {
+  if (!ctx || (n && (!rays || !occluded))) return RTGPU_ERR_ARG;
+  return host_batch(ctx, rays, n, nullptr, occluded);
+}
+
+}  // extern "C"

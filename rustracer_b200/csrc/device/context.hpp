@@ -1,0 +1,53 @@
+// Per-GPU context of librtgpu.so (product code).  One context owns one CUDA stream, the device copy of the
+// flattened scene, the film accumulator and the wavefront queues.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "shapes.cuh"
+#include "traverse.cuh"
+
+struct WaveBuffers;   // render.cu
+
+struct rtgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string error;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // scene
+  bool has_scene = false;
+  rt::DScene scene{};
+  std::vector<void*> scene_allocs;
+  // film: 4 floats (sum r, sum g, sum b, sum weight) per cropped pixel
+  float* film = nullptr; size_t film_pixels = 0; int film_w = 0, film_h = 0; float film_scale = 1.0f;
+  // wavefront queues (render.cu)
+  WaveBuffers* wave = nullptr;
+  // spatial light distribution (render.cu)
+  void* lightgrid = nullptr;
+  // scratch for the batch API
+  void* scratch_rays = nullptr; void* scratch_hits = nullptr; size_t scratch_n = 0;
+  int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
+};
+
+namespace rt {
+
+inline int fail(rtgpu_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->error = msg;
+  return code;
+}
+inline int check_cuda(rtgpu_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  int code = (e == cudaErrorMemoryAllocation) ? RTGPU_ERR_OOM : RTGPU_ERR_CUDA;
+  return fail(ctx, code, m);
+}
+#define RT_CUDA(ctx, call) do { int _rc = rt::check_cuda((ctx), (call), #call); if (_rc) return _rc; } while (0)
+
+void free_wave_buffers(rtgpu_ctx* ctx);   // render.cu
+void free_lightgrid(rtgpu_ctx* ctx);      // render.cu
+
+}  // namespace rt

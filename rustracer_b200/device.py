@@ -1,0 +1,219 @@
+"""Device binding: ctypes over librtgpu.so (include/rtgpu.h).  There is no CPU fallback: a missing library or a
+missing GPU raises."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._native import load
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+_STATUS = {-1: "CUDA error", -2: "bad argument", -3: "no scene uploaded", -4: "out of device memory", -5: "queue overflow", -6: "unsupported"}
+
+
+def _lib():
+    lib = load("rtgpu")
+    if getattr(lib, "_rtgpu_ready", False):
+        return lib
+    vp, sz = C.c_void_p, C.c_size_t
+    lib.rtgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.rtgpu_destroy.argtypes = [vp]
+    lib.rtgpu_last_error.argtypes = [vp]
+    lib.rtgpu_last_error.restype = C.c_char_p
+    lib.rtgpu_upload_scene.argtypes = [vp, C.POINTER(A.rtgpu_scene_desc)]
+    lib.rtgpu_intersect.argtypes = [vp, vp, sz, vp]
+    lib.rtgpu_occluded.argtypes = [vp, vp, sz, vp]
+    lib.rtgpu_intersect_device.argtypes = [vp, vp, sz, vp, C.POINTER(C.c_float)]
+    lib.rtgpu_occluded_device.argtypes = [vp, vp, sz, vp, C.POINTER(C.c_float)]
+    lib.rtgpu_intersect_device_stats.argtypes = [vp, vp, sz, vp, vp]
+    lib.rtgpu_occluded_device_stats.argtypes = [vp, vp, sz, vp, vp]
+    lib.rtgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.rtgpu_generate_rays.argtypes = [vp, C.POINTER(A.rtgpu_render_desc), vp, sz, vp]
+    lib.rtgpu_render.argtypes = [vp, C.POINTER(A.rtgpu_render_desc), C.POINTER(A.rtgpu_stats)]
+    lib.rtgpu_li_samples.argtypes = [vp, C.POINTER(A.rtgpu_render_desc), vp, sz, vp]
+    lib.rtgpu_read_film.argtypes = [vp, vp]
+    lib.rtgpu_resolve_film.argtypes = [vp, vp]
+    lib.rtgpu_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    lib.rtgpu_reduce_film.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.rtgpu_malloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.rtgpu_free.argtypes = [vp, vp]
+    lib.rtgpu_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    lib.rtgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    lib.rtgpu_synchronize.argtypes = [vp]
+    lib.rtgpu_launch_count.argtypes = [vp]
+    lib.rtgpu_launch_count.restype = C.c_uint64
+    lib._rtgpu_ready = True
+    return lib
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch can alias a device buffer owned by the context."""
+
+    def __init__(self, ptr, n_floats, owner):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class Device:
+    """One rtgpu context == one GPU (rtgpu_create .. rtgpu_destroy)."""
+
+    def __init__(self, index=0):
+        self._lib = _lib()
+        h = C.c_void_p()
+        rc = self._lib.rtgpu_create(index, C.byref(h))
+        if rc != 0:
+            raise DeviceError(f"rtgpu_create(device={index}) failed: {_STATUS.get(rc, rc)} — a CUDA GPU is required, there is no CPU fallback")
+        self._h = h
+        self.index = index
+        self.scene = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rtgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DeviceError(f"{_STATUS.get(rc, rc)}: {self._lib.rtgpu_last_error(self._h).decode()}")
+
+    # ---- scene -------------------------------------------------------------------------------------
+    def upload(self, scene):
+        """scene: rustracer_b200.host.Scene (flattened on demand)."""
+        self._check(self._lib.rtgpu_upload_scene(self._h, scene.desc))
+        self.scene = scene
+        return self
+
+    def set_option(self, name, value):
+        self._check(self._lib.rtgpu_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.rtgpu_launch_count(self._h))
+
+    # ---- batched BVH::intersect / intersect_p, host buffers -------------------------------------------
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        hits = np.zeros((n, 4), np.float32)
+        self._check(self._lib.rtgpu_intersect(self._h, rays.ctypes.data, n, hits.ctypes.data))
+        return dict(t=hits[:, 0].copy(), prim=hits[:, 1].copy().view(np.int32), b1=hits[:, 2].copy(), b2=hits[:, 3].copy())
+
+    def occluded(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        out = np.zeros(n, np.uint8)
+        self._check(self._lib.rtgpu_occluded(self._h, rays.ctypes.data, n, out.ctypes.data))
+        return out
+
+    # ---- device memory + device-resident batches ------------------------------------------------------
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._lib.rtgpu_malloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        self._check(self._lib.rtgpu_free(self._h, ptr))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self._lib.rtgpu_memcpy_h2d(self._h, dptr, arr.ctypes.data, arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        assert arr.flags["C_CONTIGUOUS"]
+        self._check(self._lib.rtgpu_memcpy_d2h(self._h, arr.ctypes.data, dptr, arr.nbytes))
+
+    def synchronize(self):
+        self._check(self._lib.rtgpu_synchronize(self._h))
+
+    def intersect_device(self, d_rays, n, d_hits, timed=True):
+        ms = C.c_float(0)
+        self._check(self._lib.rtgpu_intersect_device(self._h, d_rays, n, d_hits, C.byref(ms) if timed else None))
+        return ms.value
+
+    def occluded_device(self, d_rays, n, d_occ, timed=True):
+        ms = C.c_float(0)
+        self._check(self._lib.rtgpu_occluded_device(self._h, d_rays, n, d_occ, C.byref(ms) if timed else None))
+        return ms.value
+
+    def intersect_stats(self, rays):
+        """Closest-hit batch with per-ray (nodes visited, primitives tested)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        d_r, d_h, d_s = self.malloc(max(1, rays.nbytes)), self.malloc(max(1, 16 * n)), self.malloc(max(1, 8 * n))
+        try:
+            self.h2d(d_r, rays)
+            self._check(self._lib.rtgpu_intersect_device_stats(self._h, d_r, n, d_h, d_s))
+            hits = np.zeros((n, 4), np.float32)
+            st = np.zeros((n, 2), np.uint32)
+            self.d2h(hits, d_h)
+            self.d2h(st, d_s)
+        finally:
+            self.free(d_r), self.free(d_h), self.free(d_s)
+        return dict(t=hits[:, 0].copy(), prim=hits[:, 1].copy().view(np.int32), b1=hits[:, 2].copy(), b2=hits[:, 3].copy(), nodes=st[:, 0].copy(), prims=st[:, 1].copy())
+
+    def occluded_stats(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        d_r, d_o, d_s = self.malloc(max(1, rays.nbytes)), self.malloc(max(1, n)), self.malloc(max(1, 8 * n))
+        try:
+            self.h2d(d_r, rays)
+            self._check(self._lib.rtgpu_occluded_device_stats(self._h, d_r, n, d_o, d_s))
+            occ = np.zeros(n, np.uint8)
+            st = np.zeros((n, 2), np.uint32)
+            self.d2h(occ, d_o)
+            self.d2h(st, d_s)
+        finally:
+            self.free(d_r), self.free(d_o), self.free(d_s)
+        return dict(occluded=occ, nodes=st[:, 0].copy(), prims=st[:, 1].copy())
+
+    # ---- camera / render / film -----------------------------------------------------------------------
+    def generate_rays(self, rd, samples):
+        """samples: (n, 4) {p_film.x, p_film.y, p_lens.x, p_lens.y} -> (n, 8) rays (camera.rs:150-202)."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        n = samples.shape[0]
+        rays = np.zeros((n, 8), np.float32)
+        self._check(self._lib.rtgpu_generate_rays(self._h, C.byref(rd), samples.ctypes.data, n, rays.ctypes.data))
+        return rays
+
+    def render(self, rd):
+        """== renderer::render (renderer.rs:22-143): accumulates into the device film; returns rtgpu_stats."""
+        st = A.rtgpu_stats()
+        self._check(self._lib.rtgpu_render(self._h, C.byref(rd), C.byref(st)))
+        self._film_shape = (rd.cropped[3] - rd.cropped[1], rd.cropped[2] - rd.cropped[0])
+        return st
+
+    def li_samples(self, rd, pixels):
+        """Radiance of individual (x, y, sample_index) camera samples -> (n, 3) RGB."""
+        pixels = np.ascontiguousarray(pixels, np.int32)
+        n = pixels.shape[0]
+        out = np.zeros((n, 3), np.float32)
+        self._check(self._lib.rtgpu_li_samples(self._h, C.byref(rd), pixels.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def read_film(self):
+        h, w = self._film_shape
+        out = np.zeros((h, w, 4), np.float32)
+        self._check(self._lib.rtgpu_read_film(self._h, out.ctypes.data))
+        return out
+
+    def resolve_film(self):
+        h, w = self._film_shape
+        out = np.zeros((h, w, 3), np.float32)
+        self._check(self._lib.rtgpu_resolve_film(self._h, out.ctypes.data))
+        return out
+
+    def film_device_array(self):
+        """The raw film accumulator as a __cuda_array_interface__ object (for torch.as_tensor + NCCL reduce)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.rtgpu_film_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return _CudaArray(p.value, n.value, self)
