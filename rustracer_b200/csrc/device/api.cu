@@ -150,6 +150,7 @@ static void free_scene(rtgpu_ctx* ctx) {
   for (void* p : ctx->scene_allocs) cudaFree(p);
   ctx->scene_allocs.clear();
   ctx->has_scene = false;
+  ctx->h_lights.clear(); ctx->h_materials.clear();
   std::memset(&ctx->scene, 0, sizeof(ctx->scene));
   rt::free_lightgrid(ctx);
 }
@@ -231,6 +232,8 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
   d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;
   for (int i = 0; i < 3; i++) { d.world_lo[i] = s->world_lo[i]; d.world_hi[i] = s->world_hi[i]; }
+  if (s->n_lights) ctx->h_lights.assign(s->lights, s->lights + s->n_lights);
+  if (s->n_materials) ctx->h_materials.assign(s->materials, s->materials + s->n_materials);
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->has_scene = true;
   return RTGPU_OK;

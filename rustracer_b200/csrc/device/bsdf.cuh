@@ -1,0 +1,467 @@
+// Device BSDF: Bsdf frame + lobe selection (bsdf/mod.rs:64-269), the BxDFs used by Matte / Plastic / Metal /
+// Glass / Mirror (bsdf/{lambertian,oren_nayar,fresnel,microfacet}.rs) and the material -> lobe mapping
+// (material/{matte,plastic,metal,glass,mirror}.rs).  Product code; reference lines relative to rustracer-core/src/.
+#pragma once
+#include "shapes.cuh"
+
+namespace rt {
+
+enum : uint32_t { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };   // bsdf/mod.rs:24-32
+
+// geometry/mod.rs:15-95 (local shading frame)
+RT_DEV float cos_theta(V3 w) { return w.z; }
+RT_DEV float cos2_theta(V3 w) { return w.z * w.z; }
+RT_DEV float abs_cos_theta(V3 w) { return fabsf(w.z); }
+RT_DEV float sin2_theta(V3 w) { return fmaxf(1.0f - cos2_theta(w), 0.0f); }
+RT_DEV float sin_theta(V3 w) { return sqrtf(sin2_theta(w)); }
+RT_DEV float tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }
+RT_DEV float tan2_theta(V3 w) { return sin2_theta(w) / cos2_theta(w); }
+RT_DEV float cos_phi(V3 w) { float st = sin_theta(w); return st == 0.0f ? 1.0f : clampf(w.x / st, -1.0f, 1.0f); }
+RT_DEV float sin_phi(V3 w) { float st = sin_theta(w); return st == 0.0f ? 0.0f : clampf(w.y / st, -1.0f, 1.0f); }
+RT_DEV float cos2_phi(V3 w) { return cos_phi(w) * cos_phi(w); }
+RT_DEV float sin2_phi(V3 w) { return sin_phi(w) * sin_phi(w); }
+RT_DEV bool same_hemisphere(V3 w, V3 wp) { return w.z * wp.z > 0.0f; }
+RT_DEV float spherical_theta(V3 v) { return acosf(clampf(v.z, -1.0f, 1.0f)); }
+RT_DEV float spherical_phi(V3 v) { float p = atan2f(v.y, v.x); return p < 0.0f ? p + 2.0f * kPi : p; }
+
+// sampling/mod.rs
+RT_DEV V3 uniform_sample_sphere(P2 u) {                                          // :14-20
+  float z = 1.0f - 2.0f * u.x;
+  float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+  float phi = 2.0f * kPi * u.y;
+  return v3(r * cosf(phi), r * sinf(phi), z);
+}
+RT_DEV P2 concentric_sample_disk(P2 u) {                                         // :28-47
+  const float kFracPi4 = kFracPi2 / 2.0f;
+  float ox = 2.0f * u.x - 1.0f, oy = 2.0f * u.y - 1.0f;
+  if (ox == 0.0f && oy == 0.0f) return mk2(0.0f, 0.0f);
+  float r, theta;
+  if (fabsf(ox) > fabsf(oy)) { r = ox; theta = kFracPi4 * (oy / ox); }
+  else { r = oy; theta = kFracPi2 - kFracPi4 * (ox / oy); }
+  return mk2(r * cosf(theta), r * sinf(theta));
+}
+RT_DEV V3 cosine_sample_hemisphere(P2 u) {                                       // :22-26
+  P2 d = concentric_sample_disk(u);
+  float z = sqrtf(fmaxf(1.0f - d.x * d.x - d.y * d.y, 0.0f));
+  return v3(d.x, d.y, z);
+}
+RT_DEV P2 uniform_sample_triangle(P2 u) { float su0 = sqrtf(u.x); return mk2(1.0f - su0, u.y * su0); }   // :49-52
+RT_DEV float uniform_cone_pdf(float cos_theta_max) { return 1.0f / (2.0f * kPi * (1.0f - cos_theta_max)); } // :54-56
+RT_DEV float power_heuristic(float f_pdf, float g_pdf) {                                                  // :58-63 with nf = ng = 1
+  float f = 1.0f * f_pdf, g = 1.0f * g_pdf;
+  return (f * f) / (f * f + g * g);
+}
+
+// bsdf/fresnel.rs:14-31
+RT_DEV V3 reflect(V3 wo, V3 n) { return -wo + n * 2.0f * dot(wo, n); }
+RT_DEV bool refract(V3 i, V3 n, float eta, V3& wt) {
+  float cos_theta_i = dot(n, i);
+  float sin2theta_i = fmaxf(1.0f - cos_theta_i * cos_theta_i, 0.0f);
+  float sin2theta_t = eta * eta * sin2theta_i;
+  if (sin2theta_t >= 1.0f) return false;
+  float cos_theta_t = sqrtf(1.0f - sin2theta_t);
+  wt = eta * -i + (eta * cos_theta_i - cos_theta_t) * n;
+  return true;
+}
+// fresnel.rs:33-58
+RT_DEV float fr_dielectric(float cos_theta_i, float eta_i, float eta_t) {
+  cos_theta_i = clampf(cos_theta_i, -1.0f, 1.0f);
+  if (cos_theta_i <= 0.0f) { float tmp = eta_i; eta_i = eta_t; eta_t = tmp; cos_theta_i = fabsf(cos_theta_i); }
+  float sin_theta_i = sqrtf(fmaxf(1.0f - cos_theta_i * cos_theta_i, 0.0f));
+  float sin_theta_t = eta_i / eta_t * sin_theta_i;
+  if (sin_theta_t >= 1.0f) return 1.0f;
+  float cos_theta_t = sqrtf(fmaxf(1.0f - sin_theta_t * sin_theta_t, 0.0f));
+  float r_parl = ((eta_t * cos_theta_i) - (eta_i * cos_theta_t)) / ((eta_t * cos_theta_i) + (eta_i * cos_theta_t));
+  float r_perp = ((eta_i * cos_theta_i) - (eta_t * cos_theta_t)) / ((eta_i * cos_theta_i) + (eta_t * cos_theta_t));
+  return 0.5f * (r_parl * r_parl + r_perp * r_perp);
+}
+// fresnel.rs:60-82
+RT_DEV Spec fr_conductor(float cos_theta_i, Spec eta_i, Spec eta_t, Spec k) {
+  cos_theta_i = clampf(cos_theta_i, -1.0f, 1.0f);
+  Spec eta = eta_t / eta_i, eta_k = k / eta_i;
+  float cos2 = cos_theta_i * cos_theta_i, sin2 = 1.0f - cos2;
+  Spec eta2 = eta * eta, eta_k2 = eta_k * eta_k;
+  Spec t0 = eta2 - eta_k2 - sin2;
+  Spec a2plusb2 = spec_sqrt(t0 * t0 + 4.0f * eta2 * eta_k2);
+  Spec t1 = a2plusb2 + cos2;
+  Spec a = spec_sqrt(0.5f * (a2plusb2 + t0));
+  Spec t2 = 2.0f * cos_theta_i * a;
+  Spec r_s = (t1 - t2) / (t1 + t2);
+  Spec t3 = cos2 * a2plusb2 + sin2 * sin2;
+  Spec t4 = t2 * sin2;
+  Spec r_p = r_s * (t3 - t4) / (t3 + t4);
+  return 0.5f * (r_p + r_s);
+}
+
+enum { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
+enum { LOBE_LAMBERT_R = 0, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS };
+
+struct Lobe {
+  int kind;
+  Spec r, t;
+  float on_a, on_b;                 // OrenNayar A, B
+  int fr_kind; float fr_eta_i, fr_eta_t; Spec c_eta_t, c_k;   // Fresnel (conductor eta_i is always 1: metal.rs:70-75)
+  float ax, ay;                     // TrowbridgeReitz alpha
+  float eta_a, eta_b;
+};
+
+RT_DEV Spec fresnel_evaluate(const Lobe& l, float cos_theta_i) {                 // fresnel.rs:84-138 (abs(cos) for both)
+  if (l.fr_kind == FR_DIELECTRIC) return spec(fr_dielectric(fabsf(cos_theta_i), l.fr_eta_i, l.fr_eta_t));
+  if (l.fr_kind == FR_CONDUCTOR) return fr_conductor(fabsf(cos_theta_i), spec(1.0f), l.c_eta_t, l.c_k);
+  return spec(1.0f);
+}
+
+// TrowbridgeReitzDistribution (microfacet.rs:469-650), sample_visible_area = true
+RT_DEV float tr_d(float ax, float ay, V3 wh) {                                   // :576-588
+  float tan2 = tan2_theta(wh);
+  if (isinf(tan2)) return 0.0f;
+  float cos4 = cos2_theta(wh) * cos2_theta(wh);
+  float e = (cos2_phi(wh) / (ax * ax) + sin2_phi(wh) / (ay * ay)) * tan2;
+  return 1.0f / (kPi * ax * ay * cos4 * (1.0f + e) * (1.0f + e));
+}
+RT_DEV float tr_lambda(float ax, float ay, V3 w) {                               // :590-602
+  float abs_tan = fabsf(tan_theta(w));
+  if (isinf(abs_tan)) return 0.0f;
+  float alpha = sqrtf(cos2_phi(w) * ax * ax + sin2_phi(w) * ay * ay);
+  float a2t2 = (alpha * abs_tan) * (alpha * abs_tan);
+  return (-1.0f + sqrtf(1.0f + a2t2)) / 2.0f;
+}
+RT_DEV float tr_g1(float ax, float ay, V3 w) { return 1.0f / (1.0f + tr_lambda(ax, ay, w)); }                          // :235-237
+RT_DEV float tr_g(float ax, float ay, V3 wi, V3 wo) { return 1.0f / (1.0f + tr_lambda(ax, ay, wi) + tr_lambda(ax, ay, wo)); }   // :239-241
+RT_DEV float tr_pdf(float ax, float ay, V3 wo, V3 wh) { return tr_d(ax, ay, wh) * tr_g1(ax, ay, wo) * fabsf(dot(wo, wh)) / abs_cos_theta(wo); }   // :243-249
+RT_DEV void tr_sample11(float cos_t, float u1, float u2, float& slope_x, float& slope_y) {                             // :517-572
+  if (cos_t > 0.9999f) {
+    float r = sqrtf(u1 / (1.0f - u1));
+    float phi = 6.28318530717958647692f * u2;
+    slope_x = r * cosf(phi); slope_y = r * sinf(phi);
+    return;
+  }
+  float sin_t = sqrtf(fmaxf(1.0f - cos_t * cos_t, 0.0f));
+  float tan_t = sin_t / cos_t;
+  float a = 1.0f / tan_t;
+  float G1 = 2.0f / (1.0f + sqrtf(1.0f + 1.0f / (a * a)));
+  float A = 2.0f * u1 / G1 - 1.0f;
+  float tmp = 1.0f / (A * A - 1.0f);
+  if (tmp > 1e10f) tmp = 1e10f;
+  float B = tan_t;
+  float D = sqrtf(fmaxf(B * B * tmp * tmp - (A * A - B * B) * tmp, 0.0f));
+  float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+  slope_x = (A < 0.0f || slope_x_2 > 1.0f / tan_t) ? slope_x_1 : slope_x_2;
+  float S;
+  if (u2 > 0.5f) { S = 1.0f; u2 = 2.0f * (u2 - 0.5f); }
+  else { S = -1.0f; u2 = 2.0f * (0.5f - u2); }
+  float z = (u2 * (u2 * (u2 * 0.27385f - 0.73369f) + 0.46341f)) / (u2 * (u2 * (u2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+  slope_y = S * z * sqrtf(1.0f + slope_x * slope_x);
+}
+RT_DEV V3 tr_sample(float ax, float ay, V3 wi, float u1, float u2) {             // :495-515
+  V3 wis = normalize(v3(ax * wi.x, ay * wi.y, wi.z));
+  float sx, sy; tr_sample11(cos_theta(wis), u1, u2, sx, sy);
+  float tmp = cos_phi(wis) * sx - sin_phi(wis) * sy;
+  sy = sin_phi(wis) * sx + cos_phi(wis) * sy;
+  sx = tmp;
+  sx *= ax; sy *= ay;
+  return normalize(v3(-sx, -sy, 1.0f));
+}
+RT_DEV V3 tr_sample_wh(float ax, float ay, V3 wo, P2 u) {                        // :604-645 (visible-area branch)
+  bool flip = wo.z < 0.0f;
+  V3 w = flip ? -wo : wo;
+  V3 wh = tr_sample(ax, ay, w, u.x, u.y);
+  if (flip) wh = -wh;
+  return wh;
+}
+
+RT_DEV uint32_t lobe_type(int kind) {
+  switch (kind) {
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: return BSDF_DIFFUSE | BSDF_REFLECTION;
+    case LOBE_SPEC_REFL: return BSDF_SPECULAR | BSDF_REFLECTION;
+    case LOBE_SPEC_TRANS: return BSDF_SPECULAR | BSDF_TRANSMISSION;
+    case LOBE_FRESNEL_SPEC: return BSDF_SPECULAR | BSDF_REFLECTION | BSDF_TRANSMISSION;
+    case LOBE_MICRO_REFL: return BSDF_REFLECTION | BSDF_GLOSSY;
+    default: return BSDF_TRANSMISSION | BSDF_GLOSSY;
+  }
+}
+RT_DEV bool lobe_matches(int kind, uint32_t flags) { uint32_t t = lobe_type(kind); return (t & flags) == t; }   // bxdf.rs:29-31
+
+RT_DEV Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
+  switch (l.kind) {
+    case LOBE_LAMBERT_R: return l.r * kInvPi;                                    // lambertian.rs:19-21
+    case LOBE_OREN_NAYAR: {                                                      // oren_nayar.rs:30-52
+      float sti = sin_theta(wi), sto = sin_theta(wo);
+      float max_cos = 0.0f;
+      if (sti > 1e-4f && sto > 1e-4f) {
+        float d_cos = sin_phi(wi) * sin_phi(wo) + cos_phi(wi) * cos_phi(wo);
+        max_cos = fmaxf(d_cos, 0.0f);
+      }
+      float sin_alpha, tan_beta;
+      if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sto; tan_beta = sti / abs_cos_theta(wi); }
+      else { sin_alpha = sti; tan_beta = sto / abs_cos_theta(wo); }
+      return l.r * kInvPi * (l.on_a + l.on_b * max_cos * sin_alpha * tan_beta);
+    }
+    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:36-53
+      float cto = abs_cos_theta(wo), cti = abs_cos_theta(wi);
+      V3 wh = wi + wo;
+      if (cto == 0.0f || cti == 0.0f) return spec(0.0f);
+      if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return spec(0.0f);
+      wh = normalize(wh);
+      Spec F = fresnel_evaluate(l, dot(wi, wh));
+      return l.r * tr_d(l.ax, l.ay, wh) * tr_g(l.ax, l.ay, wo, wi) * F / (4.0f * cti * cto);
+    }
+    case LOBE_MICRO_TRANS: {                                                     // microfacet.rs:125-169
+      if (same_hemisphere(wo, wi)) return spec(0.0f);
+      float cto = cos_theta(wo), cti = cos_theta(wi);
+      if (cto == 0.0f || cti == 0.0f) return spec(0.0f);
+      float eta = cto > 0.0f ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+      V3 wh = normalize(wo + wi * eta);
+      if (wh.z < 0.0f) wh = -wh;
+      Spec F = fresnel_evaluate(l, dot(wo, wh));
+      float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+      float factor = 1.0f / eta;                                                 // TransportMode::RADIANCE on this path
+      return (spec(1.0f) - F) * l.t *
+             fabsf(tr_d(l.ax, l.ay, wh) * tr_g(l.ax, l.ay, wo, wi) * eta * eta * fabsf(dot(wi, wh)) * fabsf(dot(wo, wh)) * factor * factor /
+                   (cti * cto * sqrt_denom * sqrt_denom));
+    }
+    default: return spec(0.0f);                                                  // specular lobes: f() is zero
+  }
+}
+RT_DEV float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+  switch (l.kind) {
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR:                                   // bxdf.rs:38-44
+      return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
+    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:87-94
+      if (!same_hemisphere(wo, wi)) return 0.0f;
+      V3 wh = normalize(wo + wi);
+      return tr_pdf(l.ax, l.ay, wo, wh) / (4.0f * dot(wo, wh));
+    }
+    case LOBE_MICRO_TRANS: {                                                     // microfacet.rs:207-222
+      if (same_hemisphere(wo, wi)) return 0.0f;
+      float eta = cos_theta(wo) > 0.0f ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
+      V3 wh = normalize(wo + wi * eta);
+      float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
+      float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrt_denom * sqrt_denom));
+      return tr_pdf(l.ax, l.ay, wo, wh) * dwh_dwi;
+    }
+    default: return 0.0f;
+  }
+}
+// `sampled` is the BxdfType the lobe reports (bxdf.rs:18-25: the default sample_f reports EMPTY)
+RT_DEV void lobe_sample_f(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
+  switch (l.kind) {
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
+      wi = cosine_sample_hemisphere(u);
+      if (wo.z < 0.0f) wi.z *= -1.0f;
+      pdf_out = lobe_pdf(l, wo, wi); f_out = lobe_f(l, wo, wi); sampled = 0;
+      return;
+    }
+    case LOBE_SPEC_REFL: {                                                       // fresnel.rs:159-164
+      wi = v3(-wo.x, -wo.y, wo.z);
+      f_out = fresnel_evaluate(l, cos_theta(wi)) * l.r / abs_cos_theta(wi);
+      pdf_out = 1.0f; sampled = lobe_type(l.kind);
+      return;
+    }
+    case LOBE_SPEC_TRANS: {                                                      // fresnel.rs:203-230
+      bool entering = cos_theta(wo) > 0.0f;
+      float ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
+      V3 w;
+      if (refract(wo, face_forward(v3(0, 0, 1), wo), ei / et, w)) {
+        wi = w;
+        Spec ft = l.t * (spec(1.0f) - fresnel_evaluate(l, cos_theta(wi)));
+        ft = ft * (ei * ei) / (et * et);
+        f_out = ft / abs_cos_theta(wi); pdf_out = 1.0f; sampled = lobe_type(l.kind);
+      } else { f_out = spec(1.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; }
+      return;
+    }
+    case LOBE_FRESNEL_SPEC: {                                                    // fresnel.rs:273-322
+      float fr = fr_dielectric(cos_theta(wo), l.eta_a, l.eta_b);
+      if (u.x < fr) {
+        wi = v3(-wo.x, -wo.y, wo.z);
+        f_out = fr * l.r / abs_cos_theta(wi); pdf_out = fr; sampled = BSDF_SPECULAR | BSDF_REFLECTION;
+      } else {
+        bool entering = cos_theta(wo) > 0.0f;
+        float ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
+        V3 w;
+        if (refract(wo, face_forward(v3(0, 0, 1), wo), ei / et, w)) {
+          wi = w;
+          Spec ft = l.t * (1.0f - fr);
+          ft = ft * ((ei * ei) / (et * et));
+          f_out = ft / abs_cos_theta(wi); pdf_out = 1.0f - fr; sampled = BSDF_SPECULAR | BSDF_TRANSMISSION;
+        } else { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; }
+      }
+      return;
+    }
+    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:61-85
+      sampled = lobe_type(l.kind);
+      if (wo.z == 0.0f) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
+      V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
+      wi = reflect(wo, wh);
+      if (!same_hemisphere(wo, wi)) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
+      pdf_out = tr_pdf(l.ax, l.ay, wo, wh) / (4.0f * dot(wo, wh));
+      f_out = lobe_f(l, wo, wi);
+      return;
+    }
+    default: {                                                                   // LOBE_MICRO_TRANS microfacet.rs:177-205
+      sampled = lobe_type(l.kind);
+      if (wo.z == 0.0f) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
+      V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
+      float eta = cos_theta(wo) > 0.0f ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
+      V3 w;
+      if (refract(wo, wh, eta, w)) { wi = w; pdf_out = lobe_pdf(l, wo, wi); f_out = lobe_f(l, wo, wi); }
+      else { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; }
+      return;
+    }
+  }
+}
+
+constexpr int kMaxLobes = 2;     // the five materials on this path build at most two lobes
+
+struct Bsdf {                                                                    // bsdf/mod.rs:64-269
+  float eta;
+  V3 ns, ng, ss, ts;
+  Lobe lobes[kMaxLobes]; int n;
+};
+RT_DEV void bsdf_init(Bsdf& b, const SurfHit& si, float eta) {                   // :77-92
+  b.eta = eta;
+  b.ss = normalize(si.dpdu_s);
+  b.ns = si.ns; b.ng = si.n;
+  b.ts = cross(si.ns, b.ss);
+  b.n = 0;
+}
+RT_DEV V3 world_to_local(const Bsdf& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }   // :253-255
+RT_DEV V3 local_to_world(const Bsdf& b, V3 v) {                                                        // :257-263
+  return v3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z, b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+RT_DEV int bsdf_num_components(const Bsdf& b, uint32_t flags) {                  // :265-268
+  int c = 0;
+  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) c++;
+  return c;
+}
+RT_DEV Spec bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {            // :94-112
+  V3 wi = world_to_local(b, wi_w), wo = world_to_local(b, wo_w);
+  if (wo.z == 0.0f) return spec(0.0f);
+  bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+  Spec c = spec(0.0f);
+  for (int i = 0; i < b.n; i++) {
+    uint32_t t = lobe_type(b.lobes[i].kind);
+    if (lobe_matches(b.lobes[i].kind, flags) && ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION)))) c = c + lobe_f(b.lobes[i], wo, wi);
+  }
+  return c;
+}
+RT_DEV float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {         // :114-136
+  if (b.n == 0) return 0.0f;
+  V3 wo = world_to_local(b, wo_w);
+  if (wo.z == 0.0f) return 0.0f;
+  V3 wi = world_to_local(b, wi_w);
+  int matched = 0; float p = 0.0f;
+  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) { matched++; p += lobe_pdf(b.lobes[i], wo, wi); }
+  return matched == 0 ? 0.0f : p / (float)matched;
+}
+RT_DEV void bsdf_sample_f(const Bsdf& b, V3 wo_w, P2 u, uint32_t flags, Spec& f_out, V3& wi_w, float& pdf_out, uint32_t& sampled) {   // :138-251
+  int m[kMaxLobes]; int nm = 0;
+  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) m[nm++] = i;
+  if (nm == 0) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
+  int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));
+  const Lobe& bxdf = b.lobes[m[comp]];
+  const uint32_t btype = lobe_type(bxdf.kind);
+  P2 ur = mk2(fminf(u.x * (float)nm - (float)comp, kOneMinusEpsilon), u.y);
+  V3 wo = world_to_local(b, wo_w);
+  if (wo.z == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = btype; return; }
+  Spec f; V3 wi; float pdf;
+  lobe_sample_f(bxdf, wo, ur, f, wi, pdf, sampled);
+  if (pdf == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
+  wi_w = local_to_world(b, wi);
+  if (!(btype & BSDF_SPECULAR) && nm > 1)
+    for (int i = 0; i < nm; i++) if (i != comp) pdf += lobe_pdf(b.lobes[m[i]], wo, wi);
+  if (nm > 1) pdf /= (float)nm;
+  if (!(btype & BSDF_SPECULAR)) {
+    bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+    f = spec(0.0f);
+    for (int i = 0; i < nm; i++) {
+      uint32_t t = lobe_type(b.lobes[m[i]].kind);
+      if ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION))) f = f + lobe_f(b.lobes[m[i]], wo, wi);
+    }
+  }
+  f_out = f; pdf_out = pdf;
+}
+
+RT_DEV Lobe blank_lobe() {
+  Lobe l;
+  l.kind = LOBE_LAMBERT_R; l.r = spec(0.0f); l.t = spec(0.0f); l.on_a = 0.0f; l.on_b = 0.0f;
+  l.fr_kind = FR_NOOP; l.fr_eta_i = 1.0f; l.fr_eta_t = 1.0f; l.c_eta_t = spec(1.0f); l.c_k = spec(0.0f);
+  l.ax = 0.0f; l.ay = 0.0f; l.eta_a = 1.0f; l.eta_b = 1.0f;
+  return l;
+}
+
+// Material::compute_scattering_functions for constant textures.  The host already evaluated the textures and
+// the libm-dependent scalars (roughness_to_alpha, OrenNayar A/B): see rtgpu_material.  allow_multiple_lobes:
+// Path passes true (path.rs:145), Whitted / DirectLighting false (whitted.rs:57, directlighting.rs:104).
+// Returns false for "no material" (bsdf = None, path.rs:146-152).
+// `type` is mt.type; the material-sorted shade kernels pass it as a compile-time constant so the switch folds.
+RT_DEV bool make_bsdf(uint32_t type, const rtgpu_material& mt, const SurfHit& si, bool allow_multiple_lobes, Bsdf& bsdf) {
+  switch (type) {
+    case RTGPU_MAT_MATTE: {                                                      // matte.rs:37-62
+      Spec r = spec3(mt.kd);
+      bsdf_init(bsdf, si, 1.0f);
+      if (!is_black(r)) {
+        Lobe l = blank_lobe();
+        l.r = r;
+        if (!mt.use_oren_nayar) l.kind = LOBE_LAMBERT_R;
+        else { l.kind = LOBE_OREN_NAYAR; l.on_a = mt.oren_a; l.on_b = mt.oren_b; }
+        bsdf.lobes[bsdf.n++] = l;
+      }
+      return true;
+    }
+    case RTGPU_MAT_PLASTIC: {                                                    // plastic.rs:45-74
+      Spec kd = spec3(mt.kd), ks = spec3(mt.ks);
+      bsdf_init(bsdf, si, 1.0f);
+      if (!is_black(kd)) { Lobe l = blank_lobe(); l.kind = LOBE_LAMBERT_R; l.r = kd; bsdf.lobes[bsdf.n++] = l; }
+      if (!is_black(ks)) {
+        Lobe l = blank_lobe(); l.kind = LOBE_MICRO_REFL; l.r = ks;
+        l.fr_kind = FR_DIELECTRIC; l.fr_eta_i = 1.5f; l.fr_eta_t = 1.0f;
+        l.ax = mt.alpha_u; l.ay = mt.alpha_v;
+        bsdf.lobes[bsdf.n++] = l;
+      }
+      return true;
+    }
+    case RTGPU_MAT_METAL: {                                                      // metal.rs:50-81
+      Lobe l = blank_lobe(); l.kind = LOBE_MICRO_REFL; l.r = spec(1.0f);
+      l.fr_kind = FR_CONDUCTOR; l.c_eta_t = spec3(mt.eta_rgb); l.c_k = spec3(mt.k_rgb);
+      l.ax = mt.alpha_u; l.ay = mt.alpha_v;
+      bsdf_init(bsdf, si, 1.0f);
+      bsdf.lobes[bsdf.n++] = l;
+      return true;
+    }
+    case RTGPU_MAT_GLASS: {                                                      // glass.rs:53-106
+      const float eta = mt.eta;
+      Spec r = spec3(mt.kr), t = spec3(mt.kt);
+      bsdf_init(bsdf, si, eta);
+      if (!is_black(r) || !is_black(t)) {
+        const bool is_specular = mt.glass_specular != 0;
+        if (is_specular && allow_multiple_lobes) {
+          Lobe l = blank_lobe(); l.kind = LOBE_FRESNEL_SPEC; l.r = r; l.t = t; l.eta_a = 1.0f; l.eta_b = eta;
+          bsdf.lobes[bsdf.n++] = l;
+        } else {
+          if (!is_black(r)) {
+            Lobe l = blank_lobe(); l.r = r; l.fr_kind = FR_DIELECTRIC; l.fr_eta_i = 1.0f; l.fr_eta_t = eta;
+            if (is_specular) l.kind = LOBE_SPEC_REFL; else { l.kind = LOBE_MICRO_REFL; l.ax = mt.alpha_u; l.ay = mt.alpha_v; }
+            bsdf.lobes[bsdf.n++] = l;
+          }
+          if (!is_black(t)) {
+            Lobe l = blank_lobe(); l.eta_a = 1.0f; l.eta_b = eta; l.fr_kind = FR_DIELECTRIC; l.fr_eta_i = 1.0f; l.fr_eta_t = eta;
+            if (is_specular) { l.kind = LOBE_SPEC_TRANS; l.t = t; }
+            else { l.kind = LOBE_MICRO_TRANS; l.t = r; l.ax = mt.alpha_u; l.ay = mt.alpha_v; }   // built with Kr: glass.rs:97
+            bsdf.lobes[bsdf.n++] = l;
+          }
+        }
+      }
+      return true;
+    }
+    case RTGPU_MAT_MIRROR: {                                                     // mirror.rs:30-48
+      Spec R = spec3(mt.kr);
+      bsdf_init(bsdf, si, 1.0f);
+      if (!is_black(R)) { Lobe l = blank_lobe(); l.kind = LOBE_SPEC_REFL; l.r = R; l.fr_kind = FR_NOOP; bsdf.lobes[bsdf.n++] = l; }
+      return true;
+    }
+    default: return false;
+  }
+}
+
+}  // namespace rt

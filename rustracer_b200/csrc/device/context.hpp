@@ -22,6 +22,8 @@ struct rtgpu_ctx {
   bool has_scene = false;
   rt::DScene scene{};
   std::vector<void*> scene_allocs;
+  std::vector<rtgpu_light> h_lights;          // host copies of the small tables (wave planning reads them)
+  std::vector<rtgpu_material> h_materials;
   // film: 4 floats (sum r, sum g, sum b, sum weight) per cropped pixel
   float* film = nullptr; size_t film_pixels = 0; int film_w = 0, film_h = 0; float film_scale = 1.0f;
   // wavefront queues (render.cu)

@@ -1,0 +1,89 @@
+// Material-sorted shading kernels of the path integrator (product code, sm_100a).
+#pragma once
+#include "shade_common.cuh"
+
+namespace rt {
+
+// ---- path integrator: one bounce of PathIntegrator::li (integrator/path.rs:96-215) -------------------------------
+template <int MAT>
+__global__ void __launch_bounds__(128) k_shade_path(RenderParams p, int parity) {
+  const uint32_t n = p.w.counters[C_MATQ0 + MAT];
+  uint32_t* out_list = p.w.list[1 - parity];
+  uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
+  const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;            // `max_ray_depth as u8` (path.rs:42)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+    bool alive = false;
+    uint32_t slot = 0;
+    if (i < n) {
+      slot = p.w.matq[MAT][i];
+      Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
+      ray.t_max = inf_f();
+      const HitRec h = p.w.hit[slot];
+      const float4 bt = p.w.beta[slot];
+      Spec beta = spec(bt.x, bt.y, bt.z); float eta_scale = bt.w;
+      uint4 ps = p.w.pstate[slot];
+      const uint32_t sample = ps.x;
+      uint32_t bounces = ps.y & 0xffu; bool specular_bounce = (ps.z & 1u) != 0;
+      const uint2 sinf = p.w.sinfo[sample];
+      SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = ps.w & 0xffffu; ss.d2 = ps.w >> 16; ss.da = 0;
+      SurfHit si; float t_hit;
+      slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+      const uint4 info = p.sc.info[h.slot];
+      Spec l_add = spec(0.0f);
+      if ((bounces == 0 || specular_bounce) && info.z != kNoLight) l_add = beta * area_L(p.sc.lights[info.z], si.n, -ray.d);   // path.rs:127-131
+      if (bounces < max_depth) {                                        // path.rs:139-141
+        const Inter it = inter_of(si);
+        if (MAT == Q_NONE) {                                            // path.rs:146-152 (u8 wrap)
+          Ray nr = spawn_ray(it, ray.d);
+          store_ray(p.w.ray_o, p.w.ray_d, slot, nr, 0);
+          bounces = (bounces - 1u) & 0xffu;
+          alive = true;
+        } else {
+          Bsdf bsdf;
+          make_bsdf((uint32_t)MAT, p.sc.materials[info.y], si, true, bsdf);
+          if (bsdf_num_components(bsdf, kBsdfNonSpecular) > 0 && p.sc.n_lights > 0) {   // path.rs:161-171 -> uniform_sample_one_light
+            const Distrib dist = lookup_distrib(p, si.p);
+            const float s = ss.get_1d(p.scfg);
+            float light_pdf;
+            const int light_num = dist1d_sample_discrete(dist.func, dist.cdf, dist.n, dist.func_int, s, light_pdf);
+            if (light_pdf != 0.0f) {
+              const P2 u_light = ss.get_2d(p.scfg);
+              const P2 u_scattering = ss.get_2d(p.scfg);
+              estimate_direct(p, si, bsdf, u_scattering, (uint32_t)light_num, u_light, beta / light_pdf, sample);
+            }
+          }
+          const V3 wo = -ray.d;
+          Spec f; V3 wi; float pdf; uint32_t flags;
+          bsdf_sample_f(bsdf, wo, ss.get_2d(p.scfg), BSDF_ALL, f, wi, pdf, flags);
+          if (!(is_black(f) || pdf <= 0.0f)) {                          // path.rs:174-176
+            beta = beta * f * fabsf(dot(wi, si.ns)) / pdf;
+            specular_bounce = (flags & BSDF_SPECULAR) != 0;
+            if ((flags & BSDF_SPECULAR) && (flags & BSDF_TRANSMISSION)) {
+              const float eta = bsdf.eta;
+              eta_scale *= dot(wo, si.n) > 0.0f ? eta * eta : 1.0f / (eta * eta);
+            }
+            Ray nr = spawn_ray(it, wi);
+            alive = true;
+            const Spec rr_beta = beta * eta_scale;                      // path.rs:199-209
+            if (max_component_value(rr_beta) < p.rr_threshold && bounces > 3) {
+              const float q = fmaxf(1.0f - max_component_value(rr_beta), 0.05f);
+              if (ss.get_1d(p.scfg) < q) alive = false;
+              beta = beta / (1.0f - q);
+            }
+            bounces = (bounces + 1u) & 0xffu;
+            if (alive) store_ray(p.w.ray_o, p.w.ray_d, slot, nr, 0);
+          }
+        }
+        if (alive) {
+          p.w.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
+          p.w.pstate[slot] = make_uint4(sample, bounces, specular_bounce ? 1u : 0u, (ss.d1 & 0xffffu) | (ss.d2 << 16));
+        }
+      }
+      if (!is_black(l_add)) { float4 L = p.w.L[sample]; L.x += l_add.r; L.y += l_add.g; L.z += l_add.b; p.w.L[sample] = L; }
+    }
+    const uint32_t pos = warp_append(out_count, alive);
+    if (alive) out_list[pos] = slot;
+  }
+}
+
+}  // namespace rt

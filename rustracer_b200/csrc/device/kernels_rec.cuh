@@ -1,0 +1,128 @@
+// Shading kernels of the Whitted / DirectLighting / AmbientOcclusion / Normal integrators (product code, sm_100a).
+#pragma once
+#include "shade_common.cuh"
+
+namespace rt {
+
+// ---- Whitted / DirectLighting: one level of the recursion (whitted.rs:41-99, directlighting.rs:89-143,
+// integrator/mod.rs:49-142).  Radiance is linear, so every item carries its throughput and adds into its
+// camera sample; specular reflection / transmission spawn child items for the next level.
+__global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int parity) {
+  const uint32_t n = p.w.counters[C_LIVE0 + parity];
+  const float4* ray_o = parity ? p.w.ray_o2 : p.w.ray_o; const float4* ray_d = parity ? p.w.ray_d2 : p.w.ray_d;
+  const float4* beta_in = parity ? p.w.beta2 : p.w.beta; const uint4* ps_in = parity ? p.w.pstate2 : p.w.pstate;
+  float4* oray_o = parity ? p.w.ray_o : p.w.ray_o2; float4* oray_d = parity ? p.w.ray_d : p.w.ray_d2;
+  float4* obeta = parity ? p.w.beta : p.w.beta2; uint4* ops = parity ? p.w.pstate : p.w.pstate2;
+  uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
+  const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Ray ray = load_ray(ray_o, ray_d, i, nullptr);
+    ray.t_max = inf_f();
+    const HitRec h = p.w.hit[i];
+    const float4 bt = beta_in[i];
+    const Spec beta = spec(bt.x, bt.y, bt.z);
+    const uint4 ps = ps_in[i];
+    const uint32_t sample = ps.x, node = ps.y, depth = ps.z;
+    float4* L = &p.w.L[sample];
+    Spec colour = spec(0.0f);
+    if (h.slot == kMiss) {                                              // whitted.rs:91-94: every light's le(ray)
+      for (uint32_t j = 0; j < p.sc.n_lights; j++) colour = colour + light_le(p.sc, p.sc.lights[j], ray.d);
+    } else {
+      SurfHit si; float t_hit;
+      slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+      const uint4 info = p.sc.info[h.slot];
+      const Inter it = inter_of(si);
+      const uint32_t mtype = info.y < p.sc.n_materials ? p.sc.materials[info.y].type : (uint32_t)RTGPU_MAT_NONE;
+      Bsdf bsdf;
+      if (mtype > RTGPU_MAT_MIRROR || !make_bsdf(mtype, p.sc.materials[info.y], si, false, bsdf)) {
+        // no material: continue the same node through the surface (whitted.rs:60-63)
+        const uint32_t pos = warp_append(out_count, true);
+        if (pos < p.w.cap_items) { store_ray(oray_o, oray_d, pos, spawn_ray(it, ray.d), 0); obeta[pos] = bt; ops[pos] = ps; }
+        else p.w.counters[C_OVERFLOW] = 1;
+        continue;
+      }
+      const uint2 sinf = p.w.sinfo[sample];
+      SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y;
+      if (node == 1) { ss.d1 = 1; ss.d2 = 2; ss.da = 0; } else { ss.d1 = ss.d2 = ss.da = 64u * node; }   // oracle-twin node keying
+      const V3 wo = si.wo, ns = si.ns;
+      if (info.z != kNoLight) colour = colour + area_L(p.sc.lights[info.z], si.n, wo);
+      if (p.integrator == RTGPU_INTEGRATOR_WHITTED) {                   // whitted.rs:70-82
+        for (uint32_t j = 0; j < p.sc.n_lights; j++) {
+          V3 wi; float pdf; Inter p1;
+          Spec li = light_sample_li(p.sc, p.sc.lights[j], it, ss.get_2d(p.scfg), wi, pdf, p1);
+          if (is_black(li) || pdf == 0.0f) continue;
+          Spec f = bsdf_f(bsdf, wo, wi, BSDF_ALL);
+          if (!is_black(f)) push_shadow(p, spawn_ray_to(it, p1), sample, beta * (f * li * fabsf(dot(wi, ns)) / pdf));
+        }
+      } else if (p.sc.n_lights > 0) {
+        if (p.direct_strategy == 0) {                                   // uniform_sample_all_light (integrator/mod.rs:145-184)
+          for (uint32_t j = 0; j < p.sc.n_lights; j++) {
+            const uint32_t ns_j = p.n_light_samples[j];
+            const uint32_t ca = ss.da++, cb = ss.da++;
+            for (uint32_t k = 0; k < ns_j; k++) {
+              P2 ul = draw_2d_array(ss.ph, ss.s, p.scfg, ns_j, k, ca);
+              P2 us = draw_2d_array(ss.ph, ss.s, p.scfg, ns_j, k, cb);
+              estimate_direct(p, si, bsdf, us, j, ul, beta / (float)ns_j, sample);
+            }
+          }
+        } else {                                                        // uniform_sample_one_light, no distribution (:186-220)
+          const uint32_t nl = p.sc.n_lights;
+          const float s = ss.get_1d(p.scfg);
+          const uint32_t light_num = min(nl - 1u, f2u32(s * (float)nl));
+          const float light_pdf = 1.0f / (float)nl;
+          const P2 u_light = ss.get_2d(p.scfg);
+          const P2 u_scattering = ss.get_2d(p.scfg);
+          estimate_direct(p, si, bsdf, u_scattering, light_num, u_light, beta / light_pdf, sample);
+        }
+      }
+      if (depth + 1 < max_depth) {                                      // whitted.rs:83-88
+#pragma unroll 1
+        for (uint32_t pass = 0; pass < 2; pass++) {
+          const uint32_t flags = (pass == 0 ? BSDF_REFLECTION : BSDF_TRANSMISSION) | BSDF_SPECULAR;
+          Spec f; V3 wi; float pdf; uint32_t st;
+          bsdf_sample_f(bsdf, wo, ss.get_2d(p.scfg), flags, f, wi, pdf, st);
+          if (pdf > 0.0f && !is_black(f) && fabsf(dot(wi, ns)) != 0.0f) {
+            const Spec cb = beta * (f * fabsf(dot(wi, ns)) / pdf);
+            const uint32_t pos = warp_append(out_count, true);
+            if (pos < p.w.cap_items) {
+              store_ray(oray_o, oray_d, pos, spawn_ray(it, wi), 0);
+              obeta[pos] = make_float4(cb.r, cb.g, cb.b, 1.0f);
+              ops[pos] = make_uint4(sample, node * 2u + pass, depth + 1u, 0u);
+            } else p.w.counters[C_OVERFLOW] = 1;
+          }
+        }
+      }
+    }
+    if (!is_black(colour)) { const Spec c = beta * colour; atomicAdd(&L->x, c.r); atomicAdd(&L->y, c.g); atomicAdd(&L->z, c.b); }
+  }
+}
+
+// ---- AmbientOcclusion::li (integrator/ao.rs:32-58) and Normal::li (normal.rs:20-34) ---------------------------
+__global__ void __launch_bounds__(128) k_shade_ao(RenderParams p) {
+  const uint32_t n = p.w.counters[C_LIVE0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = p.w.list[0][i];
+    const HitRec h = p.w.hit[slot];
+    if (h.slot == kMiss) continue;
+    Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
+    ray.t_max = inf_f();
+    SurfHit si; float t_hit;
+    slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+    const Inter it = inter_of(si);
+    const uint32_t sample = p.w.pstate[slot].x;
+    const uint2 sinf = p.w.sinfo[sample];
+    SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = 1; ss.d2 = 2; ss.da = 0;
+    if (p.integrator == RTGPU_INTEGRATOR_NORMAL) {
+      const float v = fabsf(dot(ray.d, si.n));
+      float4 L = p.w.L[sample]; L.x = v; L.y = v; L.z = v; p.w.L[sample] = L;
+      continue;
+    }
+    for (int k = 0; k < p.ao_samples; k++) {
+      V3 w = uniform_sample_sphere(ss.get_2d(p.scfg));
+      if (dot(w, si.n) < 0.0f) w = -w;
+      push_shadow(p, spawn_ray(it, w), sample, spec(1.0f));              // counts clear rays; k_film_add divides by n_samples
+    }
+  }
+}
+
+}  // namespace rt

@@ -1,0 +1,303 @@
+// Wavefront kernels: ray generation, queue traversal (closest / shadow / MIS), bounce bookkeeping, film accumulation and
+// resolve, spatial light-distribution prepass (product code, sm_100a).  Each kernel names the rustracer code it replaces.
+#pragma once
+#include "shade_common.cuh"
+
+namespace rt {
+
+__global__ void __launch_bounds__(256) k_generate_rays(RenderParams p, const float4* __restrict__ samples, uint32_t n, float4* __restrict__ rays) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 s = samples[i];
+  Ray r = camera_ray(p.r2c, p.c2w, p.lens_radius, p.focal_distance, mk2(s.x, s.y), mk2(s.z, s.w));
+  rays[2 * (size_t)i] = make_float4(r.o.x, r.o.y, r.o.z, r.t_max);
+  rays[2 * (size_t)i + 1] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+}
+
+// ---- k_raygen: get_camera_sample + generate_ray (renderer.rs:109-111, zerotwosequence.rs:182-192) ------------
+// Item i of the wave -> (pixel, sample index): sample-major, then my tiles, then the 16x16 pixels of a tile, so
+// the 32 lanes of a warp are two adjacent pixel rows of one tile.
+__global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < p.n_items;
+  int x = 0, y = 0; uint32_t s = 0;
+  if (valid) {
+    if (p.explicit_pixels) { x = p.explicit_pixels[3 * (size_t)i]; y = p.explicit_pixels[3 * (size_t)i + 1]; s = (uint32_t)p.explicit_pixels[3 * (size_t)i + 2]; }
+    else {
+      const uint32_t per_sample = (uint32_t)p.n_tiles * 256u;
+      const uint32_t j = i / per_sample, rem = i - j * per_sample;
+      const uint32_t tile_ord = (uint32_t)p.tile_first + rem / 256u, pix = rem & 255u;
+      const uint32_t tile = (uint32_t)p.tile_rank + tile_ord * (uint32_t)p.tile_world;
+      const int tx = (int)(tile % (uint32_t)p.tiles_x), ty = (int)(tile / (uint32_t)p.tiles_x);
+      x = p.sample_bounds[0] + tx * 16 + (int)(pix & 15u);
+      y = p.sample_bounds[1] + ty * 16 + (int)(pix >> 4);
+      s = (uint32_t)p.sample_first + j;
+      valid = x < p.sample_bounds[2] && y < p.sample_bounds[3] &&
+              x >= p.pixel_bounds[0] && x < p.pixel_bounds[2] && y >= p.pixel_bounds[1] && y < p.pixel_bounds[3];   // renderer.rs:103-105
+    }
+  }
+  const uint32_t pos = warp_append(&p.w.counters[C_LIVE0], valid);
+  if (i < p.n_items) {
+    SamplerState ss; ss.ph = pixel_hash(x, y, p.seed); ss.s = s; ss.d1 = 0; ss.d2 = 0; ss.da = 0;
+    P2 u = ss.get_2d(p.scfg);
+    P2 p_film = mk2((float)x + u.x, (float)y + u.y);
+    (void)ss.get_1d(p.scfg);                                          // time: drawn, unused by the camera
+    P2 p_lens = ss.get_2d(p.scfg);
+    p.w.L[i] = make_float4(0.0f, 0.0f, 0.0f, valid ? 1.0f : 0.0f);
+    p.w.pfilm[i] = make_float2(p_film.x, p_film.y);
+    p.w.sinfo[i] = make_uint2(ss.ph, s);
+    if (valid) {                                                      // items are compacted: item slot = queue position
+      Ray ray = camera_ray(p.r2c, p.c2w, p.lens_radius, p.focal_distance, p_film, p_lens);
+      store_ray(p.w.ray_o, p.w.ray_d, pos, ray, 0);
+      p.w.beta[pos] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+      p.w.pstate[pos] = make_uint4(i, p.integrator == RTGPU_INTEGRATOR_PATH ? 0u : 1u, 0u, ss.d1 | (ss.d2 << 16));
+      p.w.list[0][pos] = pos;
+    }
+  }
+}
+
+// ---- queue traversal ----------------------------------------------------------------------------------------
+// Persistent warps pull 32-entry packets from the queue with an atomic cursor.  CLASSIFY appends each path to the
+// queue of its hit material (or the miss queue) for the material-sorted shade kernels.
+template <bool CLASSIFY>
+__global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                        const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
+  const uint32_t n = p.w.counters[count_idx];
+  while (true) {
+    const uint32_t base = warp_fetch(&p.w.counters[C_CUR_CLOSEST]);
+    if (base >= n) break;
+    const uint32_t i = base + lane_id();
+    const bool act = i < n;
+    uint32_t slot = 0; int q = -1;
+    if (act) {
+      slot = list ? list[i] : i;
+      Ray ray = load_ray(ray_o, ray_d, slot, nullptr);
+      HitRec h;
+      bvh_traverse<false, false>(p.sc, ray, h, nullptr);
+      hits[slot] = h;
+      if (CLASSIFY) {
+        if (h.slot == kMiss) q = Q_MISS;
+        else {
+          const uint32_t mrow = p.sc.info[h.slot].y;
+          const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+          q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
+        }
+      }
+    }
+    if (CLASSIFY) {
+#pragma unroll
+      for (int k = 0; k < Q_COUNT; k++) {
+        const uint32_t pos = warp_append(&p.w.counters[C_MATQ0 + k], act && q == k);
+        if (act && q == k) p.w.matq[k][pos] = slot;
+      }
+    }
+  }
+}
+
+// Shadow rays: VisibilityTester::unoccluded (light/mod.rs:52-55) -> Scene::intersect_p; adds the pending
+// contribution to the sample's radiance when the segment is clear.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) k_trace_shadow(RenderParams p) {
+  const uint32_t n = min(p.w.counters[C_SHADOW], p.w.cap_shadow);
+  while (true) {
+    const uint32_t base = warp_fetch(&p.w.counters[C_CUR_ANY]);
+    if (base >= n) break;
+    const uint32_t i = base + lane_id();
+    if (i >= n) continue;
+    uint32_t sample;
+    Ray ray = load_ray(p.w.sh_o, p.w.sh_d, i, &sample);
+    HitRec h;
+    if (!bvh_traverse<true, false>(p.sc, ray, h, nullptr)) {
+      const float4 c = p.w.sh_c[i];
+      float4* L = &p.w.L[sample];
+      if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
+      else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
+    }
+  }
+}
+
+// MIS rays: second half of estimate_direct (integrator/mod.rs:291-313): closest hit of the BSDF-sampled ray; it
+// contributes only if it lands on the sampled light (or escapes to the sampled infinite light).
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
+  const uint32_t n = min(p.w.counters[C_MIS], p.w.cap_mis);
+  while (true) {
+    const uint32_t base = warp_fetch(&p.w.counters[C_CUR_MIS]);
+    if (base >= n) break;
+    const uint32_t i = base + lane_id();
+    if (i >= n) continue;
+    uint32_t sample;
+    Ray ray = load_ray(p.w.mi_o, p.w.mi_d, i, &sample);
+    const Ray ray0 = ray;
+    const float4 c = p.w.mi_c[i];
+    const uint32_t light_row = __float_as_uint(c.w);
+    const rtgpu_light& light = p.sc.lights[light_row];
+    HitRec h;
+    Spec li = spec(0.0f);
+    if (bvh_traverse<false, false>(p.sc, ray, h, nullptr)) {
+      if (p.sc.info[h.slot].z == light_row) {                         // same light id (integrator/mod.rs:294-299)
+        SurfHit si; float t;
+        if (slot_intersect_surface(p.sc, h.slot, ray0, t, si)) li = area_L(light, si.n, -ray0.d);
+      }
+    } else li = light_le(p.sc, light, ray0.d);
+    if (!is_black(li)) {
+      float4* L = &p.w.L[sample];
+      const float r = c.x * li.r, g = c.y * li.g, b = c.z * li.b;
+      if (ATOMIC) { atomicAdd(&L->x, r); atomicAdd(&L->y, g); atomicAdd(&L->z, b); }
+      else { float4 v = *L; v.x += r; v.y += g; v.z += b; *L = v; }
+    }
+  }
+}
+
+// compute_distribution (lightdistrib.rs:101-179), first half: one thread per (voxel, light) accumulates the
+// 128 Halton-point estimates sequentially, in the reference's order.
+__global__ void __launch_bounds__(128) k_lightgrid_contrib(DScene sc, int nvx, int nvy, int nvz, float* __restrict__ table) {
+  const int n = (int)sc.n_lights;
+  const size_t total = (size_t)nvx * nvy * nvz * n;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % n);
+  const size_t voxel = idx / n;
+  const int pz = (int)(voxel % nvz), py = (int)((voxel / nvz) % nvy), px = (int)(voxel / ((size_t)nvz * nvy));
+  const float lo[3] = {sc.world_lo[0], sc.world_lo[1], sc.world_lo[2]}, hi[3] = {sc.world_hi[0], sc.world_hi[1], sc.world_hi[2]};
+  const int pi[3] = {px, py, pz}, nv[3] = {nvx, nvy, nvz};
+  float vlo[3], vhi[3];
+  for (int k = 0; k < 3; k++) {
+    float t0 = (float)pi[k] / (float)nv[k], t1 = ((float)pi[k] + 1.0f) / (float)nv[k];
+    float a = lo[k] * (1.0f - t0) + hi[k] * t0, b = lo[k] * (1.0f - t1) + hi[k] * t1;   // Bounds3::lerp
+    vlo[k] = pmin(a, b); vhi[k] = pmax(a, b);                                             // Bounds3::from_points
+  }
+  const rtgpu_light& light = sc.lights[j];
+  float contrib = 0.0f;
+  for (uint64_t i = 0; i < 128; i++) {
+    float t[3] = {radical_inverse(0, i), radical_inverse(1, i), radical_inverse(2, i)};
+    V3 po = v3(vlo[0] * (1.0f - t[0]) + vhi[0] * t[0], vlo[1] * (1.0f - t[1]) + vhi[1] * t[1], vlo[2] * (1.0f - t[2]) + vhi[2] * t[2]);
+    Inter intr = inter_point(po);
+    P2 u = mk2(radical_inverse(3, i), radical_inverse(4, i));
+    V3 wi; float pdf; Inter p1;
+    Spec li = light_sample_li(sc, light, intr, u, wi, pdf, p1);
+    if (pdf > 0.0f) contrib += lum(li) / pdf;
+  }
+  table[voxel * (size_t)(2 * n + 2) + j] = contrib;
+}
+// second half: floor at 0.1 % of the average, then Distribution1D::new (distribution1d.rs:11-45)
+__global__ void __launch_bounds__(128) k_lightgrid_build(int n, size_t n_voxels, float* __restrict__ table) {
+  const size_t voxel = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (voxel >= n_voxels) return;
+  float* func = table + voxel * (size_t)(2 * n + 2);
+  float* cdf = func + n;
+  float sum = 0.0f;
+  for (int j = 0; j < n; j++) sum += func[j];
+  const float avg = sum / (float)(128ull * (unsigned long long)n);
+  const float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
+  for (int j = 0; j < n; j++) func[j] = fmaxf(func[j], min_contrib);
+  cdf[0] = 0.0f;
+  for (int i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + func[i - 1] / (float)n;
+  const float func_int = cdf[n];
+  if (func_int == 0.0f) for (int i = 1; i < n + 1; i++) cdf[i] = (float)i / (float)n;
+  else for (int i = 1; i < n + 1; i++) cdf[i] /= func_int;
+  func[2 * n + 1] = func_int;
+}
+
+// Escaped paths: emission of the infinite lights, then the path ends (path.rs:127-141).
+__global__ void __launch_bounds__(128) k_shade_miss(RenderParams p) {
+  const uint32_t n = p.w.counters[C_MATQ0 + Q_MISS];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = p.w.matq[Q_MISS][i];
+    const uint4 ps = p.w.pstate[slot];
+    const uint32_t bounces = ps.y & 0xffu; const bool specular_bounce = (ps.z & 1u) != 0;
+    if (bounces == 0 || specular_bounce) {
+      const float4 bt = p.w.beta[slot];
+      const Spec beta = spec(bt.x, bt.y, bt.z);
+      const float4 d = p.w.ray_d[slot];
+      float4 L = p.w.L[ps.x];
+      for (uint32_t j = 0; j < p.sc.n_lights; j++) {
+        if (p.sc.lights[j].kind != RTGPU_LIGHT_INFINITE) continue;
+        Spec c = beta * light_le(p.sc, p.sc.lights[j], v3(d.x, d.y, d.z));
+        L.x += c.r; L.y += c.g; L.z += c.b;
+      }
+      p.w.L[ps.x] = L;
+    }
+  }
+}
+
+// End of a bounce: fold the queue sizes into the reference's ray counters and reset the per-bounce queues.
+__global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t* c = p.w.counters;
+  const uint32_t live = c[live_idx];
+  p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis);
+  p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
+  if (count_camera) p.w.stats[S_CAMERA] += live;
+  if (c[C_OVERFLOW]) p.w.stats[S_COUNT - 1] = 1;
+  c[live_idx] = 0;
+  for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;
+  c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_CUR_CLOSEST] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0;
+}
+
+// ---- film (film.rs) -----------------------------------------------------------------------------------------------
+// renderer.rs:115-126 guards + FilmTile::add_sample (film.rs:298-361) + merge (film.rs:177-194, kept as RGB sums)
+__global__ void __launch_bounds__(256) k_film_add(FilmParams f, const float4* __restrict__ L, const float2* __restrict__ pfilm, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 l = L[i];
+  if (l.w == 0.0f) return;
+  Spec c = spec(l.x, l.y, l.z) / f.ao_div;                             // AO: n_clear / n_samples (ao.rs:57); 1 otherwise
+  if (has_nan(c)) c = spec(0.0f);
+  if (lum(c) < -1e-5f) c = spec(0.0f);
+  if (isinf(lum(c))) c = spec(0.0f);
+  if (lum(c) > f.max_lum) c = c * f.max_lum / lum(c);
+  const float2 pf = pfilm[i];
+  const float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
+  const float p0x = ceilf(dx - f.rx), p0y = ceilf(dy - f.ry);
+  const float p1x = floorf(dx + f.rx + 1.0f), p1y = floorf(dy + f.ry + 1.0f);
+  const int x0 = f2i32(pmax(pmin(p0x, p1x), (float)f.crop[0])), y0 = f2i32(pmax(pmin(p0y, p1y), (float)f.crop[1]));
+  const int x1 = f2i32(pmin(pmax(p0x, p1x), (float)f.crop[2])), y1 = f2i32(pmin(pmax(p0y, p1y), (float)f.crop[3]));
+  const int w = f.crop[2] - f.crop[0];
+  for (int y = y0; y < y1; y++) {
+    const float fy = fabsf(((float)y - dy) * f.iry * 16.0f);
+    const int iy = (int)f2u32(fminf(floorf(fy), 15.0f));
+    for (int x = x0; x < x1; x++) {
+      const float fx = fabsf(((float)x - dx) * f.irx * 16.0f);
+      const int ix = (int)f2u32(fminf(floorf(fx), 15.0f));
+      const float wgt = f.table[iy * 16 + ix];
+      const Spec cw = c * wgt;
+      atomicAdd(&f.film[(size_t)(y - f.crop[1]) * w + (x - f.crop[0])], make_float4(cw.r, cw.g, cw.b, wgt));
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_li_out(const float4* __restrict__ L, float ao_div, uint32_t n, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 l = L[i];
+  out[3 * (size_t)i] = l.x / ao_div; out[3 * (size_t)i + 1] = l.y / ao_div; out[3 * (size_t)i + 2] = l.z / ao_div;
+}
+// Film pixel accumulators as the reference keeps them: XYZ + weight (film.rs:38-43,187-192)
+__global__ void __launch_bounds__(256) k_film_xyz(const float4* __restrict__ film, size_t n, float4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = film[i];
+  float xyz[3]; to_xyz(spec(v.x, v.y, v.z), xyz);
+  out[i] = make_float4(xyz[0], xyz[1], xyz[2], v.w);
+}
+// Film::write_image arithmetic (film.rs:196-234)
+__global__ void __launch_bounds__(256) k_film_resolve(const float4* __restrict__ film, size_t n, float scale, float* __restrict__ rgb) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = film[i];
+  float xyz[3]; to_xyz(spec(v.x, v.y, v.z), xyz);
+  Spec c = from_xyz(xyz[0], xyz[1], xyz[2]);
+  if (v.w != 0.0f) { const float inv = 1.0f / v.w; c = spec(fmaxf(0.0f, c.r * inv), fmaxf(0.0f, c.g * inv), fmaxf(0.0f, c.b * inv)); }
+  const Spec sp = from_xyz(0.0f, 0.0f, 0.0f);                          // splat term (film.rs:222-230): zero on this path
+  c = spec(c.r + 1.0f * sp.r, c.g + 1.0f * sp.g, c.b + 1.0f * sp.b);
+  rgb[3 * i] = c.r * scale; rgb[3 * i + 1] = c.g * scale; rgb[3 * i + 2] = c.b * scale;
+}
+__global__ void __launch_bounds__(256) k_film_accumulate(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = dst[i]; const float4 b = src[i];
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  dst[i] = a;
+}
+
+}  // namespace rt

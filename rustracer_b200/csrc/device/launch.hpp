@@ -1,0 +1,31 @@
+// Launch wrappers: each kernel group is its own translation unit so nvcc can build them in parallel.
+#pragma once
+#include "wave.cuh"
+
+namespace rt {
+
+void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t n, float4* rays, cudaStream_t s);
+void launch_raygen(const RenderParams& p, cudaStream_t s);
+void launch_trace_closest(bool classify, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
+                          HitRec* hits, unsigned blocks, cudaStream_t s);
+void launch_trace_shadow(bool atomic, const RenderParams& p, unsigned blocks, cudaStream_t s);
+void launch_trace_mis(bool atomic, const RenderParams& p, unsigned blocks, cudaStream_t s);
+void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);
+void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s);
+void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s);
+void launch_film_add(const FilmParams& f, const float4* L, const float2* pfilm, uint32_t n, cudaStream_t s);
+void launch_li_out(const float4* L, float ao_div, uint32_t n, float* out, cudaStream_t s);
+void launch_film_xyz(const float4* film, size_t n, float4* out, cudaStream_t s);
+void launch_film_resolve(const float4* film, size_t n, float scale, float* rgb, cudaStream_t s);
+void launch_film_accumulate(float4* dst, const float4* src, size_t n, cudaStream_t s);
+// material-sorted path shading: one translation unit per material class (tu_path.cu with -DRT_PATH_MAT=n)
+void launch_shade_path_0(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_path_1(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_path_2(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_path_3(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_path_4(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_path_5(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_recursive(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
+void launch_shade_ao(const RenderParams& p, unsigned blocks, cudaStream_t s);
+
+}  // namespace rt

@@ -1,14 +1,468 @@
+// librtgpu.so — host orchestration of the wavefront renderer: rtgpu_render / rtgpu_li_samples /
+// rtgpu_generate_rays / film read-out and reduction (include/rtgpu.h).  Replaces the tile loop of
+// renderer::render (rustracer-core/src/renderer.rs:22-143).  All kernel launches of one render are queued on the
+// context's stream without host synchronisation: queue sizes live in device memory.
 #include "context.hpp"
+#include "launch.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace rt;
+
+struct WaveBuffers {
+  WaveView v{};
+  std::vector<void*> allocs;
+  bool recursive = false;
+  float* uniform_table = nullptr; int uniform_n = 0;          // UniformLightDistribution
+  float* grid_table = nullptr; int grid_nv[3] = {0, 0, 0}; int grid_n = 0; bool grid_valid = false;
+  uint32_t* n_light_samples = nullptr; uint32_t n_light_samples_cap = 0;
+  float4* film_tmp = nullptr; size_t film_tmp_n = 0;
+};
+
 namespace rt {
-void free_wave_buffers(rtgpu_ctx*) {}
-void free_lightgrid(rtgpu_ctx*) {}
+
+static void release(WaveBuffers* w) {
+  for (void* p : w->allocs) cudaFree(p);
+  w->allocs.clear();
+  w->v = WaveView{};
 }
+void free_wave_buffers(rtgpu_ctx* ctx) {
+  if (!ctx->wave) return;
+  release(ctx->wave);
+  if (ctx->wave->uniform_table) cudaFree(ctx->wave->uniform_table);
+  if (ctx->wave->grid_table) cudaFree(ctx->wave->grid_table);
+  if (ctx->wave->n_light_samples) cudaFree(ctx->wave->n_light_samples);
+  if (ctx->wave->film_tmp) cudaFree(ctx->wave->film_tmp);
+  delete ctx->wave;
+  ctx->wave = nullptr;
+}
+void free_lightgrid(rtgpu_ctx* ctx) {
+  if (!ctx->wave) return;
+  WaveBuffers* w = ctx->wave;
+  if (w->uniform_table) { cudaFree(w->uniform_table); w->uniform_table = nullptr; w->uniform_n = 0; }
+  if (w->grid_table) { cudaFree(w->grid_table); w->grid_table = nullptr; }
+  w->grid_valid = false;
+}
+
+template <class T> static int dalloc(rtgpu_ctx* ctx, WaveBuffers* w, T** out, size_t count) {
+  void* p = nullptr;
+  RT_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  w->allocs.push_back(p);
+  *out = (T*)p;
+  return 0;
+}
+
+static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples, uint32_t cap_shadow, uint32_t cap_mis, bool recursive) {
+  if (!ctx->wave) ctx->wave = new WaveBuffers();
+  WaveBuffers* w = ctx->wave;
+  WaveView& v = w->v;
+  if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters)
+    return 0;
+  release(w);
+  int rc = 0;
+#define A(field, n) if ((rc = dalloc(ctx, w, &v.field, (n)))) return rc
+  A(ray_o, cap_items); A(ray_d, cap_items); A(hit, cap_items); A(beta, cap_items); A(pstate, cap_items);
+  if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
+  A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
+  A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
+  A(mi_o, cap_mis); A(mi_d, cap_mis); A(mi_c, cap_mis);
+  A(list[0], cap_items); A(list[1], cap_items);
+  for (int k = 0; k < Q_COUNT; k++) A(matq[k], cap_items);
+  A(counters, C_COUNT); A(stats, S_COUNT);
+#undef A
+  v.cap_items = cap_items; v.cap_samples = cap_samples; v.cap_shadow = cap_shadow; v.cap_mis = cap_mis;
+  w->recursive = recursive;
+  return 0;
+}
+
+// UniformLightDistribution (lightdistrib.rs:37-54): Distribution1D over n ones, built as distribution1d.rs:11-45
+static int ensure_uniform_table(rtgpu_ctx* ctx, int n) {
+  WaveBuffers* w = ctx->wave;
+  if (w->uniform_table && w->uniform_n == n) return 0;
+  if (w->uniform_table) { cudaFree(w->uniform_table); w->uniform_table = nullptr; }
+  std::vector<float> t((size_t)2 * n + 2, 0.0f);
+  float* func = t.data(); float* cdf = func + n;
+  for (int i = 0; i < n; i++) func[i] = 1.0f;
+  cdf[0] = 0.0f;
+  for (int i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + func[i - 1] / (float)n;
+  float func_int = cdf[n];
+  if (func_int == 0.0f) for (int i = 1; i < n + 1; i++) cdf[i] = (float)i / (float)n;
+  else for (int i = 1; i < n + 1; i++) cdf[i] /= func_int;
+  t[(size_t)2 * n + 1] = func_int;
+  RT_CUDA(ctx, cudaMalloc((void**)&w->uniform_table, t.size() * sizeof(float)));
+  RT_CUDA(ctx, cudaMemcpyAsync(w->uniform_table, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  w->uniform_n = n;
+  return 0;
+}
+
+// SpatialLightDistribution::new (lightdistrib.rs:67-99) + compute_distribution for every voxel (device prepass
+// instead of the reference's lazily filled hash table: same per-voxel values).
+static int ensure_light_grid(rtgpu_ctx* ctx) {
+  WaveBuffers* w = ctx->wave;
+  if (w->grid_valid) return 0;
+  const DScene& sc = ctx->scene;
+  float diag[3]; int widest = 0;
+  for (int k = 0; k < 3; k++) diag[k] = sc.world_hi[k] - sc.world_lo[k];
+  widest = diag[0] > diag[1] ? (diag[0] > diag[2] ? 0 : 2) : (diag[1] > diag[2] ? 1 : 2);       // Bounds3::maximum_extent
+  const float b_max = diag[widest];
+  size_t n_voxels = 1;
+  for (int k = 0; k < 3; k++) {
+    float r = std::round(diag[k] / b_max * 64.0f);
+    uint32_t u = !(r == r) ? 0u : (r <= 0.0f ? 0u : (r >= 4294967296.0f ? 0xffffffffu : (uint32_t)r));   // saturating `as u32`
+    w->grid_nv[k] = (int)std::max<uint32_t>(1u, std::min<uint32_t>(u, 64u));
+    n_voxels *= (size_t)w->grid_nv[k];
+  }
+  const int n = (int)sc.n_lights;
+  const size_t floats = n_voxels * (size_t)(2 * n + 2);
+  if (floats * sizeof(float) > ((size_t)16 << 30))
+    return fail(ctx, RTGPU_ERR_UNSUPPORTED, "spatial light distribution: dense voxel table would exceed 16 GiB; use lightsamplestrategy \"uniform\"");
+  if (w->grid_table) { cudaFree(w->grid_table); w->grid_table = nullptr; }
+  RT_CUDA(ctx, cudaMalloc((void**)&w->grid_table, floats * sizeof(float)));
+  launch_lightgrid(sc, w->grid_nv[0], w->grid_nv[1], w->grid_nv[2], w->grid_table, ctx->stream);
+  ctx->launches += 2;
+  RT_CUDA(ctx, cudaGetLastError());
+  w->grid_n = n; w->grid_valid = true;
+  return 0;
+}
+
+static uint32_t next_pow2_u32(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+struct Plan {
+  RenderParams p{};
+  FilmParams film{};
+  bool recursive = false;
+  uint32_t samples_per_wave_cap = 0;
+  bool mat_present[Q_COUNT] = {false, false, false, false, false, false, true};
+  int extra_rounds = 0;
+};
+
+static int fill_params(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const rtgpu_material* host_materials_unused, Plan& plan) {
+  (void)host_materials_unused;
+  RenderParams& p = plan.p;
+  p.sc = ctx->scene;
+  std::memcpy(p.r2c, rd->raster_to_camera, 64); std::memcpy(p.c2w, rd->camera_to_world, 64);
+  p.lens_radius = rd->lens_radius; p.focal_distance = rd->focal_distance;
+  for (int i = 0; i < 4; i++) { p.sample_bounds[i] = rd->sample_bounds[i]; p.pixel_bounds[i] = rd->pixel_bounds[i]; }
+  p.scfg.spp = (uint32_t)std::max(1, rd->spp); p.scfg.dims = (uint32_t)std::max(0, rd->sampler_dims); p.scfg.n_arrays = 0;
+  p.seed = rd->seed;
+  p.integrator = rd->integrator; p.max_depth = rd->max_depth; p.direct_strategy = rd->direct_strategy; p.ao_samples = rd->ao_samples;
+  p.rr_threshold = rd->rr_threshold;
+  p.tile_rank = rd->tile_rank; p.tile_world = std::max(1, rd->tile_world);
+  if (p.tile_rank < 0 || p.tile_rank >= p.tile_world) return fail(ctx, RTGPU_ERR_ARG, "tile_rank outside [0, tile_world)");
+  if (rd->integrator < RTGPU_INTEGRATOR_PATH || rd->integrator > RTGPU_INTEGRATOR_NORMAL) return fail(ctx, RTGPU_ERR_ARG, "unknown integrator");
+  if (rd->integrator == RTGPU_INTEGRATOR_AO && rd->ao_samples <= 0) return fail(ctx, RTGPU_ERR_ARG, "ambient occlusion needs ao_samples > 0");
+  plan.recursive = rd->integrator == RTGPU_INTEGRATOR_WHITTED || rd->integrator == RTGPU_INTEGRATOR_DIRECT;
+  return 0;
+}
+
+// Everything between `renderer::render` entry and the film merge, for my (tile, sample) share or an explicit
+// sample list.  d_explicit: device {x,y,s} triples (n_explicit of them) or null.  d_li_out: device rgb or null.
+static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t* d_explicit, size_t n_explicit, float* d_li_out, rtgpu_stats* stats) {
+  if (!ctx->has_scene) return fail(ctx, RTGPU_ERR_NO_SCENE, "no scene uploaded");
+  cudaSetDevice(ctx->device);
+  Plan plan;
+  int rc = fill_params(ctx, rd, nullptr, plan); if (rc) return rc;
+  RenderParams& p = plan.p;
+  const DScene& sc = ctx->scene;
+  const uint32_t max_depth = (uint32_t)rd->max_depth & 0xffu;
+
+  // ---- capacities --------------------------------------------------------------------------------------------
+  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (1u << 23);
+  uint32_t cap_items = P, cap_samples = P, cap_shadow = P, cap_mis = P;
+  uint32_t rays_per_item = 1;
+  std::vector<uint32_t> nls;
+  if (plan.recursive) {
+    if (rd->integrator == RTGPU_INTEGRATOR_WHITTED) rays_per_item = std::max(1u, sc.n_lights);
+    else if (rd->direct_strategy == 0) {
+      // DirectLightingIntegrator::preprocess (directlighting.rs:70-87): n_samples rounded by the sampler, 2 arrays per light and depth
+      const std::vector<rtgpu_light>& hl = ctx->h_lights;
+      rays_per_item = 0;
+      for (uint32_t j = 0; j < sc.n_lights; j++) { nls.push_back(next_pow2_u32(std::max(1u, hl[j].n_samples))); rays_per_item += nls.back(); }
+      rays_per_item = std::max(1u, rays_per_item);
+      p.scfg.n_arrays = max_depth * sc.n_lights * 2u;
+    }
+    const uint32_t fan = 1u << std::min(20u, max_depth > 0 ? max_depth - 1 : 0);      // items of the deepest level per camera sample
+    cap_samples = std::max(256u, std::min(P / fan, (uint32_t)(((size_t)4 * P) / ((size_t)fan * rays_per_item))));
+    cap_items = cap_samples * fan;
+    cap_shadow = (uint32_t)std::min<size_t>((size_t)cap_items * rays_per_item, (size_t)4 * P);
+    cap_mis = rd->integrator == RTGPU_INTEGRATOR_WHITTED ? 1 : cap_shadow;
+  } else if (rd->integrator == RTGPU_INTEGRATOR_AO) {
+    cap_shadow = 2 * P;
+    cap_samples = cap_items = std::max(256u, cap_shadow / (uint32_t)rd->ao_samples);
+    cap_mis = 1;
+  } else if (rd->integrator == RTGPU_INTEGRATOR_NORMAL) { cap_shadow = 1; cap_mis = 1; }
+  rc = ensure_wave(ctx, cap_items, cap_samples, cap_shadow, cap_mis, plan.recursive); if (rc) return rc;
+  WaveBuffers* wb = ctx->wave;
+  p.w = wb->v;
+  // the capacities the sizing rules assume (buffers may be larger from an earlier render)
+  p.w.cap_items = cap_items; p.w.cap_samples = cap_samples; p.w.cap_shadow = cap_shadow; p.w.cap_mis = cap_mis;
+
+  // ---- light distribution (path.rs:86-94) and DirectLighting sample counts -------------------------------------------
+  if (rd->integrator == RTGPU_INTEGRATOR_PATH && sc.n_lights > 0) {
+    if (rd->light_strategy == 0 || sc.n_lights == 1) {
+      rc = ensure_uniform_table(ctx, (int)sc.n_lights); if (rc) return rc;
+      p.grid.table = wb->uniform_table; p.grid.nv[0] = p.grid.nv[1] = p.grid.nv[2] = 0; p.grid.n_lights = (int)sc.n_lights;
+    } else {
+      rc = ensure_light_grid(ctx); if (rc) return rc;
+      p.grid.table = wb->grid_table; for (int k = 0; k < 3; k++) p.grid.nv[k] = wb->grid_nv[k]; p.grid.n_lights = wb->grid_n;
+    }
+  }
+  if (!nls.empty()) {
+    if (wb->n_light_samples_cap < nls.size()) {
+      if (wb->n_light_samples) cudaFree(wb->n_light_samples);
+      RT_CUDA(ctx, cudaMalloc((void**)&wb->n_light_samples, nls.size() * 4)); wb->n_light_samples_cap = (uint32_t)nls.size();
+    }
+    RT_CUDA(ctx, cudaMemcpyAsync(wb->n_light_samples, nls.data(), nls.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p.n_light_samples = wb->n_light_samples;
+  }
+  // which material classes exist (skip empty shade launches)
+  {
+    const std::vector<rtgpu_material>& hm = ctx->h_materials;
+    for (const rtgpu_material& m : hm) plan.mat_present[m.type <= RTGPU_MAT_MIRROR ? m.type : Q_NONE] = true;
+    plan.mat_present[Q_NONE] = true;     // primitives without a material row also land here
+    bool any_none = false; for (const rtgpu_material& m : hm) any_none |= m.type > RTGPU_MAT_MIRROR;
+    plan.extra_rounds = any_none ? 4 : 0;
+  }
+
+  // ---- film --------------------------------------------------------------------------------------------------------
+  const int fw = rd->cropped[2] - rd->cropped[0], fh = rd->cropped[3] - rd->cropped[1];
+  FilmParams& fp = plan.film;
+  if (!d_li_out) {
+    if (fw <= 0 || fh <= 0) return fail(ctx, RTGPU_ERR_ARG, "empty film");
+    const size_t npix = (size_t)fw * fh;
+    if (ctx->film_pixels != npix || !ctx->film) {
+      if (ctx->film) cudaFree(ctx->film);
+      ctx->film = nullptr; ctx->film_pixels = 0;
+      RT_CUDA(ctx, cudaMalloc((void**)&ctx->film, npix * sizeof(float4)));
+      ctx->film_pixels = npix;
+      RT_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, npix * sizeof(float4), ctx->stream));
+    } else if (rd->clear_film) RT_CUDA(ctx, cudaMemsetAsync(ctx->film, 0, npix * sizeof(float4), ctx->stream));
+    ctx->film_w = fw; ctx->film_h = fh; ctx->film_scale = rd->scale;
+    fp.film = (float4*)ctx->film;
+    for (int i = 0; i < 4; i++) fp.crop[i] = rd->cropped[i];
+    fp.rx = rd->filter_radius[0]; fp.ry = rd->filter_radius[1]; fp.irx = 1.0f / fp.rx; fp.iry = 1.0f / fp.ry;
+    fp.max_lum = rd->max_sample_luminance;
+    std::memcpy(fp.table, rd->filter_table, sizeof(fp.table));
+  }
+  fp.ao_div = rd->integrator == RTGPU_INTEGRATOR_AO ? (float)rd->ao_samples : 1.0f;
+
+  // ---- work decomposition ----------------------------------------------------------------------------------------
+  const int sbw = rd->sample_bounds[2] - rd->sample_bounds[0], sbh = rd->sample_bounds[3] - rd->sample_bounds[1];
+  const int tiles_x = std::max(0, (sbw + 15) / 16), tiles_y = std::max(0, (sbh + 15) / 16);
+  const long long n_tiles_total = (long long)tiles_x * tiles_y;
+  const long long my_tiles = d_explicit ? 0 : (n_tiles_total > p.tile_rank ? (n_tiles_total - p.tile_rank + p.tile_world - 1) / p.tile_world : 0);
+  const int s_begin = std::max(0, rd->sample_begin), s_end = std::min(rd->spp, rd->sample_end);
+  p.tiles_x = std::max(1, tiles_x);
+
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  RT_CUDA(ctx, cudaMemsetAsync(p.w.stats, 0, S_COUNT * sizeof(unsigned long long), ctx->stream));
+  uint64_t waves = 0, launches0 = ctx->launches;
+  const unsigned pblocks = (unsigned)ctx->sm_count * 8u;                // persistent / grid-stride kernels: 8 x 128 threads per SM
+
+  auto run_wave = [&](uint32_t n_items) -> int {
+    p.n_items = n_items;
+    RT_CUDA(ctx, cudaMemsetAsync(p.w.counters, 0, C_COUNT * sizeof(uint32_t), ctx->stream));
+    launch_raygen(p, ctx->stream);
+    ctx->launches++;
+    if (rd->integrator == RTGPU_INTEGRATOR_PATH) {
+      const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
+      for (uint32_t b = 0; b < rounds; b++) {
+        const int in = (int)(b & 1u);
+        launch_trace_closest(true, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream);
+        launch_shade_miss(p, pblocks, ctx->stream);
+        ctx->launches += 2;
+        if (plan.mat_present[Q_MATTE]) { launch_shade_path_0(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (plan.mat_present[Q_PLASTIC]) { launch_shade_path_1(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (plan.mat_present[Q_METAL]) { launch_shade_path_2(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (plan.mat_present[Q_GLASS]) { launch_shade_path_3(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (plan.mat_present[Q_MIRROR]) { launch_shade_path_4(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (plan.extra_rounds) { launch_shade_path_5(p, in, pblocks, ctx->stream); ctx->launches++; }
+        if (sc.n_lights > 0) {
+          launch_trace_shadow(false, p, pblocks, ctx->stream);
+          launch_trace_mis(false, p, pblocks, ctx->stream);
+          ctx->launches += 2;
+        }
+        launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, ctx->stream);
+        ctx->launches++;
+      }
+    } else if (plan.recursive) {
+      const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
+      for (uint32_t lvl = 0; lvl < rounds; lvl++) {
+        const int par = (int)(lvl & 1u);
+        launch_trace_closest(false, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream);
+        launch_shade_recursive(p, par, pblocks, ctx->stream);
+        launch_trace_shadow(true, p, pblocks, ctx->stream);
+        ctx->launches += 3;
+        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) { launch_trace_mis(true, p, pblocks, ctx->stream); ctx->launches++; }
+        launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream);
+        ctx->launches++;
+      }
+    } else {
+      launch_trace_closest(false, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream);
+      launch_shade_ao(p, pblocks, ctx->stream);
+      ctx->launches += 2;
+      if (rd->integrator == RTGPU_INTEGRATOR_AO) { launch_trace_shadow(true, p, pblocks, ctx->stream); ctx->launches++; }
+      launch_next_bounce(p, C_LIVE0, 1, ctx->stream);
+      ctx->launches++;
+    }
+    waves++;
+    return check_cuda(ctx, cudaGetLastError(), "kernel launch");
+  };
+
+  if (d_explicit) {
+    for (size_t first = 0; first < n_explicit; first += cap_samples) {
+      const uint32_t m = (uint32_t)std::min<size_t>(cap_samples, n_explicit - first);
+      p.explicit_pixels = d_explicit + 3 * first;
+      rc = run_wave(m); if (rc) return rc;
+      launch_li_out(p.w.L, fp.ao_div, m, d_li_out + 3 * first, ctx->stream);
+      ctx->launches++;
+    }
+  } else if (my_tiles > 0 && s_end > s_begin) {
+    const long long per_sample = my_tiles * 256;
+    long long tiles_per_wave = my_tiles, samples_per_wave = 1;
+    if (per_sample <= (long long)cap_samples) samples_per_wave = std::max<long long>(1, (long long)cap_samples / per_sample);
+    else tiles_per_wave = std::max<long long>(1, (long long)cap_samples / 256);
+    for (long long t0 = 0; t0 < my_tiles; t0 += tiles_per_wave) {
+      const long long nt = std::min(tiles_per_wave, my_tiles - t0);
+      for (int s0 = s_begin; s0 < s_end; s0 += (int)samples_per_wave) {
+        const int ns = (int)std::min<long long>(samples_per_wave, s_end - s0);
+        p.tile_first = (int)t0; p.n_tiles = (int)nt; p.sample_first = s0; p.n_samples = ns;
+        const uint32_t n_items = (uint32_t)(nt * 256 * ns);
+        rc = run_wave(n_items); if (rc) return rc;
+        launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream);
+        ctx->launches++;
+      }
+    }
+  }
+  RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  RT_CUDA(ctx, cudaGetLastError());
+  unsigned long long hs[S_COUNT];
+  RT_CUDA(ctx, cudaMemcpy(hs, p.w.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+  if (hs[S_COUNT - 1]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; lower wave_paths or the light sample counts");
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->camera_rays = hs[S_CAMERA]; stats->regular_rays = hs[S_REGULAR]; stats->shadow_rays = hs[S_SHADOW];
+    stats->waves = waves; stats->kernel_launches = ctx->launches - launches0;
+    cudaEventElapsedTime(&stats->ms_total, ctx->ev0, ctx->ev1);
+  }
+  return RTGPU_OK;
+}
+
+}  // namespace rt
+
 extern "C" {
-int rtgpu_generate_rays(rtgpu_ctx* ctx, const rtgpu_render_desc*, const float*, size_t, rtgpu_ray*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_render(rtgpu_ctx* ctx, const rtgpu_render_desc*, rtgpu_stats*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_li_samples(rtgpu_ctx* ctx, const rtgpu_render_desc*, const int32_t*, size_t, float*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_read_film(rtgpu_ctx* ctx, float*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_resolve_film(rtgpu_ctx* ctx, float*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_film_device_ptr(rtgpu_ctx* ctx, void**, size_t*) { return rt::fail(ctx, RTGPU_ERR_UNSUPPORTED, "todo"); }
-int rtgpu_reduce_film(rtgpu_ctx**, int, int) { return RTGPU_ERR_UNSUPPORTED; }
+
+int rtgpu_render(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, rtgpu_stats* stats) {
+  if (!ctx || !desc) return RTGPU_ERR_ARG;
+  return run_render(ctx, desc, nullptr, 0, nullptr, stats);
 }
+
+int rtgpu_li_samples(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const int32_t* pixels, size_t n, float* rgb) {
+  if (!ctx || !desc || (n && (!pixels || !rgb))) return RTGPU_ERR_ARG;
+  if (n == 0) return RTGPU_OK;
+  cudaSetDevice(ctx->device);
+  int32_t* d_pix = nullptr; float* d_out = nullptr;
+  RT_CUDA(ctx, cudaMalloc((void**)&d_pix, n * 3 * sizeof(int32_t)));
+  cudaError_t e = cudaMalloc((void**)&d_out, n * 3 * sizeof(float));
+  if (e != cudaSuccess) { cudaFree(d_pix); return check_cuda(ctx, e, "cudaMalloc"); }
+  int rc = check_cuda(ctx, cudaMemcpy(d_pix, pixels, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice), "cudaMemcpy");
+  if (!rc) rc = run_render(ctx, desc, d_pix, n, d_out, nullptr);
+  if (!rc) rc = check_cuda(ctx, cudaMemcpy(rgb, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost), "cudaMemcpy");
+  cudaFree(d_pix); cudaFree(d_out);
+  return rc;
+}
+
+int rtgpu_generate_rays(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const float* samples, size_t n, rtgpu_ray* rays) {
+  if (!ctx || !desc || (n && (!samples || !rays))) return RTGPU_ERR_ARG;
+  if (n == 0) return RTGPU_OK;
+  cudaSetDevice(ctx->device);
+  RenderParams p{};
+  std::memcpy(p.r2c, desc->raster_to_camera, 64); std::memcpy(p.c2w, desc->camera_to_world, 64);
+  p.lens_radius = desc->lens_radius; p.focal_distance = desc->focal_distance;
+  float4* d_s = nullptr; float4* d_r = nullptr;
+  RT_CUDA(ctx, cudaMalloc((void**)&d_s, n * sizeof(float4)));
+  cudaError_t e = cudaMalloc((void**)&d_r, n * 2 * sizeof(float4));
+  if (e != cudaSuccess) { cudaFree(d_s); return check_cuda(ctx, e, "cudaMalloc"); }
+  int rc = check_cuda(ctx, cudaMemcpyAsync(d_s, samples, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream), "h2d");
+  if (!rc) {
+    launch_generate_rays(p, d_s, (uint32_t)n, d_r, ctx->stream);
+    ctx->launches++;
+    rc = check_cuda(ctx, cudaMemcpyAsync(rays, d_r, n * 2 * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream), "d2h");
+  }
+  if (!rc) rc = check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+  cudaFree(d_s); cudaFree(d_r);
+  return rc;
+}
+
+static int film_tmp(rtgpu_ctx* ctx, size_t n_float4) {
+  if (!ctx->wave) ctx->wave = new WaveBuffers();
+  WaveBuffers* w = ctx->wave;
+  if (w->film_tmp_n >= n_float4) return 0;
+  if (w->film_tmp) cudaFree(w->film_tmp);
+  w->film_tmp = nullptr; w->film_tmp_n = 0;
+  RT_CUDA(ctx, cudaMalloc((void**)&w->film_tmp, n_float4 * sizeof(float4)));
+  w->film_tmp_n = n_float4;
+  return 0;
+}
+
+int rtgpu_read_film(rtgpu_ctx* ctx, float* xyzw) {
+  if (!ctx || !xyzw) return RTGPU_ERR_ARG;
+  if (!ctx->film) return fail(ctx, RTGPU_ERR_ARG, "no film: call rtgpu_render first");
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->film_pixels;
+  int rc = film_tmp(ctx, n); if (rc) return rc;
+  launch_film_xyz((const float4*)ctx->film, n, ctx->wave->film_tmp, ctx->stream);
+  ctx->launches++;
+  RT_CUDA(ctx, cudaMemcpyAsync(xyzw, ctx->wave->film_tmp, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RTGPU_OK;
+}
+
+int rtgpu_resolve_film(rtgpu_ctx* ctx, float* rgb) {
+  if (!ctx || !rgb) return RTGPU_ERR_ARG;
+  if (!ctx->film) return fail(ctx, RTGPU_ERR_ARG, "no film: call rtgpu_render first");
+  cudaSetDevice(ctx->device);
+  const size_t n = ctx->film_pixels;
+  int rc = film_tmp(ctx, n); if (rc) return rc;
+  launch_film_resolve((const float4*)ctx->film, n, ctx->film_scale, (float*)ctx->wave->film_tmp, ctx->stream);
+  ctx->launches++;
+  RT_CUDA(ctx, cudaMemcpyAsync(rgb, ctx->wave->film_tmp, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RTGPU_OK;
+}
+
+int rtgpu_film_device_ptr(rtgpu_ctx* ctx, void** d_ptr, size_t* n_floats) {
+  if (!ctx || !d_ptr || !n_floats) return RTGPU_ERR_ARG;
+  if (!ctx->film) return fail(ctx, RTGPU_ERR_ARG, "no film: call rtgpu_render first");
+  *d_ptr = ctx->film; *n_floats = ctx->film_pixels * 4;
+  return RTGPU_OK;
+}
+
+// Single-process multi-GPU: films of ctxs[0..n) summed into ctxs[root] (peer copy into a staging buffer + add).
+int rtgpu_reduce_film(rtgpu_ctx** ctxs, int n, int root) {
+  if (!ctxs || n <= 0 || root < 0 || root >= n || !ctxs[root]) return RTGPU_ERR_ARG;
+  rtgpu_ctx* r = ctxs[root];
+  if (!r->film) return fail(r, RTGPU_ERR_ARG, "root has no film");
+  const size_t npix = r->film_pixels;
+  cudaSetDevice(r->device);
+  int rc = film_tmp(r, npix); if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    if (i == root) continue;
+    rtgpu_ctx* c = ctxs[i];
+    if (!c || !c->film || c->film_pixels != npix) return fail(r, RTGPU_ERR_ARG, "film sizes differ between contexts");
+    cudaSetDevice(c->device);
+    RT_CUDA(r, cudaStreamSynchronize(c->stream));
+    cudaSetDevice(r->device);
+    RT_CUDA(r, cudaMemcpyPeerAsync(r->wave->film_tmp, r->device, c->film, c->device, npix * sizeof(float4), r->stream));
+    launch_film_accumulate((float4*)r->film, r->wave->film_tmp, npix, r->stream);
+    r->launches++;
+  }
+  RT_CUDA(r, cudaStreamSynchronize(r->stream));
+  return RTGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,8 @@
+// Translation unit: Whitted / DirectLighting / AmbientOcclusion / Normal shading kernels.
+#include "kernels_rec.cuh"
+#include "launch.hpp"
+
+namespace rt {
+void launch_shade_recursive(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s) { k_shade_recursive<<<blocks, 128, 0, s>>>(p, parity); }
+void launch_shade_ao(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_ao<<<blocks, 128, 0, s>>>(p); }
+}  // namespace rt

@@ -1,0 +1,35 @@
+// Translation unit: ray generation, queue traversal, bounce bookkeeping, film and light-grid kernels.
+#include "kernels_trace.cuh"
+#include "launch.hpp"
+
+namespace rt {
+
+void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t n, float4* rays, cudaStream_t s) {
+  k_generate_rays<<<(n + 255) / 256, 256, 0, s>>>(p, samples, n, rays);
+}
+void launch_raygen(const RenderParams& p, cudaStream_t s) { k_raygen<<<(p.n_items + 255) / 256, 256, 0, s>>>(p); }
+void launch_trace_closest(bool classify, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
+                          HitRec* hits, unsigned blocks, cudaStream_t s) {
+  if (classify) k_trace_closest<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  else k_trace_closest<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+}
+void launch_trace_shadow(bool atomic, const RenderParams& p, unsigned blocks, cudaStream_t s) {
+  if (atomic) k_trace_shadow<true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false><<<blocks, 128, 0, s>>>(p);
+}
+void launch_trace_mis(bool atomic, const RenderParams& p, unsigned blocks, cudaStream_t s) {
+  if (atomic) k_trace_mis<true><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false><<<blocks, 128, 0, s>>>(p);
+}
+void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
+void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }
+void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s) {
+  const size_t n_voxels = (size_t)nvx * nvy * nvz, total = n_voxels * sc.n_lights;
+  k_lightgrid_contrib<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(sc, nvx, nvy, nvz, table);
+  k_lightgrid_build<<<(unsigned)((n_voxels + 127) / 128), 128, 0, s>>>((int)sc.n_lights, n_voxels, table);
+}
+void launch_film_add(const FilmParams& f, const float4* L, const float2* pfilm, uint32_t n, cudaStream_t s) { k_film_add<<<(n + 255) / 256, 256, 0, s>>>(f, L, pfilm, n); }
+void launch_li_out(const float4* L, float ao_div, uint32_t n, float* out, cudaStream_t s) { k_li_out<<<(n + 255) / 256, 256, 0, s>>>(L, ao_div, n, out); }
+void launch_film_xyz(const float4* film, size_t n, float4* out, cudaStream_t s) { k_film_xyz<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(film, n, out); }
+void launch_film_resolve(const float4* film, size_t n, float scale, float* rgb, cudaStream_t s) { k_film_resolve<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(film, n, scale, rgb); }
+void launch_film_accumulate(float4* dst, const float4* src, size_t n, cudaStream_t s) { k_film_accumulate<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n); }
+
+}  // namespace rt

@@ -1,0 +1,99 @@
+// Wavefront state: ray / path-state queues in coalesced float4 SoA buffers, device-side queue counters,
+// warp-aggregated queue appends (product code).
+#pragma once
+#include "lights.cuh"
+#include "sampler.cuh"
+#include "traverse.cuh"
+
+namespace rt {
+
+// material queues of the path integrator (one shade launch per non-empty class)
+enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_MISS, Q_COUNT };
+
+// device counters (uint32)
+enum {
+  C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_COUNT = 32
+};
+// device statistics (uint64): the reference's counters (scene.rs:9-16, renderer.rs:17)
+enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_COUNT = 8 };
+
+// Spatial / uniform light distribution tables (lightdistrib.rs).  Per voxel: func[n], cdf[n+1], func_int.
+struct LightGrid {
+  const float* table;        // dense voxel table, or the single uniform distribution when nv = {0,0,0}
+  int nv[3];
+  int n_lights;
+};
+
+struct WaveView {            // device pointers, passed to kernels by value
+  // items (path: item slot == sample slot)
+  float4 *ray_o, *ray_d;     // {o.xyz, t_max}, {d.xyz, -}
+  HitRec* hit;
+  float4* beta;              // rgb throughput, w = eta_scale (path)
+  uint4* pstate;             // x = sample slot, y = bounces (path) | node id (recursive), z = flags | depth, w = d1 | d2 << 16
+  // second item buffer (recursive integrators ping-pong between levels)
+  float4 *ray_o2, *ray_d2; float4* beta2; uint4* pstate2;
+  // camera samples
+  float4* L;                 // rgb radiance accumulator, w = 1 if the sample exists
+  float2* pfilm;
+  uint2* sinfo;              // pixel hash, sample index
+  // shadow (any-hit) queue and MIS (closest-hit) queue
+  float4 *sh_o, *sh_d, *sh_c;          // ray; d.w = bits(sample slot); c = rgb contribution if unoccluded
+  float4 *mi_o, *mi_d, *mi_c;          // ray; d.w = bits(sample slot); c = rgb weight, w = bits(light row)
+  uint32_t* list[2];
+  uint32_t* matq[Q_COUNT];
+  uint32_t* counters;
+  unsigned long long* stats;
+  uint32_t cap_items, cap_samples, cap_shadow, cap_mis;
+};
+
+struct RenderParams {
+  DScene sc;
+  WaveView w;
+  LightGrid grid;
+  float r2c[16], c2w[16]; float lens_radius, focal_distance;
+  int sample_bounds[4], pixel_bounds[4];
+  SamplerCfg scfg; unsigned long long seed;
+  int integrator, max_depth, direct_strategy, ao_samples; float rr_threshold;
+  const uint32_t* n_light_samples;     // DirectLighting "all": per light, rounded to a power of two
+  // wave decomposition: my tiles [tile_first, tile_first + n_tiles) x samples [sample_first, sample_first + n_samples)
+  int tiles_x, tile_rank, tile_world, tile_first, n_tiles, sample_first, n_samples;
+  const int32_t* explicit_pixels;      // li_samples mode: {x, y, sample} triples, else null
+  uint32_t n_items;
+};
+
+// k_film_add parameters (film.rs): cropped bounds, filter radius and the 16x16 filter table
+struct FilmParams {
+  float4* film; int crop[4]; float rx, ry, irx, iry; float max_lum; float ao_div;
+  float table[256];
+};
+
+RT_DEV uint32_t lane_id() { return threadIdx.x & 31u; }
+// Append to a device queue: one atomicAdd per warp (ballot + popc), lanes get consecutive entries.
+RT_DEV uint32_t warp_append(uint32_t* counter, bool pred) {
+  const unsigned active = __activemask();
+  const unsigned mask = __ballot_sync(active, pred);
+  if (!pred) return 0xffffffffu;
+  const int leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
+}
+// Next packet of 32 queue entries for a persistent warp (atomic cursor).
+RT_DEV uint32_t warp_fetch(uint32_t* cursor) {
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+
+RT_DEV void store_ray(float4* o, float4* d, uint32_t i, const Ray& r, uint32_t tag) {
+  o[i] = make_float4(r.o.x, r.o.y, r.o.z, r.t_max);
+  d[i] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(tag));
+}
+RT_DEV Ray load_ray(const float4* o, const float4* d, uint32_t i, uint32_t* tag) {
+  const float4 a = o[i], b = d[i];
+  if (tag) *tag = __float_as_uint(b.w);
+  return make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
+}
+
+}  // namespace rt
