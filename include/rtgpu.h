@@ -134,6 +134,8 @@ typedef struct rtgpu_stats {
   uint64_t waves, kernel_launches;
   float ms_total, ms_closest, ms_anyhit, ms_shade, ms_other;
   uint64_t closest_launches, anyhit_launches;
+  /* with option "count_traversal": BVH nodes visited / primitives tested by the closest-hit (incl. MIS) and any-hit rays */
+  uint64_t nodes_closest, prims_closest, nodes_anyhit, prims_anyhit;
 } rtgpu_stats;
 
 int rtgpu_create(int device, rtgpu_ctx** out);
@@ -153,7 +155,9 @@ int rtgpu_occluded_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uin
  * pointer): the N and T of the roofline's algorithmic bytes per ray; equal to the oracle's counts. */
 int rtgpu_intersect_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, uint32_t* d_stats);
 int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, uint32_t* d_stats);
-/* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1). */
+/* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
+ * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
+ * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);
 
 /* == PerspectiveCamera::generate_ray_differential's ray (camera.rs:150-202) for explicit camera samples

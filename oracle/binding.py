@@ -50,7 +50,7 @@ def lib(native=False):
     l.orc_intersect_full.argtypes = [C.c_void_p, PF, C.c_uint64, PF]
     l.orc_camera_rays.argtypes = [C.c_void_p, PF, C.c_uint64, PF]
     l.orc_film_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-    l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, PF, PF, C.POINTER(orc_stats)]
+    l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, PF, PF, C.POINTER(orc_stats), C.c_int]
     l.orc_li_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, PF, PF]
     l.orc_find_interval_le.argtypes = [PF, C.c_uint64, C.c_float]
     l.orc_find_interval_le.restype = C.c_uint64
@@ -162,7 +162,7 @@ class OracleScene:
         self._l.orc_film_bounds(self._h, c, s)
         return list(c), list(s)
 
-    def render(self, integrator=None, sampler=None, sampler_kind=0, seed=0, threads=0, tile_stride=1):
+    def render(self, integrator=None, sampler=None, sampler_kind=0, seed=0, threads=0, tile_stride=1, tile_offset=0):
         """Returns (film_xyzw (H,W,4), rgb (H,W,3), stats). sampler_kind 0 = ZeroTwoSequence, 1 = counter sampler."""
         c, _ = self.film_bounds()
         w, h = c[2] - c[0], c[3] - c[1]
@@ -171,7 +171,7 @@ class OracleScene:
         st = orc_stats()
         ip = C.cast(C.byref(integrator), C.c_void_p) if integrator is not None else None
         sp = C.cast(C.byref(sampler), C.c_void_p) if sampler is not None else None
-        self._l.orc_render(self._h, ip, sp, sampler_kind, seed, threads, tile_stride, _pf(film), _pf(rgb), C.byref(st))
+        self._l.orc_render(self._h, ip, sp, sampler_kind, seed, threads, tile_stride, _pf(film), _pf(rgb), C.byref(st), tile_offset)
         return film, rgb, st
 
     def li_samples(self, pixels, integrator=None, sampler=None, seed=0):

@@ -224,12 +224,12 @@ struct orc_stats {
 // film_xyzw: 4 floats per cropped pixel (may be NULL); rgb: 3 floats per cropped pixel (may be NULL).
 // integrator_override: NULL = the scene's.
 int orc_render(orc_scene* s, const rt_integrator* integrator_override, const rt_sampler* sampler_override, int sampler_kind, uint64_t seed,
-               int threads, int tile_stride, float* film_xyzw, float* rgb, orc_stats* st) {
+               int threads, int tile_stride, float* film_xyzw, float* rgb, orc_stats* st, int tile_offset) {
   Film film; film.init(s->film_desc);
   Integrator integ; integ.desc = integrator_override ? *integrator_override : s->integrator;
   rt_sampler sd = sampler_override ? *sampler_override : s->sampler;
   RenderStats rs;
-  render(s->scene, integ, s->camera, film, sd, sampler_kind, seed, threads, tile_stride, &rs);
+  render(s->scene, integ, s->camera, film, sd, sampler_kind, seed, threads, tile_stride, &rs, tile_offset);
   if (film_xyzw) std::memcpy(film_xyzw, film.pixels.data(), film.pixels.size() * sizeof(float));
   if (rgb) film_resolve(film, rgb);
   if (st) {

@@ -625,9 +625,9 @@ inline Bounds2i integrator_pixel_bounds(const rt_integrator& d, const Film& film
 }
 
 // sampler_kind: 0 = ZeroTwoSequence (reference), 1 = CounterSampler (device twin).
-// tile_stride / spp_override allow the bounded CPU-baseline sample (every k-th tile).
+// tile_stride / tile_offset select every k-th tile (bounded CPU-baseline sample; rank partition in the multi-process tests).
 inline void render(const Scene& scene, Integrator& integ, const Camera& camera, Film& film, const rt_sampler& sd, int sampler_kind, uint64_t seed,
-                   int num_threads, int tile_stride, RenderStats* stats) {
+                   int num_threads, int tile_stride, RenderStats* stats, int tile_offset = 0) {
   auto t_start = std::chrono::steady_clock::now();
   std::unique_ptr<Sampler> proto;
   if (sampler_kind == 0) proto.reset(new ZeroTwoSequence((size_t)sd.spp, (size_t)sd.dimensions));
@@ -649,7 +649,7 @@ inline void render(const Scene& scene, Integrator& integ, const Camera& camera, 
     while (true) {
       int ti = next_tile.fetch_add(1);                           // row-major tile order, as the Bounds2i iterator (bounds.rs:387-406)
       if (ti >= n_tiles) break;
-      if (tile_stride > 1 && (ti % tile_stride) != 0) continue;
+      if (tile_stride > 1 && (ti % tile_stride) != tile_offset) continue;
       int tx = ti % ntx, ty = ti / ntx;
       sampler->reseed((uint64_t)(ty * ntx + tx));
       int x0 = sb.x0 + tx * bs, x1 = std::min(x0 + bs, sb.x1), y0 = sb.y0 + ty * bs, y1 = std::min(y0 + bs, sb.y1);

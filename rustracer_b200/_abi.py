@@ -112,4 +112,5 @@ class rtgpu_render_desc(C.Structure):
 class rtgpu_stats(C.Structure):
     _fields_ = [("camera_rays", c_u64), ("regular_rays", c_u64), ("shadow_rays", c_u64), ("waves", c_u64), ("kernel_launches", c_u64),
                 ("ms_total", c_f), ("ms_closest", c_f), ("ms_anyhit", c_f), ("ms_shade", c_f), ("ms_other", c_f),
-                ("closest_launches", c_u64), ("anyhit_launches", c_u64)]
+                ("closest_launches", c_u64), ("anyhit_launches", c_u64),
+                ("nodes_closest", c_u64), ("prims_closest", c_u64), ("nodes_anyhit", c_u64), ("prims_anyhit", c_u64)]

@@ -186,6 +186,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
   if (ctx->scratch_hits) cudaFree(ctx->scratch_hits);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return RTGPU_OK;
@@ -197,6 +198,8 @@ uint64_t rtgpu_launch_count(rtgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
+  if (std::strcmp(name, "profile") == 0) { ctx->profile = value; return RTGPU_OK; }
+  if (std::strcmp(name, "count_traversal") == 0) { ctx->count_traversal = value; return RTGPU_OK; }
   return fail(ctx, RTGPU_ERR_ARG, std::string("unknown option ") + name);
 }
 

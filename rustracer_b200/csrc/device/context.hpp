@@ -32,6 +32,9 @@ struct rtgpu_ctx {
   void* lightgrid = nullptr;
   // scratch for the batch API
   void* scratch_rays = nullptr; void* scratch_hits = nullptr; size_t scratch_n = 0;
+  int profile = 0;            // rtgpu_render: time every launch with CUDA events, per kernel class (rtgpu_stats.ms_*)
+  int count_traversal = 0;    // rtgpu_render: count BVH nodes visited / primitives tested (rtgpu_stats.nodes_* / prims_*)
+  std::vector<cudaEvent_t> event_pool;
   int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
 };
 

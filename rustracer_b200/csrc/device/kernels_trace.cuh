@@ -59,10 +59,18 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
 // ---- queue traversal ----------------------------------------------------------------------------------------
 // Persistent warps pull 32-entry packets from the queue with an atomic cursor.  CLASSIFY appends each path to the
 // queue of its hit material (or the miss queue) for the material-sorted shade kernels.
-template <bool CLASSIFY>
+// STATS variants also count BVH nodes visited / primitives tested (the N and T of the roofline's bytes per ray).
+RT_DEV void flush_trav_stats(const RenderParams& p, const TravStats& st, int s_nodes, int s_prims) {
+  unsigned long long nn = st.nodes, np = st.prims;
+  for (int off = 16; off > 0; off >>= 1) { nn += __shfl_down_sync(0xffffffffu, nn, off); np += __shfl_down_sync(0xffffffffu, np, off); }
+  if (lane_id() == 0) { atomicAdd(&p.w.stats[s_nodes], nn); atomicAdd(&p.w.stats[s_prims], np); }
+}
+
+template <bool CLASSIFY, bool STATS>
 __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                         const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
   const uint32_t n = p.w.counters[count_idx];
+  TravStats st; st.nodes = 0; st.prims = 0;
   while (true) {
     const uint32_t base = warp_fetch(&p.w.counters[C_CUR_CLOSEST]);
     if (base >= n) break;
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const flo
       slot = list ? list[i] : i;
       Ray ray = load_ray(ray_o, ray_d, slot, nullptr);
       HitRec h;
-      bvh_traverse<false, false>(p.sc, ray, h, nullptr);
+      bvh_traverse<false, STATS>(p.sc, ray, h, &st);
       hits[slot] = h;
       if (CLASSIFY) {
         if (h.slot == kMiss) q = Q_MISS;
@@ -92,13 +100,15 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const flo
       }
     }
   }
+  if (STATS) flush_trav_stats(p, st, S_NODES_CLOSEST, S_PRIMS_CLOSEST);
 }
 
 // Shadow rays: VisibilityTester::unoccluded (light/mod.rs:52-55) -> Scene::intersect_p; adds the pending
 // contribution to the sample's radiance when the segment is clear.
-template <bool ATOMIC>
+template <bool ATOMIC, bool STATS>
 __global__ void __launch_bounds__(128) k_trace_shadow(RenderParams p) {
   const uint32_t n = min(p.w.counters[C_SHADOW], p.w.cap_shadow);
+  TravStats st; st.nodes = 0; st.prims = 0;
   while (true) {
     const uint32_t base = warp_fetch(&p.w.counters[C_CUR_ANY]);
     if (base >= n) break;
@@ -107,20 +117,22 @@ __global__ void __launch_bounds__(128) k_trace_shadow(RenderParams p) {
     uint32_t sample;
     Ray ray = load_ray(p.w.sh_o, p.w.sh_d, i, &sample);
     HitRec h;
-    if (!bvh_traverse<true, false>(p.sc, ray, h, nullptr)) {
+    if (!bvh_traverse<true, STATS>(p.sc, ray, h, &st)) {
       const float4 c = p.w.sh_c[i];
       float4* L = &p.w.L[sample];
       if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
       else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
     }
   }
+  if (STATS) flush_trav_stats(p, st, S_NODES_ANY, S_PRIMS_ANY);
 }
 
 // MIS rays: second half of estimate_direct (integrator/mod.rs:291-313): closest hit of the BSDF-sampled ray; it
 // contributes only if it lands on the sampled light (or escapes to the sampled infinite light).
-template <bool ATOMIC>
+template <bool ATOMIC, bool STATS>
 __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
   const uint32_t n = min(p.w.counters[C_MIS], p.w.cap_mis);
+  TravStats st; st.nodes = 0; st.prims = 0;
   while (true) {
     const uint32_t base = warp_fetch(&p.w.counters[C_CUR_MIS]);
     if (base >= n) break;
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
     const rtgpu_light& light = p.sc.lights[light_row];
     HitRec h;
     Spec li = spec(0.0f);
-    if (bvh_traverse<false, false>(p.sc, ray, h, nullptr)) {
+    if (bvh_traverse<false, STATS>(p.sc, ray, h, &st)) {
       if (p.sc.info[h.slot].z == light_row) {                         // same light id (integrator/mod.rs:294-299)
         SurfHit si; float t;
         if (slot_intersect_surface(p.sc, h.slot, ray0, t, si)) li = area_L(light, si.n, -ray0.d);
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
       else { float4 v = *L; v.x += r; v.y += g; v.z += b; *L = v; }
     }
   }
+  if (STATS) flush_trav_stats(p, st, S_NODES_CLOSEST, S_PRIMS_CLOSEST);
 }
 
 // compute_distribution (lightdistrib.rs:101-179), first half: one thread per (voxel, light) accumulates the
@@ -229,7 +242,7 @@ __global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera) {
   p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis);
   p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
   if (count_camera) p.w.stats[S_CAMERA] += live;
-  if (c[C_OVERFLOW]) p.w.stats[S_COUNT - 1] = 1;
+  if (c[C_OVERFLOW]) p.w.stats[S_OVERFLOW] = 1;
   c[live_idx] = 0;
   for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;
   c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_CUR_CLOSEST] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0;

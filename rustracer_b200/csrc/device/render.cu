@@ -262,51 +262,59 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   uint64_t waves = 0, launches0 = ctx->launches;
   const unsigned pblocks = (unsigned)ctx->sm_count * 8u;                // persistent / grid-stride kernels: 8 x 128 threads per SM
 
+  // optional per-class device timing (set_option "profile"): CUDA events around every launch on the context's stream
+  enum { K_CLOSEST = 0, K_ANYHIT, K_SHADE, K_OTHER, K_CLASSES };
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  const bool prof = ctx->profile != 0, tstats = ctx->count_traversal != 0;
+  size_t ev_used = 0;
+  auto next_event = [&]() -> cudaEvent_t {
+    if (ev_used == ctx->event_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->event_pool.push_back(e); }
+    return ctx->event_pool[ev_used++];
+  };
+  uint64_t n_closest_launches = 0, n_anyhit_launches = 0;
+#define RT_LAUNCH(kclass, call) do { \
+    if (prof) { Span sp_; sp_.cls = (kclass); sp_.a = next_event(); sp_.b = next_event(); cudaEventRecord(sp_.a, ctx->stream); call; cudaEventRecord(sp_.b, ctx->stream); spans.push_back(sp_); } \
+    else { call; } \
+    ctx->launches++; if ((kclass) == K_CLOSEST) n_closest_launches++; else if ((kclass) == K_ANYHIT) n_anyhit_launches++; } while (0)
+
   auto run_wave = [&](uint32_t n_items) -> int {
     p.n_items = n_items;
     RT_CUDA(ctx, cudaMemsetAsync(p.w.counters, 0, C_COUNT * sizeof(uint32_t), ctx->stream));
-    launch_raygen(p, ctx->stream);
-    ctx->launches++;
+    RT_LAUNCH(K_OTHER, launch_raygen(p, ctx->stream));
     if (rd->integrator == RTGPU_INTEGRATOR_PATH) {
       const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
       for (uint32_t b = 0; b < rounds; b++) {
         const int in = (int)(b & 1u);
-        launch_trace_closest(true, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream);
-        launch_shade_miss(p, pblocks, ctx->stream);
-        ctx->launches += 2;
-        if (plan.mat_present[Q_MATTE]) { launch_shade_path_0(p, in, pblocks, ctx->stream); ctx->launches++; }
-        if (plan.mat_present[Q_PLASTIC]) { launch_shade_path_1(p, in, pblocks, ctx->stream); ctx->launches++; }
-        if (plan.mat_present[Q_METAL]) { launch_shade_path_2(p, in, pblocks, ctx->stream); ctx->launches++; }
-        if (plan.mat_present[Q_GLASS]) { launch_shade_path_3(p, in, pblocks, ctx->stream); ctx->launches++; }
-        if (plan.mat_present[Q_MIRROR]) { launch_shade_path_4(p, in, pblocks, ctx->stream); ctx->launches++; }
-        if (plan.extra_rounds) { launch_shade_path_5(p, in, pblocks, ctx->stream); ctx->launches++; }
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(true, tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
+        if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_METAL]) RT_LAUNCH(K_SHADE, launch_shade_path_2(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_GLASS]) RT_LAUNCH(K_SHADE, launch_shade_path_3(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
+        if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
         if (sc.n_lights > 0) {
-          launch_trace_shadow(false, p, pblocks, ctx->stream);
-          launch_trace_mis(false, p, pblocks, ctx->stream);
-          ctx->launches += 2;
+          RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, pblocks, ctx->stream));
+          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, ctx->stream));
         }
-        launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, ctx->stream);
-        ctx->launches++;
+        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, ctx->stream));
       }
     } else if (plan.recursive) {
       const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
         const int par = (int)(lvl & 1u);
-        launch_trace_closest(false, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream);
-        launch_shade_recursive(p, par, pblocks, ctx->stream);
-        launch_trace_shadow(true, p, pblocks, ctx->stream);
-        ctx->launches += 3;
-        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) { launch_trace_mis(true, p, pblocks, ctx->stream); ctx->launches++; }
-        launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream);
-        ctx->launches++;
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
+        RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, pblocks, ctx->stream));
+        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, ctx->stream));
+        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream));
       }
     } else {
-      launch_trace_closest(false, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream);
-      launch_shade_ao(p, pblocks, ctx->stream);
-      ctx->launches += 2;
-      if (rd->integrator == RTGPU_INTEGRATOR_AO) { launch_trace_shadow(true, p, pblocks, ctx->stream); ctx->launches++; }
-      launch_next_bounce(p, C_LIVE0, 1, ctx->stream);
-      ctx->launches++;
+      RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
+      RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));
+      if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, pblocks, ctx->stream));
+      RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, ctx->stream));
     }
     waves++;
     return check_cuda(ctx, cudaGetLastError(), "kernel launch");
@@ -317,8 +325,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       const uint32_t m = (uint32_t)std::min<size_t>(cap_samples, n_explicit - first);
       p.explicit_pixels = d_explicit + 3 * first;
       rc = run_wave(m); if (rc) return rc;
-      launch_li_out(p.w.L, fp.ao_div, m, d_li_out + 3 * first, ctx->stream);
-      ctx->launches++;
+      RT_LAUNCH(K_OTHER, launch_li_out(p.w.L, fp.ao_div, m, d_li_out + 3 * first, ctx->stream));
     }
   } else if (my_tiles > 0 && s_end > s_begin) {
     const long long per_sample = my_tiles * 256;
@@ -332,8 +339,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         p.tile_first = (int)t0; p.n_tiles = (int)nt; p.sample_first = s0; p.n_samples = ns;
         const uint32_t n_items = (uint32_t)(nt * 256 * ns);
         rc = run_wave(n_items); if (rc) return rc;
-        launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream);
-        ctx->launches++;
+        RT_LAUNCH(K_OTHER, launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream));
       }
     }
   }
@@ -342,13 +348,20 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   RT_CUDA(ctx, cudaGetLastError());
   unsigned long long hs[S_COUNT];
   RT_CUDA(ctx, cudaMemcpy(hs, p.w.stats, sizeof(hs), cudaMemcpyDeviceToHost));
-  if (hs[S_COUNT - 1]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; lower wave_paths or the light sample counts");
+  if (hs[S_OVERFLOW]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; lower wave_paths or the light sample counts");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->camera_rays = hs[S_CAMERA]; stats->regular_rays = hs[S_REGULAR]; stats->shadow_rays = hs[S_SHADOW];
     stats->waves = waves; stats->kernel_launches = ctx->launches - launches0;
     cudaEventElapsedTime(&stats->ms_total, ctx->ev0, ctx->ev1);
+    stats->closest_launches = n_closest_launches; stats->anyhit_launches = n_anyhit_launches;
+    stats->nodes_closest = hs[S_NODES_CLOSEST]; stats->prims_closest = hs[S_PRIMS_CLOSEST];
+    stats->nodes_anyhit = hs[S_NODES_ANY]; stats->prims_anyhit = hs[S_PRIMS_ANY];
+    float acc[K_CLASSES] = {0, 0, 0, 0};
+    for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b); acc[sp.cls] += ms; }
+    stats->ms_closest = acc[K_CLOSEST]; stats->ms_anyhit = acc[K_ANYHIT]; stats->ms_shade = acc[K_SHADE]; stats->ms_other = acc[K_OTHER];
   }
+#undef RT_LAUNCH
   return RTGPU_OK;
 }
 

@@ -15,7 +15,7 @@ enum {
   C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_COUNT = 32
 };
 // device statistics (uint64): the reference's counters (scene.rs:9-16, renderer.rs:17)
-enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_COUNT = 8 };
+enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_COUNT = 8 };
 
 // Spatial / uniform light distribution tables (lightdistrib.rs).  Per voxel: func[n], cdf[n+1], func_int.
 struct LightGrid {

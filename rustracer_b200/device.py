@@ -200,10 +200,14 @@ class Device:
         self._check(self._lib.rtgpu_li_samples(self._h, C.byref(rd), pixels.ctypes.data, n, out.ctypes.data))
         return out
 
-    def read_film(self):
+    def read_film(self, out=None):
+        """X, Y, Z, weight per cropped pixel.  `out`: optional preallocated (H, W, 4) float32 buffer (numpy array or a
+        pinned torch tensor) written in place."""
         h, w = self._film_shape
-        out = np.zeros((h, w, 4), np.float32)
-        self._check(self._lib.rtgpu_read_film(self._h, out.ctypes.data))
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._check(self._lib.rtgpu_read_film(self._h, ptr))
         return out
 
     def resolve_film(self):

@@ -1,0 +1,171 @@
+"""Host front end (C++ restatement of pbrt/lexer.rs, pbrt/parser.rs, api.rs, paramset.rs): the reference's lexer / parser
+KATs, the defaults of SURVEY App. D and the reference's failure modes."""
+import numpy as np
+import pytest
+
+from rustracer_b200 import Scene, SceneError, host, scenes
+
+LEXER_SCENE = r'''
+LookAt 0 0 5 0 0 0 0 1 0
+Camera "perspective" "float fov" [50]
+
+
+Film "image" "integer xresolution" [800] "integer yresolution" [600]
+    "string filename" "test-whitted.tga"
+
+Integrator "whitted"
+
+WorldBegin
+  LightSource "distant" "point from" [0 1 5] "point to" [0 0 0]
+
+  #Material "matte" "rgb Kd" [1.0 0.0 0.0] "float sigma" [20]
+  AttributeBegin
+    #Material "matte" "rgb Kd" [1.0 0.0 0.0]
+    Material "plastic" "rgb Kd" [1.0 0.0 0.0] "rgb Ks" [1.0 1.0 1.0]
+
+    Shape "sphere"
+  AttributeEnd
+
+  AttributeBegin
+    Rotate -90 1 0 0
+    Material "matte" "rgb Kd" [1.0 1.0 1.0]
+    Shape "disk" "float radius" [20] "float height" [-1]
+  AttributeEnd
+
+  AttributeBegin
+    AreaLightSource "diffuse" "rgb L" [2.0 2.0 2.0]
+    Rotate 90 1 0 0
+    Shape "disk" "float height" [-2] "float radius" [0.5]
+  AttributeEnd
+WorldEnd
+        '''
+
+
+def test_tokenize_sample_scene(native_libs):
+    """pbrt/lexer.rs:269-309 `test_tokenize`: the whole sample scene tokenises with nothing left over."""
+    toks = host.tokenize(LEXER_SCENE)
+    assert toks[0] == "LookAt" and toks[-1] == "WorldEnd"
+    assert toks.count("COMMENT") == 2
+    assert "STR:test-whitted.tga" in toks and "NUMBER:-90" in toks
+
+
+def test_token_kats(native_libs):
+    """pbrt/lexer.rs:311-336: float, string, keyword and comment tokens."""
+    assert host.tokenize("-1.23e2") == ["NUMBER:-123"]
+    assert host.tokenize('"this is a string"') == ["STR:this is a string"]
+    assert host.tokenize("Accelerator") == ["Accelerator"]
+    assert host.tokenize("[") == ["["]
+    assert host.tokenize("#foo\n") == ["COMMENT"]
+    with pytest.raises(SceneError):
+        host.tokenize("#comment without newline")       # lexer.rs:258-263: a comment must end with a newline
+
+
+def test_param_header_kats(native_libs):
+    """pbrt/parser.rs:345-363: "float fov" -> (Float, "fov")."""
+    assert host.param_header("float fov") == (2, "fov")
+    assert host.param_header("integer indices")[1] == "indices"
+    assert host.param_header("rgb Kd")[1] == "Kd"
+    assert host.param_header("bogus x") is None
+
+
+def test_defaults_app_d(native_libs):
+    """what an empty parameter list means (path.rs:49-78, film.rs:117-150, zerotwosequence.rs:58-63, ...)."""
+    sc = Scene.from_string('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    ir = sc.ir
+    assert (ir.film.xres, ir.film.yres) == (1280, 720) and ir.film.scale == 1.0
+    assert ir.film.filter == 0 and (ir.film.filter_xw, ir.film.filter_yw) == (0.5, 0.5)      # box 0.5 (api.rs:285)
+    assert ir.sampler.spp == 16 and ir.sampler.dimensions == 4
+    assert ir.integrator.type == 0 and ir.integrator.max_depth == 5 and ir.integrator.rr_threshold == 1.0 and ir.integrator.light_strategy == 1
+    assert ir.accel.split_method == 0 and ir.accel.max_node_prims == 4
+    assert ir.camera.fov == 90.0 and ir.camera.lens_radius == 0.0 and ir.camera.focal_distance == 1e6
+    s = ir.shapes[0]
+    assert s.kind == 1 and s.radius == 1.0 and s.zmin == -1.0 and s.zmax == 1.0 and s.phimax == 360.0
+    m = ir.materials[s.material]
+    assert m.type == 0 and list(m.kd) == [0.5, 0.5, 0.5] and m.sigma == 0.0                   # default material: matte (api.rs:349)
+    assert sc.film_filename == "image.png"                                                   # film.rs:118-125
+    sc2 = Scene.from_string('Camera "perspective"\nFilm "image" "string filename" "out.png"\nSampler "02sequence"\nWorldBegin\nWorldEnd\n')
+    assert sc2.film_filename == "rt-out.png"
+
+
+def test_material_defaults(native_libs):
+    txt = ('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nMaterial "plastic"\nShape "sphere"\nMaterial "glass"\nShape "sphere"\n'
+           'Material "mirror"\nShape "sphere"\nMaterial "metal"\nShape "sphere"\nWorldEnd\n')
+    sc = Scene.from_string(txt)          # keep the owner alive: `ir` is a view into it
+    ir = sc.ir
+    pl, gl, mi, me = (ir.materials[ir.shapes[i].material] for i in range(4))
+    assert pl.type == 1 and list(pl.kd) == [0.25] * 3 and list(pl.ks) == [0.25] * 3 and abs(pl.roughness - 0.1) < 1e-7 and pl.remap_roughness == 1
+    assert gl.type == 3 and list(gl.kr) == [1.0] * 3 and list(gl.kt) == [1.0] * 3 and gl.eta == 1.5 and gl.uroughness == 0.0
+    assert mi.type == 4 and all(abs(v - 0.9) < 1e-7 for v in mi.kr)
+    assert me.type == 2 and abs(me.roughness - 0.01) < 1e-8 and me.has_uroughness == 0
+
+
+def test_reference_failure_modes(native_libs):
+    """The same inputs the reference rejects are rejected."""
+    ok = 'Camera "perspective"\nSampler "02sequence"\nWorldBegin\nWorldEnd\n'
+    Scene.from_string(ok)
+    with pytest.raises(SceneError):      # default sampler "halton" is not constructible (api.rs:205-215,287)
+        Scene.from_string('Camera "perspective"\nWorldBegin\nWorldEnd\n')
+    with pytest.raises(SceneError):      # tokenised but never parsed (lexer.rs:201-240 vs parser.rs:150-185)
+        Scene.from_string('Identity\n' + ok)
+    with pytest.raises(SceneError):
+        Scene.from_string(ok.replace('"perspective"', '"orthographic"'))
+    with pytest.raises(SceneError):      # api.rs:1109-1115 unimplemented! shapes
+        Scene.from_string('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nShape "cone"\nWorldEnd\n')
+    with pytest.raises(SceneError):      # Shape outside the world block
+        Scene.from_string('Camera "perspective"\nSampler "02sequence"\nShape "sphere"\nWorldBegin\nWorldEnd\n')
+    with pytest.raises(SceneError):
+        Scene.from_string('Camera "perspective"\nSampler "02sequence"\nIntegrator "bidir"\nWorldBegin\nWorldEnd\n')
+
+
+def test_integrator_names(native_libs):
+    """make_integrator's names (api.rs:231-246) plus the GPU aliases and the harness-added ambient occlusion."""
+    base = 'Camera "perspective"\nSampler "02sequence"\nIntegrator "%s"\nWorldBegin\nWorldEnd\n'
+    for name, typ in (("path", 0), ("whitted", 1), ("directlighting", 2), ("ambientocclusion", 3), ("normal", 4),
+                      ("gpupath", 0), ("gpuwhitted", 1), ("gpudirectlighting", 2), ("gpuao", 3), ("gpunormal", 4)):
+        sc = Scene.from_string(base % name)
+        assert sc.ir.integrator.type == typ
+    sc = Scene.from_string('Camera "perspective"\nSampler "02sequence"\nIntegrator "directlighting" "string strategy" "one"\nWorldBegin\nWorldEnd\n')
+    assert sc.ir.integrator.direct_strategy == 1
+
+
+def test_primitive_and_light_numbering(native_libs):
+    """App. B: primitives numbered in Shape order, triangles in face order; one area light per triangle appended after the
+    shape's primitives (api.rs:933-963)."""
+    sc = Scene.from_string(scenes.cornell_box(xres=32, yres=32, spp=1))
+    sc.flatten()
+    d = sc.desc.contents
+    assert d.n_prims == 36 and d.n_lights == 2
+    info = sc.prim_info()
+    slot = sc.slot_of_prim()
+    assert sorted(info[:, 0].tolist()) == list(range(36))
+    assert info[slot[34], 2] == 0 and info[slot[35], 2] == 1            # the light quad is the last Shape: prims 34, 35
+    assert (info[[slot[i] for i in range(34)], 2] == 0xFFFFFFFF).all()
+    lights = [d.lights[i] for i in range(2)]
+    assert [l.prim_slot for l in lights] == [slot[34], slot[35]] and all(l.kind == 3 for l in lights)
+    assert np.allclose([l.area for l in lights], 130 * 105 / 2)
+
+
+def test_render_desc_camera_and_bounds(native_libs):
+    """Film::new / get_sample_bounds (film.rs:66-75,249-257) with a crop window and the spp power-of-two rounding
+    (zerotwosequence.rs:32)."""
+    sc = Scene.from_string(scenes.cornell_box(xres=100, yres=60, spp=12, crop=[0.25, 0.75, 0.5, 1.0]))
+    rd = sc.render_desc()
+    assert list(rd.cropped) == [25, 30, 75, 60] and list(rd.sample_bounds) == [25, 30, 75, 60] and list(rd.pixel_bounds) == [25, 30, 75, 60]
+    assert rd.spp == 16
+    sc = Scene.from_string(scenes.cornell_box(xres=64, yres=64, spp=4).replace('PixelFilter "box"', 'PixelFilter "gaussian"'))
+    rd = sc.render_desc()
+    assert list(rd.sample_bounds) == [-2, -2, 66, 66] and rd.filter_radius[0] == 2.0
+    assert rd.filter_table[0] > rd.filter_table[255] >= 0.0
+
+
+def test_ply_round_trip(native_libs, tmp_path):
+    """plymesh.rs:18-178: binary little-endian PLY with `list uchar int vertex_indices`."""
+    v, f = scenes.icosphere(1)
+    scenes.write_ply(tmp_path / "m.ply", v, f)
+    txt = scenes.header(16, 16, 1, 'Integrator "path"', 40, ([0, 0, -5], [0, 0, 0], [0, 1, 0])) + 'WorldBegin\nShape "plymesh" "string filename" "m.ply"\nWorldEnd\n'
+    sc = Scene.from_string(txt, search_dir=tmp_path)
+    s = sc.ir.shapes[0]
+    assert s.n_indices == 3 * len(f) and s.n_vertices == len(v)
+    got = np.ctypeslib.as_array(s.P, shape=(s.n_vertices, 3))
+    assert np.array_equal(got, v.astype(np.float32))
+    assert np.array_equal(np.ctypeslib.as_array(s.indices, shape=(len(f), 3)), f)

@@ -1,0 +1,211 @@
+"""Parity of the wavefront integrators (through the C ABI) with the oracle's PathIntegrator / Whitted / DirectLighting /
+AmbientOcclusion / Normal (rustracer-core/src/integrator/*.rs).
+
+Sample-exact comparisons use the counter sampler (the oracle carries the device sampler's integer twin), so each camera
+sample sees the same random numbers on both sides; what remains is CUDA libm vs glibc (sin, cos, atan2, acos differ by
+ulps) and the re-association of the deferred NEE / MIS products.  Tolerance: 1e-4 relative per sample.  Against the
+reference's own ZeroTwoSequence sampler parity is statistical: <= 1 % mean relative error, no bias."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import gen_oracle_vectors as gen  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev(native_libs):
+    from rustracer_b200.device import Device
+    return Device(0)
+
+
+def _cases(tmp):
+    from rustracer_b200 import scenes
+    c = dict(gen.CASES)
+    c["cornell_path_spatial"] = lambda: scenes.cornell_box(xres=64, yres=64, spp=8, integrator='Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "spatial"')
+    c["balls_normal"] = lambda: scenes.balls(xres=96, yres=72, spp=4, integrator='Integrator "normal"')
+    c["field_path_spatial"] = lambda: scenes.c3_scene(str(tmp), level=2, xres=96, yres=54, spp=8)
+    c["field_ao"] = lambda: scenes.c3_scene(str(tmp), level=2, xres=96, yres=54, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [16]')
+    c["cornell_rr"] = lambda: scenes.cornell_box(xres=48, yres=48, spp=8, integrator='Integrator "path" "integer maxdepth" [12] "float rrthreshold" [1] "string lightsamplestrategy" "uniform"')
+    return c
+
+
+NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_li_and_image_match_oracle(dev, tmp_path, name):
+    from oracle import binding as ob
+    from rustracer_b200 import Scene
+    sc = Scene.from_string(_cases(tmp_path)[name](), search_dir=tmp_path)
+    dev.upload(sc)
+    o = ob.OracleScene(sc.ir_ptr)
+    rd = sc.render_desc()
+    rd.seed = 7
+    rng = np.random.default_rng(1)
+    sb = list(rd.sample_bounds)
+    n = 3000
+    pix = np.stack([rng.integers(sb[0], sb[2], n), rng.integers(sb[1], sb[3], n), rng.integers(0, rd.spp, n)], 1).astype(np.int32)
+    ref, _ = o.li_samples(pix, seed=7)
+    got = dev.li_samples(rd, pix)
+    tol = 1e-4 * np.maximum(np.abs(ref), 1e-3) + 1e-6
+    bad = (np.abs(got - ref) > tol).any(1)
+    # a ulp in a transcendental can flip a discrete choice (light pick, lobe pick, roulette) on a rare sample
+    assert bad.mean() <= 2e-3, (bad.sum(), pix[bad][:3], ref[bad][:3], got[bad][:3])
+    if name.endswith("_ao"):
+        assert np.array_equal(got, ref)            # integer visibility counts: exact
+    # whole image through rtgpu_render + film, and the reference's ray counters
+    st = dev.render(rd)
+    film, rgb = dev.read_film(), dev.resolve_film()
+    film_ref, rgb_ref, ost = o.render(sampler_kind=1, seed=7)
+    assert np.array_equal(film[..., 3], film_ref[..., 3])                              # filter weights
+    assert np.abs(rgb - rgb_ref).sum() / np.abs(rgb_ref).sum() < 1e-4
+    assert st.camera_rays == ost.camera_rays
+    assert abs(int(st.regular_rays) - int(ost.regular_rays)) <= 1e-3 * ost.regular_rays + 2
+    assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 1e-3 * ost.shadow_rays + 2
+
+
+@pytest.mark.parametrize("name", list(gen.CASES))
+def test_device_reproduces_committed_golden_vectors(dev, name):
+    from rustracer_b200 import Scene, scenes
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_vectors.npz"))
+    sc = Scene.from_string(gen.CASES[name]())
+    dev.upload(sc)
+    lo, hi = sc.nodes()
+    h = dev.intersect_stats(scenes.ray_batch(gen.N_RAYS, lo[0, :3], hi[0, :3]))
+    assert np.array_equal(h["prim"], gold[f"{name}/prim"]) and np.array_equal(h["t"], gold[f"{name}/t"])
+    assert np.array_equal(h["nodes"], gold[f"{name}/nodes"]) and np.array_equal(h["prims"], gold[f"{name}/prims_tested"])
+    assert np.array_equal(dev.occluded(scenes.ray_batch(gen.N_RAYS, lo[0, :3], hi[0, :3], any_hit=True)), gold[f"{name}/occluded"])
+    rd = sc.render_desc()
+    rd.seed = gen.SEED
+    li = dev.li_samples(rd, gen.pixel_samples(rd, gen.N_LI))
+    ref = gold[f"{name}/li"]
+    bad = (np.abs(li - ref) > 1e-4 * np.maximum(np.abs(ref), 1e-3) + 1e-6).any(1)
+    assert bad.mean() <= 5e-3
+
+
+def test_filters_crop_and_wave_splitting(dev):
+    """Gaussian filter (footprint > 1 pixel -> atomics into neighbours), crop window, and a tiny wave size that forces many
+    waves and tile splitting: the image must not depend on the wave decomposition."""
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, scenes
+    txt = scenes.cornell_box(xres=80, yres=60, spp=4, crop=[0.1, 0.9, 0.2, 0.8]).replace('PixelFilter "box"', 'PixelFilter "gaussian" "float xwidth" [1.5] "float ywidth" [1.5]')
+    sc = Scene.from_string(txt)
+    dev.upload(sc)
+    o = ob.OracleScene(sc.ir_ptr)
+    _, rgb_ref, _ = o.render(sampler_kind=1, seed=2)
+    imgs = []
+    for wave in (0, 4096, 700):
+        rd = sc.render_desc()
+        rd.seed = 2
+        rd.wave_paths = wave
+        st = dev.render(rd)
+        imgs.append(dev.resolve_film())
+        assert np.abs(imgs[-1] - rgb_ref).sum() / np.abs(rgb_ref).sum() < 1e-4
+    assert st.waves > 4
+    assert np.allclose(imgs[0], imgs[2], rtol=1e-5, atol=1e-6)
+
+
+def test_sample_ranges_accumulate(dev):
+    """sample_begin / sample_end + clear_film: rendering [0,4) then [4,8) without clearing equals [0,8) (the multi-GPU
+    sample-index partition and the bench's step structure rely on this)."""
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.cornell_box(xres=48, yres=48, spp=8))
+    dev.upload(sc)
+    rd = sc.render_desc()
+    dev.render(rd)
+    full = dev.read_film()
+    rd.sample_begin, rd.sample_end, rd.clear_film = 0, 4, 1
+    dev.render(rd)
+    rd.sample_begin, rd.sample_end, rd.clear_film = 4, 8, 0
+    dev.render(rd)
+    two = dev.read_film()
+    assert np.array_equal(full[..., 3], two[..., 3])
+    assert np.allclose(full, two, rtol=1e-5, atol=1e-6)
+
+
+def test_tile_partition_sums_to_full_image(dev):
+    """tile_rank / tile_world: the films of the ranks' tile shares add up to the single-GPU film."""
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.balls(xres=80, yres=48, spp=4))
+    dev.upload(sc)
+    rd = sc.render_desc()
+    dev.render(rd)
+    full = dev.read_film()
+    acc = np.zeros_like(full)
+    cams = 0
+    for r in range(3):
+        rd.tile_rank, rd.tile_world = r, 3
+        st = dev.render(rd)
+        cams += st.camera_rays
+        acc += dev.read_film()
+    assert cams == 80 * 48 * 4
+    assert np.array_equal(acc[..., 3], full[..., 3]) and np.allclose(acc, full, rtol=1e-6, atol=1e-7)
+
+
+def test_statistical_parity_with_reference_sampler(dev):
+    """Converged-image parity against the reference's own sampler (ZeroTwoSequence + per-tile PCG32): mean relative
+    per-pixel error <= 1 % and no significant bias (two-sided t-test on per-tile mean differences), BASELINE north_star.
+    Noise floor: two independent 4096-spp renders of this Cornell box (small light) differ by 1.9 % mean relative per
+    pixel — pure Monte-Carlo noise (measured oracle vs oracle with different seeds), so "converged" needs more samples:
+    the reference side runs 16384 spp on 32x32 pixels (~10 s of CPU) and the device 65536 spp."""
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.cornell_box(xres=32, yres=32, spp=16384))
+    o = ob.OracleScene(sc.ir_ptr)
+    _, ref, _ = o.render(sampler_kind=0)
+    sc.ir.sampler.spp = 65536
+    dev.upload(sc)
+    rd = sc.render_desc()
+    assert rd.spp == 65536
+    rd.seed = 1234
+    dev.render(rd)
+    got = dev.resolve_film()
+    lum_ref, lum_got = ref.mean(2), got.mean(2)
+    rel = np.abs(lum_got - lum_ref) / np.maximum(lum_ref, 1e-3)
+    assert rel.mean() < 0.01, rel.mean()
+    d = (lum_got - lum_ref).reshape(4, 8, 4, 8).mean((1, 3)).ravel()            # 8x8 tile mean differences
+    t = d.mean() / (d.std(ddof=1) / np.sqrt(d.size))
+    assert abs(t) < 3.5, t
+    assert abs(got.mean() - ref.mean()) / ref.mean() < 2e-3
+
+
+def test_furnace_on_device(dev):
+    """Analytic value (see tests/test_oracle_kats.py::test_oracle_furnace): diffuse sphere of albedo a in a unit environment."""
+    from rustracer_b200 import Scene
+    a = 0.5
+    txt = ('LookAt 0 0 -5  0 0 0  0 1 0\nCamera "perspective" "float fov" [10]\n'
+           'Film "image" "integer xresolution" [16] "integer yresolution" [16]\nSampler "02sequence" "integer pixelsamples" [1024]\nPixelFilter "box"\n'
+           f'Integrator "path" "integer maxdepth" [5]\nWorldBegin\nLightSource "infinite" "rgb L" [1 1 1]\n'
+           f'Material "matte" "rgb Kd" [{a} {a} {a}]\nShape "sphere" "float radius" [1]\nWorldEnd\n')
+    sc = Scene.from_string(txt)
+    dev.upload(sc)
+    dev.render(sc.render_desc())
+    rgb = dev.resolve_film()
+    assert abs(rgb[6:10, 6:10].mean() - a) / a < 0.005
+
+
+def test_single_process_multi_gpu_reduce(native_libs):
+    """rtgpu_reduce_film: two contexts render disjoint tile shares and the root sums them over peer copies."""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from rustracer_b200 import Scene, scenes
+    from rustracer_b200.device import Device
+    sc = Scene.from_string(scenes.cornell_box(xres=64, yres=64, spp=4))
+    d0, d1 = Device(0).upload(sc), Device(1).upload(sc)
+    rd = sc.render_desc()
+    d0.render(rd)
+    full = d0.read_film()
+    for r, d in enumerate((d0, d1)):
+        rd.tile_rank, rd.tile_world = r, 2
+        d.render(rd)
+    arr = (C.c_void_p * 2)(d0._h, d1._h)
+    assert d0._lib.rtgpu_reduce_film(arr, 2, 0) == 0
+    assert np.allclose(d0.read_film(), full, rtol=1e-6, atol=1e-7)

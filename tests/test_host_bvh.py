@@ -1,0 +1,86 @@
+"""Host SAH BVH builder + flattening (product, C++) against the oracle's independent restatement of
+BVH::recursive_build / flatten_bvh (rustracer-core/src/bvh/mod.rs:137-358): same tree, node for node, slot for slot."""
+import numpy as np
+import pytest
+
+from rustracer_b200 import Scene, scenes
+
+
+def _compare(sc):
+    from oracle import binding as ob
+    sc.flatten()
+    lo, hi = sc.nodes()
+    o = ob.OracleScene(sc.ir_ptr)
+    bounds, meta, ordered = o.bvh()
+    assert lo.shape[0] == o.n_nodes
+    assert np.array_equal(lo[:, :3], bounds[:, :3]) and np.array_equal(hi[:, :3], bounds[:, 3:])
+    off, m = lo[:, 3].copy().view(np.uint32), hi[:, 3].copy().view(np.uint32)
+    assert np.array_equal(off, meta[:, 2].astype(np.uint32))                 # primitives_offset / second_child_offset
+    assert np.array_equal(m >> 2, meta[:, 0].astype(np.uint32))              # n_prims (0 = interior)
+    interior = meta[:, 0] == 0
+    assert np.array_equal((m & 3)[interior], meta[interior, 1].astype(np.uint32))   # split axis
+    assert np.array_equal(sc.prim_info()[:, 0], ordered.astype(np.uint32))   # ordered_prims
+    # world-space triangle vertices (mesh.rs:61) in slot order
+    wv = o.prim_world_vertices()
+    geom = sc.prim_geom()
+    tri = (geom[:, 3].copy().view(np.uint32) & 3) == 0
+    got = geom[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]]
+    assert np.array_equal(got[tri], wv[ordered][tri])
+    return o
+
+
+def test_cornell_and_balls_trees_are_identical(native_libs):
+    _compare(Scene.from_string(scenes.cornell_box(xres=16, yres=16, spp=1)))
+    _compare(Scene.from_string(scenes.balls(xres=16, yres=16, spp=1)))
+
+
+def test_icosphere_field_tree_is_identical_and_thread_invariant(native_libs, tmp_path):
+    txt = scenes.c3_scene(str(tmp_path), level=3, xres=16, yres=16, spp=1)
+    sc = Scene.from_string(txt, search_dir=tmp_path)
+    _compare(sc)
+    lo1, hi1 = sc.nodes()
+    info1 = sc.prim_info()
+    sc.flatten(threads=1)
+    lo2, hi2 = sc.nodes()
+    assert np.array_equal(lo1.view(np.uint32), lo2.view(np.uint32)) and np.array_equal(hi1.view(np.uint32), hi2.view(np.uint32))
+    assert np.array_equal(info1, sc.prim_info())
+
+
+def test_maxnodeprims_and_leaf_structure(native_libs):
+    """bvh/mod.rs:63-78,264-285: leaves hold at most max(maxnodeprims, ...) primitives unless the SAH says otherwise;
+    every primitive appears in exactly one leaf."""
+    txt = scenes.cornell_box(xres=16, yres=16, spp=1).replace("WorldBegin", 'Accelerator "bvh" "integer maxnodeprims" [1]\nWorldBegin')
+    sc = Scene.from_string(txt)
+    _compare(sc)
+    lo, hi = sc.nodes()
+    m = hi[:, 3].copy().view(np.uint32)
+    n_prims = m >> 2
+    assert n_prims.sum() == 36
+    leaves = n_prims > 0
+    starts = lo[:, 3].copy().view(np.uint32)[leaves]
+    assert sorted(starts.tolist()) == np.concatenate([[0], np.cumsum(n_prims[leaves][np.argsort(starts)])[:-1]]).tolist()
+
+
+def test_degenerate_scenes(native_libs):
+    """Empty world and single-primitive world (bvh/mod.rs:84-90,146-152)."""
+    from oracle import binding as ob
+    sc = Scene.from_string('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nWorldEnd\n')
+    sc.flatten()
+    assert sc.desc.contents.n_nodes == 0 and sc.desc.contents.n_prims == 0
+    sc = Scene.from_string('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    o = _compare(sc)
+    assert o.n_nodes == 1
+
+
+def test_middle_split_matches_or_rejects(native_libs):
+    """SplitMethod::Middle computes `start + partition + start` (bvh/mod.rs:186-190): for start > 0 the index can
+    leave the range and the reference panics; the host builder either builds the same tree as the oracle or refuses."""
+    from rustracer_b200 import SceneError
+    txt = scenes.cornell_box(xres=16, yres=16, spp=1).replace("WorldBegin", 'Accelerator "bvh" "string splitmethod" "middle"\nWorldBegin')
+    sc = Scene.from_string(txt)
+    try:
+        sc.flatten()
+    except SceneError as e:
+        assert "middle" in str(e)
+        return
+    _compare(sc)
