@@ -1,7 +1,9 @@
 // librtgpu.so — context, scene upload and the batched BVH::intersect / BVH::intersect_p entry points
 // (include/rtgpu.h).  Hand-written CUDA for sm_100a; compiled with -fmad=false.
 #include "context.hpp"
+#include "trace_engine.cuh"
 #include <cstring>
+#include <algorithm>
 #include <new>
 
 using namespace rt;
@@ -97,24 +99,61 @@ __global__ void __launch_bounds__(128) k_anyhit_batch(DScene sc, const float4* _
   if (STATS) stats[r] = make_uint2(st.nodes, st.prims);
 }
 
+// Engine variants (trace_engine.cuh): persistent warps, queue = the batch itself (optionally through `perm`).
+struct BatchClosestPolicy {
+  const float4* rays; const uint32_t* perm; HitRec* hits; const uint4* info; uint32_t r;
+  RT_DEV void load(uint32_t idx, Ray& ray) {
+    r = perm ? perm[idx] : idx;
+    const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
+    ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
+  }
+  RT_DEV void commit(bool has, uint32_t, const HitRec& h) {
+    if (!has) return;
+    HitRec o = h;
+    o.slot = h.slot == kMiss ? kMiss : info[h.slot].x;                 // slot -> prim_number (bvh/mod.rs:92)
+    hits[r] = o;
+  }
+};
+struct BatchAnyPolicy {
+  const float4* rays; const uint32_t* perm; uint8_t* occluded; uint32_t r;
+  RT_DEV void load(uint32_t idx, Ray& ray) {
+    r = perm ? perm[idx] : idx;
+    const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
+    ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
+  }
+  RT_DEV void commit(bool has, uint32_t, const HitRec& h) { if (has) occluded[r] = h.slot != kMiss ? 1 : 0; }
+};
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_closest_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
+                                                               HitRec* __restrict__ hits, uint32_t* cursor) {
+  BatchClosestPolicy pol; pol.rays = rays; pol.perm = perm; pol.hits = hits; pol.info = sc.info; pol.r = 0;
+  trace_engine<false>(sc, cursor, n, pol);
+}
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_anyhit_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
+                                                              uint8_t* __restrict__ occluded, uint32_t* cursor) {
+  BatchAnyPolicy pol; pol.rays = rays; pol.perm = perm; pol.occluded = occluded; pol.r = 0;
+  trace_engine<true>(sc, cursor, n, pol);
+}
+
 static int ensure_sort_scratch(rtgpu_ctx* ctx, size_t n, uint32_t** keys, uint32_t** perm, uint32_t** hist) {
-  // layout in one allocation: hist[kSortBins] | keys[n] | perm[n]
-  size_t need = (size_t)kSortBins * 4 + n * 8;
+  // layout in one allocation: cursor[64] | hist[kSortBins] | keys[n] | perm[n]
+  size_t need = 256 + (size_t)kSortBins * 4 + n * 8;
   if (ctx->scratch_n < need) {
     if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
     ctx->scratch_rays = nullptr; ctx->scratch_n = 0;
     RT_CUDA(ctx, cudaMalloc(&ctx->scratch_rays, need));
     ctx->scratch_n = need;
   }
-  *hist = (uint32_t*)ctx->scratch_rays; *keys = *hist + kSortBins; *perm = *keys + n;
+  *hist = (uint32_t*)ctx->scratch_rays + 64; *keys = *hist + kSortBins; *perm = *keys + n;
   return 0;
 }
 
-static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_t** perm_out) {
+static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_t** perm_out, uint32_t** cursor_out) {
   *perm_out = nullptr;
-  if (!ctx->sort_rays || n < 4096) return 0;
   uint32_t *keys, *perm, *hist;
   int rc = ensure_sort_scratch(ctx, n, &keys, &perm, &hist); if (rc) return rc;
+  *cursor_out = (uint32_t*)ctx->scratch_rays;
+  RT_CUDA(ctx, cudaMemsetAsync(*cursor_out, 0, 256, ctx->stream));
+  if (!ctx->sort_rays || n < 4096) return 0;
   SortParams sp;
   for (int k = 0; k < 3; k++) {
     float ext = ctx->scene.world_hi[k] - ctx->scene.world_lo[k];
@@ -198,6 +237,9 @@ uint64_t rtgpu_launch_count(rtgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
+  if (std::strcmp(name, "node_threshold") == 0) { ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK; }
+  if (std::strcmp(name, "refill_threshold") == 0) { ctx->refill_threshold = value; ctx->scene.tune_refill_threshold = value; return RTGPU_OK; }
+  if (std::strcmp(name, "simple_traversal") == 0) { ctx->simple_traversal = value; return RTGPU_OK; }
   if (std::strcmp(name, "profile") == 0) { ctx->profile = value; return RTGPU_OK; }
   if (std::strcmp(name, "count_traversal") == 0) { ctx->count_traversal = value; return RTGPU_OK; }
   return fail(ctx, RTGPU_ERR_ARG, std::string("unknown option ") + name);
@@ -224,7 +266,38 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   }
   int rc;
   const float* pf = nullptr; const uint32_t* pu = nullptr;
-  if ((rc = upload(ctx, s->prim_geom, (size_t)s->n_prims * 12, &pf))) return rc; d.geom = (const float4*)pf;
+  // wide nodes for the traversal engine (trace_engine.cuh) + "last primitive of the leaf" marks in the geometry copy
+  {
+    const size_t nn = s->n_nodes;
+    auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    auto fbits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+    std::vector<uint32_t> interior_index(nn, 0);
+    uint32_t n_interior = 0;
+    for (size_t i = 0; i < nn; i++) if ((bits(s->node_hi[i * 4 + 3]) >> 2) == 0) interior_index[i] = n_interior++;
+    auto ref_of = [&](size_t i) -> uint32_t {
+      const uint32_t n_prims = bits(s->node_hi[i * 4 + 3]) >> 2;
+      return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];
+    };
+    std::vector<float> wide((size_t)n_interior * 16, 0.0f);
+    std::vector<float> geom(s->prim_geom, s->prim_geom + (size_t)s->n_prims * 12);
+    for (size_t i = 0; i < nn; i++) {
+      const uint32_t meta = bits(s->node_hi[i * 4 + 3]), n_prims = meta >> 2, off = bits(s->node_lo[i * 4 + 3]);
+      if (n_prims > 0) {
+        if ((size_t)off + n_prims > s->n_prims) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
+        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(1u);
+        continue;
+      }
+      const size_t L = i + 1, R = off;
+      if (L >= nn || R >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
+      float* w = &wide[(size_t)interior_index[i] * 16];
+      for (int k = 0; k < 3; k++) { w[k] = s->node_lo[L * 4 + k]; w[4 + k] = s->node_hi[L * 4 + k]; w[8 + k] = s->node_lo[R * 4 + k]; w[12 + k] = s->node_hi[R * 4 + k]; }
+      w[3] = fbits(ref_of(L)); w[7] = fbits(ref_of(R)); w[11] = fbits(meta & 3u); w[15] = 0.0f;
+    }
+    d.root_ref = nn > 0 ? ref_of(0) : 0xffffffffu;
+    if ((rc = upload(ctx, wide.data(), wide.size(), &pf))) return rc; d.wide = (const float4*)pf;
+    if ((rc = upload(ctx, geom.data(), geom.size(), &pf))) return rc; d.geom = (const float4*)pf;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die at scope end
+  }
   if ((rc = upload(ctx, s->prim_info, (size_t)s->n_prims * 4, &pu))) return rc; d.info = (const uint4*)pu;
   if ((rc = upload(ctx, s->tri_n, s->tri_n ? (size_t)s->n_prims * 9 : 0, &d.tri_n))) return rc;
   if ((rc = upload(ctx, s->tri_s, s->tri_s ? (size_t)s->n_prims * 9 : 0, &d.tri_s))) return rc;
@@ -235,6 +308,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
   d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;
   for (int i = 0; i < 3; i++) { d.world_lo[i] = s->world_lo[i]; d.world_hi[i] = s->world_hi[i]; }
+  d.tune_node_threshold = ctx->node_threshold; d.tune_refill_threshold = ctx->refill_threshold;
   if (s->n_lights) ctx->h_lights.assign(s->lights, s->lights + s->n_lights);
   if (s->n_materials) ctx->h_materials.assign(s->materials, s->materials + s->n_materials);
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -281,11 +355,14 @@ static int run_closest(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_
   if (n > 0xfffffff0ull) return fail(ctx, RTGPU_ERR_ARG, "batch too large (max 2^32-16 rays)");
   cudaSetDevice(ctx->device);
   if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  uint32_t* perm = nullptr;
-  int rc = build_perm(ctx, d_rays, n, &perm); if (rc) return rc;
+  uint32_t *perm = nullptr, *cursor = nullptr;
+  int rc = build_perm(ctx, d_rays, n, &perm, &cursor); if (rc) return rc;
   unsigned blocks = (unsigned)((n + 127) / 128);
+  const unsigned pblocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, blocks);
+  // the counting variant is the plain one-thread-one-ray reference walk; the fast path is the persistent engine
   if (d_stats) k_closest_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, (uint2*)d_stats);
-  else k_closest_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, nullptr);
+  else if (ctx->simple_traversal) k_closest_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, nullptr);
+  else k_closest_batch_engine<<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, cursor);
   ctx->launches += 1;
   RT_CUDA(ctx, cudaGetLastError());
   if (elapsed_ms) {
@@ -301,11 +378,13 @@ static int run_anyhit(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t
   if (n > 0xfffffff0ull) return fail(ctx, RTGPU_ERR_ARG, "batch too large (max 2^32-16 rays)");
   cudaSetDevice(ctx->device);
   if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-  uint32_t* perm = nullptr;
-  int rc = build_perm(ctx, d_rays, n, &perm); if (rc) return rc;
+  uint32_t *perm = nullptr, *cursor = nullptr;
+  int rc = build_perm(ctx, d_rays, n, &perm, &cursor); if (rc) return rc;
   unsigned blocks = (unsigned)((n + 127) / 128);
+  const unsigned pblocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, blocks);
   if (d_stats) k_anyhit_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, (uint2*)d_stats);
-  else k_anyhit_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, nullptr);
+  else if (ctx->simple_traversal) k_anyhit_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, nullptr);
+  else k_anyhit_batch_engine<<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, cursor);
   ctx->launches += 1;
   RT_CUDA(ctx, cudaGetLastError());
   if (elapsed_ms) {

@@ -35,6 +35,8 @@ struct rtgpu_ctx {
   int profile = 0;            // rtgpu_render: time every launch with CUDA events, per kernel class (rtgpu_stats.ms_*)
   int count_traversal = 0;    // rtgpu_render: count BVH nodes visited / primitives tested (rtgpu_stats.nodes_* / prims_*)
   std::vector<cudaEvent_t> event_pool;
+  int node_threshold = 12, refill_threshold = 16;   // trace_engine.cuh scheduling knobs
+  int simple_traversal = 0;   // 1 = one-thread-one-ray reference walk everywhere (validation); 0 = persistent engine
   int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
 };
 

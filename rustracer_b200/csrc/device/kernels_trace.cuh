@@ -2,6 +2,7 @@
 // resolve, spatial light-distribution prepass (product code, sm_100a).  Each kernel names the rustracer code it replaces.
 #pragma once
 #include "shade_common.cuh"
+#include "trace_engine.cuh"
 
 namespace rt {
 
@@ -160,6 +161,92 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
     }
   }
   if (STATS) flush_trav_stats(p, st, S_NODES_CLOSEST, S_PRIMS_CLOSEST);
+}
+
+// ---- the same three kernels on the persistent while-while engine (trace_engine.cuh): the production path ------------
+template <bool CLASSIFY>
+struct ClosestPolicy {
+  const RenderParams& p; const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t slot;
+  RT_DEV ClosestPolicy(const RenderParams& p_, const float4* o, const float4* d, const uint32_t* l, HitRec* h) : p(p_), ray_o(o), ray_d(d), list(l), hits(h), slot(0) {}
+  RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
+  RT_DEV void commit(bool has, uint32_t, const HitRec& h) {
+    int q = -1;
+    if (has) {
+      hits[slot] = h;
+      if (CLASSIFY) {
+        if (h.slot == kMiss) q = Q_MISS;
+        else {
+          const uint32_t mrow = p.sc.info[h.slot].y;
+          const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+          q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
+        }
+      }
+    }
+    if (CLASSIFY) {
+#pragma unroll
+      for (int k = 0; k < Q_COUNT; k++) {
+        const uint32_t pos = warp_append(&p.w.counters[C_MATQ0 + k], has && q == k);
+        if (has && q == k) p.w.matq[k][pos] = slot;
+      }
+    }
+  }
+};
+template <bool CLASSIFY>
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                               const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
+  ClosestPolicy<CLASSIFY> pol(p, ray_o, ray_d, list, hits);
+  trace_engine<false>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
+}
+
+template <bool ATOMIC>
+struct ShadowPolicy {
+  const RenderParams& p; uint32_t sample;
+  RT_DEV ShadowPolicy(const RenderParams& p_) : p(p_), sample(0) {}
+  RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.sh_o, p.w.sh_d, idx, &sample); }
+  RT_DEV void commit(bool has, uint32_t idx, const HitRec& h) {
+    if (!has || h.slot != kMiss) return;
+    const float4 c = p.w.sh_c[idx];
+    float4* L = &p.w.L[sample];
+    if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
+    else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
+  }
+};
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_shadow_engine(RenderParams p) {
+  ShadowPolicy<ATOMIC> pol(p);
+  trace_engine<true>(p.sc, &p.w.counters[C_CUR_ANY], min(p.w.counters[C_SHADOW], p.w.cap_shadow), pol);
+}
+
+template <bool ATOMIC>
+struct MisPolicy {
+  const RenderParams& p; uint32_t sample;
+  RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
+  RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
+  RT_DEV void commit(bool has, uint32_t idx, const HitRec& h) {
+    if (!has) return;
+    const float4 c = p.w.mi_c[idx];
+    const uint32_t light_row = __float_as_uint(c.w);
+    const rtgpu_light& light = p.sc.lights[light_row];
+    const Ray ray0 = load_ray(p.w.mi_o, p.w.mi_d, idx, nullptr);
+    Spec li = spec(0.0f);
+    if (h.slot != kMiss) {
+      if (p.sc.info[h.slot].z == light_row) {                           // same light id (integrator/mod.rs:294-299)
+        SurfHit si; float t;
+        if (slot_intersect_surface(p.sc, h.slot, ray0, t, si)) li = area_L(light, si.n, -ray0.d);
+      }
+    } else li = light_le(p.sc, light, ray0.d);
+    if (!is_black(li)) {
+      float4* L = &p.w.L[sample];
+      const float r = c.x * li.r, g = c.y * li.g, b = c.z * li.b;
+      if (ATOMIC) { atomicAdd(&L->x, r); atomicAdd(&L->y, g); atomicAdd(&L->z, b); }
+      else { float4 v = *L; v.x += r; v.y += g; v.z += b; *L = v; }
+    }
+  }
+};
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_mis_engine(RenderParams p) {
+  MisPolicy<ATOMIC> pol(p);
+  trace_engine<false>(p.sc, &p.w.counters[C_CUR_MIS], min(p.w.counters[C_MIS], p.w.cap_mis), pol);
 }
 
 // compute_distribution (lightdistrib.rs:101-179), first half: one thread per (voxel, light) accumulates the

@@ -266,7 +266,8 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   enum { K_CLOSEST = 0, K_ANYHIT, K_SHADE, K_OTHER, K_CLASSES };
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
-  const bool prof = ctx->profile != 0, tstats = ctx->count_traversal != 0;
+  const bool prof = ctx->profile != 0;
+  const int tstats = ctx->count_traversal ? TRACE_COUNTING : (ctx->simple_traversal ? TRACE_SIMPLE : TRACE_ENGINE);
   size_t ev_used = 0;
   auto next_event = [&]() -> cudaEvent_t {
     if (ev_used == ctx->event_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->event_pool.push_back(e); }

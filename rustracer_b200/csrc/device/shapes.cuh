@@ -10,7 +10,11 @@ namespace rt {
 // Device-resident scene (all pointers are device pointers).  Layout: DESIGN.md "Data layout in HBM".
 struct DScene {
   const float4* nodes;       // 2 float4 per LinearBVHNode: {min.xyz, bits(offset)}, {max.xyz, bits(n_prims<<2 | axis)}
-  const float4* geom;        // 3 float4 per ordered slot: triangle v0,v1,v2 (w of v0 = bits(kind | quadric<<2))
+  const float4* wide;        // 4 float4 per INTERIOR node (compact numbering): {L.min, bits(ref L)}, {L.max, bits(ref R)},
+                             //   {R.min, bits(axis)}, {R.max, 0}; ref = interior index, or 0x80000000 | first slot for a leaf
+  uint32_t root_ref;         // ref of the root node
+  const float4* geom;        // 3 float4 per ordered slot: triangle v0,v1,v2 (w of v0 = bits(kind | quadric<<2),
+                             //   w of v1 bit 0 = last primitive of its leaf)
   const uint4* info;         // per slot: prim_number, material row, light row (0xffffffff none), RTGPU_PRIMFLAG_*
   const float* tri_n;        // 9 per slot or null
   const float* tri_s;        // 9 per slot or null
@@ -21,6 +25,7 @@ struct DScene {
   const float* env;
   uint32_t n_nodes, n_prims, n_quadrics, n_materials, n_lights;
   float world_lo[3], world_hi[3];
+  int tune_node_threshold, tune_refill_threshold;   // trace_engine.cuh scheduling knobs (rtgpu_set_option)
 };
 
 // What the integrators need of `SurfaceInteraction` (interaction.rs:78-147).  Ray differentials, dndu/dndv and

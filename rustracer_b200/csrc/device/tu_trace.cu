@@ -8,23 +8,30 @@ void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t
   k_generate_rays<<<(n + 255) / 256, 256, 0, s>>>(p, samples, n, rays);
 }
 void launch_raygen(const RenderParams& p, cudaStream_t s) { k_raygen<<<(p.n_items + 255) / 256, 256, 0, s>>>(p); }
-void launch_trace_closest(bool classify, bool stats, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
+// mode: TRACE_ENGINE = persistent while-while engine (production), TRACE_SIMPLE = one-thread-one-ray reference walk
+// (validation), TRACE_COUNTING = the reference walk that also counts nodes visited / primitives tested.
+void launch_trace_closest(bool classify, int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
                           HitRec* hits, unsigned blocks, cudaStream_t s) {
-  if (stats) {
+  if (mode == TRACE_COUNTING) {
     if (classify) k_trace_closest<true, true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
     else k_trace_closest<false, true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-  } else {
+  } else if (mode == TRACE_SIMPLE) {
     if (classify) k_trace_closest<true, false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
     else k_trace_closest<false, false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  } else {
+    if (classify) k_trace_closest_engine<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+    else k_trace_closest_engine<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
   }
 }
-void launch_trace_shadow(bool atomic, bool stats, const RenderParams& p, unsigned blocks, cudaStream_t s) {
-  if (stats) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p); }
-  else { if (atomic) k_trace_shadow<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, false><<<blocks, 128, 0, s>>>(p); }
+void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s) {
+  if (mode == TRACE_COUNTING) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p); }
+  else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_shadow<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, false><<<blocks, 128, 0, s>>>(p); }
+  else { if (atomic) k_trace_shadow_engine<true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow_engine<false><<<blocks, 128, 0, s>>>(p); }
 }
-void launch_trace_mis(bool atomic, bool stats, const RenderParams& p, unsigned blocks, cudaStream_t s) {
-  if (stats) { if (atomic) k_trace_mis<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, true><<<blocks, 128, 0, s>>>(p); }
-  else { if (atomic) k_trace_mis<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, false><<<blocks, 128, 0, s>>>(p); }
+void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s) {
+  if (mode == TRACE_COUNTING) { if (atomic) k_trace_mis<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, true><<<blocks, 128, 0, s>>>(p); }
+  else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_mis<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, false><<<blocks, 128, 0, s>>>(p); }
+  else { if (atomic) k_trace_mis_engine<true><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false><<<blocks, 128, 0, s>>>(p); }
 }
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }

@@ -43,12 +43,14 @@ def throughput(dev, sc, n, label, reps=3):
         d_r = dev.malloc(rays.nbytes)
         d_o = dev.malloc(16 * n)
         dev.h2d(d_r, rays)
-        for sort in (0, 1):
-            dev.set_option("sort_rays", sort)
-            f = dev.occluded_device if any_hit else dev.intersect_device
-            f(d_r, n, d_o)
-            ms = min(f(d_r, n, d_o) for _ in range(reps))
-            print(f"[{label}] {'any' if any_hit else 'closest'} sort={sort}: {n/ms/1e3:.1f} Mrays/s ({ms:.2f} ms for {n} rays)")
+        for simple in (1, 0):
+            dev.set_option("simple_traversal", simple)
+            for sort in (0, 1):
+                dev.set_option("sort_rays", sort)
+                f = dev.occluded_device if any_hit else dev.intersect_device
+                f(d_r, n, d_o)
+                ms = min(f(d_r, n, d_o) for _ in range(reps))
+                print(f"[{label}] {'any' if any_hit else 'closest'} {'simple' if simple else 'engine'} sort={sort}: {n/ms/1e3:.1f} Mrays/s ({ms:.2f} ms for {n} rays)")
         dev.free(d_r), dev.free(d_o)
 
 
