@@ -106,20 +106,32 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const flo
 
 // Shadow rays: VisibilityTester::unoccluded (light/mod.rs:52-55) -> Scene::intersect_p; adds the pending
 // contribution to the sample's radiance when the segment is clear.
+// An any-hit queue: q = 0 the NEE shadow rays, q = 1 the MIS rays towards infinite lights (shade_common.cuh).  Each
+// camera sample has at most one entry per queue and bounce in the path integrator, so the plain read-modify-write of
+// the non-ATOMIC variant is race-free and the sum order is fixed.
+struct AnyQueue { const float4 *o, *d, *c; uint32_t n; uint32_t* cursor; };
+RT_DEV AnyQueue any_queue(const RenderParams& p, int q) {
+  AnyQueue a;
+  if (q == 0) { a.o = p.w.sh_o; a.d = p.w.sh_d; a.c = p.w.sh_c; a.n = min(p.w.counters[C_SHADOW], p.w.cap_shadow); a.cursor = &p.w.counters[C_CUR_ANY]; }
+  else { a.o = p.w.ma_o; a.d = p.w.ma_d; a.c = p.w.ma_c; a.n = min(p.w.counters[C_MIS_ANY], p.w.cap_mis); a.cursor = &p.w.counters[C_CUR_MISANY]; }
+  return a;
+}
+
 template <bool ATOMIC, bool STATS>
-__global__ void __launch_bounds__(128) k_trace_shadow(RenderParams p) {
-  const uint32_t n = min(p.w.counters[C_SHADOW], p.w.cap_shadow);
+__global__ void __launch_bounds__(128) k_trace_shadow(RenderParams p, int q) {
+  const AnyQueue aq = any_queue(p, q);
+  const uint32_t n = aq.n;
   TravStats st; st.nodes = 0; st.prims = 0;
   while (true) {
-    const uint32_t base = warp_fetch(&p.w.counters[C_CUR_ANY]);
+    const uint32_t base = warp_fetch(aq.cursor);
     if (base >= n) break;
     const uint32_t i = base + lane_id();
     if (i >= n) continue;
     uint32_t sample;
-    Ray ray = load_ray(p.w.sh_o, p.w.sh_d, i, &sample);
+    Ray ray = load_ray(aq.o, aq.d, i, &sample);
     HitRec h;
     if (!bvh_traverse<true, STATS>(p.sc, ray, h, &st)) {
-      const float4 c = p.w.sh_c[i];
+      const float4 c = aq.c[i];
       float4* L = &p.w.L[sample];
       if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
       else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
@@ -200,21 +212,22 @@ __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_eng
 
 template <bool ATOMIC>
 struct ShadowPolicy {
-  const RenderParams& p; uint32_t sample;
-  RT_DEV ShadowPolicy(const RenderParams& p_) : p(p_), sample(0) {}
-  RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.sh_o, p.w.sh_d, idx, &sample); }
+  const RenderParams& p; AnyQueue aq; uint32_t sample;
+  RT_DEV ShadowPolicy(const RenderParams& p_, const AnyQueue& a) : p(p_), aq(a), sample(0) {}
+  RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
   RT_DEV void commit(bool has, uint32_t idx, const HitRec& h) {
     if (!has || h.slot != kMiss) return;
-    const float4 c = p.w.sh_c[idx];
+    const float4 c = aq.c[idx];
     float4* L = &p.w.L[sample];
     if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
     else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
   }
 };
 template <bool ATOMIC>
-__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_shadow_engine(RenderParams p) {
-  ShadowPolicy<ATOMIC> pol(p);
-  trace_engine<true>(p.sc, &p.w.counters[C_CUR_ANY], min(p.w.counters[C_SHADOW], p.w.cap_shadow), pol);
+__global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_shadow_engine(RenderParams p, int q) {
+  const AnyQueue aq = any_queue(p, q);
+  ShadowPolicy<ATOMIC> pol(p, aq);
+  trace_engine<true>(p.sc, aq.cursor, aq.n, pol);
 }
 
 template <bool ATOMIC>
@@ -326,13 +339,14 @@ __global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint32_t* c = p.w.counters;
   const uint32_t live = c[live_idx];
-  p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis);
+  // MIS rays towards infinite lights travel in the shadow queue (shade_common.cuh) but are "regular" rays for the reference
+  p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis) + min(c[C_MIS_ANY], p.w.cap_mis) + c[C_MIS_SKIPPED];
   p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
   if (count_camera) p.w.stats[S_CAMERA] += live;
   if (c[C_OVERFLOW]) p.w.stats[S_OVERFLOW] = 1;
   c[live_idx] = 0;
   for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;
-  c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_CUR_CLOSEST] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0;
+  c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MIS_ANY] = 0; c[C_MIS_SKIPPED] = 0; c[C_CUR_CLOSEST] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0; c[C_CUR_MISANY] = 0;
 }
 
 // ---- film (film.rs) -----------------------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
   A(mi_o, cap_mis); A(mi_d, cap_mis); A(mi_c, cap_mis);
+  A(ma_o, cap_mis); A(ma_d, cap_mis); A(ma_c, cap_mis);
   A(list[0], cap_items); A(list[1], cap_items);
   for (int k = 0; k < Q_COUNT; k++) A(matq[k], cap_items);
   A(counters, C_COUNT); A(stats, S_COUNT);
@@ -267,6 +268,8 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
   const bool prof = ctx->profile != 0;
+  bool has_infinite = false;
+  for (const rtgpu_light& l : ctx->h_lights) has_infinite |= l.kind == RTGPU_LIGHT_INFINITE;
   const int tstats = ctx->count_traversal ? TRACE_COUNTING : (ctx->simple_traversal ? TRACE_SIMPLE : TRACE_ENGINE);
   size_t ev_used = 0;
   auto next_event = [&]() -> cudaEvent_t {
@@ -296,7 +299,8 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
         if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
         if (sc.n_lights > 0) {
-          RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, pblocks, ctx->stream));
+          RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, ctx->stream));
+          if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, ctx->stream));
           RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, ctx->stream));
         }
         RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, ctx->stream));
@@ -307,14 +311,15 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         const int par = (int)(lvl & 1u);
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
-        RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, pblocks, ctx->stream));
+        RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
+        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, ctx->stream));
         RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream));
       }
     } else {
       RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
       RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));
-      if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, pblocks, ctx->stream));
+      if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
       RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, ctx->stream));
     }
     waves++;

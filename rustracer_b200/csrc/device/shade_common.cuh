@@ -91,7 +91,21 @@ RT_DEV void estimate_direct(const RenderParams& p, const SurfHit& si, const Bsdf
         if (lp == 0.0f) return;
         weight = power_heuristic(scattering_pdf, lp);
       }
-      push_mis(p, spawn_ray(it, wi2), sample, scale * (f * weight / scattering_pdf), light_row);
+      const Spec w = scale * (f * weight / scattering_pdf);
+      if (light.kind == RTGPU_LIGHT_INFINITE) {
+        // The MIS ray towards an infinite light contributes light.le(ray) exactly when its closest-hit query finds
+        // nothing (a hit can never carry the infinite light's id, integrator/mod.rs:293-310) — i.e. when an any-hit
+        // query finds nothing.  Same ray, same result, cheaper walk: queue it with the shadow rays, radiance folded in.
+        // It stays a "regular" ray in the reference's counters (C_MIS_ANY).
+        const Spec le = light_le(p.sc, light, wi2);
+        if (!is_black(le)) {
+          const uint32_t pos = warp_append(&p.w.counters[C_MIS_ANY], true);
+          if (pos < p.w.cap_mis) {
+            store_ray(p.w.ma_o, p.w.ma_d, pos, spawn_ray(it, wi2), sample);
+            p.w.ma_c[pos] = make_float4(w.r * le.r, w.g * le.g, w.b * le.b, 0.0f);
+          } else p.w.counters[C_OVERFLOW] = 1;
+        } else warp_append(&p.w.counters[C_MIS_SKIPPED], true);       // traced by the reference, contributes nothing
+      } else push_mis(p, spawn_ray(it, wi2), sample, w, light_row);
     }
   }
 }

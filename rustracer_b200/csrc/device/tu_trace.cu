@@ -23,10 +23,11 @@ void launch_trace_closest(bool classify, int mode, const RenderParams& p, const 
     else k_trace_closest_engine<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
   }
 }
-void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s) {
-  if (mode == TRACE_COUNTING) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p); }
-  else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_shadow<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_shadow<false, false><<<blocks, 128, 0, s>>>(p); }
-  else { if (atomic) k_trace_shadow_engine<true><<<blocks, 128, 0, s>>>(p); else k_trace_shadow_engine<false><<<blocks, 128, 0, s>>>(p); }
+// q: 0 = NEE shadow queue, 1 = queue of the MIS rays towards infinite lights (both any-hit)
+void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s) {
+  if (mode == TRACE_COUNTING) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p, q); }
+  else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_shadow<true, false><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow<false, false><<<blocks, 128, 0, s>>>(p, q); }
+  else { if (atomic) k_trace_shadow_engine<true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow_engine<false><<<blocks, 128, 0, s>>>(p, q); }
 }
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s) {
   if (mode == TRACE_COUNTING) { if (atomic) k_trace_mis<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, true><<<blocks, 128, 0, s>>>(p); }

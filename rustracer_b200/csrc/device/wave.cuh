@@ -12,7 +12,7 @@ enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_MISS, Q_COU
 
 // device counters (uint32)
 enum {
-  C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_COUNT = 32
+  C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_MIS_ANY, C_MIS_SKIPPED, C_CUR_MISANY, C_COUNT = 32
 };
 // device statistics (uint64): the reference's counters (scene.rs:9-16, renderer.rs:17)
 enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_COUNT = 8 };
@@ -39,6 +39,7 @@ struct WaveView {            // device pointers, passed to kernels by value
   // shadow (any-hit) queue and MIS (closest-hit) queue
   float4 *sh_o, *sh_d, *sh_c;          // ray; d.w = bits(sample slot); c = rgb contribution if unoccluded
   float4 *mi_o, *mi_d, *mi_c;          // ray; d.w = bits(sample slot); c = rgb weight, w = bits(light row)
+  float4 *ma_o, *ma_d, *ma_c;          // MIS rays towards infinite lights, traced any-hit: c = rgb contribution if the ray escapes
   uint32_t* list[2];
   uint32_t* matq[Q_COUNT];
   uint32_t* counters;
