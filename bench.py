@@ -6,8 +6,8 @@
 
 Workload (config.workload = "c3_path"): SURVEY 8d config C3 — synthetic 1,003,520-triangle subdivided-icosphere PLY
 field + ground + 2-triangle area light + constant infinite light, PathIntegrator maxdepth 5, lightsamplestrategy
-"spatial", 1920x1080, Sampler "02sequence" 256 spp.  One step = `--spp-per-step` sample indices (default 4) of every
-pixel: 8.3 M camera paths.  Successive steps take successive sample-index ranges of the 256-spp job; with N GPUs rank r
+"spatial", 1920x1080, Sampler "02sequence" 256 spp.  One step = `--spp-per-step` sample indices (default 8) of every
+pixel: 16.6 M camera paths.  Successive steps take successive sample-index ranges of the 256-spp job; with N GPUs rank r
 takes the r-th range of each step (scene replicated, sample indices partitioned) and the films are summed with one NCCL
 reduce at the end of the job.  metric = camera path samples per second (the reference's "Camera rays traced" / s).
 """
@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--spp-per-step", type=int, default=8)
     ap.add_argument("--level", type=int, default=5, help="icosphere subdivision level (5 = the 1M-triangle config)")
     ap.add_argument("--xres", type=int, default=1920)
     ap.add_argument("--yres", type=int, default=1080)

@@ -18,6 +18,7 @@ struct WaveBuffers {
   float* grid_table = nullptr; int grid_nv[3] = {0, 0, 0}; int grid_n = 0; bool grid_valid = false;
   uint32_t* n_light_samples = nullptr; uint32_t n_light_samples_cap = 0;
   float4* film_tmp = nullptr; size_t film_tmp_n = 0;
+  unsigned long long* stats_backup = nullptr;
 };
 
 namespace rt {
@@ -72,6 +73,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   for (int k = 0; k < Q_COUNT; k++) A(matq[k], cap_items);
   A(counters, C_COUNT); A(stats, S_COUNT);
 #undef A
+  if ((rc = dalloc(ctx, w, &w->stats_backup, (size_t)S_COUNT))) return rc;
   v.cap_items = cap_items; v.cap_samples = cap_samples; v.cap_shadow = cap_shadow; v.cap_mis = cap_mis;
   w->recursive = recursive;
   return 0;
@@ -170,7 +172,10 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   const uint32_t max_depth = (uint32_t)rd->max_depth & 0xffu;
 
   // ---- capacities --------------------------------------------------------------------------------------------
-  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (1u << 23);
+  // default wave size (tools/wave_sweep.py on B200): the path integrator keeps gaining up to 16 M paths per wave (fewer, fuller
+  // launches); the recursive integrators peak at 4 M items (their per-sample atomics and level queues stay L2-resident)
+  const bool recursive_integrator = rd->integrator == RTGPU_INTEGRATOR_WHITTED || rd->integrator == RTGPU_INTEGRATOR_DIRECT;
+  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (recursive_integrator ? (1u << 22) : (1u << 24));
   uint32_t cap_items = P, cap_samples = P, cap_shadow = P, cap_mis = P;
   uint32_t rays_per_item = 1;
   std::vector<uint32_t> nls;
@@ -184,10 +189,10 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       rays_per_item = std::max(1u, rays_per_item);
       p.scfg.n_arrays = max_depth * sc.n_lights * 2u;
     }
-    const uint32_t fan = 1u << std::min(20u, max_depth > 0 ? max_depth - 1 : 0);      // items of the deepest level per camera sample
-    cap_samples = std::max(256u, std::min(P / fan, (uint32_t)(((size_t)4 * P) / ((size_t)fan * rays_per_item))));
-    cap_items = cap_samples * fan;
+    // level queues hold P items; a wave starts with P/2 camera samples (the ray tree rarely doubles) and is split on overflow
+    cap_items = P;
     cap_shadow = (uint32_t)std::min<size_t>((size_t)cap_items * rays_per_item, (size_t)4 * P);
+    cap_samples = std::max(256u, std::min(P / 2, cap_shadow / std::max(1u, rays_per_item)));
     cap_mis = rd->integrator == RTGPU_INTEGRATOR_WHITTED ? 1 : cap_shadow;
   } else if (rd->integrator == RTGPU_INTEGRATOR_AO) {
     cap_shadow = 2 * P;
@@ -260,7 +265,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
 
   RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   RT_CUDA(ctx, cudaMemsetAsync(p.w.stats, 0, S_COUNT * sizeof(unsigned long long), ctx->stream));
-  uint64_t waves = 0, launches0 = ctx->launches;
+  uint64_t waves = 0, launches0 = ctx->launches, splits = 0;
   const unsigned pblocks = (unsigned)ctx->sm_count * 8u;                // persistent / grid-stride kernels: 8 x 128 threads per SM
 
   // optional per-class device timing (set_option "profile"): CUDA events around every launch on the context's stream
@@ -326,35 +331,62 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     return check_cuda(ctx, cudaGetLastError(), "kernel launch");
   };
 
+  // Work list of waves.  The recursive integrators size their waves for the EXPECTED growth of the ray tree (most hits
+  // spawn no specular children), not the 2^depth worst case; a wave whose queues overflow is discarded (nothing has
+  // reached the film yet), the counters are rolled back and the wave is split in two.
+  struct Chunk { long long a0, an; int s0, sn; };          // tiles [a0, a0+an) x samples [s0, s0+sn)  |  explicit items [a0, a0+an)
+  std::vector<Chunk> work;
   if (d_explicit) {
-    for (size_t first = 0; first < n_explicit; first += cap_samples) {
-      const uint32_t m = (uint32_t)std::min<size_t>(cap_samples, n_explicit - first);
-      p.explicit_pixels = d_explicit + 3 * first;
-      rc = run_wave(m); if (rc) return rc;
-      RT_LAUNCH(K_OTHER, launch_li_out(p.w.L, fp.ao_div, m, d_li_out + 3 * first, ctx->stream));
+    for (size_t first = n_explicit; first > 0;) {
+      const size_t m = std::min<size_t>(cap_samples, first);
+      first -= m;
+      work.push_back(Chunk{(long long)first, (long long)m, 0, 0});
     }
   } else if (my_tiles > 0 && s_end > s_begin) {
     const long long per_sample = my_tiles * 256;
     long long tiles_per_wave = my_tiles, samples_per_wave = 1;
     if (per_sample <= (long long)cap_samples) samples_per_wave = std::max<long long>(1, (long long)cap_samples / per_sample);
     else tiles_per_wave = std::max<long long>(1, (long long)cap_samples / 256);
-    for (long long t0 = 0; t0 < my_tiles; t0 += tiles_per_wave) {
-      const long long nt = std::min(tiles_per_wave, my_tiles - t0);
-      for (int s0 = s_begin; s0 < s_end; s0 += (int)samples_per_wave) {
-        const int ns = (int)std::min<long long>(samples_per_wave, s_end - s0);
-        p.tile_first = (int)t0; p.n_tiles = (int)nt; p.sample_first = s0; p.n_samples = ns;
-        const uint32_t n_items = (uint32_t)(nt * 256 * ns);
-        rc = run_wave(n_items); if (rc) return rc;
-        RT_LAUNCH(K_OTHER, launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream));
+    std::vector<Chunk> fwd;
+    for (long long t0 = 0; t0 < my_tiles; t0 += tiles_per_wave)
+      for (int s0 = s_begin; s0 < s_end; s0 += (int)samples_per_wave)
+        fwd.push_back(Chunk{t0, std::min(tiles_per_wave, my_tiles - t0), s0, (int)std::min<long long>(samples_per_wave, s_end - s0)});
+    work.assign(fwd.rbegin(), fwd.rend());                  // processed from the back
+  }
+  while (!work.empty()) {
+    const Chunk c = work.back();
+    work.pop_back();
+    uint32_t n_items;
+    if (d_explicit) { p.explicit_pixels = d_explicit + 3 * c.a0; n_items = (uint32_t)c.an; }
+    else { p.tile_first = (int)c.a0; p.n_tiles = (int)c.an; p.sample_first = c.s0; p.n_samples = c.sn; n_items = (uint32_t)(c.an * 256 * c.sn); }
+    if (plan.recursive) RT_CUDA(ctx, cudaMemcpyAsync(wb->stats_backup, p.w.stats, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = run_wave(n_items); if (rc) return rc;
+    if (plan.recursive) {
+      unsigned long long over = 0;
+      RT_CUDA(ctx, cudaMemcpyAsync(&over, p.w.stats + S_OVERFLOW, sizeof(over), cudaMemcpyDeviceToHost, ctx->stream));
+      RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (over) {
+        RT_CUDA(ctx, cudaMemcpyAsync(p.w.stats, wb->stats_backup, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_explicit ? c.an < 2 : (c.sn < 2 && c.an < 2))
+          return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed on a minimal wave; raise wave_paths or lower the light sample counts");
+        Chunk lo = c, hi = c;
+        if (!d_explicit && c.sn >= 2) { lo.sn = c.sn / 2; hi.s0 = c.s0 + lo.sn; hi.sn = c.sn - lo.sn; }
+        else { lo.an = c.an / 2; hi.a0 = c.a0 + lo.an; hi.an = c.an - lo.an; }
+        work.push_back(hi); work.push_back(lo);
+        splits++;
+        continue;
       }
     }
+    if (d_explicit) RT_LAUNCH(K_OTHER, launch_li_out(p.w.L, fp.ao_div, n_items, d_li_out + 3 * c.a0, ctx->stream));
+    else RT_LAUNCH(K_OTHER, launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream));
   }
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
   RT_CUDA(ctx, cudaGetLastError());
   unsigned long long hs[S_COUNT];
   RT_CUDA(ctx, cudaMemcpy(hs, p.w.stats, sizeof(hs), cudaMemcpyDeviceToHost));
-  if (hs[S_OVERFLOW]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; lower wave_paths or the light sample counts");
+  (void)splits;
+  if (hs[S_OVERFLOW]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; raise wave_paths or lower the light sample counts");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->camera_rays = hs[S_CAMERA]; stats->regular_rays = hs[S_REGULAR]; stats->shadow_rays = hs[S_SHADOW];

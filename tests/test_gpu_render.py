@@ -111,6 +111,24 @@ def test_filters_crop_and_wave_splitting(dev):
     assert np.allclose(imgs[0], imgs[2], rtol=1e-5, atol=1e-6)
 
 
+def test_recursive_wave_overflow_splits(dev):
+    """Whitted / DirectLighting waves are sized for the expected growth of the ray tree; a wave that overflows its queues
+    is discarded and split.  A tiny wave_paths forces overflows: image and counters must equal the roomy render's."""
+    from rustracer_b200 import Scene, scenes
+    for integ in ('Integrator "whitted" "integer maxdepth" [5]', 'Integrator "directlighting" "string strategy" "all" "integer maxdepth" [5]'):
+        sc = Scene.from_string(scenes.balls(xres=96, yres=64, spp=4, integrator=integ))
+        dev.upload(sc)
+        rd = sc.render_desc()
+        st0 = dev.render(rd)
+        img0 = dev.resolve_film()
+        rd.wave_paths = 1500
+        st1 = dev.render(rd)
+        img1 = dev.resolve_film()
+        assert st1.waves > st0.waves
+        assert (st1.camera_rays, st1.regular_rays, st1.shadow_rays) == (st0.camera_rays, st0.regular_rays, st0.shadow_rays)
+        assert np.allclose(img0, img1, rtol=2e-5, atol=1e-6)
+
+
 def test_sample_ranges_accumulate(dev):
     """sample_begin / sample_end + clear_film: rendering [0,4) then [4,8) without clearing equals [0,8) (the multi-GPU
     sample-index partition and the bench's step structure rely on this)."""
