@@ -1,9 +1,10 @@
 #!/bin/bash
 # Build the in-tree native libraries (librthost.so: g++; librtgpu.so: nvcc for sm_100a).  Called by __graft_entry__.build().
-#   ./build_native.sh [host|device]     RT_NVCC_EXTRA="-Xptxas -v" adds flags
+#   ./build_native.sh [host|device]     RT_NVCC_EXTRA="-Xptxas -v" adds flags; RT_LIB_VARIANT=_x builds librtgpu_x.so (tuning sweeps)
 set -e
 cd "$(dirname "$0")"
-mkdir -p rustracer_b200/lib build/obj
+OBJ=build/obj${RT_LIB_VARIANT}
+mkdir -p rustracer_b200/lib $OBJ
 NVFLAGS="-std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC -Iinclude $RT_NVCC_EXTRA"
 D=rustracer_b200/csrc/device
 if [ "$1" != "device" ]; then
@@ -12,15 +13,15 @@ fi
 if [ "$1" != "host" ]; then
   pids=()
   for tu in api render tu_trace tu_rec; do
-    nvcc $NVFLAGS -c $D/$tu.cu -o build/obj/$tu.o > build/obj/$tu.log 2>&1 & pids+=($!)
+    nvcc $NVFLAGS -c $D/$tu.cu -o $OBJ/$tu.o > $OBJ/$tu.log 2>&1 & pids+=($!)
   done
   for m in 0 1 2 3 4 5; do
-    nvcc $NVFLAGS -DRT_PATH_MAT=$m -c $D/tu_path.cu -o build/obj/tu_path_$m.o > build/obj/tu_path_$m.log 2>&1 & pids+=($!)
+    nvcc $NVFLAGS -DRT_PATH_MAT=$m -c $D/tu_path.cu -o $OBJ/tu_path_$m.o > $OBJ/tu_path_$m.log 2>&1 & pids+=($!)
   done
   fail=0
   for p in "${pids[@]}"; do wait $p || fail=1; done
-  cat build/obj/*.log
+  cat $OBJ/*.log
   [ $fail -eq 0 ] || { echo "nvcc failed"; exit 1; }
-  nvcc -shared -o rustracer_b200/lib/librtgpu.so build/obj/*.o -lcudart
+  nvcc -shared -o rustracer_b200/lib/librtgpu${RT_LIB_VARIANT}.so $OBJ/*.o -lcudart
 fi
 wait

@@ -17,7 +17,9 @@ def load(name):
     """name: 'rthost' | 'rtgpu'.  Raises NativeLibraryMissing with the build hint if the .so is absent."""
     if name in _cache:
         return _cache[name]
-    path = os.path.join(LIB_DIR, f"lib{name}.so")
+    # RT_LIB_VARIANT selects a differently-tuned build of the same sources (tools/engine_sweep.sh); never a fallback
+    variant = os.environ.get("RT_LIB_VARIANT", "") if name == "rtgpu" else ""
+    path = os.path.join(LIB_DIR, f"lib{name}{variant}.so")
     if not os.path.exists(path):
         raise NativeLibraryMissing(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

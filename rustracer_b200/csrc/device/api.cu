@@ -107,8 +107,7 @@ struct BatchClosestPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(bool has, uint32_t, const HitRec& h) {
-    if (!has) return;
+  RT_DEV void commit(uint32_t, const HitRec& h) {
     HitRec o = h;
     o.slot = h.slot == kMiss ? kMiss : info[h.slot].x;                 // slot -> prim_number (bvh/mod.rs:92)
     hits[r] = o;
@@ -121,7 +120,7 @@ struct BatchAnyPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(bool has, uint32_t, const HitRec& h) { if (has) occluded[r] = h.slot != kMiss ? 1 : 0; }
+  RT_DEV void commit(uint32_t, const HitRec& h) { occluded[r] = h.slot != kMiss ? 1 : 0; }
 };
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_closest_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
                                                                HitRec* __restrict__ hits, uint32_t* cursor) {

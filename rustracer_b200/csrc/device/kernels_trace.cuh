@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
 }
 
 // ---- queue traversal ----------------------------------------------------------------------------------------
-// Persistent warps pull 32-entry packets from the queue with an atomic cursor.  CLASSIFY appends each path to the
-// queue of its hit material (or the miss queue) for the material-sorted shade kernels.
+// Persistent warps pull 32-entry packets from the queue with an atomic cursor (validation / counting walk; the
+// production path is the engine below).  Material classification is k_classify's job.
 // STATS variants also count BVH nodes visited / primitives tested (the N and T of the roofline's bytes per ray).
 RT_DEV void flush_trav_stats(const RenderParams& p, const TravStats& st, int s_nodes, int s_prims) {
   unsigned long long nn = st.nodes, np = st.prims;
@@ -67,7 +67,7 @@ RT_DEV void flush_trav_stats(const RenderParams& p, const TravStats& st, int s_n
   if (lane_id() == 0) { atomicAdd(&p.w.stats[s_nodes], nn); atomicAdd(&p.w.stats[s_prims], np); }
 }
 
-template <bool CLASSIFY, bool STATS>
+template <bool STATS>
 __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                         const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
   const uint32_t n = p.w.counters[count_idx];
@@ -76,29 +76,12 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const flo
     const uint32_t base = warp_fetch(&p.w.counters[C_CUR_CLOSEST]);
     if (base >= n) break;
     const uint32_t i = base + lane_id();
-    const bool act = i < n;
-    uint32_t slot = 0; int q = -1;
-    if (act) {
-      slot = list ? list[i] : i;
+    if (i < n) {
+      const uint32_t slot = list ? list[i] : i;
       Ray ray = load_ray(ray_o, ray_d, slot, nullptr);
       HitRec h;
       bvh_traverse<false, STATS>(p.sc, ray, h, &st);
       hits[slot] = h;
-      if (CLASSIFY) {
-        if (h.slot == kMiss) q = Q_MISS;
-        else {
-          const uint32_t mrow = p.sc.info[h.slot].y;
-          const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
-          q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
-        }
-      }
-    }
-    if (CLASSIFY) {
-#pragma unroll
-      for (int k = 0; k < Q_COUNT; k++) {
-        const uint32_t pos = warp_append(&p.w.counters[C_MATQ0 + k], act && q == k);
-        if (act && q == k) p.w.matq[k][pos] = slot;
-      }
     }
   }
   if (STATS) flush_trav_stats(p, st, S_NODES_CLOSEST, S_PRIMS_CLOSEST);
@@ -176,38 +159,43 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
 }
 
 // ---- the same three kernels on the persistent while-while engine (trace_engine.cuh): the production path ------------
-template <bool CLASSIFY>
 struct ClosestPolicy {
-  const RenderParams& p; const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t slot;
-  RT_DEV ClosestPolicy(const RenderParams& p_, const float4* o, const float4* d, const uint32_t* l, HitRec* h) : p(p_), ray_o(o), ray_d(d), list(l), hits(h), slot(0) {}
+  const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t slot;
+  RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h) : ray_o(o), ray_d(d), list(l), hits(h), slot(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
-  RT_DEV void commit(bool has, uint32_t, const HitRec& h) {
-    int q = -1;
-    if (has) {
-      hits[slot] = h;
-      if (CLASSIFY) {
-        if (h.slot == kMiss) q = Q_MISS;
-        else {
-          const uint32_t mrow = p.sc.info[h.slot].y;
-          const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
-          q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
-        }
-      }
-    }
-    if (CLASSIFY) {
-#pragma unroll
-      for (int k = 0; k < Q_COUNT; k++) {
-        const uint32_t pos = warp_append(&p.w.counters[C_MATQ0 + k], has && q == k);
-        if (has && q == k) p.w.matq[k][pos] = slot;
-      }
-    }
-  }
+  RT_DEV void commit(uint32_t, const HitRec& h) { hits[slot] = h; }
 };
-template <bool CLASSIFY>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                                const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
-  ClosestPolicy<CLASSIFY> pol(p, ray_o, ray_d, list, hits);
+  ClosestPolicy pol(ray_o, ray_d, list, hits);
   trace_engine<false>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
+}
+
+// Material classification of the traced paths: appends each path to the queue of its hit material (or the miss queue)
+// for the material-sorted shade kernels.  A streaming pass over the live list at full lane occupancy (one atomic per
+// distinct class and warp via match_any) instead of seven ballot rounds inside every refill of the traversal engine.
+__global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const HitRec* __restrict__ hits) {
+  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t lane = lane_id(), lane_lt = (1u << lane) - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+    int q = -1; uint32_t slot = 0;
+    if (i < n) {
+      slot = list ? list[i] : i;
+      const uint32_t hslot = hits[slot].slot;
+      if (hslot == kMiss) q = Q_MISS;
+      else {
+        const uint32_t mrow = p.sc.info[hslot].y;
+        const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+        q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, q);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (q >= 0 && (int)lane == leader) base = atomicAdd(&p.w.counters[C_MATQ0 + q], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (q >= 0) p.w.matq[q][base + (uint32_t)__popc(peers & lane_lt)] = slot;
+  }
 }
 
 template <bool ATOMIC>
@@ -215,8 +203,8 @@ struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;
   RT_DEV ShadowPolicy(const RenderParams& p_, const AnyQueue& a) : p(p_), aq(a), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
-  RT_DEV void commit(bool has, uint32_t idx, const HitRec& h) {
-    if (!has || h.slot != kMiss) return;
+  RT_DEV void commit(uint32_t idx, const HitRec& h) {
+    if (h.slot != kMiss) return;
     const float4 c = aq.c[idx];
     float4* L = &p.w.L[sample];
     if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
@@ -235,8 +223,7 @@ struct MisPolicy {
   const RenderParams& p; uint32_t sample;
   RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
-  RT_DEV void commit(bool has, uint32_t idx, const HitRec& h) {
-    if (!has) return;
+  RT_DEV void commit(uint32_t idx, const HitRec& h) {
     const float4 c = p.w.mi_c[idx];
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];

@@ -8,8 +8,9 @@ enum { TRACE_ENGINE = 0, TRACE_SIMPLE = 1, TRACE_COUNTING = 2 };
 
 void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t n, float4* rays, cudaStream_t s);
 void launch_raygen(const RenderParams& p, cudaStream_t s);
-void launch_trace_closest(bool classify, int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
+void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
                           HitRec* hits, unsigned blocks, cudaStream_t s);
+void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, unsigned blocks, cudaStream_t s);
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s);
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s);
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);

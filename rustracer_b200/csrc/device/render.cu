@@ -295,7 +295,8 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
       for (uint32_t b = 0; b < rounds; b++) {
         const int in = (int)(b & 1u);
-        RT_LAUNCH(K_CLOSEST, launch_trace_closest(true, tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_SHADE, launch_classify(p, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks / 2, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
         if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));
@@ -314,7 +315,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
         const int par = (int)(lvl & 1u);
-        RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
         RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, ctx->stream));
@@ -322,7 +323,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream));
       }
     } else {
-      RT_LAUNCH(K_CLOSEST, launch_trace_closest(false, tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
+      RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
       RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));
       if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
       RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, ctx->stream));

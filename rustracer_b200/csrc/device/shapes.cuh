@@ -89,6 +89,12 @@ RT_DEV bool tri_hit_test(V3 p0, V3 p1, V3 p2, const Ray& ray, float& b0, float& 
 struct TriRay {
   V3 o; int kx, ky, kz; float sx, sy, sz;
 };
+// Vector3::permute(kx, ky, kz) for the watertight test's cyclic choice kx = kz + 1, ky = kx + 1 (mesh.rs:229-238): a
+// rotation of the components selected by two predicates (six selects per vector instead of three dynamic index chains).
+RT_DEV V3 permute_cyclic(V3 v, int kz) {
+  const bool r1 = kz == 0, r2 = kz == 1;
+  return v3(r1 ? v.y : (r2 ? v.z : v.x), r1 ? v.z : (r2 ? v.x : v.y), r1 ? v.x : (r2 ? v.y : v.z));
+}
 RT_DEV TriRay make_tri_ray(const Ray& ray) {
   TriRay tr; tr.o = ray.o;
   tr.kz = max_dimension(vabs(ray.d));
@@ -100,7 +106,7 @@ RT_DEV TriRay make_tri_ray(const Ray& ray) {
 }
 RT_DEV bool tri_hit_test_pre(const TriRay& tr, float t_max, V3 p0, V3 p1, V3 p2, float& b0, float& b1, float& b2, float& t) {
   V3 p0t = p0 - tr.o, p1t = p1 - tr.o, p2t = p2 - tr.o;
-  p0t = permute(p0t, tr.kx, tr.ky, tr.kz); p1t = permute(p1t, tr.kx, tr.ky, tr.kz); p2t = permute(p2t, tr.kx, tr.ky, tr.kz);
+  p0t = permute_cyclic(p0t, tr.kz); p1t = permute_cyclic(p1t, tr.kz); p2t = permute_cyclic(p2t, tr.kz);
   p0t.x += tr.sx * p0t.z; p0t.y += tr.sy * p0t.z;
   p1t.x += tr.sx * p1t.z; p1t.y += tr.sy * p1t.z;
   p2t.x += tr.sx * p2t.z; p2t.y += tr.sy * p2t.z;

@@ -10,10 +10,13 @@
 //     depends on t_max only through the final `tmin < t_max`).
 //   * scheduled while-while: each round the warp runs ONE node step for the lanes standing on an interior node, as long
 //     as at least `tune_node_threshold` lanes want one; otherwise it serves the lanes standing on a leaf (all primitive
-//     tests of that leaf).  Lanes never wait for the slowest lane's whole descent (the plain while-while measured 9 of
-//     32 lanes active: the node loop lasted until the last lane found its leaf).
-//   * persistent lanes: a lane whose ray is finished commits its result and pulls the next ray from the queue's atomic
-//     cursor as soon as enough lanes are idle (ballot + popc aggregated), instead of waiting for the slowest ray.
+//     tests of that leaf).  Lanes never wait for the slowest lane's whole descent.
+//   * persistent lanes: a lane whose ray is finished pulls the next ray from the queue's atomic cursor as soon as
+//     `tune_refill_threshold` lanes are idle (ballot + popc aggregated).  A refill is cheap on purpose — the policy's
+//     commit is a plain store executed by the finished lanes only, and everything that needs the whole warp (material
+//     classification) lives in its own streaming kernel (k_classify) — so the threshold can be low and few lanes idle.
+//   * the lane state is encoded in `cur` (interior ref / leaf ref / kDoneRef), two ballots per round (profiles/r01c: the
+//     six-ballot version spent 20 % of its issue slots on scheduling).
 #pragma once
 #include "traverse.cuh"
 
@@ -21,6 +24,9 @@ namespace rt {
 
 #ifndef RT_ENGINE_MIN_BLOCKS
 #define RT_ENGINE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the engine kernels are compiled for (register cap 64)
+#endif
+#ifndef RT_ENGINE_SMEM_DEPTH
+#define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
 #endif
 RT_DEV uint32_t lane_id_() { return threadIdx.x & 31u; }
 constexpr uint32_t kLeafBit = 0x80000000u;
@@ -44,99 +50,122 @@ RT_DEV bool slab_interval(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bool 
   return tmin < t_max && tmax > 0.0f;
 }
 
-// Policy: RT_DEV void load(uint32_t idx, Ray& ray)          — fetch queue entry idx (lane-private bookkeeping inside)
-//         RT_DEV void commit(bool has, uint32_t idx, const HitRec& h)   — called by ALL lanes of the warp, converged;
-//                                                               `has` marks lanes with a finished ray
+// Bounds3::intersect_p_fast, branch-free: the same comparisons on the same values (NaN compares false, exactly like
+// the early returns of the reference), evaluated for every lane so that the two boxes of a wide node interleave.
+RT_DEV bool slab_interval_bf(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_max, float& tmin_out) {
+  float tmin = ((nx ? hi.x : lo.x) - o.x) * inv_dir.x;
+  float tmax = ((nx ? lo.x : hi.x) - o.x) * inv_dir.x;
+  const float tymin = ((ny ? hi.y : lo.y) - o.y) * inv_dir.y;
+  const float tymax = ((ny ? lo.y : hi.y) - o.y) * inv_dir.y;
+  const bool r1 = (tmin > tymax) | (tymin > tmax);
+  tmin = tymin > tmin ? tymin : tmin;
+  tmax = tymax < tmax ? tymax : tmax;
+  const float tzmin = ((nz ? hi.z : lo.z) - o.z) * inv_dir.z;
+  const float tzmax = ((nz ? lo.z : hi.z) - o.z) * inv_dir.z;
+  const bool r2 = (tmin > tzmax) | (tzmin > tmax);
+  tmin = tzmin > tmin ? tzmin : tmin;
+  tmax = tzmax < tmax ? tzmax : tmax;
+  tmin_out = tmin;
+  return !r1 & !r2 & (tmin < t_max) & (tmax > 0.0f);
+}
+
+// Policy: RT_DEV void load(uint32_t idx, Ray& ray)             — fetch queue entry idx (lane-private bookkeeping inside)
+//         RT_DEV void commit(uint32_t idx, const HitRec& h)    — called by the lanes holding a finished ray (divergent)
 template <bool ANY, class Policy>
 RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy& pol) {
-  enum { NEED = 0, ACTIVE = 1, FINISHED = 2, EXHAUSTED = 3 };
   const unsigned FULL = 0xffffffffu;
   const float4* __restrict__ wide = sc.wide;
   const float4* __restrict__ geom = sc.geom;
-  int st = NEED;
-  uint32_t idx = 0, cur = kDoneRef;
-  Ray ray; V3 inv_dir = v3(0, 0, 0); bool nx = false, ny = false, nz = false;
+  const uint32_t lane = lane_id_(), lane_lt = (1u << lane) - 1u;
+  uint32_t idx = 0, cur = kDoneRef;         // cur: interior ref (top bit clear) | leaf ref (kLeafBit | slot) | kDoneRef (no ray in flight)
+  bool pending = false;                     // a finished ray whose result is not committed yet
+  Ray ray = make_ray(v3(0, 0, 0), v3(0, 0, 1), 0.0f);
+  V3 inv_dir = v3(0, 0, 0); bool nx = false, ny = false, nz = false;
   TriRay tr; tr.o = v3(0, 0, 0); tr.kx = 0; tr.ky = 1; tr.kz = 2; tr.sx = tr.sy = tr.sz = 0.0f;
-  ray = make_ray(v3(0, 0, 0), v3(0, 0, 1), 0.0f);
   HitRec hit; hit.t = inf_f(); hit.slot = kMiss; hit.b1 = hit.b2 = 0.0f;
-  uint2 stack[kStackSize];
+  // Traversal stack (64 entries, bvh/mod.rs:372): the bottom RT_ENGINE_SMEM_DEPTH entries of every lane live in shared
+  // memory as [entry][thread] (conflict-free, ~25-cycle pops, no L1 traffic: profiles/r01c-v2a showed more local-memory
+  // sectors than global ones and 19 % of the stall samples on the pop), the rarely used rest in local memory.
+  __shared__ uint2 s_stack[RT_ENGINE_SMEM_DEPTH][128];
+  uint2 stack_l[kStackSize - RT_ENGINE_SMEM_DEPTH];
+  const uint32_t tid = threadIdx.x;
   int sp = 0;
-  bool queue_empty = false;
+  bool queue_empty = n == 0;
+  uint32_t negmask = 0;                     // bit k = dir_is_neg[k]
   const int node_threshold = sc.tune_node_threshold, refill_threshold = sc.tune_refill_threshold;
 
+  // next subtree whose entry distance is still in front of the hit (the reference's test at visit time), or finished
+#define RT_ENGINE_POP() do { \
+    cur = kDoneRef; \
+    while (sp > 0) { \
+      --sp; \
+      const uint2 e_ = sp < RT_ENGINE_SMEM_DEPTH ? s_stack[sp][tid] : stack_l[sp - RT_ENGINE_SMEM_DEPTH]; \
+      if (ANY || __uint_as_float(e_.y) < ray.t_max) { cur = e_.x; break; } } \
+    pending = cur == kDoneRef; } while (0)
+
   while (true) {
-    // ---- commit finished rays and pull new ones ------------------------------------------------------------
-    const unsigned waiting = __ballot_sync(FULL, st == NEED || st == FINISHED);
-    const unsigned active = __ballot_sync(FULL, st == ACTIVE);
-    if (active == 0 || __popc(waiting) >= refill_threshold) {
-      if (waiting == 0) break;                                         // nothing active, nothing to commit or fetch
-      pol.commit(st == FINISHED, idx, hit);
-      if (st == FINISHED) st = NEED;
-      if (!queue_empty) {
-        const bool want = st == NEED;
-        const unsigned wmask = __ballot_sync(FULL, want);
-        uint32_t base = 0;
-        const int leader = __ffs(wmask) - 1;
-        if ((int)lane_id_() == leader) base = atomicAdd(cursor, (uint32_t)__popc(wmask));
-        base = __shfl_sync(FULL, base, leader);
-        if (want) {
-          idx = base + (uint32_t)__popc(wmask & ((1u << lane_id_()) - 1u));
-          if (idx < n) {
-            pol.load(idx, ray);
-            inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);                    // bvh/mod.rs:375-380
-            nx = inv_dir.x < 0.0f; ny = inv_dir.y < 0.0f; nz = inv_dir.z < 0.0f;
-            tr = make_tri_ray(ray);
-            hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
-            sp = 0;
-            st = ACTIVE;
-            // root: the reference tests the root's own bounds first
-            float t0;
-            const float4 rlo = make_float4(sc.world_lo[0], sc.world_lo[1], sc.world_lo[2], 0.0f);
-            const float4 rhi = make_float4(sc.world_hi[0], sc.world_hi[1], sc.world_hi[2], 0.0f);
-            cur = (sc.n_nodes > 0 && slab_interval(rlo, rhi, ray.o, inv_dir, nx, ny, nz, ray.t_max, t0)) ? sc.root_ref : kDoneRef;
-          }
+    const unsigned m_n = __ballot_sync(FULL, !(cur & kLeafBit));
+    const unsigned m_l = __ballot_sync(FULL, (cur & kLeafBit) != 0u && cur != kDoneRef);
+    const unsigned busy = m_n | m_l;
+    if (busy == 0u || (!queue_empty && 32 - __popc(busy) >= refill_threshold)) {
+      // ---- commit finished rays and pull new ones ----------------------------------------------------------
+      if (pending) { pol.commit(idx, hit); pending = false; }
+      if (queue_empty) break;                                          // busy == 0 and nothing left to fetch
+      const unsigned wmask = ~busy;
+      const int leader = __ffs(wmask) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(wmask));
+      base = __shfl_sync(FULL, base, leader);
+      if ((wmask >> lane) & 1u) {
+        idx = base + (uint32_t)__popc(wmask & lane_lt);
+        if (idx < n) {
+          pol.load(idx, ray);
+          inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);                      // bvh/mod.rs:375-380
+          nx = inv_dir.x < 0.0f; ny = inv_dir.y < 0.0f; nz = inv_dir.z < 0.0f;
+          negmask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
+          tr = make_tri_ray(ray);
+          hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
+          sp = 0;
+          // root: the reference tests the root's own bounds first
+          float t0;
+          const float4 rlo = make_float4(sc.world_lo[0], sc.world_lo[1], sc.world_lo[2], 0.0f);
+          const float4 rhi = make_float4(sc.world_hi[0], sc.world_hi[1], sc.world_hi[2], 0.0f);
+          const bool in = sc.n_nodes > 0 && slab_interval(rlo, rhi, ray.o, inv_dir, nx, ny, nz, ray.t_max, t0);
+          cur = in ? sc.root_ref : kDoneRef;
+          pending = !in;                                               // a ray that misses the world is finished: commit the miss
         }
-        if (__ballot_sync(FULL, want && idx >= n)) queue_empty = true;  // the cursor ran past the end
       }
-      if (st == NEED) st = EXHAUSTED;
-      if (__ballot_sync(FULL, st == ACTIVE) == 0) {
-        if (queue_empty) break;
-        continue;
-      }
+      if (base + (uint32_t)__popc(wmask) >= n) queue_empty = true;     // warp-uniform: the cursor ran past the end
+      continue;
     }
 
     // ---- schedule: node steps while enough lanes want one, otherwise serve the lanes standing on a leaf ---------
-    const bool is_n = st == ACTIVE && cur != kDoneRef && !(cur & kLeafBit);
-    const bool is_l = st == ACTIVE && cur != kDoneRef && (cur & kLeafBit);
-    const unsigned m_n = __ballot_sync(FULL, is_n), m_l = __ballot_sync(FULL, is_l);
-    if (m_l == 0 || __popc(m_n) >= node_threshold) {
+    if (m_l == 0u || __popc(m_n) >= node_threshold) {
       // ---- node step: one wide node = both children's slab tests ----------------------------------------------
-      if (is_n) {
+      if (!(cur & kLeafBit)) {
         const float4 a = __ldg(&wide[4 * (size_t)cur]);
         const float4 b = __ldg(&wide[4 * (size_t)cur + 1]);
         const float4 c = __ldg(&wide[4 * (size_t)cur + 2]);
         const float4 d = __ldg(&wide[4 * (size_t)cur + 3]);
         float tl, trr;
-        const bool hl = slab_interval(a, b, ray.o, inv_dir, nx, ny, nz, ray.t_max, tl);
-        const bool hr = slab_interval(c, d, ray.o, inv_dir, nx, ny, nz, ray.t_max, trr);
+        const bool hl = slab_interval_bf(a, b, ray.o, inv_dir, nx, ny, nz, ray.t_max, tl);
+        const bool hr = slab_interval_bf(c, d, ray.o, inv_dir, nx, ny, nz, ray.t_max, trr);
         const uint32_t rl = __float_as_uint(a.w), rr = __float_as_uint(b.w), axis = __float_as_uint(c.w);
-        const bool neg = axis == 0 ? nx : (axis == 1 ? ny : nz);       // bvh/mod.rs:408-421: right child first when negative
+        const bool neg = ((negmask >> axis) & 1u) != 0u;               // bvh/mod.rs:408-421: right child first when negative
         const uint32_t first = neg ? rr : rl, second = neg ? rl : rr;
         const bool hfirst = neg ? hr : hl, hsecond = neg ? hl : hr;
         const float tsecond = neg ? tl : trr;
         if (hfirst) {
-          if (hsecond) stack[sp++] = make_uint2(second, __float_as_uint(tsecond));
+          if (hsecond) {
+            const uint2 e = make_uint2(second, __float_as_uint(tsecond));
+            if (sp < RT_ENGINE_SMEM_DEPTH) s_stack[sp][tid] = e; else stack_l[sp - RT_ENGINE_SMEM_DEPTH] = e;
+            sp++;
+          }
           cur = first;
         } else if (hsecond) cur = second;
-        else {
-          cur = kDoneRef;
-          while (sp > 0) {
-            const uint2 e = stack[--sp];
-            if (ANY || __uint_as_float(e.y) < ray.t_max) { cur = e.x; break; }   // the reference's test at visit time
-          }
-        }
+        else RT_ENGINE_POP();
       }
-    } else if (is_l) {
+    } else if ((cur & kLeafBit) != 0u && cur != kDoneRef) {
       // ---- leaf step: every primitive of the leaf, in slot order (bvh/mod.rs:392-396) ---------------------------
       uint32_t slot = cur & ~kLeafBit;
       bool last = false, done = false;
@@ -161,16 +190,11 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         }
         slot++;
       } while (!last);
-      cur = kDoneRef;
-      if (!done) {
-        while (sp > 0) {
-          const uint2 e = stack[--sp];
-          if (ANY || __uint_as_float(e.y) < ray.t_max) { cur = e.x; break; }
-        }
-      }
+      if (done) { cur = kDoneRef; pending = true; }
+      else RT_ENGINE_POP();
     }
-    if (st == ACTIVE && cur == kDoneRef) st = FINISHED;
   }
+#undef RT_ENGINE_POP
 }
 
 }  // namespace rt

@@ -10,18 +10,14 @@ void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t
 void launch_raygen(const RenderParams& p, cudaStream_t s) { k_raygen<<<(p.n_items + 255) / 256, 256, 0, s>>>(p); }
 // mode: TRACE_ENGINE = persistent while-while engine (production), TRACE_SIMPLE = one-thread-one-ray reference walk
 // (validation), TRACE_COUNTING = the reference walk that also counts nodes visited / primitives tested.
-void launch_trace_closest(bool classify, int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
+void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
                           HitRec* hits, unsigned blocks, cudaStream_t s) {
-  if (mode == TRACE_COUNTING) {
-    if (classify) k_trace_closest<true, true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-    else k_trace_closest<false, true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-  } else if (mode == TRACE_SIMPLE) {
-    if (classify) k_trace_closest<true, false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-    else k_trace_closest<false, false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-  } else {
-    if (classify) k_trace_closest_engine<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-    else k_trace_closest_engine<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-  }
+  if (mode == TRACE_COUNTING) k_trace_closest<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  else if (mode == TRACE_SIMPLE) k_trace_closest<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  else k_trace_closest_engine<<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+}
+void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, unsigned blocks, cudaStream_t s) {
+  k_classify<<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
 }
 // q: 0 = NEE shadow queue, 1 = queue of the MIS rays towards infinite lights (both any-hit)
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s) {

@@ -14,7 +14,12 @@ from rustracer_b200.device import Device
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--nt", default="8,12,16,20")
+    ap.add_argument("--rt", default="4,8,12,16")
     a = ap.parse_args()
+    NT = [int(x) for x in a.nt.split(",")]
+    RT = [int(x) for x in a.rt.split(",")]
+    print("variant:", os.environ.get("RT_LIB_VARIANT", "(default)"))
     dev = Device(0)
     tmp = tempfile.mkdtemp()
     sc = Scene.from_string(scenes.c3_scene(tmp, level=5), search_dir=tmp)
@@ -29,8 +34,8 @@ def main():
     dev.h2d(d_r, rays)
     dev.set_option("sort_rays", 0)
     print("node_thr refill | c3 random closest Mrays/s | c3 path 4spp ms (closest/any/shade)")
-    for nt in (12, 16, 20):
-        for rt in (8, 16, 24):
+    for nt in NT:
+        for rt in RT:
             dev.set_option("node_threshold", nt)
             dev.set_option("refill_threshold", rt)
             dev.intersect_device(d_r, n, d_o)
@@ -52,7 +57,7 @@ def main():
         dev.h2d(d_r, rays)
         for sort in (0, 1):
             dev.set_option("sort_rays", sort)
-            for nt in (12, 16, 20):
+            for nt in NT:
                 for rt in (8, 16):
                     dev.set_option("node_threshold", nt)
                     dev.set_option("refill_threshold", rt)
