@@ -15,7 +15,7 @@ if [ "$1" != "host" ]; then
   for tu in api render tu_trace tu_rec; do
     nvcc $NVFLAGS -c $D/$tu.cu -o $OBJ/$tu.o > $OBJ/$tu.log 2>&1 & pids+=($!)
   done
-  for m in 0 1 2 3 4 5; do
+  for m in 0 1 2 3 4 5 6; do
     nvcc $NVFLAGS -DRT_PATH_MAT=$m -c $D/tu_path.cu -o $OBJ/tu_path_$m.o > $OBJ/tu_path_$m.log 2>&1 & pids+=($!)
   done
   fail=0

@@ -71,10 +71,12 @@ typedef struct rt_light {
   int32_t shape;               /* RT_LIGHT_AREA: index into rt_scene.shapes */
 } rt_light;
 
-enum { RT_MAT_MATTE = 0, RT_MAT_PLASTIC = 1, RT_MAT_METAL = 2, RT_MAT_GLASS = 3, RT_MAT_MIRROR = 4, RT_MAT_NONE = 5 };
+enum { RT_MAT_MATTE = 0, RT_MAT_PLASTIC = 1, RT_MAT_METAL = 2, RT_MAT_GLASS = 3, RT_MAT_MIRROR = 4, RT_MAT_NONE = 5,
+       RT_MAT_UBER = 6, RT_MAT_SUBSTRATE = 7, RT_MAT_TRANSLUCENT = 8, RT_MAT_MIX = 9 };
 
 /* Material with every texture already evaluated to its constant (texture/constant.rs:10-39;
- * paramset.rs:406-443).  Field use per type follows material/{matte,plastic,metal,glass,mirror}.rs. */
+ * paramset.rs:406-443).  Field use per type follows material/{matte,plastic,metal,glass,mirror,uber,substrate,
+ * translucent,mixmat}.rs. */
 typedef struct rt_material {
   int32_t type;
   float kd[3];                 /* matte Kd (0.5) ; plastic Kd (0.25) */
@@ -87,8 +89,16 @@ typedef struct rt_material {
   float roughness;             /* plastic (0.1) ; metal (0.01) */
   float uroughness, vroughness;/* glass (0,0) ; metal optional */
   int32_t has_uroughness, has_vroughness; /* metal: whether "uroughness"/"vroughness" were given */
-  float eta;                   /* glass index (1.5) */
+  float eta;                   /* glass index (1.5) ; uber "eta" else "index" (1.5) */
   int32_t remap_roughness;
+  /* uber.rs:32-57: Kd Ks (0.25), Kr Kt (0), roughness (0.1), optional u/vroughness, eta, opacity (1)
+   * substrate.rs:23-38: Kd Ks (0.5), uroughness vroughness (0.1)
+   * translucent.rs:26-44: Kd Ks (0.25), reflect transmit (0.5), roughness (0.1)
+   * mixmat.rs:20-31: amount (0.5) and the two named materials (api.rs:1165-1176) as rows of rt_scene.materials */
+  float opacity[3];
+  float reflect[3], transmit[3];
+  float amount[3];
+  int32_t mix_a, mix_b;
 } rt_material;
 
 enum { RT_FILTER_BOX = 0, RT_FILTER_GAUSSIAN = 1, RT_FILTER_TRIANGLE = 2, RT_FILTER_MITCHELL = 3 };

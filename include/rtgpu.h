@@ -49,9 +49,26 @@ typedef struct rtgpu_quadric {
   uint32_t kind, flags, pad;
 } rtgpu_quadric;
 
-enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MAT_GLASS = 3, RTGPU_MAT_MIRROR = 4, RTGPU_MAT_NONE = 5 };
+enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MAT_GLASS = 3, RTGPU_MAT_MIRROR = 4, RTGPU_MAT_NONE = 5,
+       RTGPU_MAT_LOBES = 6 };   /* uber / substrate / translucent / mix: the host lists the lobes (rtgpu_lobe rows) */
+
+/* One BxDF of a material whose lobe list the host builds (constant textures make it a per-material constant):
+ * material/{uber,substrate,translucent,mixmat}.rs.  kind = RTGPU_LOBE_*. */
+enum { RTGPU_LOBE_LAMBERT_R = 0, RTGPU_LOBE_OREN_NAYAR = 1, RTGPU_LOBE_SPEC_REFL = 2, RTGPU_LOBE_SPEC_TRANS = 3, RTGPU_LOBE_FRESNEL_SPEC = 4,
+       RTGPU_LOBE_MICRO_REFL = 5, RTGPU_LOBE_MICRO_TRANS = 6, RTGPU_LOBE_LAMBERT_T = 7, RTGPU_LOBE_FRESNEL_BLEND = 8 };
+typedef struct rtgpu_lobe {
+  uint32_t kind;
+  uint32_t n_scales;           /* ScaledBxDF wrappers around the lobe (bsdf/bxdf.rs:48-71), innermost first; 0..2 */
+  float scale[2][3];
+  float r[3], t[3];            /* reflectance / transmittance ; FresnelBlend: rs in r, rd in t */
+  float on_a, on_b;            /* OrenNayar A, B */
+  uint32_t fr_kind;            /* 0 no-op, 1 dielectric, 2 conductor */
+  float fr_eta_i, fr_eta_t, c_eta_t[3], c_k[3];
+  float ax, ay;                /* TrowbridgeReitz alpha (after the optional remap) */
+  float eta_a, eta_b;
+} rtgpu_lobe;                  /* 112 B */
 /* Material constants after texture evaluation and after the host-side scalar prep the reference does with
- * libm at shading time (roughness_to_alpha: microfacet.rs:485-493; OrenNayar A/B: oren_nayar.rs:17-26). 96 B. */
+ * libm at shading time (roughness_to_alpha: microfacet.rs:485-493; OrenNayar A/B: oren_nayar.rs:17-26). 116 B. */
 typedef struct rtgpu_material {
   uint32_t type;
   float kd[3], ks[3], kr[3], kt[3], eta_rgb[3], k_rgb[3];
@@ -59,6 +76,10 @@ typedef struct rtgpu_material {
   float alpha_u, alpha_v;      /* after optional remap */
   float eta;                   /* glass index */
   uint32_t glass_specular;     /* uroughness == 0 && vroughness == 0 (glass.rs:68) */
+  /* RTGPU_MAT_LOBES: rows [lobe_first[a], +lobe_count[a]) of rtgpu_scene_desc.lobes, a = allow_multiple_lobes
+   * (path: 1, whitted / directlighting: 0 — only a glass child of a mix tells them apart); bsdf_eta = Bsdf::eta */
+  uint32_t lobe_first[2], lobe_count[2];
+  float bsdf_eta;
 } rtgpu_material;
 
 enum { RTGPU_LIGHT_POINT = 0, RTGPU_LIGHT_DISTANT = 1, RTGPU_LIGHT_INFINITE = 2, RTGPU_LIGHT_AREA = 3 };
@@ -95,6 +116,7 @@ typedef struct rtgpu_scene_desc {
   const float* tri_uv;         /* 6 per slot or NULL */
   uint32_t n_quadrics;  const rtgpu_quadric* quadrics;
   uint32_t n_materials; const rtgpu_material* materials;
+  uint32_t n_lobes;     const rtgpu_lobe* lobes;       /* lobe lists of the RTGPU_MAT_LOBES materials (may be 0 / NULL) */
   uint32_t n_lights;    const rtgpu_light* lights;
   uint32_t n_env_floats; const float* env_data;
   float world_lo[3], world_hi[3];  /* nodes[0].bounds */
@@ -136,6 +158,9 @@ typedef struct rtgpu_stats {
   uint64_t closest_launches, anyhit_launches;
   /* with option "count_traversal": BVH nodes visited / primitives tested by the closest-hit (incl. MIS) and any-hit rays */
   uint64_t nodes_closest, prims_closest, nodes_anyhit, prims_anyhit;
+  /* rays walked by the closest-hit kernels / by the any-hit kernels (MIS rays towards infinite lights are "regular" rays
+   * for the reference's counters but are answered by an any-hit walk: they count here under anyhit_rays) */
+  uint64_t closest_rays, anyhit_rays;
 } rtgpu_stats;
 
 int rtgpu_create(int device, rtgpu_ctx** out);

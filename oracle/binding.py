@@ -74,6 +74,9 @@ def lib(native=False):
     l.orc_fr_dielectric.restype = C.c_float
     l.orc_roughness_to_alpha.argtypes = [C.c_float]
     l.orc_roughness_to_alpha.restype = C.c_float
+    l.orc_fresnel_blend_pdf.argtypes = [PF, PF, C.c_float, C.c_float]
+    l.orc_fresnel_blend_pdf.restype = C.c_float
+    l.orc_material_bsdf.argtypes = [C.c_void_p, C.c_int, C.c_int, PF, PF, PF, C.c_uint32, PF]
     l.orc_selftest.argtypes = [C.c_uint64, C.c_char_p, C.c_int]
     if not native:
         _lib = l
@@ -108,6 +111,17 @@ class OracleScene:
     @property
     def build_seconds(self):
         return self._l.orc_scene_build_seconds(self._h)
+
+    def material_bsdf(self, row, wo, wi, u, allow_multiple_lobes=True, flags=31):
+        """The Bsdf material `row` builds on a canonical surface (n = +z, dpdu = +x), evaluated for world directions.
+        Returns dict(f, pdf, sf, swi, spdf, sflags, n_lobes, eta)."""
+        wo, wi, u = (np.ascontiguousarray(a, np.float32) for a in (wo, wi, u))
+        out = np.zeros(14, np.float32)
+        rc = self._l.orc_material_bsdf(self._h, row, 1 if allow_multiple_lobes else 0, _pf(wo), _pf(wi), _pf(u), flags, _pf(out))
+        if rc:
+            raise RuntimeError(f"orc_material_bsdf: {rc} {self._l.orc_scene_error(self._h)}")
+        return dict(f=out[0:3].copy(), pdf=float(out[3]), sf=out[4:7].copy(), swi=out[7:10].copy(), spdf=float(out[10]), sflags=int(out[11]),
+                    n_lobes=int(out[12]), eta=float(out[13]))
 
     def bvh(self):
         bounds = np.zeros((self.n_nodes, 6), np.float32)

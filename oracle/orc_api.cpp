@@ -286,6 +286,34 @@ void orc_counter_draws(int32_t x, int32_t y, uint64_t seed, uint32_t s, uint32_t
 }
 // fr_dielectric / TR microfacet helpers for BSDF unit parity
 float orc_fr_dielectric(float c, float ei, float et) { return fr_dielectric(c, ei, et); }
+
+// FresnelBlend::pdf for TrowbridgeReitz(ax, ay) (the reference's own property test: bsdf/fresnel.rs:427-436)
+float orc_fresnel_blend_pdf(const float* wo, const float* wi, float ax, float ay) {
+  Lobe l; l.kind = LOBE_FRESNEL_BLEND; l.r = Spectrum(1.0f); l.t = Spectrum(1.0f); l.dist.ax = ax; l.dist.ay = ay;
+  return l.pdf(V3(wo[0], wo[1], wo[2]), V3(wi[0], wi[1], wi[2]));
+}
+
+// The Bsdf a material row builds on a canonical surface (n = +z, dpdu = +x): f, pdf and sample_f for world directions.
+// out = { f.rgb, pdf, sampled f.rgb, sampled wi.xyz, sampled pdf, sampled flags, n_lobes, eta }  (14 floats)
+int orc_material_bsdf(orc_scene* s, int row, int allow_multiple_lobes, const float* wo, const float* wi, const float* u, uint32_t flags, float* out) {
+  if (row < 0 || (size_t)row >= s->scene.materials.size()) return -1;
+  SurfaceInteraction si;
+  si.hit = Interaction::make(V3(0, 0, 0), V3(0, 0, 0), V3(wo[0], wo[1], wo[2]), V3(0, 0, 1));
+  si.dpdu = V3(1, 0, 0); si.dpdv = V3(0, 1, 0);
+  si.shading.n = V3(0, 0, 1); si.shading.dpdu = V3(1, 0, 0); si.shading.dpdv = V3(0, 1, 0);
+  Bsdf b;
+  try {
+    if (!compute_scattering_functions(s->scene.materials.data(), s->scene.materials[row], si, allow_multiple_lobes != 0, b)) return -2;
+  } catch (const std::exception& e) { s->error = e.what(); return -3; }
+  V3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
+  Spectrum f = b.f(o, i, flags);
+  out[0] = f.r; out[1] = f.g; out[2] = f.b; out[3] = b.pdf(o, i, flags);
+  Spectrum sf; V3 swi; float spdf; uint32_t sampled;
+  b.sample_f(o, P2(u[0], u[1]), flags, sf, swi, spdf, sampled);
+  out[4] = sf.r; out[5] = sf.g; out[6] = sf.b; out[7] = swi.x; out[8] = swi.y; out[9] = swi.z; out[10] = spdf; out[11] = (float)sampled;
+  out[12] = (float)b.n; out[13] = b.eta;
+  return 0;
+}
 float orc_roughness_to_alpha(float r) { return TrowbridgeReitz::roughness_to_alpha(r); }
 
 // Restated reference property tests (rustracer-core/tests/efloat.rs:52-154, tests/shapes.rs:16-54,

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  BSDF, BxDFs, materials.
 // Follows /root/reference/rustracer-core/src/bsdf/*.rs and material/{matte,plastic,metal,glass,mirror}.rs.
 #pragma once
+#include <stdexcept>
 #include "orc_shapes.hpp"
 #include "../include/rt_scene.h"
 
@@ -142,7 +143,9 @@ struct TrowbridgeReitz {                                         // microfacet.r
   }
 };
 
-enum LobeKind { LOBE_LAMBERT_R, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS };
+enum LobeKind { LOBE_LAMBERT_R, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS,
+                LOBE_LAMBERT_T, LOBE_FRESNEL_BLEND };
+inline float pow5(float v) { return (v * v) * (v * v) * v; }                    // fresnel.rs:414-417
 
 struct Lobe {
   LobeKind kind;
@@ -151,20 +154,37 @@ struct Lobe {
   Fresnel fresnel;
   TrowbridgeReitz dist;
   float eta_a = 1, eta_b = 1;
+  // LOBE_FRESNEL_BLEND (fresnel.rs:335-412): rs in `r`, rd in `t`.
+  // ScaledBxDF wrappers of MixMaterial (bxdf.rs:48-71), innermost first: f and sample_f are scaled, get_type is the
+  // wrapped lobe's, and pdf() is NOT forwarded — it is the trait's default cosine pdf (bxdf.rs:38-44).
+  Spectrum scale[2]; int n_scales = 0;
   uint32_t type() const {
     switch (kind) {
       case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: return BSDF_DIFFUSE | BSDF_REFLECTION;
       case LOBE_SPEC_REFL: return BSDF_SPECULAR | BSDF_REFLECTION;
       case LOBE_SPEC_TRANS: return BSDF_SPECULAR | BSDF_TRANSMISSION;
       case LOBE_FRESNEL_SPEC: return BSDF_SPECULAR | BSDF_REFLECTION | BSDF_TRANSMISSION;
-      case LOBE_MICRO_REFL: return BSDF_REFLECTION | BSDF_GLOSSY;
+      case LOBE_MICRO_REFL: case LOBE_FRESNEL_BLEND: return BSDF_REFLECTION | BSDF_GLOSSY;
+      case LOBE_LAMBERT_T: return BSDF_DIFFUSE | BSDF_TRANSMISSION;           // lambertian.rs:43-45
       default: return BSDF_TRANSMISSION | BSDF_GLOSSY;
     }
   }
   bool matches(uint32_t flags) const { return (type() & flags) == type(); }   // bxdf.rs:29-31
-  Spectrum f(V3 wo, V3 wi) const {
+  Spectrum f_inner(V3 wo, V3 wi) const {
     switch (kind) {
       case LOBE_LAMBERT_R: return r * INV_PI;                                 // lambertian.rs:19-21
+      case LOBE_LAMBERT_T: return t * INV_PI;                                 // lambertian.rs:39-41
+      case LOBE_FRESNEL_BLEND: {                                              // fresnel.rs:358-375 (rs = r, rd = t)
+        Spectrum diffuse = (28.0f / (23.0f * PI)) * t * (Spectrum(1.0f) - r) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
+                           (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo)));
+        V3 wh = wi + wo;
+        if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spectrum(0.0f);
+        wh = normalize(wh);
+        float cwh = dot(wi, wh);
+        Spectrum schlick = r + pow5(1.0f - cwh) * (Spectrum(1.0f) - r);       // :352-354
+        Spectrum specular = dist.d(wh) / (4.0f * std::fabs(dot(wi, wh)) * fmax_(abs_cos_theta(wi), abs_cos_theta(wo))) * schlick;
+        return diffuse + specular;
+      }
       case LOBE_OREN_NAYAR: {                                                 // oren_nayar.rs:30-52
         float sti = sin_theta(wi), sto = sin_theta(wo);
         float max_cos = 0.0f;
@@ -203,10 +223,16 @@ struct Lobe {
       default: return Spectrum(0.0f);                                         // specular lobes: fresnel.rs:153-157 etc.
     }
   }
-  float pdf(V3 wo, V3 wi) const {
+  float pdf_inner(V3 wo, V3 wi) const {
     switch (kind) {
-      case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR:                              // bxdf.rs:38-44
+      case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T:         // bxdf.rs:38-44 (LambertianTransmission does not override it)
         return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI : 0.0f;
+      case LOBE_FRESNEL_BLEND: {                                              // fresnel.rs:377-385
+        if (!same_hemisphere(wo, wi)) return 0.0f;
+        V3 wh = normalize(wo + wi);
+        float pdf_wh = dist.pdf(wo, wh);
+        return 0.5f * (abs_cos_theta(wi) * INV_PI + pdf_wh / (4.0f * dot(wo, wh)));
+      }
       case LOBE_MICRO_REFL: {                                                 // microfacet.rs:87-94
         if (!same_hemisphere(wo, wi)) return 0.0f;
         V3 wh = normalize(wo + wi);
@@ -224,12 +250,27 @@ struct Lobe {
     }
   }
   // returns sampled type (bxdf.rs:18-25: default returns EMPTY — Q17)
-  void sample_f(V3 wo, P2 u, Spectrum& f_out, V3& wi, float& pdf_out, uint32_t& sampled) const {
+  void sample_f_inner(V3 wo, P2 u, Spectrum& f_out, V3& wi, float& pdf_out, uint32_t& sampled) const {
     switch (kind) {
-      case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
+      case LOBE_FRESNEL_BLEND: {                                              // fresnel.rs:387-407
+        sampled = type();
+        if (u.x < 0.5f) {
+          u.x = fmin_(2.0f * u.x, ONE_MINUS_EPSILON);
+          wi = cosine_sample_hemisphere(u);
+          if (wo.z < 0.0f) wi.z *= -1.0f;
+        } else {
+          u.x = fmin_(2.0f * (u.x - 0.5f), ONE_MINUS_EPSILON);
+          V3 wh = dist.sample_wh(wo, u);
+          wi = reflect(wo, wh);
+          if (!same_hemisphere(wo, wi)) { f_out = Spectrum(0.0f); pdf_out = 0.0f; return; }
+        }
+        f_out = f_inner(wo, wi); pdf_out = pdf_inner(wo, wi);
+        return;
+      }
+      case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T: {       // bxdf.rs:18-25 (same hemisphere as wo, also for LambertianTransmission)
         wi = cosine_sample_hemisphere(u);
         if (wo.z < 0.0f) wi.z *= -1.0f;
-        pdf_out = pdf(wo, wi); f_out = f(wo, wi); sampled = 0;
+        pdf_out = pdf_inner(wo, wi); f_out = f_inner(wo, wi); sampled = 0;
         return;
       }
       case LOBE_SPEC_REFL: {                                                  // fresnel.rs:159-164
@@ -275,7 +316,7 @@ struct Lobe {
         wi = reflect(wo, wh);
         if (!same_hemisphere(wo, wi)) { f_out = Spectrum(0.0f); wi = V3(0, 0, 0); pdf_out = 0.0f; return; }
         pdf_out = dist.pdf(wo, wh) / (4.0f * dot(wo, wh));
-        f_out = f(wo, wi);
+        f_out = f_inner(wo, wi);
         return;
       }
       default: {                                                              // LOBE_MICRO_TRANS microfacet.rs:177-205
@@ -284,11 +325,21 @@ struct Lobe {
         V3 wh = dist.sample_wh(wo, u);
         float eta = cos_theta(wo) > 0.0f ? eta_a / eta_b : eta_b / eta_a;
         V3 w;
-        if (refract(wo, wh, eta, w)) { wi = w; pdf_out = pdf(wo, wi); f_out = f(wo, wi); }
+        if (refract(wo, wh, eta, w)) { wi = w; pdf_out = pdf_inner(wo, wi); f_out = f_inner(wo, wi); }
         else { f_out = Spectrum(0.0f); wi = V3(0, 0, 0); pdf_out = 0.0f; }
         return;
       }
     }
+  }
+  // ---- the BxDF interface as Bsdf sees it: the lobe itself, or the lobe behind its ScaledBxDF wrappers (bxdf.rs:48-71) ----
+  Spectrum f(V3 wo, V3 wi) const { Spectrum v = f_inner(wo, wi); for (int i = 0; i < n_scales; i++) v = v * scale[i]; return v; }
+  float pdf(V3 wo, V3 wi) const {
+    if (n_scales > 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI : 0.0f;
+    return pdf_inner(wo, wi);
+  }
+  void sample_f(V3 wo, P2 u, Spectrum& f_out, V3& wi, float& pdf_out, uint32_t& sampled) const {
+    sample_f_inner(wo, u, f_out, wi, pdf_out, sampled);
+    for (int i = 0; i < n_scales; i++) f_out = f_out * scale[i];
   }
 };
 
@@ -355,7 +406,8 @@ struct Bsdf {                                                    // bsdf/mod.rs:
 };
 
 // material/*.rs with every texture constant.  `allow_multiple_lobes`: path=true (path.rs:145), whitted/direct=false.
-inline bool compute_scattering_functions(const rt_material& mt, const SurfaceInteraction& si, bool allow_multiple_lobes, Bsdf& bsdf) {
+// `table`: the scene's material rows (MixMaterial refers to its two children by row).
+inline bool compute_scattering_functions(const rt_material* table, const rt_material& mt, const SurfaceInteraction& si, bool allow_multiple_lobes, Bsdf& bsdf) {
   bsdf.n = 0;
   auto S = [](const float* c) { return Spectrum(c[0], c[1], c[2]); };
   switch (mt.type) {
@@ -430,6 +482,96 @@ inline bool compute_scattering_functions(const rt_material& mt, const SurfaceInt
       Spectrum R = S(mt.kr).clamp0();
       bsdf.init(si, 1.0f);
       if (!R.is_black()) { Lobe l; l.kind = LOBE_SPEC_REFL; l.r = R; l.fresnel.kind = 0; bsdf.add(l); }
+      return true;
+    }
+    case RT_MAT_UBER: {                                           // uber.rs:62-125
+      float e = mt.eta;
+      Spectrum op = S(mt.opacity).clamp0();
+      Spectrum t = (Spectrum(1.0f) - op).clamp0();
+      float eta = e;
+      if (!t.is_black()) {
+        eta = 1.0f;
+        Lobe l; l.kind = LOBE_SPEC_TRANS; l.t = t; l.eta_a = 1.0f; l.eta_b = 1.0f; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = 1.0f;
+        bsdf.add(l);
+      }
+      Spectrum kd = op * S(mt.kd).clamp0();
+      if (!kd.is_black()) { Lobe l; l.kind = LOBE_LAMBERT_R; l.r = kd; bsdf.add(l); }
+      Spectrum ks = op * S(mt.ks).clamp0();
+      if (!ks.is_black()) {
+        float roughu = mt.has_uroughness ? mt.uroughness : mt.roughness, roughv = mt.has_vroughness ? mt.vroughness : mt.roughness;
+        if (mt.remap_roughness) { roughu = TrowbridgeReitz::roughness_to_alpha(roughu); roughv = TrowbridgeReitz::roughness_to_alpha(roughv); }
+        Lobe l; l.kind = LOBE_MICRO_REFL; l.r = ks; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = e; l.dist.ax = roughu; l.dist.ay = roughv;
+        bsdf.add(l);
+      }
+      Spectrum kr = op * S(mt.kr).clamp0();
+      if (!kr.is_black()) { Lobe l; l.kind = LOBE_SPEC_REFL; l.r = kr; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = e; bsdf.add(l); }
+      Spectrum kt = op * S(mt.kt).clamp0();
+      if (!kt.is_black()) {
+        Lobe l; l.kind = LOBE_SPEC_TRANS; l.t = kt; l.eta_a = 1.0f; l.eta_b = e; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = e;
+        bsdf.add(l);
+      }
+      bsdf.init(si, eta);
+      return true;
+    }
+    case RT_MAT_SUBSTRATE: {                                      // substrate.rs:42-71
+      Spectrum d = S(mt.kd).clamp0(), sp = S(mt.ks).clamp0();
+      float roughu = mt.uroughness, roughv = mt.vroughness;
+      if (!d.is_black() || !sp.is_black()) {
+        if (mt.remap_roughness) { roughu = TrowbridgeReitz::roughness_to_alpha(roughu); roughv = TrowbridgeReitz::roughness_to_alpha(roughv); }
+        Lobe l; l.kind = LOBE_FRESNEL_BLEND; l.r = sp; l.t = d; l.dist.ax = roughu; l.dist.ay = roughv;
+        bsdf.add(l);
+      }
+      bsdf.init(si, 1.0f);
+      return true;
+    }
+    case RT_MAT_TRANSLUCENT: {                                    // translucent.rs:48-101
+      const float eta = 1.5f;
+      Spectrum r = S(mt.reflect).clamp0(), t = S(mt.transmit).clamp0();
+      if (!r.is_black() || !t.is_black()) {
+        Spectrum kd = S(mt.kd).clamp0();
+        if (!kd.is_black()) {
+          if (!r.is_black()) { Lobe l; l.kind = LOBE_LAMBERT_R; l.r = r * kd; bsdf.add(l); }
+          if (!t.is_black()) { Lobe l; l.kind = LOBE_LAMBERT_T; l.t = t * kd; bsdf.add(l); }
+        }
+        Spectrum ks = S(mt.ks).clamp0();
+        if (!ks.is_black() && (!r.is_black() || !t.is_black())) {
+          float rough = mt.roughness;
+          if (mt.remap_roughness) rough = TrowbridgeReitz::roughness_to_alpha(rough);
+          if (!r.is_black()) {
+            Lobe l; l.kind = LOBE_MICRO_REFL; l.r = r * ks; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = eta; l.dist.ax = rough; l.dist.ay = rough;
+            bsdf.add(l);
+          }
+          if (!t.is_black()) {
+            Lobe l; l.kind = LOBE_MICRO_TRANS; l.t = t * ks; l.eta_a = 1.0f; l.eta_b = eta; l.fresnel.kind = 1; l.fresnel.eta_i = 1.0f; l.fresnel.eta_t = eta;
+            l.dist.ax = rough; l.dist.ay = rough;
+            bsdf.add(l);
+          }
+        }
+      }
+      bsdf.init(si, eta);
+      return true;
+    }
+    case RT_MAT_MIX: {                                            // mixmat.rs:34-64
+      Spectrum s1 = S(mt.amount).clamp0();
+      Spectrum s2 = (Spectrum(1.0f) - s1).clamp0();
+      Bsdf b2;
+      // both children always yield a Bsdf on this path (every material/*.rs sets si.bsdf); the result keeps mat1's Bsdf
+      // (its eta and frame) and replaces the lobe list by the scaled lobes of both
+      if (!compute_scattering_functions(table, table[mt.mix_a], si, allow_multiple_lobes, bsdf)) return false;
+      if (!compute_scattering_functions(table, table[mt.mix_b], si, allow_multiple_lobes, b2)) return false;
+      const int n1 = bsdf.n;
+      for (int i = 0; i < n1; i++) {
+        Lobe& l = bsdf.lobes[i];
+        if (l.n_scales >= 2) throw std::runtime_error("oracle: MixMaterial nested deeper than two levels");
+        l.scale[l.n_scales++] = s1;
+      }
+      if (n1 + b2.n > 8) throw std::runtime_error("oracle: more than 8 BxDFs (the reference's BxDFHolder panics, bsdf/mod.rs:41-52)");
+      for (int i = 0; i < b2.n; i++) {
+        Lobe l = b2.lobes[i];
+        if (l.n_scales >= 2) throw std::runtime_error("oracle: MixMaterial nested deeper than two levels");
+        l.scale[l.n_scales++] = s2;
+        bsdf.add(l);
+      }
       return true;
     }
     default: return false;                                        // no material: bsdf = None (path.rs:146-152)

@@ -505,7 +505,7 @@ struct Integrator {
       if (!found || bounces >= max_ray_depth) break;
       Bsdf bsdf;
       int mat = scene.prims[isect.prim].material;
-      if (mat < 0 || !compute_scattering_functions(scene.materials[mat], isect, true, bsdf)) {
+      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, true, bsdf)) {
         ray = isect.hit.spawn_ray(ray.d);
         bounces -= 1;                                            // u8 wrap (Q23)
         continue;
@@ -545,7 +545,7 @@ struct Integrator {
       V3 n = isect.shading.n, wo = isect.hit.wo;
       Bsdf bsdf;
       int mat = scene.prims[isect.prim].material;
-      if (mat < 0 || !compute_scattering_functions(scene.materials[mat], isect, false, bsdf)) {
+      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, false, bsdf)) {
         Ray r = isect.hit.spawn_ray(ray.d);
         return li_recursive(scene, r, sampler, depth, node);
       }

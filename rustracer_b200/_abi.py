@@ -32,7 +32,8 @@ class rt_light(C.Structure):
 class rt_material(C.Structure):
     _fields_ = [("type", c_i32), ("kd", c_f * 3), ("ks", c_f * 3), ("kr", c_f * 3), ("kt", c_f * 3), ("eta_rgb", c_f * 3), ("k_rgb", c_f * 3),
                 ("sigma", c_f), ("roughness", c_f), ("uroughness", c_f), ("vroughness", c_f), ("has_uroughness", c_i32), ("has_vroughness", c_i32),
-                ("eta", c_f), ("remap_roughness", c_i32)]
+                ("eta", c_f), ("remap_roughness", c_i32),
+                ("opacity", c_f * 3), ("reflect", c_f * 3), ("transmit", c_f * 3), ("amount", c_f * 3), ("mix_a", c_i32), ("mix_b", c_i32)]
 
 
 class rt_camera(C.Structure):
@@ -84,7 +85,14 @@ class rtgpu_quadric(C.Structure):
 
 class rtgpu_material(C.Structure):
     _fields_ = [("type", c_u32), ("kd", c_f * 3), ("ks", c_f * 3), ("kr", c_f * 3), ("kt", c_f * 3), ("eta_rgb", c_f * 3), ("k_rgb", c_f * 3),
-                ("oren_a", c_f), ("oren_b", c_f), ("use_oren_nayar", c_u32), ("alpha_u", c_f), ("alpha_v", c_f), ("eta", c_f), ("glass_specular", c_u32)]
+                ("oren_a", c_f), ("oren_b", c_f), ("use_oren_nayar", c_u32), ("alpha_u", c_f), ("alpha_v", c_f), ("eta", c_f), ("glass_specular", c_u32),
+                ("lobe_first", c_u32 * 2), ("lobe_count", c_u32 * 2), ("bsdf_eta", c_f)]
+
+
+class rtgpu_lobe(C.Structure):
+    _fields_ = [("kind", c_u32), ("n_scales", c_u32), ("scale", (c_f * 3) * 2), ("r", c_f * 3), ("t", c_f * 3), ("on_a", c_f), ("on_b", c_f),
+                ("fr_kind", c_u32), ("fr_eta_i", c_f), ("fr_eta_t", c_f), ("c_eta_t", c_f * 3), ("c_k", c_f * 3), ("ax", c_f), ("ay", c_f),
+                ("eta_a", c_f), ("eta_b", c_f)]
 
 
 class rtgpu_light(C.Structure):
@@ -96,7 +104,8 @@ class rtgpu_light(C.Structure):
 class rtgpu_scene_desc(C.Structure):
     _fields_ = [("n_nodes", c_u32), ("node_lo", PF), ("node_hi", PF), ("n_prims", c_u32), ("prim_geom", PF), ("prim_info", PU32),
                 ("tri_n", PF), ("tri_s", PF), ("tri_uv", PF), ("n_quadrics", c_u32), ("quadrics", C.POINTER(rtgpu_quadric)),
-                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lights", c_u32), ("lights", C.POINTER(rtgpu_light)),
+                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lobes", c_u32), ("lobes", C.POINTER(rtgpu_lobe)),
+                ("n_lights", c_u32), ("lights", C.POINTER(rtgpu_light)),
                 ("n_env_floats", c_u32), ("env_data", PF), ("world_lo", c_f * 3), ("world_hi", c_f * 3)]
 
 
@@ -113,4 +122,5 @@ class rtgpu_stats(C.Structure):
     _fields_ = [("camera_rays", c_u64), ("regular_rays", c_u64), ("shadow_rays", c_u64), ("waves", c_u64), ("kernel_launches", c_u64),
                 ("ms_total", c_f), ("ms_closest", c_f), ("ms_anyhit", c_f), ("ms_shade", c_f), ("ms_other", c_f),
                 ("closest_launches", c_u64), ("anyhit_launches", c_u64),
-                ("nodes_closest", c_u64), ("prims_closest", c_u64), ("nodes_anyhit", c_u64), ("prims_anyhit", c_u64)]
+                ("nodes_closest", c_u64), ("prims_closest", c_u64), ("nodes_anyhit", c_u64), ("prims_anyhit", c_u64),
+                ("closest_rays", c_u64), ("anyhit_rays", c_u64)]

@@ -303,6 +303,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if ((rc = upload(ctx, s->tri_uv, s->tri_uv ? (size_t)s->n_prims * 6 : 0, &d.tri_uv))) return rc;
   if ((rc = upload(ctx, s->quadrics, (size_t)s->n_quadrics, &d.quadrics))) return rc;
   if ((rc = upload(ctx, s->materials, (size_t)s->n_materials, &d.materials))) return rc;
+  if ((rc = upload(ctx, s->lobes, s->lobes ? (size_t)s->n_lobes : 0, &d.lobes))) return rc;
   if ((rc = upload(ctx, s->lights, (size_t)s->n_lights, &d.lights))) return rc;
   if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
   d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;

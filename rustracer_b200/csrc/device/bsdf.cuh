@@ -94,11 +94,13 @@ RT_DEV Spec fr_conductor(float cos_theta_i, Spec eta_i, Spec eta_t, Spec k) {
 }
 
 enum { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
-enum { LOBE_LAMBERT_R = 0, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS };
+// same numbering as RTGPU_LOBE_* (include/rtgpu.h)
+enum { LOBE_LAMBERT_R = 0, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS,
+       LOBE_LAMBERT_T, LOBE_FRESNEL_BLEND };
 
 struct Lobe {
   int kind;
-  Spec r, t;
+  Spec r, t;                        // FresnelBlend: rs in r, rd in t
   float on_a, on_b;                 // OrenNayar A, B
   int fr_kind; float fr_eta_i, fr_eta_t; Spec c_eta_t, c_k;   // Fresnel (conductor eta_i is always 1: metal.rs:70-75)
   float ax, ay;                     // TrowbridgeReitz alpha
@@ -176,15 +178,28 @@ RT_DEV uint32_t lobe_type(int kind) {
     case LOBE_SPEC_REFL: return BSDF_SPECULAR | BSDF_REFLECTION;
     case LOBE_SPEC_TRANS: return BSDF_SPECULAR | BSDF_TRANSMISSION;
     case LOBE_FRESNEL_SPEC: return BSDF_SPECULAR | BSDF_REFLECTION | BSDF_TRANSMISSION;
-    case LOBE_MICRO_REFL: return BSDF_REFLECTION | BSDF_GLOSSY;
+    case LOBE_MICRO_REFL: case LOBE_FRESNEL_BLEND: return BSDF_REFLECTION | BSDF_GLOSSY;
+    case LOBE_LAMBERT_T: return BSDF_DIFFUSE | BSDF_TRANSMISSION;                // lambertian.rs:43-45
     default: return BSDF_TRANSMISSION | BSDF_GLOSSY;
   }
 }
 RT_DEV bool lobe_matches(int kind, uint32_t flags) { uint32_t t = lobe_type(kind); return (t & flags) == t; }   // bxdf.rs:29-31
 
-RT_DEV Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
+RT_DEV float pow5(float v) { return (v * v) * (v * v) * v; }                     // fresnel.rs:414-417
+RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
   switch (l.kind) {
     case LOBE_LAMBERT_R: return l.r * kInvPi;                                    // lambertian.rs:19-21
+    case LOBE_LAMBERT_T: return l.t * kInvPi;                                    // lambertian.rs:39-41
+    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:358-375 (rs = r, rd = t)
+      Spec diffuse = (28.0f / (23.0f * kPi)) * l.t * (spec(1.0f) - l.r) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
+                     (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo)));
+      V3 wh = wi + wo;
+      if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return spec(0.0f);
+      wh = normalize(wh);
+      Spec schlick = l.r + pow5(1.0f - dot(wi, wh)) * (spec(1.0f) - l.r);        // :352-354
+      Spec specular = tr_d(l.ax, l.ay, wh) / (4.0f * fabsf(dot(wi, wh)) * fmaxf(abs_cos_theta(wi), abs_cos_theta(wo))) * schlick;
+      return diffuse + specular;
+    }
     case LOBE_OREN_NAYAR: {                                                      // oren_nayar.rs:30-52
       float sti = sin_theta(wi), sto = sin_theta(wo);
       float max_cos = 0.0f;
@@ -223,10 +238,16 @@ RT_DEV Spec lobe_f(const Lobe& l, V3 wo, V3 wi) {
     default: return spec(0.0f);                                                  // specular lobes: f() is zero
   }
 }
-RT_DEV float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
+RT_DEV float lobe_pdf_inner(const Lobe& l, V3 wo, V3 wi) {
   switch (l.kind) {
-    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR:                                   // bxdf.rs:38-44
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T:              // bxdf.rs:38-44 (LambertianTransmission keeps the default)
       return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
+    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:377-385
+      if (!same_hemisphere(wo, wi)) return 0.0f;
+      V3 wh = normalize(wo + wi);
+      float pdf_wh = tr_pdf(l.ax, l.ay, wo, wh);
+      return 0.5f * (abs_cos_theta(wi) * kInvPi + pdf_wh / (4.0f * dot(wo, wh)));
+    }
     case LOBE_MICRO_REFL: {                                                      // microfacet.rs:87-94
       if (!same_hemisphere(wo, wi)) return 0.0f;
       V3 wh = normalize(wo + wi);
@@ -244,12 +265,27 @@ RT_DEV float lobe_pdf(const Lobe& l, V3 wo, V3 wi) {
   }
 }
 // `sampled` is the BxdfType the lobe reports (bxdf.rs:18-25: the default sample_f reports EMPTY)
-RT_DEV void lobe_sample_f(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
+RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
   switch (l.kind) {
-    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: {
+    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:387-407
+      sampled = lobe_type(l.kind);
+      if (u.x < 0.5f) {
+        u.x = fminf(2.0f * u.x, kOneMinusEpsilon);
+        wi = cosine_sample_hemisphere(u);
+        if (wo.z < 0.0f) wi.z *= -1.0f;
+      } else {
+        u.x = fminf(2.0f * (u.x - 0.5f), kOneMinusEpsilon);
+        V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
+        wi = reflect(wo, wh);
+        if (!same_hemisphere(wo, wi)) { f_out = spec(0.0f); pdf_out = 0.0f; return; }
+      }
+      f_out = lobe_f_inner(l, wo, wi); pdf_out = lobe_pdf_inner(l, wo, wi);
+      return;
+    }
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T: {            // bxdf.rs:18-25: the hemisphere of wo, also for LambertianTransmission
       wi = cosine_sample_hemisphere(u);
       if (wo.z < 0.0f) wi.z *= -1.0f;
-      pdf_out = lobe_pdf(l, wo, wi); f_out = lobe_f(l, wo, wi); sampled = 0;
+      pdf_out = lobe_pdf_inner(l, wo, wi); f_out = lobe_f_inner(l, wo, wi); sampled = 0;
       return;
     }
     case LOBE_SPEC_REFL: {                                                       // fresnel.rs:159-164
@@ -295,7 +331,7 @@ RT_DEV void lobe_sample_f(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float
       wi = reflect(wo, wh);
       if (!same_hemisphere(wo, wi)) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
       pdf_out = tr_pdf(l.ax, l.ay, wo, wh) / (4.0f * dot(wo, wh));
-      f_out = lobe_f(l, wo, wi);
+      f_out = lobe_f_inner(l, wo, wi);
       return;
     }
     default: {                                                                   // LOBE_MICRO_TRANS microfacet.rs:177-205
@@ -304,26 +340,59 @@ RT_DEV void lobe_sample_f(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float
       V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
       float eta = cos_theta(wo) > 0.0f ? l.eta_a / l.eta_b : l.eta_b / l.eta_a;
       V3 w;
-      if (refract(wo, wh, eta, w)) { wi = w; pdf_out = lobe_pdf(l, wo, wi); f_out = lobe_f(l, wo, wi); }
+      if (refract(wo, wh, eta, w)) { wi = w; pdf_out = lobe_pdf_inner(l, wo, wi); f_out = lobe_f_inner(l, wo, wi); }
       else { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; }
       return;
     }
   }
 }
 
-constexpr int kMaxLobes = 2;     // the five materials on this path build at most two lobes
+constexpr int kMaxLobes = 2;     // the five materials with their own shade kernels build at most two lobes
 
-struct Bsdf {                                                                    // bsdf/mod.rs:64-269
+// Bsdf (bsdf/mod.rs:64-269).  The lobes are either built in place (`lobes`, the five materials above) or are the
+// host-listed rows of an RTGPU_MAT_LOBES material (`g`, up to 8: uber / substrate / translucent / mix).
+struct Bsdf {
   float eta;
   V3 ns, ng, ss, ts;
   Lobe lobes[kMaxLobes]; int n;
+  const rtgpu_lobe* g;
 };
+RT_DEV Lobe load_lobe(const rtgpu_lobe& g) {
+  Lobe l;
+  l.kind = (int)g.kind;
+  l.r = spec3(g.r); l.t = spec3(g.t); l.on_a = g.on_a; l.on_b = g.on_b;
+  l.fr_kind = (int)g.fr_kind; l.fr_eta_i = g.fr_eta_i; l.fr_eta_t = g.fr_eta_t; l.c_eta_t = spec3(g.c_eta_t); l.c_k = spec3(g.c_k);
+  l.ax = g.ax; l.ay = g.ay; l.eta_a = g.eta_a; l.eta_b = g.eta_b;
+  return l;
+}
+RT_DEV Lobe bsdf_lobe(const Bsdf& b, int i) { return b.g ? load_lobe(b.g[i]) : b.lobes[i]; }
+RT_DEV int bsdf_lobe_kind(const Bsdf& b, int i) { return b.g ? (int)b.g[i].kind : b.lobes[i].kind; }
+// ---- the BxDF interface as Bsdf sees it: lobe i itself, or lobe i behind its ScaledBxDF wrappers (bxdf.rs:48-71; only the
+// host-listed lobes of a mix have any): f and sample_f are scaled, the type is the wrapped lobe's, and pdf() is NOT
+// forwarded — it is the trait's default cosine pdf (bxdf.rs:38-44).
+RT_DEV Spec scale_by_wrappers(const Bsdf& b, int i, Spec v) {
+  if (b.g) {
+    const rtgpu_lobe& g = b.g[i];
+    if (g.n_scales > 0) v = v * spec3(g.scale[0]);
+    if (g.n_scales > 1) v = v * spec3(g.scale[1]);
+  }
+  return v;
+}
+RT_DEV Spec lobe_f(const Bsdf& b, int i, V3 wo, V3 wi) { return scale_by_wrappers(b, i, lobe_f_inner(bsdf_lobe(b, i), wo, wi)); }
+RT_DEV float lobe_pdf(const Bsdf& b, int i, V3 wo, V3 wi) {
+  if (b.g && b.g[i].n_scales > 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
+  return lobe_pdf_inner(bsdf_lobe(b, i), wo, wi);
+}
+RT_DEV void lobe_sample_f(const Bsdf& b, int i, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
+  lobe_sample_f_inner(bsdf_lobe(b, i), wo, u, f_out, wi, pdf_out, sampled);
+  f_out = scale_by_wrappers(b, i, f_out);
+}
 RT_DEV void bsdf_init(Bsdf& b, const SurfHit& si, float eta) {                   // :77-92
   b.eta = eta;
   b.ss = normalize(si.dpdu_s);
   b.ns = si.ns; b.ng = si.n;
   b.ts = cross(si.ns, b.ss);
-  b.n = 0;
+  b.n = 0; b.g = nullptr;
 }
 RT_DEV V3 world_to_local(const Bsdf& b, V3 v) { return v3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }   // :253-255
 RT_DEV V3 local_to_world(const Bsdf& b, V3 v) {                                                        // :257-263
@@ -331,7 +400,7 @@ RT_DEV V3 local_to_world(const Bsdf& b, V3 v) {                                 
 }
 RT_DEV int bsdf_num_components(const Bsdf& b, uint32_t flags) {                  // :265-268
   int c = 0;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) c++;
+  for (int i = 0; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) c++;
   return c;
 }
 RT_DEV Spec bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {            // :94-112
@@ -340,8 +409,9 @@ RT_DEV Spec bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {           
   bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
   Spec c = spec(0.0f);
   for (int i = 0; i < b.n; i++) {
-    uint32_t t = lobe_type(b.lobes[i].kind);
-    if (lobe_matches(b.lobes[i].kind, flags) && ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION)))) c = c + lobe_f(b.lobes[i], wo, wi);
+    const int kind = bsdf_lobe_kind(b, i);
+    uint32_t t = lobe_type(kind);
+    if (lobe_matches(kind, flags) && ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION)))) c = c + lobe_f(b, i, wo, wi);
   }
   return c;
 }
@@ -351,32 +421,33 @@ RT_DEV float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {        
   if (wo.z == 0.0f) return 0.0f;
   V3 wi = world_to_local(b, wi_w);
   int matched = 0; float p = 0.0f;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) { matched++; p += lobe_pdf(b.lobes[i], wo, wi); }
+  for (int i = 0; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) { matched++; p += lobe_pdf(b, i, wo, wi); }
   return matched == 0 ? 0.0f : p / (float)matched;
 }
 RT_DEV void bsdf_sample_f(const Bsdf& b, V3 wo_w, P2 u, uint32_t flags, Spec& f_out, V3& wi_w, float& pdf_out, uint32_t& sampled) {   // :138-251
-  int m[kMaxLobes]; int nm = 0;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) m[nm++] = i;
+  const int nm = bsdf_num_components(b, flags);
   if (nm == 0) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
-  int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));
-  const Lobe& bxdf = b.lobes[m[comp]];
-  const uint32_t btype = lobe_type(bxdf.kind);
+  const int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));
+  int chosen = 0;                                                                // the comp-th matching lobe (:150-160)
+  for (int i = 0, c = comp; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) { if (c == 0) { chosen = i; break; } c--; }
+  const uint32_t btype = lobe_type(bsdf_lobe_kind(b, chosen));
   P2 ur = mk2(fminf(u.x * (float)nm - (float)comp, kOneMinusEpsilon), u.y);
   V3 wo = world_to_local(b, wo_w);
   if (wo.z == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = btype; return; }
   Spec f; V3 wi; float pdf;
-  lobe_sample_f(bxdf, wo, ur, f, wi, pdf, sampled);
+  lobe_sample_f(b, chosen, wo, ur, f, wi, pdf, sampled);
   if (pdf == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
   wi_w = local_to_world(b, wi);
   if (!(btype & BSDF_SPECULAR) && nm > 1)
-    for (int i = 0; i < nm; i++) if (i != comp) pdf += lobe_pdf(b.lobes[m[i]], wo, wi);
+    for (int i = 0; i < b.n; i++) if (i != chosen && lobe_matches(bsdf_lobe_kind(b, i), flags)) pdf += lobe_pdf(b, i, wo, wi);
   if (nm > 1) pdf /= (float)nm;
   if (!(btype & BSDF_SPECULAR)) {
     bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
     f = spec(0.0f);
-    for (int i = 0; i < nm; i++) {
-      uint32_t t = lobe_type(b.lobes[m[i]].kind);
-      if ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION))) f = f + lobe_f(b.lobes[m[i]], wo, wi);
+    for (int i = 0; i < b.n; i++) {
+      const int kind = bsdf_lobe_kind(b, i);
+      uint32_t t = lobe_type(kind);
+      if (lobe_matches(kind, flags) && ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION)))) f = f + lobe_f(b, i, wo, wi);
     }
   }
   f_out = f; pdf_out = pdf;
@@ -395,8 +466,15 @@ RT_DEV Lobe blank_lobe() {
 // Path passes true (path.rs:145), Whitted / DirectLighting false (whitted.rs:57, directlighting.rs:104).
 // Returns false for "no material" (bsdf = None, path.rs:146-152).
 // `type` is mt.type; the material-sorted shade kernels pass it as a compile-time constant so the switch folds.
-RT_DEV bool make_bsdf(uint32_t type, const rtgpu_material& mt, const SurfHit& si, bool allow_multiple_lobes, Bsdf& bsdf) {
+// `lobe_table`: DScene::lobes (rows of the RTGPU_MAT_LOBES materials).
+RT_DEV bool make_bsdf(uint32_t type, const rtgpu_material& mt, const rtgpu_lobe* lobe_table, const SurfHit& si, bool allow_multiple_lobes, Bsdf& bsdf) {
   switch (type) {
+    case RTGPU_MAT_LOBES: {                                                      // uber.rs / substrate.rs / translucent.rs / mixmat.rs
+      const int a = allow_multiple_lobes ? 1 : 0;
+      bsdf_init(bsdf, si, mt.bsdf_eta);
+      bsdf.g = lobe_table + mt.lobe_first[a]; bsdf.n = (int)mt.lobe_count[a];
+      return true;
+    }
     case RTGPU_MAT_MATTE: {                                                      // matte.rs:37-62
       Spec r = spec3(mt.kd);
       bsdf_init(bsdf, si, 1.0f);

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) k_shade_path(RenderParams p, int parity) 
           alive = true;
         } else {
           Bsdf bsdf;
-          make_bsdf((uint32_t)MAT, p.sc.materials[info.y], si, true, bsdf);
+          make_bsdf(MAT == Q_LOBES ? (uint32_t)RTGPU_MAT_LOBES : (uint32_t)MAT, p.sc.materials[info.y], p.sc.lobes, si, true, bsdf);
           if (bsdf_num_components(bsdf, kBsdfNonSpecular) > 0 && p.sc.n_lights > 0) {   // path.rs:161-171 -> uniform_sample_one_light
             const Distrib dist = lookup_distrib(p, si.p);
             const float s = ss.get_1d(p.scfg);

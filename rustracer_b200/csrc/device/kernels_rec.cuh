@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int par
       const Inter it = inter_of(si);
       const uint32_t mtype = info.y < p.sc.n_materials ? p.sc.materials[info.y].type : (uint32_t)RTGPU_MAT_NONE;
       Bsdf bsdf;
-      if (mtype > RTGPU_MAT_MIRROR || !make_bsdf(mtype, p.sc.materials[info.y], si, false, bsdf)) {
+      if (material_queue(mtype) == Q_NONE || !make_bsdf(mtype, p.sc.materials[info.y], p.sc.lobes, si, false, bsdf)) {
         // no material: continue the same node through the surface (whitted.rs:60-63)
         const uint32_t pos = warp_append(out_count, true);
         if (pos < p.w.cap_items) { store_ray(oray_o, oray_d, pos, spawn_ray(it, ray.d), 0); obeta[pos] = bt; ops[pos] = ps; }

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t
       else {
         const uint32_t mrow = p.sc.info[hslot].y;
         const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
-        q = type <= RTGPU_MAT_MIRROR ? (int)type : Q_NONE;
+        q = material_queue(type);
       }
     }
     const unsigned peers = __match_any_sync(0xffffffffu, q);
@@ -329,6 +329,8 @@ __global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera) {
   // MIS rays towards infinite lights travel in the shadow queue (shade_common.cuh) but are "regular" rays for the reference
   p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis) + min(c[C_MIS_ANY], p.w.cap_mis) + c[C_MIS_SKIPPED];
   p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
+  p.w.stats[S_CLOSEST_RAYS] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis);
+  p.w.stats[S_ANY_RAYS] += (unsigned long long)min(c[C_SHADOW], p.w.cap_shadow) + min(c[C_MIS_ANY], p.w.cap_mis);
   if (count_camera) p.w.stats[S_CAMERA] += live;
   if (c[C_OVERFLOW]) p.w.stats[S_OVERFLOW] = 1;
   c[live_idx] = 0;

@@ -137,7 +137,7 @@ struct Plan {
   FilmParams film{};
   bool recursive = false;
   uint32_t samples_per_wave_cap = 0;
-  bool mat_present[Q_COUNT] = {false, false, false, false, false, false, true};
+  bool mat_present[Q_COUNT] = {false, false, false, false, false, false, false, true};
   int extra_rounds = 0;
 };
 
@@ -227,9 +227,10 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   // which material classes exist (skip empty shade launches)
   {
     const std::vector<rtgpu_material>& hm = ctx->h_materials;
-    for (const rtgpu_material& m : hm) plan.mat_present[m.type <= RTGPU_MAT_MIRROR ? m.type : Q_NONE] = true;
+    auto queue_of = [](uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? (int)Q_LOBES : (int)Q_NONE); };
+    for (const rtgpu_material& m : hm) plan.mat_present[queue_of(m.type)] = true;
     plan.mat_present[Q_NONE] = true;     // primitives without a material row also land here
-    bool any_none = false; for (const rtgpu_material& m : hm) any_none |= m.type > RTGPU_MAT_MIRROR;
+    bool any_none = false; for (const rtgpu_material& m : hm) any_none |= queue_of(m.type) == Q_NONE;
     plan.extra_rounds = any_none ? 4 : 0;
   }
 
@@ -304,6 +305,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         if (plan.mat_present[Q_GLASS]) RT_LAUNCH(K_SHADE, launch_shade_path_3(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
         if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_LOBES]) RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
         if (sc.n_lights > 0) {
           RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, ctx->stream));
           if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, ctx->stream));
@@ -396,6 +398,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     stats->closest_launches = n_closest_launches; stats->anyhit_launches = n_anyhit_launches;
     stats->nodes_closest = hs[S_NODES_CLOSEST]; stats->prims_closest = hs[S_PRIMS_CLOSEST];
     stats->nodes_anyhit = hs[S_NODES_ANY]; stats->prims_anyhit = hs[S_PRIMS_ANY];
+    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS];
     float acc[K_CLASSES] = {0, 0, 0, 0};
     for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b); acc[sp.cls] += ms; }
     stats->ms_closest = acc[K_CLOSEST]; stats->ms_anyhit = acc[K_ANYHIT]; stats->ms_shade = acc[K_SHADE]; stats->ms_other = acc[K_OTHER];

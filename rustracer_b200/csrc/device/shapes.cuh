@@ -21,6 +21,7 @@ struct DScene {
   const float* tri_uv;       // 6 per slot or null
   const rtgpu_quadric* quadrics;
   const rtgpu_material* materials;
+  const rtgpu_lobe* lobes;   // lobe lists of the RTGPU_MAT_LOBES materials (or null)
   const rtgpu_light* lights;
   const float* env;
   uint32_t n_nodes, n_prims, n_quadrics, n_materials, n_lights;

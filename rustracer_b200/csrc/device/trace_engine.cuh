@@ -25,6 +25,9 @@ namespace rt {
 #ifndef RT_ENGINE_MIN_BLOCKS
 #define RT_ENGINE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the engine kernels are compiled for (register cap 64)
 #endif
+#ifndef RT_ENGINE_PREFETCH
+#define RT_ENGINE_PREFETCH 0        // 1 / 2: prefetch a pushed subtree's record into L1 / L2 (measured: see profiles/)
+#endif
 #ifndef RT_ENGINE_SMEM_DEPTH
 #define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
 #endif
@@ -160,6 +163,18 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
             const uint2 e = make_uint2(second, __float_as_uint(tsecond));
             if (sp < RT_ENGINE_SMEM_DEPTH) s_stack[sp][tid] = e; else stack_l[sp - RT_ENGINE_SMEM_DEPTH] = e;
             sp++;
+#if RT_ENGINE_PREFETCH
+            {   // the postponed subtree's record will be needed after the near subtree: start its fetch now
+              const char* pa = (second & kLeafBit) ? (const char*)&geom[3 * (size_t)(second & ~kLeafBit)] : (const char*)&wide[4 * (size_t)second];
+#if RT_ENGINE_PREFETCH == 2
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(pa + 32));
+#else
+              asm volatile("prefetch.global.L1 [%0];" :: "l"(pa));
+              asm volatile("prefetch.global.L1 [%0];" :: "l"(pa + 32));
+#endif
+            }
+#endif
           }
           cur = first;
         } else if (hsecond) cur = second;
@@ -181,7 +196,9 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
           ok = tri_hit_test_pre(tr, ray.t_max, v3(g0), v3(g1), v3(g2), b0, b1, b2, t);
         } else {
           b1 = 0.0f; b2 = 0.0f;
-          ok = quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, false, nullptr);
+          Ray rq; pol.load(idx, rq);                                   // the direction is not kept in registers across the walk:
+          rq.t_max = ray.t_max;                                        // re-read it for the (rare) quadric test
+          ok = quadric_intersect(sc.quadrics[kind_bits >> 2], rq, t, false, nullptr);
         }
         if (ok) {
           hit.t = t; hit.slot = slot; hit.b1 = b1; hit.b2 = b2;

@@ -8,14 +8,16 @@
 namespace rt {
 
 // material queues of the path integrator (one shade launch per non-empty class)
-enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_MISS, Q_COUNT };
+enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_LOBES, Q_MISS, Q_COUNT };   // Q_LOBES: uber / substrate / translucent / mix
+// material type (rtgpu_material.type, or RTGPU_MAT_NONE for a primitive without material row) -> shade queue
+RT_DEV int material_queue(uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? Q_LOBES : Q_NONE); }
 
 // device counters (uint32)
 enum {
   C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_MIS_ANY, C_MIS_SKIPPED, C_CUR_MISANY, C_COUNT = 32
 };
 // device statistics (uint64): the reference's counters (scene.rs:9-16, renderer.rs:17)
-enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_COUNT = 8 };
+enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_CLOSEST_RAYS, S_ANY_RAYS, S_COUNT = 10 };
 
 // Spatial / uniform light distribution tables (lightdistrib.rs).  Per voxel: func[n], cdf[n+1], func_int.
 struct LightGrid {

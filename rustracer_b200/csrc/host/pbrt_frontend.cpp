@@ -289,9 +289,10 @@ struct Api {
     auto put = [](float* d, Rgb c) { d[0] = c.r; d[1] = c.g; d[2] = c.b; };
     float dummy;
     if (mp.float_texture_or_none("bumpmap", dummy) || !mp.tex_name("bumpmap").empty()) throw ParseError("bump mapping is outside the GPU path's scope (SURVEY §2)");
-    if (name == "substrate" || name == "translucent" || name == "uber" || name == "disney" || name == "mix" || name == "fourier")
+    if (name == "disney" || name == "fourier")
       throw ParseError("Material \"" + name + "\" is not on the GPU hot path yet (SURVEY §8f)");
-    if (name != "matte" && name != "plastic" && name != "glass" && name != "mirror" && name != "metal") {
+    if (name != "matte" && name != "plastic" && name != "glass" && name != "mirror" && name != "metal" && name != "uber" && name != "substrate" &&
+        name != "translucent" && name != "mix") {
       warn().push_back("Unknown material " + name + ". Using matte.");
       name = "matte";
     }
@@ -307,6 +308,40 @@ struct Api {
       if (!mp.float_texture_or_none("eta", eta)) eta = mp.float_texture("index", 1.5f);
       m.eta = eta; m.uroughness = mp.float_texture("uroughness", 0.0f); m.vroughness = mp.float_texture("vroughness", 0.0f);
       m.remap_roughness = mp.find_bool("remaproughness", true);
+    } else if (name == "uber") {                                     // uber.rs:32-57
+      m.type = RT_MAT_UBER;
+      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
+      put(m.kr, mp.spectrum_texture("Kr", Rgb{0, 0, 0})); put(m.kt, mp.spectrum_texture("Kt", Rgb{0, 0, 0}));
+      m.roughness = mp.float_texture("roughness", 0.1f);
+      m.has_uroughness = mp.float_texture_or_none("uroughness", m.uroughness);
+      m.has_vroughness = mp.float_texture_or_none("vroughness", m.vroughness);
+      float eta;
+      if (!mp.float_texture_or_none("eta", eta)) eta = mp.float_texture("index", 1.5f);
+      m.eta = eta;
+      put(m.opacity, mp.spectrum_texture("opacity", Rgb{1, 1, 1}));
+      m.remap_roughness = mp.find_bool("remaproughness", true);
+    } else if (name == "substrate") {                                // substrate.rs:23-38
+      m.type = RT_MAT_SUBSTRATE;
+      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.5f, 0.5f, 0.5f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.5f, 0.5f, 0.5f}));
+      m.uroughness = mp.float_texture("uroughness", 0.1f); m.vroughness = mp.float_texture("vroughness", 0.1f);
+      m.remap_roughness = mp.find_bool("remaproughness", true);
+    } else if (name == "translucent") {                              // translucent.rs:26-44
+      m.type = RT_MAT_TRANSLUCENT;
+      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
+      put(m.reflect, mp.spectrum_texture("reflect", Rgb{0.5f, 0.5f, 0.5f})); put(m.transmit, mp.spectrum_texture("transmit", Rgb{0.5f, 0.5f, 0.5f}));
+      m.roughness = mp.float_texture("roughness", 0.1f);
+      m.remap_roughness = mp.find_bool("remaproughness", true);
+    } else if (name == "mix") {                                      // api.rs:1165-1176 + mixmat.rs:20-31
+      m.type = RT_MAT_MIX;
+      const std::string n1 = mp.find_string("namedmaterial1", ""), n2 = mp.find_string("namedmaterial2", "");
+      auto child = [&](const std::string& n) {
+        auto it = gs.named_material.find(n);
+        if (it != gs.named_material.end()) return it->second;
+        warn().push_back("Named material \"" + n + "\" undefined. Using \"matte\"");
+        return make_material("matte", mp);
+      };
+      m.mix_a = child(n1); m.mix_b = child(n2);
+      put(m.amount, mp.spectrum_texture("amount", Rgb{0.5f, 0.5f, 0.5f}));
     } else if (name == "mirror") {                                   // mirror.rs:20-26
       m.type = RT_MAT_MIRROR; put(m.kr, mp.spectrum_texture("Kr", Rgb{0.9f, 0.9f, 0.9f}));
     } else {                                                         // metal.rs:24-46

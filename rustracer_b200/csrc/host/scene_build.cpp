@@ -58,6 +58,147 @@ rtgpu_material prep_material(const rt_material& m) {
   return o;
 }
 
+// ---- lobe lists of UberMaterial / SubstrateMaterial / TranslucentMaterial / MixMaterial ------------------------------
+// With constant textures `compute_scattering_functions` adds the same BxDFs at every hit, so the host lists them once
+// per material (and per allow_multiple_lobes, which only a glass child of a mix looks at).
+struct Rgb3 { float v[3]; };
+inline Rgb3 rgb(const float* c) { return Rgb3{{c[0], c[1], c[2]}}; }
+inline Rgb3 clamp_rgb(Rgb3 c) { for (float& x : c.v) x = clampf(x, 0.0f, std::numeric_limits<float>::infinity()); return c; }   // Spectrum::clamp
+inline Rgb3 mul(Rgb3 a, Rgb3 b) { return Rgb3{{a.v[0] * b.v[0], a.v[1] * b.v[1], a.v[2] * b.v[2]}}; }
+inline Rgb3 one_minus(Rgb3 a) { return Rgb3{{1.0f - a.v[0], 1.0f - a.v[1], 1.0f - a.v[2]}}; }
+inline bool black(Rgb3 a) { return a.v[0] == 0.0f && a.v[1] == 0.0f && a.v[2] == 0.0f; }
+inline void put3(float* d, Rgb3 c) { d[0] = c.v[0]; d[1] = c.v[1]; d[2] = c.v[2]; }
+
+rtgpu_lobe new_lobe(uint32_t kind) {
+  rtgpu_lobe l; std::memset(&l, 0, sizeof(l));
+  l.kind = kind; l.fr_eta_i = l.fr_eta_t = 1.0f; l.eta_a = l.eta_b = 1.0f;
+  for (int i = 0; i < 3; i++) l.c_eta_t[i] = 1.0f;
+  return l;
+}
+void set_dielectric(rtgpu_lobe& l, float eta_i, float eta_t) { l.fr_kind = 1; l.fr_eta_i = eta_i; l.fr_eta_t = eta_t; }
+
+// Appends the BxDFs material `row` adds, in the reference's order; returns Bsdf::eta.
+float list_lobes(const rt_scene& in, int row, bool allow_multiple_lobes, std::vector<rtgpu_lobe>& out, int depth = 0) {
+  if (row < 0 || (uint32_t)row >= in.n_materials) throw std::runtime_error("material row out of range");
+  if (depth > 2) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
+  const rt_material& m = in.materials[row];
+  switch (m.type) {
+    case RT_MAT_UBER: {                                               // uber.rs:62-125
+      const float e = m.eta;
+      const Rgb3 op = clamp_rgb(rgb(m.opacity)), t = clamp_rgb(one_minus(op));
+      float eta = e;
+      if (!black(t)) {
+        eta = 1.0f;
+        rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_TRANS); put3(l.t, t); l.eta_a = 1.0f; l.eta_b = 1.0f; set_dielectric(l, 1.0f, 1.0f); out.push_back(l);
+      }
+      const Rgb3 kd = mul(op, clamp_rgb(rgb(m.kd)));
+      if (!black(kd)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, kd); out.push_back(l); }
+      const Rgb3 ks = mul(op, clamp_rgb(rgb(m.ks)));
+      if (!black(ks)) {
+        float ru = m.has_uroughness ? m.uroughness : m.roughness, rv = m.has_vroughness ? m.vroughness : m.roughness;
+        if (m.remap_roughness) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
+        rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, ks); set_dielectric(l, 1.0f, e); l.ax = ru; l.ay = rv; out.push_back(l);
+      }
+      const Rgb3 kr = mul(op, clamp_rgb(rgb(m.kr)));
+      if (!black(kr)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_REFL); put3(l.r, kr); set_dielectric(l, 1.0f, e); out.push_back(l); }
+      const Rgb3 kt = mul(op, clamp_rgb(rgb(m.kt)));
+      if (!black(kt)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_TRANS); put3(l.t, kt); l.eta_a = 1.0f; l.eta_b = e; set_dielectric(l, 1.0f, e); out.push_back(l); }
+      return eta;
+    }
+    case RT_MAT_SUBSTRATE: {                                          // substrate.rs:42-71
+      const Rgb3 d = clamp_rgb(rgb(m.kd)), s = clamp_rgb(rgb(m.ks));
+      if (!black(d) || !black(s)) {
+        float ru = m.uroughness, rv = m.vroughness;
+        if (m.remap_roughness) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
+        rtgpu_lobe l = new_lobe(RTGPU_LOBE_FRESNEL_BLEND); put3(l.r, s); put3(l.t, d); l.ax = ru; l.ay = rv; out.push_back(l);   // FresnelBlend::new(rs, rd, ..)
+      }
+      return 1.0f;
+    }
+    case RT_MAT_TRANSLUCENT: {                                        // translucent.rs:48-101
+      const float eta = 1.5f;
+      const Rgb3 r = clamp_rgb(rgb(m.reflect)), t = clamp_rgb(rgb(m.transmit));
+      if (!black(r) || !black(t)) {
+        const Rgb3 kd = clamp_rgb(rgb(m.kd));
+        if (!black(kd)) {
+          if (!black(r)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, mul(r, kd)); out.push_back(l); }
+          if (!black(t)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_T); put3(l.t, mul(t, kd)); out.push_back(l); }
+        }
+        const Rgb3 ks = clamp_rgb(rgb(m.ks));
+        if (!black(ks)) {
+          float rough = m.roughness;
+          if (m.remap_roughness) rough = roughness_to_alpha(rough);
+          if (!black(r)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, mul(r, ks)); set_dielectric(l, 1.0f, eta); l.ax = l.ay = rough; out.push_back(l); }
+          if (!black(t)) {
+            rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_TRANS); put3(l.t, mul(t, ks)); l.eta_a = 1.0f; l.eta_b = eta; set_dielectric(l, 1.0f, eta); l.ax = l.ay = rough;
+            out.push_back(l);
+          }
+        }
+      }
+      return eta;
+    }
+    case RT_MAT_MIX: {                                                // mixmat.rs:34-64: ScaledBxDF(b, s1) for mat1's, ScaledBxDF(b, s2) for mat2's
+      const Rgb3 s1 = clamp_rgb(rgb(m.amount)), s2 = clamp_rgb(one_minus(s1));
+      const size_t first = out.size();
+      const float eta = list_lobes(in, m.mix_a, allow_multiple_lobes, out, depth + 1);   // the Bsdf object (eta, frame) stays mat1's
+      const size_t mid = out.size();
+      list_lobes(in, m.mix_b, allow_multiple_lobes, out, depth + 1);
+      for (size_t i = first; i < out.size(); i++) {
+        rtgpu_lobe& l = out[i];
+        if (l.n_scales >= 2) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
+        put3(l.scale[l.n_scales++], i < mid ? s1 : s2);
+      }
+      return eta;
+    }
+    // the five materials with their own shade kernels, as children of a mix
+    case RT_MAT_MATTE: {                                              // matte.rs:37-62
+      const rtgpu_material pm = prep_material(m);
+      if (!black(rgb(pm.kd))) {
+        rtgpu_lobe l = new_lobe(pm.use_oren_nayar ? RTGPU_LOBE_OREN_NAYAR : RTGPU_LOBE_LAMBERT_R); put3(l.r, rgb(pm.kd)); l.on_a = pm.oren_a; l.on_b = pm.oren_b;
+        out.push_back(l);
+      }
+      return 1.0f;
+    }
+    case RT_MAT_PLASTIC: {                                            // plastic.rs:45-74
+      const rtgpu_material pm = prep_material(m);
+      if (!black(rgb(pm.kd))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, rgb(pm.kd)); out.push_back(l); }
+      if (!black(rgb(pm.ks))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, rgb(pm.ks)); set_dielectric(l, 1.5f, 1.0f); l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l); }
+      return 1.0f;
+    }
+    case RT_MAT_METAL: {                                              // metal.rs:50-81
+      const rtgpu_material pm = prep_material(m);
+      rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, Rgb3{{1, 1, 1}}); l.fr_kind = 2; put3(l.c_eta_t, rgb(pm.eta_rgb)); put3(l.c_k, rgb(pm.k_rgb));
+      l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
+      return 1.0f;
+    }
+    case RT_MAT_GLASS: {                                              // glass.rs:53-106
+      const rtgpu_material pm = prep_material(m);
+      const Rgb3 r = rgb(pm.kr), t = rgb(pm.kt);
+      if (!black(r) || !black(t)) {
+        if (pm.glass_specular && allow_multiple_lobes) {
+          rtgpu_lobe l = new_lobe(RTGPU_LOBE_FRESNEL_SPEC); put3(l.r, r); put3(l.t, t); l.eta_a = 1.0f; l.eta_b = pm.eta; out.push_back(l);
+        } else {
+          if (!black(r)) {
+            rtgpu_lobe l = new_lobe(pm.glass_specular ? RTGPU_LOBE_SPEC_REFL : RTGPU_LOBE_MICRO_REFL); put3(l.r, r); set_dielectric(l, 1.0f, pm.eta);
+            l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
+          }
+          if (!black(t)) {
+            rtgpu_lobe l = new_lobe(pm.glass_specular ? RTGPU_LOBE_SPEC_TRANS : RTGPU_LOBE_MICRO_TRANS);
+            put3(l.t, pm.glass_specular ? t : r);                     // the rough transmission lobe is built with Kr (glass.rs:97)
+            l.eta_a = 1.0f; l.eta_b = pm.eta; set_dielectric(l, 1.0f, pm.eta); l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
+          }
+        }
+      }
+      return pm.eta;
+    }
+    case RT_MAT_MIRROR: {                                             // mirror.rs:30-48
+      const rtgpu_material pm = prep_material(m);
+      if (!black(rgb(pm.kr))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_REFL); put3(l.r, rgb(pm.kr)); l.fr_kind = 0; out.push_back(l); }
+      return 1.0f;
+    }
+    default: throw std::runtime_error("MixMaterial: a child material has no BSDF");
+  }
+}
+
 // sampling/distribution1d.rs:11-45
 void distribution1d(const float* func, size_t n, float* cdf, float& func_int) {
   cdf[0] = 0.0f;
@@ -309,7 +450,21 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
     uint32_t* info = &out.prim_info[slot * 4];
     info[0] = pn; info[1] = s.material >= 0 ? (uint32_t)s.material : 0xffffffffu; info[2] = (uint32_t)light_of_prim[pn]; info[3] = flags;
   }
-  for (uint32_t i = 0; i < in.n_materials; i++) out.materials.push_back(prep_material(in.materials[i]));
+  for (uint32_t i = 0; i < in.n_materials; i++) {
+    rtgpu_material pm = prep_material(in.materials[i]);
+    const int ty = in.materials[i].type;
+    if (ty == RT_MAT_UBER || ty == RT_MAT_SUBSTRATE || ty == RT_MAT_TRANSLUCENT || ty == RT_MAT_MIX) {
+      pm.type = RTGPU_MAT_LOBES;
+      for (int allow = 0; allow < 2; allow++) {
+        pm.lobe_first[allow] = (uint32_t)out.lobes.size();
+        pm.bsdf_eta = list_lobes(in, (int)i, allow != 0, out.lobes);
+        pm.lobe_count[allow] = (uint32_t)out.lobes.size() - pm.lobe_first[allow];
+        if (pm.lobe_count[allow] > 8)
+          throw std::runtime_error("a material builds more than 8 BxDFs: the reference's BxDFHolder panics there (bsdf/mod.rs:41-52)");
+      }
+    }
+    out.materials.push_back(pm);
+  }
   // 5. descriptor views
   rtgpu_scene_desc& d = out.desc;
   d.n_nodes = out.bvh.n_nodes; d.node_lo = out.bvh.node_lo.data(); d.node_hi = out.bvh.node_hi.data();
@@ -317,6 +472,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   d.tri_n = any_n ? out.tri_n.data() : nullptr; d.tri_s = any_s ? out.tri_s.data() : nullptr; d.tri_uv = any_uv ? out.tri_uv.data() : nullptr;
   d.n_quadrics = (uint32_t)out.quadrics.size(); d.quadrics = out.quadrics.data();
   d.n_materials = (uint32_t)out.materials.size(); d.materials = out.materials.data();
+  d.n_lobes = (uint32_t)out.lobes.size(); d.lobes = out.lobes.empty() ? nullptr : out.lobes.data();
   d.n_lights = (uint32_t)out.lights.size(); d.lights = out.lights.data();
   d.n_env_floats = (uint32_t)out.env_data.size(); d.env_data = out.env_data.data();
   make_render_desc(in, out.render);

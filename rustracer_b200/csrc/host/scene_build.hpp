@@ -17,6 +17,7 @@ struct FlatScene {
   std::vector<float> tri_n, tri_s, tri_uv;
   std::vector<rtgpu_quadric> quadrics;
   std::vector<rtgpu_material> materials;
+  std::vector<rtgpu_lobe> lobes;         // lobe lists of the RTGPU_MAT_LOBES materials
   std::vector<rtgpu_light> lights;
   std::vector<float> env_data;
   std::vector<uint32_t> slot_of_prim;    // prim_number -> slot

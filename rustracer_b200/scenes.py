@@ -203,11 +203,40 @@ _MATERIALS = [
 ]
 
 
-def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None):
+# the materials that reuse the path's lobes (uber, substrate, translucent, mix incl. a nested mix and a
+# glass child, which is the one case where allow_multiple_lobes changes the lobe list)
+_MATERIALS_EXT = [
+    'Material "uber" "rgb Kd" [{c}] "rgb Ks" [0.3 0.3 0.3] "rgb Kr" [0.1 0.1 0.1] "float roughness" [0.08]',
+    'Material "uber" "rgb Kd" [{c}] "rgb opacity" [0.6 0.6 0.6] "rgb Kt" [0.2 0.2 0.2] "float index" [1.3]',
+    'Material "substrate" "rgb Kd" [{c}] "rgb Ks" [0.2 0.2 0.2] "float uroughness" [0.05] "float vroughness" [0.2]',
+    'Material "translucent" "rgb Kd" [{c}] "rgb Ks" [0.2 0.2 0.2] "rgb reflect" [0.6 0.6 0.6] "rgb transmit" [0.4 0.4 0.4]',
+    'NamedMaterial "mix_pm"',
+    'NamedMaterial "mix_gs"',
+    'NamedMaterial "mix_nested"',
+    'Material "matte" "rgb Kd" [{c}] "float sigma" [20]',
+]
+_MATERIALS_EXT_PREAMBLE = """MakeNamedMaterial "pl" "string type" "plastic" "rgb Kd" [0.3 0.5 0.2] "float roughness" [0.1]
+MakeNamedMaterial "mi" "string type" "mirror"
+MakeNamedMaterial "gl" "string type" "glass"
+MakeNamedMaterial "su" "string type" "substrate" "rgb Kd" [0.5 0.2 0.2]
+MakeNamedMaterial "mt" "string type" "matte" "rgb Kd" [0.2 0.3 0.7] "float sigma" [30]
+MakeNamedMaterial "mix_pm" "string type" "mix" "string namedmaterial1" "pl" "string namedmaterial2" "mi" "rgb amount" [0.7 0.7 0.7]
+MakeNamedMaterial "mix_gs" "string type" "mix" "string namedmaterial1" "gl" "string namedmaterial2" "su"
+MakeNamedMaterial "mix_nested" "string type" "mix" "string namedmaterial1" "mix_pm" "string namedmaterial2" "mt" "rgb amount" [0.3 0.5 0.7]
+"""
+
+
+def balls_ext(**kw):
+    """The balls scene with the SURVEY 8f rank-1 materials on the spheres."""
+    return balls(materials=_MATERIALS_EXT, preamble=_MATERIALS_EXT_PREAMBLE, **kw)
+
+
+def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None, materials=None, preamble=""):
+    materials = _MATERIALS if materials is None else materials
     if integrator is None:
         integrator = 'Integrator "whitted" "integer maxdepth" [5]'
     s = header(xres, yres, spp, integrator, 40, ([0, 7.5, -13], [0, 0.3, 0], [0, 1, 0]), crop)
-    s += "WorldBegin\n"
+    s += "WorldBegin\n" + preamble
     s += 'LightSource "point" "rgb I" [220 220 220] "point from" [-6 9 -6]\n'
     s += 'LightSource "point" "rgb I" [120 110 100] "point from" [7 6 -3]\n'
     s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [12 12 12]\nTranslate 0 6 2\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "sphere" "float radius" [0.6]\nAttributeEnd\n'
@@ -220,7 +249,7 @@ def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None):
         x = (gx - (n_side - 1) / 2) * 1.25 + float(rng.f32()[0] - 0.5) * 0.3
         z = (gz - (n_side - 1) / 2) * 1.25 + float(rng.f32()[0] - 0.5) * 0.3
         col = f"{0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f}"
-        s += "AttributeBegin\n" + _MATERIALS[i % 5].format(c=col) + f"\nTranslate {x:.5f} {float(r):.5f} {z:.5f}\n"
+        s += "AttributeBegin\n" + materials[i % len(materials)].format(c=col) + f"\nTranslate {x:.5f} {float(r):.5f} {z:.5f}\n"
         s += f'Shape "sphere" "float radius" [{float(r):.5f}]\nAttributeEnd\n'
     s += "WorldEnd\n"
     return s

@@ -25,6 +25,10 @@ CASES = {
     "balls_direct_all": lambda: scenes.balls(xres=96, yres=72, spp=8, integrator='Integrator "directlighting" "string strategy" "all" "integer maxdepth" [5]'),
     "balls_direct_one": lambda: scenes.balls(xres=96, yres=72, spp=8, integrator='Integrator "directlighting" "string strategy" "one" "integer maxdepth" [5]'),
     "balls_ao": lambda: scenes.balls(xres=96, yres=72, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [16]'),
+    # uber / substrate / translucent / mix
+    "balls_ext_path": lambda: scenes.balls_ext(xres=96, yres=72, spp=8, integrator='Integrator "path" "integer maxdepth" [5]'),
+    "balls_ext_whitted": lambda: scenes.balls_ext(xres=96, yres=72, spp=8),
+    "balls_ext_direct_all": lambda: scenes.balls_ext(xres=96, yres=72, spp=8, integrator='Integrator "directlighting" "string strategy" "all" "integer maxdepth" [5]'),
 }
 N_RAYS, N_LI, SEED = 2000, 400, 11
 

@@ -99,6 +99,48 @@ def test_material_defaults(native_libs):
     assert me.type == 2 and abs(me.roughness - 0.01) < 1e-8 and me.has_uroughness == 0
 
 
+def test_f1_material_defaults_and_lobe_lists(native_libs):
+    """uber / substrate / translucent / mix: parameter defaults of material/{uber,substrate,translucent,
+    mixmat}.rs `create`, and the host's lobe lists (scene_build.cpp) against the oracle's independent restatement."""
+    import ctypes as C
+    from oracle import binding as ob
+    from rustracer_b200 import _abi as A
+    txt = ('Camera "perspective"\nSampler "02sequence"\nWorldBegin\nMaterial "uber"\nShape "sphere"\nMaterial "substrate"\nShape "sphere"\n'
+           'Material "translucent"\nShape "sphere"\nMakeNamedMaterial "a" "string type" "glass"\nMakeNamedMaterial "b" "string type" "uber" "rgb opacity" [0.5 0.5 0.5] "rgb Kr" [0.1 0.1 0.1]\n'
+           'Material "mix" "string namedmaterial1" "a" "string namedmaterial2" "b"\nShape "sphere"\n'
+           'Material "mix" "string namedmaterial1" "nope" "string namedmaterial2" "a" "rgb Kd" [0.1 0.2 0.3]\nShape "sphere"\nWorldEnd\n')
+    sc = Scene.from_string(txt)
+    ir = sc.ir
+    ub, su, tr, mx, mx2 = (ir.materials[ir.shapes[i].material] for i in range(5))
+    assert ub.type == 6 and list(ub.kd) == [0.25] * 3 and list(ub.ks) == [0.25] * 3 and list(ub.kr) == [0.0] * 3 and list(ub.kt) == [0.0] * 3
+    assert list(ub.opacity) == [1.0] * 3 and ub.eta == 1.5 and abs(ub.roughness - 0.1) < 1e-7 and ub.has_uroughness == 0 and ub.remap_roughness == 1
+    assert su.type == 7 and list(su.kd) == [0.5] * 3 and list(su.ks) == [0.5] * 3 and abs(su.uroughness - 0.1) < 1e-7 and abs(su.vroughness - 0.1) < 1e-7
+    assert tr.type == 8 and list(tr.reflect) == [0.5] * 3 and list(tr.transmit) == [0.5] * 3 and list(tr.kd) == [0.25] * 3
+    assert mx.type == 9 and list(mx.amount) == [0.5] * 3 and ir.materials[mx.mix_a].type == 3 and ir.materials[mx.mix_b].type == 6
+    # an undefined named material falls back to matte built from the mix's own parameters (api.rs:1168-1171)
+    assert ir.materials[mx2.mix_a].type == 0 and np.allclose(list(ir.materials[mx2.mix_a].kd), [0.1, 0.2, 0.3]) and any("undefined" in w for w in sc.warnings)
+    d = sc.desc.contents
+    o = ob.OracleScene(sc.ir_ptr)
+    wo = np.array([0.0, 0.6, 0.8], np.float32)
+    for i in range(5):
+        row = ir.shapes[i].material
+        m = d.materials[row]
+        assert m.type == 6                                                    # RTGPU_MAT_LOBES
+        for allow in (0, 1):
+            r = o.material_bsdf(row, wo, wo, [0.5, 0.5], allow_multiple_lobes=bool(allow))
+            assert m.lobe_count[allow] == r["n_lobes"] and m.bsdf_eta == r["eta"], (i, allow)
+            kinds = [d.lobes[m.lobe_first[allow] + k].kind for k in range(m.lobe_count[allow])]
+            if i == 3:    # glass + uber(opacity 0.5, Kr): FresnelSpecular | SpecRefl + SpecTrans, then pass-through, Lambert, microfacet, SpecRefl
+                assert kinds == ([4] if allow else [2, 3]) + [3, 0, 5, 2]
+                assert all(d.lobes[m.lobe_first[allow] + k].n_scales == 1 for k in range(m.lobe_count[allow]))
+    # nine BxDFs: the reference's BxDFHolder holds eight (bsdf/mod.rs:41-52, index out of bounds)
+    many = ('Camera "perspective"\nSampler "02sequence"\nWorldBegin\n'
+            'MakeNamedMaterial "u" "string type" "uber" "rgb opacity" [0.5 0.5 0.5] "rgb Kr" [0.1 0.1 0.1] "rgb Kt" [0.1 0.1 0.1]\n'
+            'MakeNamedMaterial "t" "string type" "translucent"\nMaterial "mix" "string namedmaterial1" "u" "string namedmaterial2" "t"\nShape "sphere"\nWorldEnd\n')
+    with pytest.raises(SceneError):
+        Scene.from_string(many).flatten()
+
+
 def test_reference_failure_modes(native_libs):
     """The same inputs the reference rejects are rejected."""
     ok = 'Camera "perspective"\nSampler "02sequence"\nWorldBegin\nWorldEnd\n'

@@ -36,3 +36,13 @@ for _ in range(5):
     st = dev.render(rd)
 dt = (time.perf_counter() - t) / 5
 print(f"render wall {dt * 1e3:.2f} ms, device {st.ms_total:.2f} ms")
+# replica of bench.py's e2e loop, timing each part
+for rep in range(2):
+    tr = tf = 0.0
+    t0 = time.perf_counter()
+    for k in range(8):
+        rd.sample_begin, rd.sample_end = (k * 8) % 256, (k * 8) % 256 + 8
+        a = time.perf_counter(); st = dev.render(rd); b = time.perf_counter(); dev.read_film(out=pinned); c = time.perf_counter()
+        tr += b - a; tf += c - b
+    torch.cuda.synchronize()
+    print(f"e2e loop: {(time.perf_counter() - t0) / 8 * 1e3:.2f} ms/step (render {tr / 8 * 1e3:.2f}, read_film {tf / 8 * 1e3:.2f}); last device ms {st.ms_total:.2f}")
