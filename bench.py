@@ -168,6 +168,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line (NCCL prints its version banner to stdout)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tmp = tempfile.mkdtemp(prefix=f"rtb200_{rank}_")
