@@ -278,6 +278,10 @@ def run_ours(a):
         bytes_step = 48.0 * n_rays + 32.0 * stc.nodes_closest + 48.0 * stc.prims_closest     # 32 B ray + 16 B hit + 32 N + 48 T
         bytes_any = 33.0 * stc.anyhit_rays + 32.0 * stc.nodes_anyhit + 48.0 * stc.prims_anyhit   # 32 B ray + 1 B flag + 32 N + 48 T
         reps = min(a.steps, 4)
+        traffic = None                       # measured DRAM bytes per launch of the same kernels, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath) and a.spp_per_step == 8 and a.level == 5 and (a.xres, a.yres) == (1920, 1080):
+            traffic = float(json.load(open(tpath))["dram_bytes_per_launch"])
         t_closest = acc["closest"] / reps * 1e-3
         achieved = bytes_step / t_closest / 1e9
         t_any = acc["anyhit"] / reps * 1e-3
@@ -287,7 +291,8 @@ def run_ours(a):
                                    "nodes_per_ray": stc.nodes_anyhit / max(1, stc.anyhit_rays), "prims_per_ray": stc.prims_anyhit / max(1, stc.anyhit_rays)}
         line["roofline"] = {"bound": "hbm", "kernel": "k_trace_closest_engine + k_trace_mis_engine (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "algorithmic_bytes_per_step": bytes_step, "rays_per_step": int(n_rays),
+                            "traffic": traffic, "traffic_source": "profiles/roofline_traffic.json (ncu --set full, DRAM read+write per launch)" if traffic else None,
+                            "algorithmic_bytes_per_launch": bytes_step / max(1.0, acc["launches"] / reps), "algorithmic_bytes_per_step": bytes_step, "rays_per_step": int(n_rays),
                             "nodes_per_ray": stc.nodes_closest / max(1, n_rays), "prims_per_ray": stc.prims_closest / max(1, n_rays),
                             "launches_per_step": acc["launches"] / reps, "avg_launch_ms": acc["closest"] / max(1, acc["launches"]),
                             "share_of_step": {k: acc[k] / acc["total"] for k in ("closest", "anyhit", "shade", "other")},

@@ -24,7 +24,8 @@ extern "C" {
 
 typedef struct rt_transform { float m[16]; float m_inv[16]; } rt_transform;
 
-enum { RT_SHAPE_TRIMESH = 0, RT_SHAPE_SPHERE = 1, RT_SHAPE_DISK = 2, RT_SHAPE_CYLINDER = 3 };
+enum { RT_SHAPE_TRIMESH = 0, RT_SHAPE_SPHERE = 1, RT_SHAPE_DISK = 2, RT_SHAPE_CYLINDER = 3,
+       RT_SHAPE_INSTANCE = 4 };   /* an `ObjectInstance` directive: one TransformedPrimitive (api.rs:1052-1090, primitive.rs:79-118) */
 
 /* One `Shape` directive (api.rs:913-966).  A trimesh expands to n_indices/3 primitives, a
  * quadric to one.  Primitive numbering = shape order, triangles in face order. */
@@ -45,6 +46,13 @@ typedef struct rt_shape {
   float zmin, zmax;            /* sphere: zmin/zmax ; cylinder: z_min/z_max */
   float phimax;                /* degrees */
   float height, inner_radius;  /* disk */
+  /* Object instancing (api.rs:1019-1090).  A shape declared between ObjectBegin/ObjectEnd belongs to object definition
+   * `object_def` (>= 0) and is NOT a primitive of the scene; its o2w is the CTM inside the definition.  An
+   * RT_SHAPE_INSTANCE entry stands at the place of an `ObjectInstance "name"` directive in the primitive list: it is the
+   * TransformedPrimitive over definition `instance_of` with primitive_to_world = o2w (the CTM at the directive).
+   * Top-level shapes have object_def = -1. */
+  int32_t object_def;
+  int32_t instance_of;
 } rt_shape;
 
 /* `AreaLightSource "diffuse"` bound to a shape (light/diffuse.rs:39-51): one DiffuseAreaLight
@@ -140,6 +148,7 @@ typedef struct rt_integrator {
 typedef struct rt_accel { int32_t split_method; int32_t max_node_prims; } rt_accel; /* bvh/mod.rs:63-78 */
 
 typedef struct rt_scene {
+  uint32_t n_objects;     /* object definitions (ObjectBegin blocks), numbered in file order */
   uint32_t n_shapes;      const rt_shape* shapes;
   uint32_t n_area_lights; const rt_area_light* area_lights;
   uint32_t n_lights;      const rt_light* lights;

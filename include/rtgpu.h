@@ -49,6 +49,18 @@ typedef struct rtgpu_quadric {
   uint32_t kind, flags, pad;
 } rtgpu_quadric;
 
+/* One `ObjectInstance` (TransformedPrimitive, primitive.rs:79-118).  Its slot in the top-level BVH has bit 1 of the second
+ * geometry float4's w set and the row number in the third float4's w.  The definition's own BVH nodes and primitive slots live
+ * in the same node / primitive arrays (absolute indices). */
+typedef struct rtgpu_instance {
+  float w2o[12], o2w[12];      /* rows 0..2 of primitive_to_world.m_inv and .m (affine only) */
+  uint32_t root_node;          /* node index of the definition's BVH root, or 0xffffffff when it holds one primitive (api.rs:1071) */
+  uint32_t first_slot;         /* that single primitive's slot (root_node == 0xffffffff) */
+  float lo[3], hi[3];          /* bounds of the definition's BVH root (object space) */
+  uint32_t prim_number;        /* number of the TransformedPrimitive in the scene's primitive list */
+  uint32_t root_ref;           /* filled by rtgpu_upload_scene: traversal-engine reference of the root */
+} rtgpu_instance;
+
 enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MAT_GLASS = 3, RTGPU_MAT_MIRROR = 4, RTGPU_MAT_NONE = 5,
        RTGPU_MAT_LOBES = 6 };   /* uber / substrate / translucent / mix: the host lists the lobes (rtgpu_lobe rows) */
 
@@ -117,6 +129,7 @@ typedef struct rtgpu_scene_desc {
   uint32_t n_quadrics;  const rtgpu_quadric* quadrics;
   uint32_t n_materials; const rtgpu_material* materials;
   uint32_t n_lobes;     const rtgpu_lobe* lobes;       /* lobe lists of the RTGPU_MAT_LOBES materials (may be 0 / NULL) */
+  uint32_t n_instances; const rtgpu_instance* instances; /* object instances (may be 0 / NULL) */
   uint32_t n_lights;    const rtgpu_light* lights;
   uint32_t n_env_floats; const float* env_data;
   float world_lo[3], world_hi[3];  /* nodes[0].bounds */

@@ -20,6 +20,7 @@ struct orc_scene {
   std::vector<size_t> shape_first_prim, shape_n_prims;
   double build_seconds = 0;
   std::string error;
+  std::vector<std::shared_ptr<ObjectDef>> defs;
 };
 
 static Transform to_transform(const rt_transform& t) { return Transform(Matrix4::from(t.m), Matrix4::from(t.m_inv)); }
@@ -31,11 +32,23 @@ orc_scene* orc_scene_create(const rt_scene* in) {
   Scene& sc = o->scene;
   o->film_desc = in->film; o->sampler = in->sampler; o->integrator = in->integrator;
   sc.materials.assign(in->materials, in->materials + in->n_materials);
-  // shapes -> primitives in directive order (api.rs:913-966, mesh.rs:636-679)
+  // shapes -> primitives in directive order (api.rs:913-966, mesh.rs:636-679); shapes of an object definition go to the
+  // definition's own list (api.rs:951-957), an ObjectInstance adds one TransformedPrimitive (api.rs:1081-1085)
+  std::vector<std::shared_ptr<ObjectDef>> defs(in->n_objects);
+  for (auto& d : defs) d = std::make_shared<ObjectDef>();
   for (uint32_t si = 0; si < in->n_shapes; si++) {
     const rt_shape& s = in->shapes[si];
     Transform o2w = to_transform(s.o2w);
     o->shape_first_prim.push_back(sc.prims.size());
+    if (s.kind == RT_SHAPE_INSTANCE) {
+      Primitive p; p.material = -1;
+      p.shape = std::make_shared<InstanceShape>(defs[s.instance_of], o2w);
+      sc.prims.push_back(p);
+      o->shape_n_prims.push_back(1);
+      continue;
+    }
+    std::vector<Primitive>& dst = s.object_def >= 0 ? defs[s.object_def]->prims : sc.prims;
+    const size_t dst_before = dst.size();
     if (s.kind == RT_SHAPE_TRIMESH) {
       auto mesh = std::make_shared<TriangleMesh>();
       mesh->o2w = o2w;
@@ -50,17 +63,19 @@ orc_scene* orc_scene_create(const rt_scene* in) {
       size_t ntri = s.n_indices / 3;
       for (size_t t = 0; t < ntri; t++) {
         Primitive p; p.shape = std::make_shared<Triangle>(mesh, t, s.reverse_orientation != 0); p.material = s.material;
-        sc.prims.push_back(p);
+        dst.push_back(p);
       }
     } else {
       Primitive p; p.material = s.material;
       if (s.kind == RT_SHAPE_SPHERE) p.shape = std::make_shared<Sphere>(o2w, s.radius, s.zmin, s.zmax, s.phimax, s.reverse_orientation != 0);
       else if (s.kind == RT_SHAPE_DISK) p.shape = std::make_shared<Disk>(s.height, s.radius, s.inner_radius, s.phimax, o2w, s.reverse_orientation != 0);
       else p.shape = std::make_shared<Cylinder>(o2w, s.radius, s.zmin, s.zmax, s.phimax, s.reverse_orientation != 0);
-      sc.prims.push_back(p);
+      dst.push_back(p);
     }
-    o->shape_n_prims.push_back(sc.prims.size() - o->shape_first_prim.back());
+    o->shape_n_prims.push_back(s.object_def >= 0 ? 0 : dst.size() - dst_before);
   }
+  for (auto& d : defs) if (!d->prims.empty()) d->finish(in->accel.max_node_prims, in->accel.split_method);
+  o->defs = defs;
   // lights in creation order; ids = get_next_id order (light/mod.rs:58-64)
   for (uint32_t li = 0; li < in->n_lights; li++) {
     const rt_light& l = in->lights[li];

@@ -224,4 +224,65 @@ struct BVH {
   }
 };
 
+// ---- object instancing: TransformedPrimitive (primitive.rs:79-118) over the aggregate built at the first
+// ObjectInstance (api.rs:1071-1080: a BVH when the definition holds more than one primitive, else the primitive itself) ----
+struct ObjectDef {
+  std::vector<Primitive> prims;
+  BVH bvh;
+  bool aggregate = false;
+  void finish(int max_prims_per_node, int split_method) {
+    aggregate = prims.size() > 1;
+    if (aggregate) bvh.build(prims, max_prims_per_node, split_method);
+  }
+  Bounds3 world_bounds() const { return aggregate ? bvh.world_bounds() : prims[0].shape->world_bounds(); }
+};
+
+// SurfaceInteraction::transform (interaction.rs:156-190)
+inline SurfaceInteraction transform_interaction(const SurfaceInteraction& s, const Transform& t) {
+  SurfaceInteraction o = s;
+  V3 p_err;
+  V3 p = t.point_with_error(s.hit.p, s.hit.p_error, p_err);
+  o.hit = Interaction::make(p, p_err, normalize(t.vector(s.hit.wo)), normalize(t.normal(s.hit.n)));
+  o.dpdu = t.vector(s.dpdu); o.dpdv = t.vector(s.dpdv);
+  o.shading.n = normalize(t.normal(s.shading.n));
+  o.shading.dpdu = t.vector(s.shading.dpdu); o.shading.dpdv = t.vector(s.shading.dpdv);
+  o.shading.n = face_forward(o.shading.n, o.hit.n);
+  return o;
+}
+
+struct InstanceShape : Shape {
+  std::shared_ptr<ObjectDef> def;
+  Transform p2w;
+  InstanceShape(std::shared_ptr<ObjectDef> d, const Transform& t) : def(std::move(d)), p2w(t) {}
+  Bounds3 world_bounds() const override { return p2w.bounds(def->world_bounds()); }                   // primitive.rs:86-88
+  // `primitive_to_world.inverse() * ray` (ray.rs:83-93): origin and direction only, no error offset, t_max kept
+  Ray to_object(const Ray& ray) const { Transform w2p = p2w.inverse(); return Ray(w2p.point(ray.o), w2p.vector(ray.d), ray.t_max); }
+  bool intersect(const Ray& ray, SurfaceInteraction& si, float& t) const override {                   // primitive.rs:90-97
+    Ray r = to_object(ray);
+    SurfaceInteraction inner;
+    int material;
+    if (def->aggregate) {
+      int pn = def->bvh.intersect(r, inner);
+      if (pn < 0) return false;
+      material = def->prims[pn].material;
+      t = r.t_max;
+    } else {
+      tls_counters().prims_tested++;
+      if (!def->prims[0].shape->intersect(r, inner, t)) return false;
+      material = def->prims[0].material;
+    }
+    si = transform_interaction(inner, p2w);
+    si.material_override = material;
+    return true;
+  }
+  bool intersect_p(const Ray& ray) const override {                                                   // primitive.rs:99-102
+    Ray r = to_object(ray);
+    if (def->aggregate) return def->bvh.intersect_p(r);
+    tls_counters().prims_tested++;
+    return def->prims[0].shape->intersect_p(r);
+  }
+  float area() const override { return 0.0f; }
+  void sample(P2, Interaction&, float& pdf) const override { pdf = 0.0f; }                            // never a light (primitive.rs:104-106)
+};
+
 }  // namespace orc

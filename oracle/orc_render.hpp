@@ -179,6 +179,7 @@ struct Scene {                                                   // scene.rs:22-
     Ray r = p0.spawn_ray_to_interaction(p1);
     return !intersect_p(r);
   }
+  int material_of(const SurfaceInteraction& si) const { return si.material_override != -2 ? si.material_override : prims[si.prim].material; }
   Spectrum le(const SurfaceInteraction& si, V3 w) const {        // interaction.rs:149-154
     int al = prims[si.prim].area_light;
     return al >= 0 ? lights[al].L(si.hit, w) : Spectrum(0.0f);
@@ -504,7 +505,7 @@ struct Integrator {
       }
       if (!found || bounces >= max_ray_depth) break;
       Bsdf bsdf;
-      int mat = scene.prims[isect.prim].material;
+      int mat = scene.material_of(isect);
       if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, true, bsdf)) {
         ray = isect.hit.spawn_ray(ray.d);
         bounces -= 1;                                            // u8 wrap (Q23)
@@ -544,7 +545,7 @@ struct Integrator {
     if (scene.intersect(ray, isect) >= 0) {
       V3 n = isect.shading.n, wo = isect.hit.wo;
       Bsdf bsdf;
-      int mat = scene.prims[isect.prim].material;
+      int mat = scene.material_of(isect);
       if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, false, bsdf)) {
         Ray r = isect.hit.spawn_ray(ray.d);
         return li_recursive(scene, r, sampler, depth, node);

@@ -69,6 +69,9 @@ struct SurfaceInteraction {
   struct { V3 n, dpdu, dpdv; } shading;
   int prim = -1;           // prim_number of the GeometricPrimitive (primitive.rs:45-51)
   const Shape* shape = nullptr;
+  // hit inside an object instance: `isect.primitive` is the instance's inner GeometricPrimitive (primitive.rs:91-97 maps the
+  // inner interaction), so the material is the inner one's; `prim` stays the TransformedPrimitive's number.  -2 = not set.
+  int material_override = -2;
 };
 
 struct Shape {

@@ -17,7 +17,8 @@ class rt_transform(C.Structure):
 class rt_shape(C.Structure):
     _fields_ = [("kind", c_i32), ("o2w", rt_transform), ("reverse_orientation", c_i32), ("material", c_i32), ("area_light", c_i32),
                 ("n_indices", c_u32), ("indices", PI32), ("n_vertices", c_u32), ("P", PF), ("N", PF), ("S", PF), ("uv", PF),
-                ("radius", c_f), ("zmin", c_f), ("zmax", c_f), ("phimax", c_f), ("height", c_f), ("inner_radius", c_f)]
+                ("radius", c_f), ("zmin", c_f), ("zmax", c_f), ("phimax", c_f), ("height", c_f), ("inner_radius", c_f),
+                ("object_def", c_i32), ("instance_of", c_i32)]
 
 
 class rt_area_light(C.Structure):
@@ -59,7 +60,7 @@ class rt_accel(C.Structure):
 
 
 class rt_scene(C.Structure):
-    _fields_ = [("n_shapes", c_u32), ("shapes", C.POINTER(rt_shape)), ("n_area_lights", c_u32), ("area_lights", C.POINTER(rt_area_light)),
+    _fields_ = [("n_objects", c_u32), ("n_shapes", c_u32), ("shapes", C.POINTER(rt_shape)), ("n_area_lights", c_u32), ("area_lights", C.POINTER(rt_area_light)),
                 ("n_lights", c_u32), ("lights", C.POINTER(rt_light)), ("n_materials", c_u32), ("materials", C.POINTER(rt_material)),
                 ("camera", rt_camera), ("film", rt_film), ("sampler", rt_sampler), ("integrator", rt_integrator), ("accel", rt_accel)]
 
@@ -95,6 +96,11 @@ class rtgpu_lobe(C.Structure):
                 ("eta_a", c_f), ("eta_b", c_f)]
 
 
+class rtgpu_instance(C.Structure):
+    _fields_ = [("w2o", c_f * 12), ("o2w", c_f * 12), ("root_node", c_u32), ("first_slot", c_u32), ("lo", c_f * 3), ("hi", c_f * 3),
+                ("prim_number", c_u32), ("root_ref", c_u32)]
+
+
 class rtgpu_light(C.Structure):
     _fields_ = [("kind", c_u32), ("pos", c_f * 3), ("dir", c_f * 3), ("I", c_f * 3), ("prim_slot", c_u32), ("two_sided", c_u32), ("n_samples", c_u32),
                 ("area", c_f), ("world_radius", c_f), ("l2w", c_f * 9), ("w2l", c_f * 9), ("env_w", c_u32), ("env_h", c_u32), ("env_texels", c_u32),
@@ -104,7 +110,7 @@ class rtgpu_light(C.Structure):
 class rtgpu_scene_desc(C.Structure):
     _fields_ = [("n_nodes", c_u32), ("node_lo", PF), ("node_hi", PF), ("n_prims", c_u32), ("prim_geom", PF), ("prim_info", PU32),
                 ("tri_n", PF), ("tri_s", PF), ("tri_uv", PF), ("n_quadrics", c_u32), ("quadrics", C.POINTER(rtgpu_quadric)),
-                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lobes", c_u32), ("lobes", C.POINTER(rtgpu_lobe)),
+                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lobes", c_u32), ("lobes", C.POINTER(rtgpu_lobe)), ("n_instances", c_u32), ("instances", C.POINTER(rtgpu_instance)),
                 ("n_lights", c_u32), ("lights", C.POINTER(rtgpu_light)),
                 ("n_env_floats", c_u32), ("env_data", PF), ("world_lo", c_f * 3), ("world_hi", c_f * 3)]
 

@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(128) k_closest_batch(DScene sc, const float4* 
   const uint32_t r = perm ? perm[i] : i;
   const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
   Ray ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
-  HitRec h; TravStats st; st.nodes = 0; st.prims = 0;
-  bvh_traverse<false, STATS>(sc, ray, h, &st);
-  if (to_prim_number) h.slot = h.slot == kMiss ? kMiss : sc.info[h.slot].x;
+  HitRec h; TravStats st; st.nodes = 0; st.prims = 0; uint32_t inst;
+  bvh_traverse<false, STATS>(sc, ray, h, &st, &inst);
+  // slot -> prim_number (bvh/mod.rs:92); a hit inside an object instance reports the TransformedPrimitive's number
+  if (to_prim_number) h.slot = h.slot == kMiss ? kMiss : (inst != kNoInst ? sc.instances[inst].prim_number : sc.info[h.slot].x);
   hits[r] = h;
   if (STATS) stats[r] = make_uint2(st.nodes, st.prims);
 }
@@ -101,15 +102,15 @@ __global__ void __launch_bounds__(128) k_anyhit_batch(DScene sc, const float4* _
 
 // Engine variants (trace_engine.cuh): persistent warps, queue = the batch itself (optionally through `perm`).
 struct BatchClosestPolicy {
-  const float4* rays; const uint32_t* perm; HitRec* hits; const uint4* info; uint32_t r;
+  const float4* rays; const uint32_t* perm; HitRec* hits; const uint4* info; const rtgpu_instance* instances; uint32_t r;
   RT_DEV void load(uint32_t idx, Ray& ray) {
     r = perm ? perm[idx] : idx;
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h) {
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst) {
     HitRec o = h;
-    o.slot = h.slot == kMiss ? kMiss : info[h.slot].x;                 // slot -> prim_number (bvh/mod.rs:92)
+    o.slot = h.slot == kMiss ? kMiss : (inst != kNoInst ? instances[inst].prim_number : info[h.slot].x);   // slot -> prim_number (bvh/mod.rs:92)
     hits[r] = o;
   }
 };
@@ -120,17 +121,19 @@ struct BatchAnyPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h) { occluded[r] = h.slot != kMiss ? 1 : 0; }
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t) { occluded[r] = h.slot != kMiss ? 1 : 0; }
 };
+template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_closest_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
                                                                HitRec* __restrict__ hits, uint32_t* cursor) {
-  BatchClosestPolicy pol; pol.rays = rays; pol.perm = perm; pol.hits = hits; pol.info = sc.info; pol.r = 0;
-  trace_engine<false>(sc, cursor, n, pol);
+  BatchClosestPolicy pol; pol.rays = rays; pol.perm = perm; pol.hits = hits; pol.info = sc.info; pol.instances = sc.instances; pol.r = 0;
+  trace_engine<false, INST>(sc, cursor, n, pol);
 }
+template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_anyhit_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
                                                               uint8_t* __restrict__ occluded, uint32_t* cursor) {
   BatchAnyPolicy pol; pol.rays = rays; pol.perm = perm; pol.occluded = occluded; pol.r = 0;
-  trace_engine<true>(sc, cursor, n, pol);
+  trace_engine<true, INST>(sc, cursor, n, pol);
 }
 
 static int ensure_sort_scratch(rtgpu_ctx* ctx, size_t n, uint32_t** keys, uint32_t** perm, uint32_t** hist) {
@@ -283,7 +286,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
       const uint32_t meta = bits(s->node_hi[i * 4 + 3]), n_prims = meta >> 2, off = bits(s->node_lo[i * 4 + 3]);
       if (n_prims > 0) {
         if ((size_t)off + n_prims > s->n_prims) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
-        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(1u);
+        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | 1u);
         continue;
       }
       const size_t L = i + 1, R = off;
@@ -293,6 +296,20 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
       w[3] = fbits(ref_of(L)); w[7] = fbits(ref_of(R)); w[11] = fbits(meta & 3u); w[15] = 0.0f;
     }
     d.root_ref = nn > 0 ? ref_of(0) : 0xffffffffu;
+    // object instances: the engine's reference of each definition's root (a one-primitive definition is a one-slot leaf)
+    if (s->n_instances && !s->instances) return fail(ctx, RTGPU_ERR_ARG, "instance table missing");
+    std::vector<rtgpu_instance> inst(s->instances, s->instances + s->n_instances);
+    for (rtgpu_instance& I : inst) {
+      if (I.root_node == 0xffffffffu) {
+        if (I.first_slot >= s->n_prims) return fail(ctx, RTGPU_ERR_ARG, "instance slot outside the primitive arrays");
+        I.root_ref = 0x80000000u | I.first_slot;
+      } else {
+        if (I.root_node >= nn) return fail(ctx, RTGPU_ERR_ARG, "instance root outside the node arrays");
+        I.root_ref = ref_of(I.root_node);
+      }
+    }
+    if ((rc = upload(ctx, inst.data(), inst.size(), &d.instances))) return rc;
+    d.n_instances = s->n_instances;
     if ((rc = upload(ctx, wide.data(), wide.size(), &pf))) return rc; d.wide = (const float4*)pf;
     if ((rc = upload(ctx, geom.data(), geom.size(), &pf))) return rc; d.geom = (const float4*)pf;
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die at scope end
@@ -362,7 +379,8 @@ static int run_closest(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_
   // the counting variant is the plain one-thread-one-ray reference walk; the fast path is the persistent engine
   if (d_stats) k_closest_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, (uint2*)d_stats);
   else if (ctx->simple_traversal) k_closest_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, 1, nullptr);
-  else k_closest_batch_engine<<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, cursor);
+  else if (ctx->scene.n_instances) k_closest_batch_engine<true><<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, cursor);
+  else k_closest_batch_engine<false><<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, (HitRec*)d_hits, cursor);
   ctx->launches += 1;
   RT_CUDA(ctx, cudaGetLastError());
   if (elapsed_ms) {
@@ -384,7 +402,8 @@ static int run_anyhit(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t
   const unsigned pblocks = (unsigned)std::min<size_t>((size_t)ctx->sm_count * 8, blocks);
   if (d_stats) k_anyhit_batch<true><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, (uint2*)d_stats);
   else if (ctx->simple_traversal) k_anyhit_batch<false><<<blocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, nullptr);
-  else k_anyhit_batch_engine<<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, cursor);
+  else if (ctx->scene.n_instances) k_anyhit_batch_engine<true><<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, cursor);
+  else k_anyhit_batch_engine<false><<<pblocks, 128, 0, ctx->stream>>>(ctx->scene, (const float4*)d_rays, perm, (uint32_t)n, d_occ, cursor);
   ctx->launches += 1;
   RT_CUDA(ctx, cudaGetLastError());
   if (elapsed_ms) {

@@ -348,6 +348,13 @@ RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi,
 }
 
 constexpr int kMaxLobes = 2;     // the five materials with their own shade kernels build at most two lobes
+// Translation units that only ever shade one of those five materials (tu_path.cu with RT_PATH_MAT != Q_LOBES) compile the
+// host-listed-lobes path out (it cost the matte kernel 10 % when left to a run-time test: profiles/r01g).
+#if defined(RT_PATH_MAT) && RT_PATH_MAT != 6
+constexpr bool kListedLobes = false;
+#else
+constexpr bool kListedLobes = true;
+#endif
 
 // Bsdf (bsdf/mod.rs:64-269).  The lobes are either built in place (`lobes`, the five materials above) or are the
 // host-listed rows of an RTGPU_MAT_LOBES material (`g`, up to 8: uber / substrate / translucent / mix).
@@ -365,13 +372,13 @@ RT_DEV Lobe load_lobe(const rtgpu_lobe& g) {
   l.ax = g.ax; l.ay = g.ay; l.eta_a = g.eta_a; l.eta_b = g.eta_b;
   return l;
 }
-RT_DEV Lobe bsdf_lobe(const Bsdf& b, int i) { return b.g ? load_lobe(b.g[i]) : b.lobes[i]; }
-RT_DEV int bsdf_lobe_kind(const Bsdf& b, int i) { return b.g ? (int)b.g[i].kind : b.lobes[i].kind; }
+RT_DEV Lobe bsdf_lobe(const Bsdf& b, int i) { return (kListedLobes && b.g) ? load_lobe(b.g[i]) : b.lobes[i]; }
+RT_DEV int bsdf_lobe_kind(const Bsdf& b, int i) { return (kListedLobes && b.g) ? (int)b.g[i].kind : b.lobes[i].kind; }
 // ---- the BxDF interface as Bsdf sees it: lobe i itself, or lobe i behind its ScaledBxDF wrappers (bxdf.rs:48-71; only the
 // host-listed lobes of a mix have any): f and sample_f are scaled, the type is the wrapped lobe's, and pdf() is NOT
 // forwarded — it is the trait's default cosine pdf (bxdf.rs:38-44).
 RT_DEV Spec scale_by_wrappers(const Bsdf& b, int i, Spec v) {
-  if (b.g) {
+  if (kListedLobes && b.g) {
     const rtgpu_lobe& g = b.g[i];
     if (g.n_scales > 0) v = v * spec3(g.scale[0]);
     if (g.n_scales > 1) v = v * spec3(g.scale[1]);
@@ -380,7 +387,7 @@ RT_DEV Spec scale_by_wrappers(const Bsdf& b, int i, Spec v) {
 }
 RT_DEV Spec lobe_f(const Bsdf& b, int i, V3 wo, V3 wi) { return scale_by_wrappers(b, i, lobe_f_inner(bsdf_lobe(b, i), wo, wi)); }
 RT_DEV float lobe_pdf(const Bsdf& b, int i, V3 wo, V3 wi) {
-  if (b.g && b.g[i].n_scales > 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
+  if (kListedLobes && b.g && b.g[i].n_scales > 0) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
   return lobe_pdf_inner(bsdf_lobe(b, i), wo, wi);
 }
 RT_DEV void lobe_sample_f(const Bsdf& b, int i, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
@@ -424,7 +431,36 @@ RT_DEV float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {        
   for (int i = 0; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) { matched++; p += lobe_pdf(b, i, wo, wi); }
   return matched == 0 ? 0.0f : p / (float)matched;
 }
+// the lobes built in place: the matching lobes are listed once (kernels that never see host-listed lobes use this form)
+RT_DEV void bsdf_sample_f_built(const Bsdf& b, V3 wo_w, P2 u, uint32_t flags, Spec& f_out, V3& wi_w, float& pdf_out, uint32_t& sampled) {   // :138-251
+  int m[kMaxLobes]; int nm = 0;
+  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) m[nm++] = i;
+  if (nm == 0) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
+  int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));
+  const Lobe& bxdf = b.lobes[m[comp]];
+  const uint32_t btype = lobe_type(bxdf.kind);
+  P2 ur = mk2(fminf(u.x * (float)nm - (float)comp, kOneMinusEpsilon), u.y);
+  V3 wo = world_to_local(b, wo_w);
+  if (wo.z == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = btype; return; }
+  Spec f; V3 wi; float pdf;
+  lobe_sample_f_inner(bxdf, wo, ur, f, wi, pdf, sampled);
+  if (pdf == 0.0f) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
+  wi_w = local_to_world(b, wi);
+  if (!(btype & BSDF_SPECULAR) && nm > 1)
+    for (int i = 0; i < nm; i++) if (i != comp) pdf += lobe_pdf_inner(b.lobes[m[i]], wo, wi);
+  if (nm > 1) pdf /= (float)nm;
+  if (!(btype & BSDF_SPECULAR)) {
+    bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
+    f = spec(0.0f);
+    for (int i = 0; i < nm; i++) {
+      uint32_t t = lobe_type(b.lobes[m[i]].kind);
+      if ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION))) f = f + lobe_f_inner(b.lobes[m[i]], wo, wi);
+    }
+  }
+  f_out = f; pdf_out = pdf;
+}
 RT_DEV void bsdf_sample_f(const Bsdf& b, V3 wo_w, P2 u, uint32_t flags, Spec& f_out, V3& wi_w, float& pdf_out, uint32_t& sampled) {   // :138-251
+  if (!kListedLobes) { bsdf_sample_f_built(b, wo_w, u, flags, f_out, wi_w, pdf_out, sampled); return; }
   const int nm = bsdf_num_components(b, flags);
   if (nm == 0) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
   const int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));

@@ -145,6 +145,11 @@ RT_DEV V3 xf_vector(const float* m, V3 v) {                                     
   float x = v.x, y = v.y, z = v.z;
   return v3(m[0] * x + m[1] * y + m[2] * z, m[4] * x + m[5] * y + m[6] * z, m[8] * x + m[9] * y + m[10] * z);
 }
+// affine transform given by its rows 0..2 (row 3 = 0 0 0 1, so transform.rs:263-287 takes its `wp == 1` branch)
+RT_DEV V3 xf_point_affine(const float* m, V3 p) {
+  float x = p.x, y = p.y, z = p.z;
+  return v3(m[0] * x + m[1] * y + m[2] * z + m[3], m[4] * x + m[5] * y + m[6] * z + m[7], m[8] * x + m[9] * y + m[10] * z + m[11]);
+}
 // Normal transform uses the transpose of the inverse: pass m_inv (transform.rs:244-254, :306-320).
 RT_DEV V3 xf_normal(const float* mi, V3 n) {
   float x = n.x, y = n.y, z = n.z;
@@ -158,9 +163,11 @@ RT_DEV V3 xf_abs_sum(const float* m, V3 p) {                                    
 }
 RT_DEV V3 xf_point_err(const float* m, V3 p, V3& p_err) { p_err = gamma_f(3) * xf_abs_sum(m, p); return xf_point(m, p); }      // :175-189
 RT_DEV V3 xf_vector_err(const float* m, V3 v, V3& v_err) { v_err = gamma_f(3) * xf_abs_sum(m, v); return xf_vector(m, v); }   // :222-242 (keeps the |m[i][3]| term)
+// AFFINE: m holds rows 0..2 only (row 3 = 0 0 0 1)
+template <bool AFFINE = false>
 RT_DEV V3 xf_point_with_error(const float* m, V3 p, V3 pe, V3& out_err) {                     // :191-220
   float x = p.x, y = p.y, z = p.z;
-  V3 tp = xf_point(m, p);
+  V3 tp = AFFINE ? xf_point_affine(m, p) : xf_point(m, p);
   float e[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {

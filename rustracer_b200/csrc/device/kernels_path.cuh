@@ -5,8 +5,11 @@
 namespace rt {
 
 // ---- path integrator: one bounce of PathIntegrator::li (integrator/path.rs:96-215) -------------------------------
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 4      // resident 128-thread blocks per SM the path shade kernels are compiled for (register cap 128)
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(128) k_shade_path(RenderParams p, int parity) {
+__global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) k_shade_path(RenderParams p, int parity) {
   const uint32_t n = p.w.counters[C_MATQ0 + MAT];
   uint32_t* out_list = p.w.list[1 - parity];
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(128) k_shade_path(RenderParams p, int parity) 
       const uint2 sinf = p.w.sinfo[sample];
       SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = ps.w & 0xffffu; ss.d2 = ps.w >> 16; ss.da = 0;
       SurfHit si; float t_hit;
-      slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+      hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
       const uint4 info = p.sc.info[h.slot];
       Spec l_add = spec(0.0f);
       if ((bounces == 0 || specular_bounce) && info.z != kNoLight) l_add = beta * area_L(p.sc.lights[info.z], si.n, -ray.d);   // path.rs:127-131

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int par
       for (uint32_t j = 0; j < p.sc.n_lights; j++) colour = colour + light_le(p.sc, p.sc.lights[j], ray.d);
     } else {
       SurfHit si; float t_hit;
-      slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+      hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[i] : kNoInst, ray, t_hit, si);
       const uint4 info = p.sc.info[h.slot];
       const Inter it = inter_of(si);
       const uint32_t mtype = info.y < p.sc.n_materials ? p.sc.materials[info.y].type : (uint32_t)RTGPU_MAT_NONE;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) k_shade_ao(RenderParams p) {
     Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
     ray.t_max = inf_f();
     SurfHit si; float t_hit;
-    slot_intersect_surface(p.sc, h.slot, ray, t_hit, si);
+    hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
     const Inter it = inter_of(si);
     const uint32_t sample = p.w.pstate[slot].x;
     const uint2 sinf = p.w.sinfo[sample];

@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const flo
     if (i < n) {
       const uint32_t slot = list ? list[i] : i;
       Ray ray = load_ray(ray_o, ray_d, slot, nullptr);
-      HitRec h;
-      bvh_traverse<false, STATS>(p.sc, ray, h, &st);
+      HitRec h; uint32_t inst;
+      bvh_traverse<false, STATS>(p.sc, ray, h, &st, &inst);
       hits[slot] = h;
+      if (p.w.hit_inst) p.w.hit_inst[slot] = inst;
     }
   }
   if (STATS) flush_trav_stats(p, st, S_NODES_CLOSEST, S_PRIMS_CLOSEST);
@@ -140,10 +141,10 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
     const float4 c = p.w.mi_c[i];
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];
-    HitRec h;
+    HitRec h; uint32_t inst;
     Spec li = spec(0.0f);
-    if (bvh_traverse<false, STATS>(p.sc, ray, h, &st)) {
-      if (p.sc.info[h.slot].z == light_row) {                         // same light id (integrator/mod.rs:294-299)
+    if (bvh_traverse<false, STATS>(p.sc, ray, h, &st, &inst)) {
+      if (inst == kNoInst && p.sc.info[h.slot].z == light_row) {      // same light id (integrator/mod.rs:294-299)
         SurfHit si; float t;
         if (slot_intersect_surface(p.sc, h.slot, ray0, t, si)) li = area_L(light, si.n, -ray0.d);
       }
@@ -159,16 +160,18 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
 }
 
 // ---- the same three kernels on the persistent while-while engine (trace_engine.cuh): the production path ------------
+template <bool INST>
 struct ClosestPolicy {
-  const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t slot;
-  RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h) : ray_o(o), ray_d(d), list(l), hits(h), slot(0) {}
+  const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t* hit_inst; uint32_t slot;
+  RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h, uint32_t* hi) : ray_o(o), ray_d(d), list(l), hits(h), hit_inst(hi), slot(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
-  RT_DEV void commit(uint32_t, const HitRec& h) { hits[slot] = h; }
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst) { hits[slot] = h; if (INST) hit_inst[slot] = inst; }
 };
+template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                                const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
-  ClosestPolicy pol(ray_o, ray_d, list, hits);
-  trace_engine<false>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
+  ClosestPolicy<INST> pol(ray_o, ray_d, list, hits, p.w.hit_inst);
+  trace_engine<false, INST>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
 }
 
 // Material classification of the traced paths: appends each path to the queue of its hit material (or the miss queue)
@@ -203,7 +206,7 @@ struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;
   RT_DEV ShadowPolicy(const RenderParams& p_, const AnyQueue& a) : p(p_), aq(a), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t) {
     if (h.slot != kMiss) return;
     const float4 c = aq.c[idx];
     float4* L = &p.w.L[sample];
@@ -211,11 +214,11 @@ struct ShadowPolicy {
     else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
   }
 };
-template <bool ATOMIC>
+template <bool ATOMIC, bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_shadow_engine(RenderParams p, int q) {
   const AnyQueue aq = any_queue(p, q);
   ShadowPolicy<ATOMIC> pol(p, aq);
-  trace_engine<true>(p.sc, aq.cursor, aq.n, pol);
+  trace_engine<true, INST>(p.sc, aq.cursor, aq.n, pol);
 }
 
 template <bool ATOMIC>
@@ -223,14 +226,15 @@ struct MisPolicy {
   const RenderParams& p; uint32_t sample;
   RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst) {
     const float4 c = p.w.mi_c[idx];
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];
     const Ray ray0 = load_ray(p.w.mi_o, p.w.mi_d, idx, nullptr);
     Spec li = spec(0.0f);
     if (h.slot != kMiss) {
-      if (p.sc.info[h.slot].z == light_row) {                           // same light id (integrator/mod.rs:294-299)
+      // an area light is never inside an object instance (the front end rejects it), so a hit there cannot be the sampled light
+      if (inst == kNoInst && p.sc.info[h.slot].z == light_row) {        // same light id (integrator/mod.rs:294-299)
         SurfHit si; float t;
         if (slot_intersect_surface(p.sc, h.slot, ray0, t, si)) li = area_L(light, si.n, -ray0.d);
       }
@@ -243,10 +247,10 @@ struct MisPolicy {
     }
   }
 };
-template <bool ATOMIC>
+template <bool ATOMIC, bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_mis_engine(RenderParams p) {
   MisPolicy<ATOMIC> pol(p);
-  trace_engine<false>(p.sc, &p.w.counters[C_CUR_MIS], min(p.w.counters[C_MIS], p.w.cap_mis), pol);
+  trace_engine<false, INST>(p.sc, &p.w.counters[C_CUR_MIS], min(p.w.counters[C_MIS], p.w.cap_mis), pol);
 }
 
 // compute_distribution (lightdistrib.rs:101-179), first half: one thread per (voxel, light) accumulates the

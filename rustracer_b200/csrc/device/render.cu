@@ -58,12 +58,14 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   if (!ctx->wave) ctx->wave = new WaveBuffers();
   WaveBuffers* w = ctx->wave;
   WaveView& v = w->v;
-  if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters)
+  if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
+      (v.hit_inst != nullptr || ctx->scene.n_instances == 0))
     return 0;
   release(w);
   int rc = 0;
 #define A(field, n) if ((rc = dalloc(ctx, w, &v.field, (n)))) return rc
   A(ray_o, cap_items); A(ray_d, cap_items); A(hit, cap_items); A(beta, cap_items); A(pstate, cap_items);
+  if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);

@@ -22,6 +22,8 @@ struct DScene {
   const rtgpu_quadric* quadrics;
   const rtgpu_material* materials;
   const rtgpu_lobe* lobes;   // lobe lists of the RTGPU_MAT_LOBES materials (or null)
+  const rtgpu_instance* instances;   // object instances (or null); n_instances > 0 selects the instance-aware kernels
+  uint32_t n_instances;
   const rtgpu_light* lights;
   const float* env;
   uint32_t n_nodes, n_prims, n_quadrics, n_materials, n_lights;
@@ -338,6 +340,30 @@ RT_DEV bool slot_intersect_surface(const DScene& sc, uint32_t slot, const Ray& r
     return true;
   }
   return quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, true, &out);
+}
+
+// ---- object instances: TransformedPrimitive (primitive.rs:79-118) -----------------------------------------------------
+constexpr uint32_t kNoInst = 0xffffffffu;
+// `primitive_to_world.inverse() * ray` (ray.rs:83-93): origin and direction only, no error offset, t_max kept
+RT_DEV Ray instance_ray(const rtgpu_instance& I, const Ray& ray) { return make_ray(xf_point_affine(I.w2o, ray.o), xf_vector(I.w2o, ray.d), ray.t_max); }
+// SurfaceInteraction::transform (interaction.rs:156-190) for the fields SurfHit keeps
+RT_DEV void instance_surface(const rtgpu_instance& I, const SurfHit& o, SurfHit& si) {
+  si.p = xf_point_with_error<true>(I.o2w, o.p, o.p_error, si.p_error);
+  si.wo = normalize(normalize(xf_vector(I.o2w, o.wo)));                          // `(t * wo).normalize()`, then Interaction::new normalises again
+  si.n = normalize(xf_normal(I.w2o, o.n));
+  si.ns = normalize(xf_normal(I.w2o, o.ns));
+  si.dpdu_s = xf_vector(I.o2w, o.dpdu_s);
+  si.ns = face_forward(si.ns, si.n);
+}
+// The surface record of a final closest hit: slot_intersect_surface, through the instance's transform when the hit lies
+// inside an object instance (inst = row of DScene::instances, or kNoInst).
+RT_DEV bool hit_surface(const DScene& sc, uint32_t slot, uint32_t inst, const Ray& ray, float& t, SurfHit& si) {
+  if (inst == kNoInst) return slot_intersect_surface(sc, slot, ray, t, si);
+  const rtgpu_instance& I = sc.instances[inst];
+  SurfHit o;
+  if (!slot_intersect_surface(sc, slot, instance_ray(I, ray), t, o)) return false;
+  instance_surface(I, o, si);
+  return true;
 }
 
 }  // namespace rt

@@ -34,6 +34,7 @@ namespace rt {
 RT_DEV uint32_t lane_id_() { return threadIdx.x & 31u; }
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDoneRef = 0xffffffffu;        // (a leaf ref never has all 31 payload bits set: slots < 2^31 - 1)
+constexpr uint32_t kExitInstance = 0xfffffffeu;   // stack marker: the walk below this entry happens in world space again
 
 // Bounds3::intersect_p_fast (bounds.rs:127-157) split into its t_max-independent part and the entry distance.
 RT_DEV bool slab_interval(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bool ny, bool nz, float t_max, float& tmin_out) {
@@ -72,9 +73,15 @@ RT_DEV bool slab_interval_bf(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bo
   return !r1 & !r2 & (tmin < t_max) & (tmax > 0.0f);
 }
 
-// Policy: RT_DEV void load(uint32_t idx, Ray& ray)             — fetch queue entry idx (lane-private bookkeeping inside)
-//         RT_DEV void commit(uint32_t idx, const HitRec& h)    — called by the lanes holding a finished ray (divergent)
-template <bool ANY, class Policy>
+// Policy: RT_DEV void load(uint32_t idx, Ray& ray)                            — fetch queue entry idx (lane-private bookkeeping inside)
+//         RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst)    — called by the lanes holding a finished ray (divergent);
+//                                                                               inst = instance row of the hit or kNoInst
+// INST: the scene holds object instances (TransformedPrimitive, primitive.rs:79-118).  A leaf primitive flagged as an
+// instance suspends the leaf: an exit marker with the resume point goes on the stack, the ray moves to object space
+// (`primitive_to_world.inverse() * ray`, same t parametrisation) and the walk continues at the definition's root; popping
+// the marker restores the world-space ray (re-read from the queue) and resumes the leaf.  Same visit order as the
+// reference's nested BVH::intersect call.  Compiled out entirely for scenes without instances.
+template <bool ANY, bool INST, class Policy>
 RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy& pol) {
   const unsigned FULL = 0xffffffffu;
   const float4* __restrict__ wide = sc.wide;
@@ -95,14 +102,32 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
   int sp = 0;
   bool queue_empty = n == 0;
   uint32_t negmask = 0;                     // bit k = dir_is_neg[k]
+  uint32_t inst = kNoInst, hit_inst = kNoInst;   // INST: instance the walk is inside of / instance of the best hit
   const int node_threshold = sc.tune_node_threshold, refill_threshold = sc.tune_refill_threshold;
 
+  // (re)derive the per-ray constants of the walk from a ray's origin and direction; ray.t_max is left alone
+#define RT_ENGINE_SET_RAY(r_) do { \
+    ray.o = (r_).o; \
+    inv_dir = v3(1.0f / (r_).d.x, 1.0f / (r_).d.y, 1.0f / (r_).d.z);                         /* bvh/mod.rs:375-380 */ \
+    nx = inv_dir.x < 0.0f; ny = inv_dir.y < 0.0f; nz = inv_dir.z < 0.0f; \
+    negmask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u); \
+    tr = make_tri_ray(r_); } while (0)
+#define RT_ENGINE_PUSH(e_) do { \
+    const uint2 pe_ = (e_); \
+    if (sp < RT_ENGINE_SMEM_DEPTH) s_stack[sp][tid] = pe_; else stack_l[sp - RT_ENGINE_SMEM_DEPTH] = pe_; \
+    sp++; } while (0)
   // next subtree whose entry distance is still in front of the hit (the reference's test at visit time), or finished
 #define RT_ENGINE_POP() do { \
     cur = kDoneRef; \
     while (sp > 0) { \
       --sp; \
       const uint2 e_ = sp < RT_ENGINE_SMEM_DEPTH ? s_stack[sp][tid] : stack_l[sp - RT_ENGINE_SMEM_DEPTH]; \
+      if (INST && e_.x == kExitInstance) { \
+        Ray wr_; pol.load(idx, wr_); \
+        RT_ENGINE_SET_RAY(wr_); \
+        inst = kNoInst; \
+        if (e_.y != kDoneRef) { cur = e_.y; break; } \
+        continue; } \
       if (ANY || __uint_as_float(e_.y) < ray.t_max) { cur = e_.x; break; } } \
     pending = cur == kDoneRef; } while (0)
 
@@ -112,7 +137,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     const unsigned busy = m_n | m_l;
     if (busy == 0u || (!queue_empty && 32 - __popc(busy) >= refill_threshold)) {
       // ---- commit finished rays and pull new ones ----------------------------------------------------------
-      if (pending) { pol.commit(idx, hit); pending = false; }
+      if (pending) { pol.commit(idx, hit, hit_inst); pending = false; }
       if (queue_empty) break;                                          // busy == 0 and nothing left to fetch
       const unsigned wmask = ~busy;
       const int leader = __ffs(wmask) - 1;
@@ -123,12 +148,10 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         idx = base + (uint32_t)__popc(wmask & lane_lt);
         if (idx < n) {
           pol.load(idx, ray);
-          inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);                      // bvh/mod.rs:375-380
-          nx = inv_dir.x < 0.0f; ny = inv_dir.y < 0.0f; nz = inv_dir.z < 0.0f;
-          negmask = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
-          tr = make_tri_ray(ray);
+          RT_ENGINE_SET_RAY(ray);
           hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
           sp = 0;
+          if (INST) { inst = kNoInst; hit_inst = kNoInst; }
           // root: the reference tests the root's own bounds first
           float t0;
           const float4 rlo = make_float4(sc.world_lo[0], sc.world_lo[1], sc.world_lo[2], 0.0f);
@@ -160,9 +183,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         const float tsecond = neg ? tl : trr;
         if (hfirst) {
           if (hsecond) {
-            const uint2 e = make_uint2(second, __float_as_uint(tsecond));
-            if (sp < RT_ENGINE_SMEM_DEPTH) s_stack[sp][tid] = e; else stack_l[sp - RT_ENGINE_SMEM_DEPTH] = e;
-            sp++;
+            RT_ENGINE_PUSH(make_uint2(second, __float_as_uint(tsecond)));
 #if RT_ENGINE_PREFETCH
             {   // the postponed subtree's record will be needed after the near subtree: start its fetch now
               const char* pa = (second & kLeafBit) ? (const char*)&geom[3 * (size_t)(second & ~kLeafBit)] : (const char*)&wide[4 * (size_t)second];
@@ -183,7 +204,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     } else if ((cur & kLeafBit) != 0u && cur != kDoneRef) {
       // ---- leaf step: every primitive of the leaf, in slot order (bvh/mod.rs:392-396) ---------------------------
       uint32_t slot = cur & ~kLeafBit;
-      bool last = false, done = false;
+      bool last = false, done = false, entered = false;
       do {
         const float4 g0 = __ldg(&geom[3 * (size_t)slot]);
         const float4 g1 = __ldg(&geom[3 * (size_t)slot + 1]);
@@ -191,27 +212,52 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         last = (__float_as_uint(g1.w) & 1u) != 0;
         float t, b0, b1, b2;
         bool ok;
+        if (INST && (__float_as_uint(g1.w) & 2u)) {                    // TransformedPrimitive::intersect / intersect_p (primitive.rs:90-102)
+          const uint32_t row = __float_as_uint(__ldg(&geom[3 * (size_t)slot + 2]).w);
+          const rtgpu_instance& I = sc.instances[row];
+          Ray wr; pol.load(idx, wr);
+          const Ray orr = instance_ray(I, wr);
+          const V3 iinv = v3(1.0f / orr.d.x, 1.0f / orr.d.y, 1.0f / orr.d.z);
+          float t0;
+          // an aggregate tests its root bounds first (bvh/mod.rs:382-386); a one-primitive definition is the primitive itself
+          const bool in = I.root_node == 0xffffffffu ||
+                          slab_interval(make_float4(I.lo[0], I.lo[1], I.lo[2], 0.0f), make_float4(I.hi[0], I.hi[1], I.hi[2], 0.0f), orr.o, iinv,
+                                        iinv.x < 0.0f, iinv.y < 0.0f, iinv.z < 0.0f, ray.t_max, t0);
+          if (in) {
+            RT_ENGINE_PUSH(make_uint2(kExitInstance, last ? kDoneRef : (kLeafBit | (slot + 1u))));
+            RT_ENGINE_SET_RAY(orr);
+            inst = row; cur = I.root_ref;
+            entered = true;
+            break;
+          }
+          slot++;
+          continue;
+        }
         if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) {
           const float4 g2 = __ldg(&geom[3 * (size_t)slot + 2]);
           ok = tri_hit_test_pre(tr, ray.t_max, v3(g0), v3(g1), v3(g2), b0, b1, b2, t);
         } else {
           b1 = 0.0f; b2 = 0.0f;
           Ray rq; pol.load(idx, rq);                                   // the direction is not kept in registers across the walk:
+          if (INST && inst != kNoInst) rq = instance_ray(sc.instances[inst], rq);
           rq.t_max = ray.t_max;                                        // re-read it for the (rare) quadric test
           ok = quadric_intersect(sc.quadrics[kind_bits >> 2], rq, t, false, nullptr);
         }
         if (ok) {
           hit.t = t; hit.slot = slot; hit.b1 = b1; hit.b2 = b2;
+          if (INST) hit_inst = inst;
           if (ANY) { done = true; break; }
           ray.t_max = t;
         }
         slot++;
       } while (!last);
       if (done) { cur = kDoneRef; pending = true; }
-      else RT_ENGINE_POP();
+      else if (!entered) RT_ENGINE_POP();
     }
   }
 #undef RT_ENGINE_POP
+#undef RT_ENGINE_PUSH
+#undef RT_ENGINE_SET_RAY
 }
 
 }  // namespace rt

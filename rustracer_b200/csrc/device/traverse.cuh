@@ -32,18 +32,38 @@ RT_DEV bool slab_test(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bool ny, 
   return tmin < t_max && tmax > 0.0f;
 }
 
+// One primitive slot against a ray (GeometricPrimitive::intersect / intersect_p, primitive.rs:45-60).
+template <bool STATS>
+RT_DEV bool slot_hit_test(const DScene& sc, uint32_t slot, const TriRay& tr, const Ray& ray, float& t, float& b1, float& b2, TravStats* st) {
+  const float4 g0 = __ldg(&sc.geom[3 * (size_t)slot]);
+  const uint32_t kind_bits = __float_as_uint(g0.w);
+  if (STATS) st->prims++;
+  if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) {
+    const float4 g1 = __ldg(&sc.geom[3 * (size_t)slot + 1]);
+    const float4 g2 = __ldg(&sc.geom[3 * (size_t)slot + 2]);
+    float b0;
+    return tri_hit_test_pre(tr, ray.t_max, v3(g0), v3(g1), v3(g2), b0, b1, b2, t);
+  }
+  b1 = 0.0f; b2 = 0.0f;
+  return quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, false, nullptr);
+}
+
 // ANY = false: BVH::intersect (closest hit; ray.t_max shrinks; returns hit.slot != kMiss)
 // ANY = true : BVH::intersect_p (first accepted hit ends the walk)
-template <bool ANY, bool STATS>
-RT_DEV bool bvh_traverse(const DScene& sc, Ray& ray, HitRec& hit, TravStats* st) {
-  hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
+// root: node index of the tree's root (0 = the scene's; an object definition's own tree otherwise).  `inst_out`: instance row
+// of the hit (kNoInst at the top level); may be null.  Instances recurse one level: TransformedPrimitive (primitive.rs:79-118).
+// TOP: the scene's own tree (the only one that holds instances); TOP = false walks a definition's tree and keeps `hit`.
+template <bool ANY, bool STATS, bool TOP>
+RT_DEV bool bvh_walk(const DScene& sc, Ray& ray, HitRec& hit, TravStats* st, uint32_t root, uint32_t* inst_out) {
+  if (TOP) { hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f; if (inst_out) *inst_out = kNoInst; }
   if (sc.n_nodes == 0) return false;
   const V3 inv_dir = v3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);                       // bvh/mod.rs:375-380
   const bool nx = inv_dir.x < 0.0f, ny = inv_dir.y < 0.0f, nz = inv_dir.z < 0.0f;
   const TriRay tr = make_tri_ray(ray);
   uint32_t stack[kStackSize];
   int sp = 0;
-  uint32_t cur = 0;
+  uint32_t cur = root;
+  bool found = false;
   const float4* __restrict__ nodes = sc.nodes;
   const float4* __restrict__ geom = sc.geom;
   while (true) {
@@ -57,23 +77,34 @@ RT_DEV bool bvh_traverse(const DScene& sc, Ray& ray, HitRec& hit, TravStats* st)
       if (n_prims > 0) {                                                                       // leaf :387-401
         for (uint32_t i = 0; i < n_prims; i++) {
           const uint32_t slot = off + i;
-          const float4 g0 = __ldg(&geom[3 * (size_t)slot]);
-          const uint32_t kind_bits = __float_as_uint(g0.w);
-          if (STATS) st->prims++;
-          float t, b0, b1, b2;
-          bool ok;
-          if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) {
-            const float4 g1 = __ldg(&geom[3 * (size_t)slot + 1]);
-            const float4 g2 = __ldg(&geom[3 * (size_t)slot + 2]);
-            ok = tri_hit_test_pre(tr, ray.t_max, v3(g0), v3(g1), v3(g2), b0, b1, b2, t);
-          } else {
-            b1 = 0.0f; b2 = 0.0f;
-            ok = quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, false, nullptr);
+          if (TOP && sc.n_instances && (__float_as_uint(__ldg(&geom[3 * (size_t)slot + 1]).w) & 2u)) {
+            // TransformedPrimitive::intersect / intersect_p (primitive.rs:90-102)
+            const uint32_t row = __float_as_uint(__ldg(&geom[3 * (size_t)slot + 2]).w);
+            const rtgpu_instance& I = sc.instances[row];
+            if (STATS) st->prims++;
+            Ray r = instance_ray(I, ray);
+            bool ok;
+            if (I.root_node != 0xffffffffu) ok = bvh_walk<ANY, STATS, false>(sc, r, hit, st, I.root_node, nullptr);
+            else {
+              float t, b1, b2;
+              ok = slot_hit_test<STATS>(sc, I.first_slot, make_tri_ray(r), r, t, b1, b2, st);
+              if (ok) { r.t_max = t; hit.t = t; hit.slot = I.first_slot; hit.b1 = b1; hit.b2 = b2; }
+            }
+            if (ok) {
+              if (inst_out) *inst_out = row;
+              if (ANY) return true;
+              ray.t_max = r.t_max;                                                             // primitive.rs:93-94
+              found = true;
+            }
+            continue;
           }
-          if (ok) {
+          float t, b1, b2;
+          if (slot_hit_test<STATS>(sc, slot, tr, ray, t, b1, b2, st)) {
             if (ANY) { hit.t = t; hit.slot = slot; return true; }
             ray.t_max = t;                                                                     // primitive.rs:45-51
             hit.t = t; hit.slot = slot; hit.b1 = b1; hit.b2 = b2;                              // `.or(result)`: later hit wins
+            if (TOP && inst_out) *inst_out = kNoInst;
+            found = true;
           }
         }
       } else {                                                                                 // interior :403-422
@@ -89,7 +120,11 @@ RT_DEV bool bvh_traverse(const DScene& sc, Ray& ray, HitRec& hit, TravStats* st)
       cur = stack[--sp];
     }
   }
-  return hit.slot != kMiss;
+  return found;
+}
+template <bool ANY, bool STATS>
+RT_DEV bool bvh_traverse(const DScene& sc, Ray& ray, HitRec& hit, TravStats* st, uint32_t* inst_out = nullptr) {
+  return bvh_walk<ANY, STATS, true>(sc, ray, hit, st, 0u, inst_out);
 }
 
 }  // namespace rt

@@ -14,7 +14,8 @@ void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, 
                           HitRec* hits, unsigned blocks, cudaStream_t s) {
   if (mode == TRACE_COUNTING) k_trace_closest<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
   else if (mode == TRACE_SIMPLE) k_trace_closest<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
-  else k_trace_closest_engine<<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  else if (p.sc.n_instances) k_trace_closest_engine<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
+  else k_trace_closest_engine<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
 }
 void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, unsigned blocks, cudaStream_t s) {
   k_classify<<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
@@ -23,12 +24,14 @@ void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx,
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s) {
   if (mode == TRACE_COUNTING) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p, q); }
   else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_shadow<true, false><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow<false, false><<<blocks, 128, 0, s>>>(p, q); }
-  else { if (atomic) k_trace_shadow_engine<true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow_engine<false><<<blocks, 128, 0, s>>>(p, q); }
+  else if (p.sc.n_instances) { if (atomic) k_trace_shadow_engine<true, true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow_engine<false, true><<<blocks, 128, 0, s>>>(p, q); }
+  else { if (atomic) k_trace_shadow_engine<true, false><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow_engine<false, false><<<blocks, 128, 0, s>>>(p, q); }
 }
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s) {
   if (mode == TRACE_COUNTING) { if (atomic) k_trace_mis<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, true><<<blocks, 128, 0, s>>>(p); }
   else if (mode == TRACE_SIMPLE) { if (atomic) k_trace_mis<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_mis<false, false><<<blocks, 128, 0, s>>>(p); }
-  else { if (atomic) k_trace_mis_engine<true><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false><<<blocks, 128, 0, s>>>(p); }
+  else if (p.sc.n_instances) { if (atomic) k_trace_mis_engine<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false, true><<<blocks, 128, 0, s>>>(p); }
+  else { if (atomic) k_trace_mis_engine<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false, false><<<blocks, 128, 0, s>>>(p); }
 }
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }

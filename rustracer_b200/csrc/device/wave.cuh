@@ -30,6 +30,7 @@ struct WaveView {            // device pointers, passed to kernels by value
   // items (path: item slot == sample slot)
   float4 *ray_o, *ray_d;     // {o.xyz, t_max}, {d.xyz, -}
   HitRec* hit;
+  uint32_t* hit_inst;        // instance row of each hit (kNoInst at the top level); null when the scene has no object instances
   float4* beta;              // rgb throughput, w = eta_scale (path)
   uint4* pstate;             // x = sample slot, y = bounces (path) | node id (recursive), z = flags | depth, w = d1 | d2 << 16
   // second item buffer (recursive integrators ping-pong between levels)

@@ -261,6 +261,10 @@ struct Api {
   std::map<std::string, Xform> named_cs;
   std::vector<Xform> pushed_transforms;
   GraphicsState gs; std::vector<GraphicsState> pushed_gs;
+  // object instancing (api.rs:1019-1090): RenderOptions::instances / current_instance
+  std::map<std::string, int> object_ids;      // name -> object definition id (a re-definition gets a fresh id, like the re-inserted Vec)
+  std::vector<int> object_sizes;              // primitives per definition
+  int current_object = -1;
   // RenderOptions defaults (api.rs:278-302)
   std::string film_name = "image", filter_name = "box", sampler_name = "halton", accel_name = "bvh", integrator_name = "path", camera_name = "perspective";
   ParamSet film_params, filter_params, sampler_params, accel_params, integrator_params, camera_params;
@@ -446,6 +450,7 @@ struct Api {
     check_notes(ps, "Shape");
     rt_shape s; std::memset(&s, 0, sizeof(s));
     s.o2w = to_ir(ctm); s.reverse_orientation = gs.reverse_orientation; s.material = -1; s.area_light = -1;
+    s.object_def = current_object; s.instance_of = -1;
     bool have = false;
     if (name == "sphere") {                                          // sphere.rs:53-67
       s.kind = RT_SHAPE_SPHERE; s.radius = ps.find_one_float("radius", 1.0f);
@@ -499,6 +504,14 @@ struct Api {
     } else { warn().push_back("Unknown shape " + name); return; }
     if (!have) return;
     s.material = create_material(ps);
+    if (current_object >= 0) {                                       // api.rs:951-957: the primitives go to the instance, not to the scene
+      if (!gs.area_light.empty())
+        throw ParseError("AreaLightSource inside ObjectBegin/ObjectEnd: the reference drops such lights from the light list but still lets the surface emit "
+                         "(api.rs:951-960); not supported on the GPU path");
+      object_sizes[current_object] += s.kind == RT_SHAPE_TRIMESH ? (int)(s.n_indices / 3) : 1;
+      out->store.shapes.push_back(s);
+      return;
+    }
     if (!gs.area_light.empty()) {                                    // api.rs:934-946,1185-1199 ; diffuse.rs:39-51
       if (gs.area_light != "area" && gs.area_light != "diffuse") throw ParseError("Area light " + gs.area_light + " unknown");
       const ParamSet& ap = gs.area_light_params;
@@ -514,6 +527,30 @@ struct Api {
       rt_light l; std::memset(&l, 0, sizeof(l)); l.kind = RT_LIGHT_AREA; l.shape = (int)out->store.shapes.size() - 1;
       out->store.lights.push_back(l);
     }
+  }
+
+  void d_object_begin(const std::string& name) {                     // api.rs:1019-1034
+    d_attribute_begin();
+    if (current_object >= 0) throw ParseError("ObjectBegin called inside of instance definition");
+    current_object = (int)object_sizes.size();
+    object_sizes.push_back(0);
+    object_ids[name] = current_object;
+  }
+  void d_object_end() {                                              // api.rs:1036-1050
+    need_world("ObjectEnd");
+    if (current_object < 0) throw ParseError("ObjectEnd called outside of instance definition ");
+    current_object = -1;
+    d_attribute_end();
+  }
+  void d_object_instance(const std::string& name) {                  // api.rs:1052-1090
+    need_world("ObjectInstance");
+    if (current_object >= 0) throw ParseError("ObjectInstance called inside of instance definition");
+    auto it = object_ids.find(name);
+    if (it == object_ids.end()) throw ParseError("Unable to find instance named " + name);
+    if (object_sizes[it->second] == 0) return;                       // empty definition: nothing is added (api.rs:1067-1069)
+    rt_shape s; std::memset(&s, 0, sizeof(s));
+    s.kind = RT_SHAPE_INSTANCE; s.o2w = to_ir(ctm); s.material = -1; s.area_light = -1; s.object_def = -1; s.instance_of = it->second;
+    out->store.shapes.push_back(s);
   }
 
   void d_world_end() {                                               // api.rs:977-1017 (+ make_* :181-276)
@@ -648,8 +685,9 @@ struct Parser {                                                      // pbrt/par
         case Tok::ATTRIBUTEEND: api.d_attribute_end(); break;
         case Tok::TRANSFORMBEGIN: api.d_transform_begin(); break;
         case Tok::TRANSFORMEND: api.d_transform_end(); break;
-        case Tok::OBJECTBEGIN: case Tok::OBJECTEND: case Tok::OBJECTINSTANCE:
-          throw ParseError("Object instancing (ObjectBegin/ObjectEnd/ObjectInstance) is not on the GPU hot path yet (SURVEY §8f)");
+        case Tok::OBJECTBEGIN: { std::string n = str(); api.d_object_begin(n); break; }
+        case Tok::OBJECTEND: api.d_object_end(); break;
+        case Tok::OBJECTINSTANCE: { std::string n = str(); api.d_object_instance(n); break; }
         case Tok::WORLDBEGIN: api.d_world_begin(); break;
         case Tok::WORLDEND: api.d_world_end(); break;
         case Tok::LOOKAT: {                                          // api.rs:656-680

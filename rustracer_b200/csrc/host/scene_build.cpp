@@ -277,15 +277,22 @@ void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd) {
 
 void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   // 1. primitives in Shape-directive order with world-space geometry and bounds
+  // Shapes of an object definition (api.rs:951-957) form their own primitive list; an ObjectInstance is one primitive of
+  // the scene's list, at the directive's place.
   struct Prim { uint32_t shape; uint32_t local; };                    // local: triangle number | 0
   std::vector<Prim> prims;
   std::vector<Box3> bounds;
+  std::vector<std::vector<Prim>> dprims(in.n_objects);
+  std::vector<std::vector<Box3>> dbounds(in.n_objects);
   std::vector<std::vector<Vec3>> world_p(in.n_shapes);
   std::vector<int> quadric_of_shape(in.n_shapes, -1);
   bool any_n = false, any_s = false, any_uv = false;
   for (uint32_t si = 0; si < in.n_shapes; si++) {
     const rt_shape& s = in.shapes[si];
     Xform o2w = from_ir(s.o2w);
+    if (s.kind == RT_SHAPE_INSTANCE) { prims.push_back(Prim{si, 0}); bounds.push_back(Box3()); continue; }   // bounds: below, once the definitions are built
+    std::vector<Prim>& P_ = s.object_def >= 0 ? dprims[s.object_def] : prims;
+    std::vector<Box3>& B_ = s.object_def >= 0 ? dbounds[s.object_def] : bounds;
     if (s.kind == RT_SHAPE_TRIMESH) {
       std::vector<Vec3>& wp = world_p[si];
       wp.resize(s.n_vertices);
@@ -294,7 +301,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
       for (uint32_t t = 0; t < s.n_indices / 3; t++) {
         Vec3 p0 = wp[s.indices[3 * t]], p1 = wp[s.indices[3 * t + 1]], p2 = wp[s.indices[3 * t + 2]];
         Box3 b = box_of_points(p0, p1); b.grow(p2);                   // mesh.rs:603-608
-        prims.push_back(Prim{si, t}); bounds.push_back(b);
+        P_.push_back(Prim{si, t}); B_.push_back(b);
       }
       out.n_triangles += s.n_indices / 3;
     } else {
@@ -327,15 +334,71 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
       }
       quadric_of_shape[si] = (int)out.quadrics.size();
       out.quadrics.push_back(q);
-      prims.push_back(Prim{si, 0}); bounds.push_back(b);
+      P_.push_back(Prim{si, 0}); B_.push_back(b);
     }
   }
-  // 2. same SAH BVH as the reference
+  // 2a. object definitions: the aggregate `ObjectInstance` builds when a definition holds more than one primitive
+  //     (api.rs:1071-1080, same accelerator parameters), else the primitive itself
+  std::vector<FlatBvh> dbvh(in.n_objects);
+  std::vector<Box3> def_bounds(in.n_objects);
+  for (uint32_t d = 0; d < in.n_objects; d++) {
+    if (dprims[d].empty()) continue;
+    if (dprims[d].size() > 1) {
+      build_bvh(dbounds[d], in.accel.max_node_prims, in.accel.split_method, threads, dbvh[d]);
+      def_bounds[d].lo = v3(dbvh[d].node_lo[0], dbvh[d].node_lo[1], dbvh[d].node_lo[2]);
+      def_bounds[d].hi = v3(dbvh[d].node_hi[0], dbvh[d].node_hi[1], dbvh[d].node_hi[2]);
+    } else def_bounds[d] = dbounds[d][0];
+  }
+  for (size_t pn = 0; pn < prims.size(); pn++) {                      // TransformedPrimitive::world_bounds (primitive.rs:86-88, transform.rs:342-389)
+    const rt_shape& s = in.shapes[prims[pn].shape];
+    if (s.kind != RT_SHAPE_INSTANCE) continue;
+    if (s.instance_of < 0 || (uint32_t)s.instance_of >= in.n_objects || dprims[s.instance_of].empty()) throw std::runtime_error("ObjectInstance of an empty or unknown object");
+    const float* m = s.o2w.m;
+    if (m[12] != 0.0f || m[13] != 0.0f || m[14] != 0.0f || m[15] != 1.0f) throw std::runtime_error("ObjectInstance under a projective transform is not supported");
+    Xform p2w = from_ir(s.o2w);
+    const Box3& ob = def_bounds[s.instance_of];
+    Box3 b;
+    for (int k = 0; k < 8; k++) b.grow(xf_point(p2w.m, v3((k & 1) ? ob.hi.x : ob.lo.x, (k & 2) ? ob.hi.y : ob.lo.y, (k & 4) ? ob.hi.z : ob.lo.z)));
+    bounds[pn] = b;
+  }
+  // 2b. same SAH BVH as the reference over the scene's primitive list
   build_bvh(bounds, in.accel.max_node_prims, in.accel.split_method, threads, out.bvh);
-  const size_t N = prims.size();
+  const size_t N0 = prims.size();
+  // 2c. append the definitions' trees and slots to the same arrays with absolute indices
+  std::vector<uint32_t> def_root_node(in.n_objects, 0xffffffffu), def_first_slot(in.n_objects, 0), def_first_pn(in.n_objects, 0);
+  {
+    auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+    uint32_t next_pn = (uint32_t)N0;
+    for (uint32_t d = 0; d < in.n_objects; d++) {
+      if (dprims[d].empty()) continue;
+      const uint32_t base_slot = (uint32_t)out.bvh.ordered.size(), base_node = out.bvh.n_nodes;
+      def_first_slot[d] = base_slot; def_first_pn[d] = next_pn;
+      if (dprims[d].size() > 1) {
+        const FlatBvh& b = dbvh[d];
+        def_root_node[d] = base_node;
+        for (uint32_t i = 0; i < b.n_nodes; i++) {
+          const uint32_t n_prims = bits(b.node_hi[i * 4 + 3]) >> 2;
+          for (int k = 0; k < 3; k++) { out.bvh.node_lo.push_back(b.node_lo[i * 4 + k]); out.bvh.node_hi.push_back(b.node_hi[i * 4 + k]); }
+          float w; put_bits(&w, bits(b.node_lo[i * 4 + 3]) + (n_prims > 0 ? base_slot : base_node));
+          out.bvh.node_lo.push_back(w); out.bvh.node_hi.push_back(b.node_hi[i * 4 + 3]);
+        }
+        out.bvh.n_nodes += b.n_nodes;
+        for (uint32_t local : b.ordered) out.bvh.ordered.push_back(next_pn + local);
+      } else out.bvh.ordered.push_back(next_pn);
+      next_pn += (uint32_t)dprims[d].size();
+    }
+  }
+  const size_t N = out.bvh.ordered.size();
+  // global primitive number -> (list, index): the scene's list first, then the definitions' lists
+  auto prim_of = [&](uint32_t pn) -> const Prim& {
+    if (pn < N0) return prims[pn];
+    for (uint32_t d = in.n_objects; d-- > 0;) if (!dprims[d].empty() && pn >= def_first_pn[d]) return dprims[d][pn - def_first_pn[d]];
+    throw std::runtime_error("primitive number out of range");
+  };
   // 3. lights: Scene::lights order, area lights one per primitive (api.rs:934-946,963)
   std::vector<uint32_t> first_prim(in.n_shapes + 1, 0);
-  for (uint32_t si = 0; si < in.n_shapes; si++) first_prim[si + 1] = first_prim[si] + (in.shapes[si].kind == RT_SHAPE_TRIMESH ? in.shapes[si].n_indices / 3 : 1);
+  for (uint32_t si = 0; si < in.n_shapes; si++)
+    first_prim[si + 1] = first_prim[si] + (in.shapes[si].object_def >= 0 ? 0 : (in.shapes[si].kind == RT_SHAPE_TRIMESH ? in.shapes[si].n_indices / 3 : 1));
   out.slot_of_prim.assign(N, 0);
   for (size_t slot = 0; slot < N; slot++) out.slot_of_prim[out.bvh.ordered[slot]] = (uint32_t)slot;
   std::vector<int32_t> light_of_prim(N, -1);
@@ -428,11 +491,20 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   if (any_uv) out.tri_uv.assign(N * 6, 0.0f);
   for (size_t slot = 0; slot < N; slot++) {
     uint32_t pn = out.bvh.ordered[slot];
-    const Prim& pr = prims[pn];
+    const Prim& pr = prim_of(pn);
     const rt_shape& s = in.shapes[pr.shape];
     float* g = &out.prim_geom[slot * 12];
     uint32_t flags = 0;
-    if (s.kind == RT_SHAPE_TRIMESH) {
+    if (s.kind == RT_SHAPE_INSTANCE) {                                // a degenerate triangle for walkers that do not know instances
+      const uint32_t d = (uint32_t)s.instance_of;
+      rtgpu_instance row; std::memset(&row, 0, sizeof(row));
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) { row.o2w[r * 4 + c] = s.o2w.m[r * 4 + c]; row.w2o[r * 4 + c] = s.o2w.m_inv[r * 4 + c]; }
+      row.root_node = def_root_node[d]; row.first_slot = def_first_slot[d];
+      for (int k = 0; k < 3; k++) { row.lo[k] = def_bounds[d].lo[k]; row.hi[k] = def_bounds[d].hi[k]; }
+      row.prim_number = pn;
+      put_bits(&g[3], RTGPU_PRIM_TRIANGLE); put_bits(&g[7], 2u); put_bits(&g[11], (uint32_t)out.instances.size());
+      out.instances.push_back(row);
+    } else if (s.kind == RT_SHAPE_TRIMESH) {
       const int32_t* ix = &s.indices[3 * pr.local];
       for (int v = 0; v < 3; v++) { Vec3 p = world_p[pr.shape][ix[v]]; g[4 * v] = p.x; g[4 * v + 1] = p.y; g[4 * v + 2] = p.z; }
       put_bits(&g[3], RTGPU_PRIM_TRIANGLE);
@@ -450,6 +522,8 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
     uint32_t* info = &out.prim_info[slot * 4];
     info[0] = pn; info[1] = s.material >= 0 ? (uint32_t)s.material : 0xffffffffu; info[2] = (uint32_t)light_of_prim[pn]; info[3] = flags;
   }
+  for (uint32_t d = 0; d < in.n_objects; d++)                         // a one-primitive definition has no leaf node to mark its last slot
+    if (dprims[d].size() == 1) { uint32_t u; std::memcpy(&u, &out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], 4); put_bits(&out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], u | 1u); }
   for (uint32_t i = 0; i < in.n_materials; i++) {
     rtgpu_material pm = prep_material(in.materials[i]);
     const int ty = in.materials[i].type;
@@ -473,6 +547,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   d.n_quadrics = (uint32_t)out.quadrics.size(); d.quadrics = out.quadrics.data();
   d.n_materials = (uint32_t)out.materials.size(); d.materials = out.materials.data();
   d.n_lobes = (uint32_t)out.lobes.size(); d.lobes = out.lobes.empty() ? nullptr : out.lobes.data();
+  d.n_instances = (uint32_t)out.instances.size(); d.instances = out.instances.empty() ? nullptr : out.instances.data();
   d.n_lights = (uint32_t)out.lights.size(); d.lights = out.lights.data();
   d.n_env_floats = (uint32_t)out.env_data.size(); d.env_data = out.env_data.data();
   make_render_desc(in, out.render);

@@ -18,6 +18,7 @@ struct FlatScene {
   std::vector<rtgpu_quadric> quadrics;
   std::vector<rtgpu_material> materials;
   std::vector<rtgpu_lobe> lobes;         // lobe lists of the RTGPU_MAT_LOBES materials
+  std::vector<rtgpu_instance> instances; // object instances (TransformedPrimitive rows)
   std::vector<rtgpu_light> lights;
   std::vector<float> env_data;
   std::vector<uint32_t> slot_of_prim;    // prim_number -> slot

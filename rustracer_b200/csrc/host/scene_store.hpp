@@ -23,6 +23,9 @@ struct SceneStore {
 
   const rt_scene* finish() {
     view.n_shapes = (uint32_t)shapes.size(); view.shapes = shapes.data();
+    int32_t n_obj = 0;
+    for (const rt_shape& s : shapes) { if (s.object_def >= n_obj) n_obj = s.object_def + 1; if (s.instance_of >= n_obj) n_obj = s.instance_of + 1; }
+    view.n_objects = (uint32_t)n_obj;
     view.n_area_lights = (uint32_t)area_lights.size(); view.area_lights = area_lights.data();
     view.n_lights = (uint32_t)lights.size(); view.lights = lights.data();
     view.n_materials = (uint32_t)materials.size(); view.materials = materials.data();
@@ -30,7 +33,7 @@ struct SceneStore {
   }
   size_t n_primitives() const {
     size_t n = 0;
-    for (const rt_shape& s : shapes) n += (s.kind == RT_SHAPE_TRIMESH) ? s.n_indices / 3 : 1;
+    for (const rt_shape& s : shapes) if (s.object_def < 0) n += (s.kind == RT_SHAPE_TRIMESH) ? s.n_indices / 3 : 1;   // top-level primitives
     return n;
   }
 };

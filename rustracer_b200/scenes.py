@@ -256,6 +256,51 @@ def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None, mat
 
 
 # ------------------------------------------------------------------------------------------------
+# object instancing (ObjectBegin / ObjectEnd / ObjectInstance)
+
+def _inline_icosphere(level, radius=1.0):
+    v, f = icosphere(level)
+    return _mesh(np.asarray(v) * radius, f)
+
+
+def instanced_scene(xres=96, yres=72, spp=8, integrator=None, n_side=4, baked=False, level=1):
+    """A "plant" object (icosphere mesh + sphere + cylinder + a mirrored-scale part, mixed materials) and a one-primitive object,
+    instanced on a jittered grid under translate / rotate / non-uniform scale / negative scale, over a ground disk with a point
+    light, an area light and a constant environment.  baked=True declares the same shapes directly under the composed transforms
+    (no instancing): the two scenes render the same image up to fp32 noise."""
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5]'
+    s = header(xres, yres, spp, integrator, 40, ([0, 6.5, -12], [0, 0.6, 0], [0, 1, 0]))
+    s += "WorldBegin\n"
+    s += 'LightSource "point" "rgb I" [160 160 150] "point from" [-5 9 -6]\n'
+    s += 'LightSource "infinite" "rgb L" [0.25 0.3 0.4]\n'
+    s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [10 10 9]\nTranslate 0 7 1\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "sphere" "float radius" [0.5]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "matte" "rgb Kd" [0.5 0.5 0.45]\nRotate -90 1 0 0\nShape "disk" "float radius" [20]\nAttributeEnd\n'
+    plant = ('Material "matte" "rgb Kd" [0.2 0.6 0.25]\nAttributeBegin\nTranslate 0 1.1 0\nScale 0.55 0.55 0.55\n' + _inline_icosphere(level) + 'AttributeEnd\n'
+             'Material "plastic" "rgb Kd" [0.5 0.3 0.15] "rgb Ks" [0.2 0.2 0.2] "float roughness" [0.1]\n'
+             'AttributeBegin\nRotate -90 1 0 0\nShape "cylinder" "float radius" [0.12] "float z_min" [0] "float z_max" [0.8]\nAttributeEnd\n'
+             'Material "glass"\nAttributeBegin\nTranslate 0.55 0.35 0\nShape "sphere" "float radius" [0.22]\nAttributeEnd\n'
+             'Material "metal" "float roughness" [0.05]\nAttributeBegin\nTranslate -0.5 0.3 0.1\nScale -0.3 0.3 0.3\n' + _inline_icosphere(0) + 'AttributeEnd\n')
+    pebble = 'Material "mirror"\nShape "sphere" "float radius" [0.25]\n'
+    if not baked:
+        s += 'ObjectBegin "plant"\n' + plant + 'ObjectEnd\nObjectBegin "pebble"\n' + pebble + 'ObjectEnd\nObjectBegin "empty"\nObjectEnd\n'
+    rng = PCG32([8])
+    for i in range(n_side * n_side):
+        gx, gz = i % n_side, i // n_side
+        x = (gx - (n_side - 1) / 2) * 2.2 + float(rng.f32()[0] - 0.5) * 0.5
+        z = (gz - (n_side - 1) / 2) * 2.2 + float(rng.f32()[0] - 0.5) * 0.5
+        rot = 360.0 * float(rng.f32()[0])
+        sx, sy, sz = (0.7 + 0.8 * float(rng.f32()[0]) for _ in range(3))
+        if i % 5 == 3:
+            sx = -sx                                         # mirrored instance: swaps handedness
+        xf = f"Translate {x:.5f} 0 {z:.5f}\nRotate {rot:.4f} 0 1 0\nScale {sx:.5f} {sy:.5f} {sz:.5f}\n"
+        s += "AttributeBegin\n" + xf + (plant if baked else 'ObjectInstance "plant"\n') + "AttributeEnd\n"
+        s += f"AttributeBegin\nTranslate {x + 0.9:.5f} 0.25 {z - 0.7:.5f}\n" + (pebble if baked else 'ObjectInstance "pebble"\nObjectInstance "empty"\n') + "AttributeEnd\n"
+    s += "WorldEnd\n"
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
 # C3 / C5: icosphere fields written as PLY; C4: ray-batch field
 
 

@@ -31,11 +31,15 @@ def _cases(tmp):
     c["balls_normal"] = lambda: scenes.balls(xres=96, yres=72, spp=4, integrator='Integrator "normal"')
     c["field_path_spatial"] = lambda: scenes.c3_scene(str(tmp), level=2, xres=96, yres=54, spp=8)
     c["field_ao"] = lambda: scenes.c3_scene(str(tmp), level=2, xres=96, yres=54, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [16]')
+    c["instanced_path"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=8)
+    c["instanced_whitted"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "whitted" "integer maxdepth" [4]')
+    c["instanced_ao"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [8]')
     c["cornell_rr"] = lambda: scenes.cornell_box(xres=48, yres=48, spp=8, integrator='Integrator "path" "integer maxdepth" [12] "float rrthreshold" [1] "string lightsamplestrategy" "uniform"')
     return c
 
 
-NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr"]
+NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr", "instanced_path", "instanced_whitted",
+                            "instanced_ao"]
 
 
 @pytest.mark.parametrize("name", NAMES)

@@ -30,10 +30,12 @@ def _scene(name, tmp):
         txt += 'AttributeBegin\nTranslate 0 1 1\nRotate 40 0 1 1\nShape "cylinder" "float radius" [0.5] "float z_min" [-1] "float z_max" [1.5] "float phi_max" [200]\nAttributeEnd\n'
         txt += 'AttributeBegin\nReverseOrientation\nTranslate 0 2 -1\nShape "cylinder" "float radius" [0.3]\nAttributeEnd\n'
         return Scene.from_string(txt + "WorldEnd\n")
+    if name == "instanced":     # ObjectInstance under rotations, non-uniform and mirroring scales; one-primitive objects
+        return Scene.from_string(scenes.instanced_scene(xres=32, yres=32, spp=1))
     return Scene.from_string(scenes.c3_scene(str(tmp), level=3, xres=32, yres=32, spp=1), search_dir=tmp)
 
 
-@pytest.mark.parametrize("name", ["cornell", "balls", "quadrics", "field"])
+@pytest.mark.parametrize("name", ["cornell", "balls", "quadrics", "field", "instanced"])
 def test_closest_and_any_hit_match_oracle_exactly(dev, tmp_path, name):
     from oracle import binding as ob
     from rustracer_b200 import scenes
