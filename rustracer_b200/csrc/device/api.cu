@@ -108,7 +108,7 @@ struct BatchClosestPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst) {
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst, uint32_t) {
     HitRec o = h;
     o.slot = h.slot == kMiss ? kMiss : (inst != kNoInst ? instances[inst].prim_number : info[h.slot].x);   // slot -> prim_number (bvh/mod.rs:92)
     hits[r] = o;
@@ -121,7 +121,7 @@ struct BatchAnyPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t) { occluded[r] = h.slot != kMiss ? 1 : 0; }
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t, uint32_t) { occluded[r] = h.slot != kMiss ? 1 : 0; }
 };
 template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_closest_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,
@@ -282,11 +282,19 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     };
     std::vector<float> wide((size_t)n_interior * 16, 0.0f);
     std::vector<float> geom(s->prim_geom, s->prim_geom + (size_t)s->n_prims * 12);
+    // shade-queue id of every slot's material in bits 2..4 of the second float4's w: the engine has that word in a register
+    // when it records a hit, so classification needs no second look-up (hit slots are packed into 29 bits next to it)
+    if (s->n_prims >= (1u << kHitSlotBits)) return fail(ctx, RTGPU_ERR_ARG, "more than 2^29 primitive slots");
+    for (size_t slot = 0; slot < s->n_prims; slot++) {
+      const uint32_t mrow = s->prim_info[slot * 4 + 1];
+      const uint32_t type = (mrow < s->n_materials && s->materials) ? s->materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+      geom[slot * 12 + 7] = fbits(bits(geom[slot * 12 + 7]) | ((uint32_t)material_queue(type) << kGeomClassShift));
+    }
     for (size_t i = 0; i < nn; i++) {
       const uint32_t meta = bits(s->node_hi[i * 4 + 3]), n_prims = meta >> 2, off = bits(s->node_lo[i * 4 + 3]);
       if (n_prims > 0) {
         if ((size_t)off + n_prims > s->n_prims) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
-        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | 1u);
+        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | kGeomLastBit);
         continue;
       }
       const size_t L = i + 1, R = off;

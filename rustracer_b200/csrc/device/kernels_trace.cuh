@@ -162,21 +162,24 @@ __global__ void __launch_bounds__(128) k_trace_mis(RenderParams p) {
 // ---- the same three kernels on the persistent while-while engine (trace_engine.cuh): the production path ------------
 template <bool INST>
 struct ClosestPolicy {
-  const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t* hit_inst; uint32_t slot;
-  RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h, uint32_t* hi) : ray_o(o), ray_d(d), list(l), hits(h), hit_inst(hi), slot(0) {}
+  const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t* hit_inst; uint8_t* hit_class; uint32_t slot;
+  RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h, uint32_t* hi, uint8_t* hc) : ray_o(o), ray_d(d), list(l), hits(h), hit_inst(hi), hit_class(hc), slot(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst) { hits[slot] = h; if (INST) hit_inst[slot] = inst; }
+  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst, uint32_t cls) { hits[slot] = h; hit_class[slot] = (uint8_t)cls; if (INST) hit_inst[slot] = inst; }
 };
 template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                                const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
-  ClosestPolicy<INST> pol(ray_o, ray_d, list, hits, p.w.hit_inst);
+  ClosestPolicy<INST> pol(ray_o, ray_d, list, hits, p.w.hit_inst, p.w.hit_class);
   trace_engine<false, INST>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
 }
 
 // Material classification of the traced paths: appends each path to the queue of its hit material (or the miss queue)
 // for the material-sorted shade kernels.  A streaming pass over the live list at full lane occupancy (one atomic per
 // distinct class and warp via match_any) instead of seven ballot rounds inside every refill of the traversal engine.
+// FROM_CLASS: the engine left each hit's queue id in hit_class (it rides in the hit slot's geometry record), so the pass
+// reads 5 bytes per path instead of chasing hit -> primitive info -> material row.
+template <bool FROM_CLASS>
 __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const HitRec* __restrict__ hits) {
   const uint32_t n = p.w.counters[count_idx];
   const uint32_t lane = lane_id(), lane_lt = (1u << lane) - 1u;
@@ -184,8 +187,9 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t
     int q = -1; uint32_t slot = 0;
     if (i < n) {
       slot = list ? list[i] : i;
-      const uint32_t hslot = hits[slot].slot;
-      if (hslot == kMiss) q = Q_MISS;
+      const uint32_t hslot = FROM_CLASS ? 0u : hits[slot].slot;
+      if (FROM_CLASS) q = (int)p.w.hit_class[slot];
+      else if (hslot == kMiss) q = Q_MISS;
       else {
         const uint32_t mrow = p.sc.info[hslot].y;
         const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
@@ -206,7 +210,7 @@ struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;
   RT_DEV ShadowPolicy(const RenderParams& p_, const AnyQueue& a) : p(p_), aq(a), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t, uint32_t) {
     if (h.slot != kMiss) return;
     const float4 c = aq.c[idx];
     float4* L = &p.w.L[sample];
@@ -226,7 +230,7 @@ struct MisPolicy {
   const RenderParams& p; uint32_t sample;
   RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst, uint32_t) {
     const float4 c = p.w.mi_c[idx];
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];

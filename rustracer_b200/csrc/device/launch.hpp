@@ -10,7 +10,7 @@ void launch_generate_rays(const RenderParams& p, const float4* samples, uint32_t
 void launch_raygen(const RenderParams& p, cudaStream_t s);
 void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, const float4* ray_d, const uint32_t* list, int count_idx,
                           HitRec* hits, unsigned blocks, cudaStream_t s);
-void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, unsigned blocks, cudaStream_t s);
+void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, bool from_hit_class, unsigned blocks, cudaStream_t s);
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s);
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s);
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);

@@ -65,6 +65,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   int rc = 0;
 #define A(field, n) if ((rc = dalloc(ctx, w, &v.field, (n)))) return rc
   A(ray_o, cap_items); A(ray_d, cap_items); A(hit, cap_items); A(beta, cap_items); A(pstate, cap_items);
+  A(hit_class, cap_items);
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
@@ -299,7 +300,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       for (uint32_t b = 0; b < rounds; b++) {
         const int in = (int)(b & 1u);
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
-        RT_LAUNCH(K_SHADE, launch_classify(p, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks / 2, ctx->stream));
+        RT_LAUNCH(K_SHADE, launch_classify(p, p.w.list[in], C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
         if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));

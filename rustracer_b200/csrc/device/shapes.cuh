@@ -344,6 +344,17 @@ RT_DEV bool slot_intersect_surface(const DScene& sc, uint32_t slot, const Ray& r
 
 // ---- object instances: TransformedPrimitive (primitive.rs:79-118) -----------------------------------------------------
 constexpr uint32_t kNoInst = 0xffffffffu;
+// second float4 of a geometry slot, w: bit 0 = last primitive of its leaf, bit 1 = object instance, bits 2..4 = shade queue
+// of the slot's material (wave.cuh Q_*; set at upload)
+constexpr uint32_t kGeomLastBit = 1u, kGeomInstanceBit = 2u, kGeomClassShift = 2u;
+constexpr uint32_t kHitSlotBits = 29;
+constexpr int Q_MISS_CLASS = 7;
+// material queues of the path integrator (one shade launch per non-empty class)
+enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_LOBES, Q_MISS, Q_COUNT };   // Q_LOBES: uber / substrate / translucent / mix
+// material type (rtgpu_material.type, or RTGPU_MAT_NONE for a primitive without material row) -> shade queue
+__host__ __device__ __forceinline__ int material_queue(uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? Q_LOBES : Q_NONE); }
+
+static_assert(Q_MISS == Q_MISS_CLASS && Q_COUNT <= 8, "the shade-queue id travels in three bits of the hit slot");
 // `primitive_to_world.inverse() * ray` (ray.rs:83-93): origin and direction only, no error offset, t_max kept
 RT_DEV Ray instance_ray(const rtgpu_instance& I, const Ray& ray) { return make_ray(xf_point_affine(I.w2o, ray.o), xf_vector(I.w2o, ray.d), ray.t_max); }
 // SurfaceInteraction::transform (interaction.rs:156-190) for the fields SurfHit keeps

@@ -34,6 +34,7 @@ namespace rt {
 RT_DEV uint32_t lane_id_() { return threadIdx.x & 31u; }
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDoneRef = 0xffffffffu;        // (a leaf ref never has all 31 payload bits set: slots < 2^31 - 1)
+constexpr uint32_t kHitSlotMask = (1u << kHitSlotBits) - 1u;   // inside the engine a hit slot carries its shade-queue id in the top 3 bits
 constexpr uint32_t kExitInstance = 0xfffffffeu;   // stack marker: the walk below this entry happens in world space again
 
 // Bounds3::intersect_p_fast (bounds.rs:127-157) split into its t_max-independent part and the entry distance.
@@ -97,7 +98,9 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
   // memory as [entry][thread] (conflict-free, ~25-cycle pops, no L1 traffic: profiles/r01c-v2a showed more local-memory
   // sectors than global ones and 19 % of the stall samples on the pop), the rarely used rest in local memory.
   __shared__ uint2 s_stack[RT_ENGINE_SMEM_DEPTH][128];
-  uint2 stack_l[kStackSize - RT_ENGINE_SMEM_DEPTH];
+  // capacity: the reference's 64 entries per tree (bvh/mod.rs:372); with instances the scene's tree, the exit marker and the
+  // definition's tree share this one stack
+  uint2 stack_l[(INST ? 2 * kStackSize + 1 : kStackSize) - RT_ENGINE_SMEM_DEPTH];
   const uint32_t tid = threadIdx.x;
   int sp = 0;
   bool queue_empty = n == 0;
@@ -137,7 +140,12 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     const unsigned busy = m_n | m_l;
     if (busy == 0u || (!queue_empty && 32 - __popc(busy) >= refill_threshold)) {
       // ---- commit finished rays and pull new ones ----------------------------------------------------------
-      if (pending) { pol.commit(idx, hit, hit_inst); pending = false; }
+      if (pending) {
+        HitRec hc = hit; uint32_t cls = (uint32_t)Q_MISS_CLASS;
+        if (hit.slot != kMiss) { cls = hit.slot >> kHitSlotBits; hc.slot = hit.slot & kHitSlotMask; }
+        pol.commit(idx, hc, hit_inst, cls);
+        pending = false;
+      }
       if (queue_empty) break;                                          // busy == 0 and nothing left to fetch
       const unsigned wmask = ~busy;
       const int leader = __ffs(wmask) - 1;
@@ -244,7 +252,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
           ok = quadric_intersect(sc.quadrics[kind_bits >> 2], rq, t, false, nullptr);
         }
         if (ok) {
-          hit.t = t; hit.slot = slot; hit.b1 = b1; hit.b2 = b2;
+          hit.t = t; hit.slot = slot | (((__float_as_uint(g1.w) >> kGeomClassShift) & 7u) << kHitSlotBits); hit.b1 = b1; hit.b2 = b2;
           if (INST) hit_inst = inst;
           if (ANY) { done = true; break; }
           ray.t_max = t;

@@ -17,8 +17,9 @@ void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, 
   else if (p.sc.n_instances) k_trace_closest_engine<true><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
   else k_trace_closest_engine<false><<<blocks, 128, 0, s>>>(p, ray_o, ray_d, list, count_idx, hits);
 }
-void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, unsigned blocks, cudaStream_t s) {
-  k_classify<<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
+void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, bool from_hit_class, unsigned blocks, cudaStream_t s) {
+  if (from_hit_class) k_classify<true><<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
+  else k_classify<false><<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
 }
 // q: 0 = NEE shadow queue, 1 = queue of the MIS rays towards infinite lights (both any-hit)
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s) {

@@ -7,11 +7,7 @@
 
 namespace rt {
 
-// material queues of the path integrator (one shade launch per non-empty class)
-enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_LOBES, Q_MISS, Q_COUNT };   // Q_LOBES: uber / substrate / translucent / mix
-// material type (rtgpu_material.type, or RTGPU_MAT_NONE for a primitive without material row) -> shade queue
-RT_DEV int material_queue(uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? Q_LOBES : Q_NONE); }
-
+// (the material queues Q_* and material_queue() live in shapes.cuh: the scene upload tags every geometry slot with its queue)
 // device counters (uint32)
 enum {
   C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_MIS_ANY, C_MIS_SKIPPED, C_CUR_MISANY, C_COUNT = 32
@@ -30,6 +26,7 @@ struct WaveView {            // device pointers, passed to kernels by value
   // items (path: item slot == sample slot)
   float4 *ray_o, *ray_d;     // {o.xyz, t_max}, {d.xyz, -}
   HitRec* hit;
+  uint8_t* hit_class;        // shade queue of each hit (Q_*), written by the traversal engine from the class bits of the hit slot
   uint32_t* hit_inst;        // instance row of each hit (kNoInst at the top level); null when the scene has no object instances
   float4* beta;              // rgb throughput, w = eta_scale (path)
   uint4* pstate;             // x = sample slot, y = bounces (path) | node id (recursive), z = flags | depth, w = d1 | d2 << 16
