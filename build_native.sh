@@ -8,7 +8,7 @@ mkdir -p rustracer_b200/lib $OBJ
 NVFLAGS="-std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC -Iinclude $RT_NVCC_EXTRA"
 D=rustracer_b200/csrc/device
 if [ "$1" != "device" ]; then
-  g++ -std=c++17 -O2 -ffp-contract=off -fPIC -pthread -shared -Iinclude -o rustracer_b200/lib/librthost.so rustracer_b200/csrc/host/*.cpp &
+  g++ -std=c++17 -O2 -ffp-contract=off -fPIC -pthread -shared -Iinclude -o rustracer_b200/lib/librthost.so rustracer_b200/csrc/host/*.cpp -lz &
 fi
 if [ "$1" != "host" ]; then
   pids=()

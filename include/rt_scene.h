@@ -79,11 +79,40 @@ typedef struct rt_light {
   int32_t shape;               /* RT_LIGHT_AREA: index into rt_scene.shapes */
 } rt_light;
 
+/* ---- textures (texture/*.rs, mipmap.rs) -------------------------------------------------------------
+ * One row per texture object the front end creates: every `Texture` directive, plus one RT_TEX_CONSTANT row for each literal
+ * (or defaulted) tex1 / tex2 / amount parameter of a scale / mix / checkerboard texture (paramset.rs:406-443 wraps those in a
+ * ConstantTexture), so children are always rows.  `is_float` tells Texture<f32> from Texture<Spectrum>. */
+enum { RT_TEX_CONSTANT = 0, RT_TEX_SCALE = 1, RT_TEX_MIX = 2, RT_TEX_CHECKERBOARD = 3, RT_TEX_UV = 4, RT_TEX_IMAGEMAP = 5, RT_TEX_FBM = 6 };
+enum { RT_TEXMAP_UV = 0, RT_TEXMAP_PLANAR = 1 };     /* texture/mod.rs:32-83 (spherical / cylindrical are unimplemented!() there) */
+enum { RT_WRAP_REPEAT = 0, RT_WRAP_BLACK = 1, RT_WRAP_CLAMP = 2 };   /* mipmap.rs:27-32 */
+typedef struct rt_texture {
+  int32_t kind, is_float;
+  float value[3];              /* constant (float textures use value[0]) */
+  int32_t tex1, tex2, amount;  /* scale / mix / checkerboard children: rows of rt_scene.textures (amount: a float texture) */
+  int32_t mapping;             /* checkerboard / uv / imagemap: RT_TEXMAP_* */
+  float su, sv, du, dv;        /* UVMapping2D ; planar uses du, dv as ds, dt (checkerboard.rs:71-72) */
+  float vs[3], vt[3];          /* PlanarMapping2D v1, v2 */
+  int32_t aa_none;             /* checkerboard aamode "none" (default closedform) */
+  rt_transform w2t;            /* fbm: IdentityMapping3D.world_to_texture = the CTM at the directive (fbm.rs:30, mod.rs:96-100) */
+  float omega; int32_t octaves;/* fbm */
+  /* imagemap (imagemap.rs:40-94): texels as MIPMap::new receives them — y-flipped, scaled, inverse-gamma'd, converted
+   * (RGB triples for spectrum textures, luminance for float textures); row-major, img_w * img_h texels */
+  int32_t img_w, img_h; const float* texels;
+  int32_t wrap, trilinear; float max_aniso;
+} rt_texture;
+
+/* texture slot of a material parameter: rt_material.tex[slot] = 1 + row of rt_scene.textures, or 0 = the constant field
+ * (so a zero-initialised material has no textures) */
+enum { RT_TS_KD = 0, RT_TS_KS, RT_TS_KR, RT_TS_KT, RT_TS_ETA_RGB, RT_TS_K_RGB, RT_TS_SIGMA, RT_TS_ROUGHNESS, RT_TS_UROUGHNESS, RT_TS_VROUGHNESS,
+       RT_TS_ETA, RT_TS_OPACITY, RT_TS_REFLECT, RT_TS_TRANSMIT, RT_TS_AMOUNT, RT_TS_BUMP, RT_TS_COUNT };
+
 enum { RT_MAT_MATTE = 0, RT_MAT_PLASTIC = 1, RT_MAT_METAL = 2, RT_MAT_GLASS = 3, RT_MAT_MIRROR = 4, RT_MAT_NONE = 5,
        RT_MAT_UBER = 6, RT_MAT_SUBSTRATE = 7, RT_MAT_TRANSLUCENT = 8, RT_MAT_MIX = 9 };
 
-/* Material with every texture already evaluated to its constant (texture/constant.rs:10-39;
- * paramset.rs:406-443).  Field use per type follows material/{matte,plastic,metal,glass,mirror,uber,substrate,
+/* Material.  A parameter bound to a constant texture is folded into its field (texture/constant.rs:10-39;
+ * paramset.rs:406-443); a parameter bound to any other texture has its row in tex[] and the field is unused.  Field use per
+ * type follows material/{matte,plastic,metal,glass,mirror,uber,substrate,
  * translucent,mixmat}.rs. */
 typedef struct rt_material {
   int32_t type;
@@ -107,6 +136,8 @@ typedef struct rt_material {
   float reflect[3], transmit[3];
   float amount[3];
   int32_t mix_a, mix_b;
+  int32_t tex[16];             /* RT_TS_* -> 1 + texture row, or 0 ; tex[RT_TS_BUMP] = the "bumpmap" float texture (material/mod.rs:50-92) */
+  int32_t textured;            /* 1 = some tex[] != 0 here or in a mix child: evaluated per hit on the device */
 } rt_material;
 
 enum { RT_FILTER_BOX = 0, RT_FILTER_GAUSSIAN = 1, RT_FILTER_TRIANGLE = 2, RT_FILTER_MITCHELL = 3 };
@@ -153,6 +184,7 @@ typedef struct rt_scene {
   uint32_t n_area_lights; const rt_area_light* area_lights;
   uint32_t n_lights;      const rt_light* lights;
   uint32_t n_materials;   const rt_material* materials;
+  uint32_t n_textures;    const rt_texture* textures;
   rt_camera camera; rt_film film; rt_sampler sampler; rt_integrator integrator; rt_accel accel;
 } rt_scene;
 

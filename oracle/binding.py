@@ -78,6 +78,13 @@ def lib(native=False):
     l.orc_fresnel_blend_pdf.restype = C.c_float
     l.orc_material_bsdf.argtypes = [C.c_void_p, C.c_int, C.c_int, PF, PF, PF, C.c_uint32, PF]
     l.orc_selftest.argtypes = [C.c_uint64, C.c_char_p, C.c_int]
+    l.orc_texture_eval.argtypes = [C.c_void_p, C.c_int, PF, C.c_uint64, PF]
+    l.orc_texture_mip_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), PF]
+    l.orc_noise.argtypes = [C.c_float] * 3
+    l.orc_noise.restype = C.c_float
+    l.orc_fbm.argtypes = [PF, PF, PF, C.c_float, C.c_uint32]
+    l.orc_fbm.restype = C.c_float
+    l.orc_camera_rays_diff.argtypes = [C.c_void_p, PF, C.c_uint64, C.c_float, PF]
     if not native:
         _lib = l
     return l
@@ -122,6 +129,34 @@ class OracleScene:
             raise RuntimeError(f"orc_material_bsdf: {rc} {self._l.orc_scene_error(self._h)}")
         return dict(f=out[0:3].copy(), pdf=float(out[3]), sf=out[4:7].copy(), swi=out[7:10].copy(), spdf=float(out[10]), sflags=int(out[11]),
                     n_lobes=int(out[12]), eta=float(out[13]))
+
+    def texture_eval(self, row, points):
+        """Texture row evaluated at explicit surface points: (n, 15) {uv, p, dpdx, dpdy, dudx, dvdx, dudy, dvdy} -> (n, 3)."""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 15)
+        out = np.zeros((len(pts), 3), np.float32)
+        if self._l.orc_texture_eval(self._h, row, _pf(pts), len(pts), _pf(out)):
+            raise RuntimeError("orc_texture_eval: bad texture row")
+        return out
+
+    def texture_mip(self, row):
+        """MIP pyramid of an imagemap row: list of (v, u, channels) arrays, finest first."""
+        n = self._l.orc_texture_mip_level(self._h, row, -1, None, None, None, None)
+        if n < 0:
+            raise RuntimeError("orc_texture_mip_level: not an imagemap row")
+        levels = []
+        for i in range(n):
+            u, v, c = C.c_int32(), C.c_int32(), C.c_int32()
+            self._l.orc_texture_mip_level(self._h, row, i, C.byref(u), C.byref(v), C.byref(c), None)
+            a = np.zeros((v.value, u.value, c.value), np.float32)
+            self._l.orc_texture_mip_level(self._h, row, i, C.byref(u), C.byref(v), C.byref(c), _pf(a))
+            levels.append(a)
+        return levels
+
+    def camera_rays_diff(self, samples, scale=1.0):
+        s = np.ascontiguousarray(samples, np.float32).reshape(-1, 4)
+        out = np.zeros((len(s), 20), np.float32)
+        self._l.orc_camera_rays_diff(self._h, _pf(s), len(s), scale, _pf(out))
+        return out
 
     def bvh(self):
         bounds = np.zeros((self.n_nodes, 6), np.float32)

@@ -32,6 +32,7 @@ orc_scene* orc_scene_create(const rt_scene* in) {
   Scene& sc = o->scene;
   o->film_desc = in->film; o->sampler = in->sampler; o->integrator = in->integrator;
   sc.materials.assign(in->materials, in->materials + in->n_materials);
+  sc.textures.init(in->textures, in->n_textures);
   // shapes -> primitives in directive order (api.rs:913-966, mesh.rs:636-679); shapes of an object definition go to the
   // definition's own list (api.rs:951-957), an ObjectInstance adds one TransformedPrimitive (api.rs:1081-1085)
   std::vector<std::shared_ptr<ObjectDef>> defs(in->n_objects);
@@ -265,7 +266,8 @@ void orc_li_samples(orc_scene* s, const rt_integrator* integrator_override, cons
     sampler.start_pixel(pix[3 * i], pix[3 * i + 1]);
     sampler.s = (uint32_t)pix[3 * i + 2];
     CameraSample cs = sampler.get_camera_sample(pix[3 * i], pix[3 * i + 1]);
-    Ray ray = s->camera.generate_ray(cs);
+    Ray ray = s->camera.generate_ray_differential(cs);          // renderer.rs:110-111
+    ray.scale_differentials(1.0f / std::sqrt((float)sampler.spp));
     Spectrum c = integ.li(s->scene, ray, sampler, 0);
     out[3 * i] = c.r; out[3 * i + 1] = c.g; out[3 * i + 2] = c.b;
     if (p_film_out) { p_film_out[2 * i] = cs.p_film.x; p_film_out[2 * i + 1] = cs.p_film.y; }
@@ -330,6 +332,49 @@ int orc_material_bsdf(orc_scene* s, int row, int allow_multiple_lobes, const flo
   return 0;
 }
 float orc_roughness_to_alpha(float r) { return TrowbridgeReitz::roughness_to_alpha(r); }
+
+// ---- textures (tests/test_oracle_textures.py, tests/test_gpu_textures.py) ----
+// Texture row `row` evaluated at n explicit surface points: in = 15 floats each {uv.xy, p.xyz, dpdx.xyz, dpdy.xyz, dudx, dvdx, dudy, dvdy};
+// out = 3 floats each (a float texture fills all three).
+int orc_texture_eval(orc_scene* s, int row, const float* in, uint64_t n, float* out) {
+  if (row < 0 || (size_t)row >= s->scene.textures.rows.size()) return -1;
+  for (size_t i = 0; i < n; i++) {
+    const float* a = in + 15 * i;
+    SurfaceInteraction si;
+    si.uv = P2(a[0], a[1]); si.hit.p = V3(a[2], a[3], a[4]); si.dpdx = V3(a[5], a[6], a[7]); si.dpdy = V3(a[8], a[9], a[10]);
+    si.dudx = a[11]; si.dvdx = a[12]; si.dudy = a[13]; si.dvdy = a[14];
+    Spectrum v = s->scene.textures.eval(row, si);
+    out[3 * i] = v.r; out[3 * i + 1] = v.g; out[3 * i + 2] = v.b;
+  }
+  return 0;
+}
+// MIP pyramid of imagemap row `row`: number of levels (level < 0), or the level's size (u, v) and, when out != NULL, its texels.
+int orc_texture_mip_level(orc_scene* s, int row, int level, int32_t* u, int32_t* v, int32_t* channels, float* out) {
+  if (row < 0 || (size_t)row >= s->scene.textures.rows.size() || !s->scene.textures.mips[(size_t)row]) return -1;
+  const MIPMap& m = *s->scene.textures.mips[(size_t)row];
+  if (level < 0) return (int)m.levels();
+  if ((size_t)level >= m.levels()) return -1;
+  const MIPMap::Level& l = m.pyramid[(size_t)level];
+  *u = l.u; *v = l.v; *channels = m.nc;
+  if (out) std::memcpy(out, l.d.data(), l.d.size() * sizeof(float));
+  return 0;
+}
+float orc_noise(float x, float y, float z) { return noise(x, y, z); }
+float orc_fbm(const float* p, const float* dpdx, const float* dpdy, float omega, uint32_t octaves) {
+  return fbm(V3(p[0], p[1], p[2]), V3(dpdx[0], dpdx[1], dpdx[2]), V3(dpdy[0], dpdy[1], dpdy[2]), omega, octaves);
+}
+// Camera ray with its differentials, scaled by `scale` (renderer.rs:110-111): out = 8 + 12 floats {ray, rx_o, ry_o, rx_d, ry_d}
+void orc_camera_rays_diff(orc_scene* s, const float* samples, uint64_t n, float scale, float* rays) {
+  for (size_t i = 0; i < n; i++) {
+    CameraSample cs; cs.p_film = P2(samples[4 * i], samples[4 * i + 1]); cs.p_lens = P2(samples[4 * i + 2], samples[4 * i + 3]); cs.time = 0;
+    Ray r = s->camera.generate_ray_differential(cs);
+    r.scale_differentials(scale);
+    float* o = rays + 20 * i;
+    o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.t_max; o[4] = r.d.x; o[5] = r.d.y; o[6] = r.d.z; o[7] = 0;
+    const V3 v[4] = {r.rx_o, r.ry_o, r.rx_d, r.ry_d};
+    for (int k = 0; k < 4; k++) { o[8 + 3 * k] = v[k].x; o[9 + 3 * k] = v[k].y; o[10 + 3 * k] = v[k].z; }
+  }
+}
 
 // Restated reference property tests (rustracer-core/tests/efloat.rs:52-154, tests/shapes.rs:16-54,
 // bsdf/fresnel.rs:427-436 is covered in python).  Returns the number of violations.

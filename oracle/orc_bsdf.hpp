@@ -2,7 +2,7 @@
 // Follows /root/reference/rustracer-core/src/bsdf/*.rs and material/{matte,plastic,metal,glass,mirror}.rs.
 #pragma once
 #include <stdexcept>
-#include "orc_shapes.hpp"
+#include "orc_texture.hpp"
 #include "../include/rt_scene.h"
 
 namespace orc {
@@ -407,8 +407,11 @@ struct Bsdf {                                                    // bsdf/mod.rs:
 
 // material/*.rs with every texture constant.  `allow_multiple_lobes`: path=true (path.rs:145), whitted/direct=false.
 // `table`: the scene's material rows (MixMaterial refers to its two children by row).
-inline bool compute_scattering_functions(const rt_material* table, const rt_material& mt, const SurfaceInteraction& si, bool allow_multiple_lobes, Bsdf& bsdf) {
+// `ts`: the scene's textures; a material with textured parameters is evaluated at `si` first (and its bump map applied to `si`).
+inline bool compute_scattering_functions(const rt_material* table, const rt_material& mt_in, SurfaceInteraction& si, bool allow_multiple_lobes, Bsdf& bsdf,
+                                         const TextureSet* ts = nullptr) {
   bsdf.n = 0;
+  const rt_material mt = (ts && mt_in.textured) ? ts->resolve(mt_in, si) : mt_in;
   auto S = [](const float* c) { return Spectrum(c[0], c[1], c[2]); };
   switch (mt.type) {
     case RT_MAT_MATTE: {                                          // matte.rs:37-62
@@ -557,8 +560,9 @@ inline bool compute_scattering_functions(const rt_material* table, const rt_mate
       Bsdf b2;
       // both children always yield a Bsdf on this path (every material/*.rs sets si.bsdf); the result keeps mat1's Bsdf
       // (its eta and frame) and replaces the lobe list by the scaled lobes of both
-      if (!compute_scattering_functions(table, table[mt.mix_a], si, allow_multiple_lobes, bsdf)) return false;
-      if (!compute_scattering_functions(table, table[mt.mix_b], si, allow_multiple_lobes, b2)) return false;
+      SurfaceInteraction si2 = si;                               // mixmat.rs:43: mat2 works on a clone (its bump map never reaches the caller)
+      if (!compute_scattering_functions(table, table[mt.mix_a], si, allow_multiple_lobes, bsdf, ts)) return false;
+      if (!compute_scattering_functions(table, table[mt.mix_b], si2, allow_multiple_lobes, b2, ts)) return false;
       const int n1 = bsdf.n;
       for (int i = 0; i < n1; i++) {
         Lobe& l = bsdf.lobes[i];

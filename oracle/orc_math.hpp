@@ -242,11 +242,17 @@ inline Bounds3 bunion(const Bounds3& a, const Bounds3& b) {                     
 }
 inline Bounds3 bunion_point(const Bounds3& a, V3 p) { Bounds3 b = a; b.extend(p); return b; } // bounds.rs:111-115
 
-struct Ray {                                                                    // ray.rs:9-44 (differentials dropped: constant textures only)
+struct Ray {                                                                    // ray.rs:9-44
   V3 o, d; float t_max = INF;
+  bool has_diff = false; V3 rx_o, ry_o, rx_d, ry_d;                             // `differential: Option<RayDifferential>` (ray.rs:96-102)
   Ray() {}
   Ray(V3 o_, V3 d_, float t = INF) : o(o_), d(d_), t_max(t) {}
   V3 at(float t) const { return o + t * d; }
+  void scale_differentials(float s) {                                           // ray.rs:73-80
+    if (!has_diff) return;
+    rx_o = o + (rx_o - o) * s; ry_o = o + (ry_o - o) * s;
+    rx_d = d + (rx_d - d) * s; ry_d = d + (ry_d - d) * s;
+  }
 };
 
 // bounds.rs:127-157 — no (1+2γ3) widening, NaN compares false
@@ -373,7 +379,13 @@ inline Ray ray_transform(const Ray& r, const Transform& t, V3& o_error, V3& d_er
     float dt = dot(vabs(d), o_error) / ls;
     o = o + d * dt;
   }
-  return Ray(o, d, r.t_max);
+  Ray out(o, d, r.t_max);
+  if (r.has_diff) {                                                             // ray.rs:57-62
+    out.has_diff = true;
+    out.rx_o = t.point(r.rx_o); out.ry_o = t.point(r.ry_o);
+    out.rx_d = t.vector(r.rx_d); out.ry_d = t.vector(r.ry_d);
+  }
+  return out;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -171,6 +171,7 @@ struct Scene {                                                   // scene.rs:22-
   std::vector<Light> lights;
   std::vector<int> infinite_lights;
   std::vector<rt_material> materials;
+  TextureSet textures;
   BVH bvh;
   int intersect(Ray& ray, SurfaceInteraction& si) const { tls_counters().regular_rays++; return bvh.intersect(ray, si); }
   bool intersect_p(const Ray& ray) const { tls_counters().shadow_rays++; return bvh.intersect_p(ray); }
@@ -370,6 +371,7 @@ struct Camera {
                                     Transform::translate(V3(-sw[0], -sw[3], 0.0f)));
     Transform r2s = s2r.inverse();
     r2c = Transform::mulT(c2s.inverse(), r2s);
+    init_differentials();
   }
   Ray generate_ray(const CameraSample& s) const {                 // :131-148 == differential-free part of :150-202
     V3 p_camera = r2c.point(V3(s.p_film.x, s.p_film.y, 0.0f));
@@ -381,6 +383,42 @@ struct Camera {
       V3 p_focus = ray.at(ft);
       ray.o = V3(p_lens.x, p_lens.y, 0.0f);
       ray.d = normalize(p_focus - ray.o);
+    }
+    V3 oe, de;
+    return ray_transform(ray, c2w, oe, de);
+  }
+  V3 dx_camera, dy_camera;                                        // :62-65
+  void init_differentials() {
+    dx_camera = r2c.point(V3(1, 0, 0)) - r2c.point(V3(0, 0, 0));
+    dy_camera = r2c.point(V3(0, 1, 0)) - r2c.point(V3(0, 0, 0));
+  }
+  Ray generate_ray_differential(const CameraSample& s) const {    // :150-202
+    V3 p_camera = r2c.point(V3(s.p_film.x, s.p_film.y, 0.0f));
+    Ray ray(V3(0, 0, 0), normalize(p_camera));
+    if (lens_radius > 0.0f) {
+      P2 d = concentric_sample_disk(s.p_lens);
+      P2 p_lens(lens_radius * d.x, lens_radius * d.y);
+      float ft = focal_distance / ray.d.z;
+      V3 p_focus = ray.at(ft);
+      ray.o = V3(p_lens.x, p_lens.y, 0.0f);
+      ray.d = normalize(p_focus - ray.o);
+    }
+    ray.has_diff = true;
+    if (lens_radius > 0.0f) {
+      P2 d = concentric_sample_disk(s.p_lens);
+      P2 p_lens(lens_radius * d.x, lens_radius * d.y);
+      V3 origin(p_lens.x, p_lens.y, 0.0f);
+      V3 dx = normalize(p_camera + dx_camera);
+      float ft_x = focal_distance / dx.z;
+      V3 p_focus_x = ft_x * dx;
+      V3 dy = normalize(p_camera + dy_camera);
+      float ft_y = focal_distance / dy.z;
+      V3 p_focus_y = ft_y * dy;
+      ray.rx_o = origin; ray.ry_o = origin;
+      ray.rx_d = normalize(p_focus_x - origin); ray.ry_d = normalize(p_focus_y - origin);
+    } else {
+      ray.rx_o = ray.o; ray.ry_o = ray.o;
+      ray.rx_d = normalize(p_camera + dx_camera); ray.ry_d = normalize(p_camera + dy_camera);
     }
     V3 oe, de;
     return ray_transform(ray, c2w, oe, de);
@@ -506,7 +544,8 @@ struct Integrator {
       if (!found || bounces >= max_ray_depth) break;
       Bsdf bsdf;
       int mat = scene.material_of(isect);
-      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, true, bsdf)) {
+      isect.compute_differential(ray);                           // interaction.rs:199 (compute_scattering_functions starts with it)
+      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, true, bsdf, &scene.textures)) {
         ray = isect.hit.spawn_ray(ray.d);
         bounces -= 1;                                            // u8 wrap (Q23)
         continue;
@@ -546,7 +585,8 @@ struct Integrator {
       V3 n = isect.shading.n, wo = isect.hit.wo;
       Bsdf bsdf;
       int mat = scene.material_of(isect);
-      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, false, bsdf)) {
+      isect.compute_differential(ray);
+      if (mat < 0 || !compute_scattering_functions(scene.materials.data(), scene.materials[mat], isect, false, bsdf, &scene.textures)) {
         Ray r = isect.hit.spawn_ray(ray.d);
         return li_recursive(scene, r, sampler, depth, node);
       }
@@ -572,6 +612,25 @@ struct Integrator {
           V3 ns = isect.shading.n;
           if (pdf > 0.0f && !f.is_black() && std::fabs(dot(wi, ns)) != 0.0f) {
             Ray r = isect.hit.spawn_ray(wi);
+            if (ray.has_diff) {                                  // integrator/mod.rs:64-83 (reflection), :107-136 (transmission)
+              const V3 kZeroN(0, 0, 0);                          // shading.dndu / dndv / isect.dndv (orc_shapes.hpp)
+              r.has_diff = true;
+              r.rx_o = isect.hit.p + isect.dpdx; r.ry_o = isect.hit.p + isect.dpdy;
+              V3 dndx = kZeroN * isect.dudx + kZeroN * isect.dvdx, dndy = kZeroN * isect.dudy + kZeroN * isect.dvdy;
+              V3 dwodx = -ray.rx_d - isect.hit.wo, dwody = -ray.ry_d - isect.hit.wo;
+              float dDNdx = dot(dwodx, ns) + dot(isect.hit.wo, dndx), dDNdy = dot(dwody, ns) + dot(isect.hit.wo, dndy);
+              if (pass == 0) {
+                r.rx_d = wi - dwodx + 2.0f * (dot(isect.hit.wo, ns) * dndx + dDNdx * ns);
+                r.ry_d = wi - dwody + 2.0f * (dot(isect.hit.wo, ns) * dndy + dDNdy * ns);
+              } else {
+                float eta = bsdf.eta;
+                V3 w = -isect.hit.wo;
+                if (dot(isect.hit.wo, ns) < 0.0f) eta = 1.0f / eta;
+                float mu = eta * dot(w, ns) - dot(wi, ns);
+                r.rx_d = wi + eta * dwodx - (mu * dndx + dDNdx * ns);
+                r.ry_d = wi + eta * dwody - (mu * dndy + dDNdy * ns);
+              }
+            }
             Spectrum sub = li_recursive(scene, r, sampler, depth + 1, node * 2 + (uint32_t)pass);
             colour += f * sub * std::fabs(dot(wi, ns)) / pdf;
           }
@@ -660,7 +719,8 @@ inline void render(const Scene& scene, Integrator& integ, const Camera& camera, 
         if (!(x >= pixel_bounds.x0 && x < pixel_bounds.x1 && y >= pixel_bounds.y0 && y < pixel_bounds.y1)) continue;
         while (true) {
           CameraSample s = sampler->get_camera_sample(x, y);
-          Ray ray = camera.generate_ray(s);
+          Ray ray = camera.generate_ray_differential(s);         // renderer.rs:110-111
+          ray.scale_differentials(1.0f / std::sqrt((float)sampler->spp));
           tls_counters().camera_rays++;
           Spectrum c = integ.li(scene, ray, *sampler, 0);
           if (c.has_nan()) c = Spectrum(0.0f);

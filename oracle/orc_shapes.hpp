@@ -59,14 +59,18 @@ struct Interaction {
   }
 };
 
+// interaction.rs:78-147.  dndu / dndv are not stored: every shape of the reference hands a zero to SurfaceInteraction::new
+// (mesh.rs:371-372) or goes through SurfaceInteraction::transform, which zeroes them (interaction.rs:168-169, :182-183 — Q15);
+// the places that read them (material/mod.rs:66-88, integrator/mod.rs:71-72) use kZeroN.
 struct Shape;
-// interaction.rs:78-147 (ray differentials, dndu/dndv omitted: they only feed texture filtering,
-// and every texture on this path is constant — SURVEY §2 "Interaction")
 struct SurfaceInteraction {
   Interaction hit;
   P2 uv;
   V3 dpdu, dpdv;
+  V3 dpdx, dpdy; float dudx = 0, dvdx = 0, dudy = 0, dvdy = 0;   // filled by compute_differential (interaction.rs:245-314)
   struct { V3 n, dpdu, dpdv; } shading;
+  inline void compute_differential(const Ray& ray);
+  inline void set_shading_geometry(V3 dpdus, V3 dpdvs, bool is_orientation_authoritative);
   int prim = -1;           // prim_number of the GeometricPrimitive (primitive.rs:45-51)
   const Shape* shape = nullptr;
   // hit inside an object instance: `isect.primitive` is the instance's inner GeometricPrimitive (primitive.rs:91-97 maps the
@@ -99,6 +103,45 @@ struct Shape {
     return 0.0f;
   }
 };
+
+// interaction.rs:218-242 (dndu / dndv: see above)
+inline void SurfaceInteraction::set_shading_geometry(V3 dpdus, V3 dpdvs, bool is_orientation_authoritative) {
+  shading.n = normalize(cross(dpdus, dpdvs));
+  if (shape->reverse_orientation ^ shape->swaps_handedness) shading.n = shading.n * -1.0f;
+  if (is_orientation_authoritative) hit.n = face_forward(hit.n, shading.n);
+  else shading.n = face_forward(shading.n, hit.n);
+  shading.dpdu = dpdus; shading.dpdv = dpdvs;
+}
+// transform.rs:382-394
+inline bool solve_linear_system2x2(const float A[2][2], float B0, float B1, float& x0, float& x1) {
+  float det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+  if (std::fabs(det) < 1e-10f) return false;
+  x0 = (A[1][1] * B0 - A[0][1] * B1) / det;
+  x1 = (A[0][0] * B1 - A[1][0] * B0) / det;
+  if (std::isnan(x0) || std::isnan(x1)) return false;
+  return true;
+}
+// interaction.rs:245-314
+inline void SurfaceInteraction::compute_differential(const Ray& ray) {
+  dudx = dvdx = dudy = dvdy = 0.0f; dpdx = V3(0, 0, 0); dpdy = V3(0, 0, 0);
+  if (!ray.has_diff) return;
+  const V3 n = hit.n, p = hit.p;
+  float d = dot(n, V3(p.x, p.y, p.z));
+  float tx = -(dot(n, ray.rx_o) - d) / dot(n, ray.rx_d);
+  float ty = -(dot(n, ray.ry_o) - d) / dot(n, ray.ry_d);
+  if (std::isinf(tx) || std::isnan(tx) || std::isinf(ty) || std::isnan(ty)) return;
+  V3 px = ray.rx_o + tx * ray.rx_d, py = ray.ry_o + ty * ray.ry_d;
+  dpdx = px - p; dpdy = py - p;
+  int dim[2];
+  if (std::fabs(n.x) > std::fabs(n.y) && std::fabs(n.x) > std::fabs(n.z)) { dim[0] = 1; dim[1] = 2; }
+  else if (std::fabs(n.y) > std::fabs(n.z)) { dim[0] = 0; dim[1] = 2; }
+  else { dim[0] = 0; dim[1] = 1; }
+  const float A[2][2] = {{dpdu[dim[0]], dpdv[dim[0]]}, {dpdu[dim[1]], dpdv[dim[1]]}};
+  const float Bx0 = px[dim[0]] - p[dim[0]], Bx1 = px[dim[1]] - p[dim[1]];
+  const float By0 = py[dim[0]] - p[dim[0]], By1 = py[dim[1]] - p[dim[1]];
+  if (!solve_linear_system2x2(A, Bx0, Bx1, dudx, dvdx)) { dudx = 0.0f; dvdx = 0.0f; }
+  if (!solve_linear_system2x2(A, By0, By1, dudy, dvdy)) { dudy = 0.0f; dvdy = 0.0f; }
+}
 
 // interaction.rs:103-147
 inline SurfaceInteraction make_si(V3 p, V3 p_error, P2 uv, V3 wo, V3 dpdu, V3 dpdv, const Shape* shape) {

@@ -34,7 +34,15 @@ class rt_material(C.Structure):
     _fields_ = [("type", c_i32), ("kd", c_f * 3), ("ks", c_f * 3), ("kr", c_f * 3), ("kt", c_f * 3), ("eta_rgb", c_f * 3), ("k_rgb", c_f * 3),
                 ("sigma", c_f), ("roughness", c_f), ("uroughness", c_f), ("vroughness", c_f), ("has_uroughness", c_i32), ("has_vroughness", c_i32),
                 ("eta", c_f), ("remap_roughness", c_i32),
-                ("opacity", c_f * 3), ("reflect", c_f * 3), ("transmit", c_f * 3), ("amount", c_f * 3), ("mix_a", c_i32), ("mix_b", c_i32)]
+                ("opacity", c_f * 3), ("reflect", c_f * 3), ("transmit", c_f * 3), ("amount", c_f * 3), ("mix_a", c_i32), ("mix_b", c_i32),
+                ("tex", c_i32 * 16), ("textured", c_i32)]
+
+
+class rt_texture(C.Structure):
+    _fields_ = [("kind", c_i32), ("is_float", c_i32), ("value", c_f * 3), ("tex1", c_i32), ("tex2", c_i32), ("amount", c_i32), ("mapping", c_i32),
+                ("su", c_f), ("sv", c_f), ("du", c_f), ("dv", c_f), ("vs", c_f * 3), ("vt", c_f * 3), ("aa_none", c_i32), ("w2t", rt_transform),
+                ("omega", c_f), ("octaves", c_i32), ("img_w", c_i32), ("img_h", c_i32), ("texels", PF), ("wrap", c_i32), ("trilinear", c_i32),
+                ("max_aniso", c_f)]
 
 
 class rt_camera(C.Structure):
@@ -62,6 +70,7 @@ class rt_accel(C.Structure):
 class rt_scene(C.Structure):
     _fields_ = [("n_objects", c_u32), ("n_shapes", c_u32), ("shapes", C.POINTER(rt_shape)), ("n_area_lights", c_u32), ("area_lights", C.POINTER(rt_area_light)),
                 ("n_lights", c_u32), ("lights", C.POINTER(rt_light)), ("n_materials", c_u32), ("materials", C.POINTER(rt_material)),
+                ("n_textures", c_u32), ("textures", C.POINTER(rt_texture)),
                 ("camera", rt_camera), ("film", rt_film), ("sampler", rt_sampler), ("integrator", rt_integrator), ("accel", rt_accel)]
 
 

@@ -1,5 +1,6 @@
 // See pbrt_frontend.hpp.  Reference line numbers are relative to /root/reference/rustracer-core/src/.
 #include "pbrt_frontend.hpp"
+#include <zlib.h>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -198,54 +199,145 @@ static bool read_pfm(const std::string& fn, int& w, int& h, std::vector<float>& 
   return true;
 }
 
+// 8-bit PNG reader (imageio.rs:94-113: `image::open(..).to_rgb8()`, channel / 255): colour types 0, 2, 3, 4, 6 at 8 or 16 bits,
+// non-interlaced; zlib inflates the IDAT stream.  Rows top-to-bottom.
+static bool read_png(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
+  FILE* f = std::fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  std::vector<unsigned char> file;
+  unsigned char buf[65536]; size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) file.insert(file.end(), buf, buf + n);
+  std::fclose(f);
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+  if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) return false;
+  auto be32 = [&](size_t o) { return ((uint32_t)file[o] << 24) | ((uint32_t)file[o + 1] << 16) | ((uint32_t)file[o + 2] << 8) | (uint32_t)file[o + 3]; };
+  int depth = 0, ctype = 0, interlace = 0;
+  std::vector<unsigned char> idat, plte;
+  for (size_t o = 8; o + 12 <= file.size();) {
+    const uint32_t len = be32(o);
+    if (o + 12 + len > file.size()) return false;
+    const std::string type((const char*)&file[o + 4], 4);
+    const unsigned char* d = &file[o + 8];
+    if (type == "IHDR") { w = (int)be32(o + 8); h = (int)be32(o + 12); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+    else if (type == "PLTE") plte.assign(d, d + len);
+    else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
+    else if (type == "IEND") break;
+    o += 12 + len;
+  }
+  if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return false;
+  const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (!channels) return false;
+  const size_t bpp = (size_t)channels * depth / 8, stride = (size_t)w * bpp;
+  std::vector<unsigned char> raw((stride + 1) * (size_t)h);
+  uLongf raw_len = (uLongf)raw.size();
+  if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return false;
+  std::vector<unsigned char> img(stride * (size_t)h);
+  for (int y = 0; y < h; y++) {                                      // undo the per-row filters
+    const unsigned char ft = raw[(stride + 1) * y];
+    const unsigned char* in = &raw[(stride + 1) * y + 1];
+    unsigned char* cur = &img[stride * y];
+    const unsigned char* up = y ? &img[stride * (y - 1)] : nullptr;
+    for (size_t i = 0; i < stride; i++) {
+      const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+      int pred = 0;
+      if (ft == 1) pred = a; else if (ft == 2) pred = b; else if (ft == 3) pred = (a + b) / 2;
+      else if (ft == 4) { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+      else if (ft != 0) return false;
+      cur[i] = (unsigned char)(in[i] + pred);
+    }
+  }
+  rgb.resize((size_t)w * h * 3);
+  const size_t step = depth / 8;                                     // 16-bit samples: the high byte (to_rgb8 scales 65535 -> 255)
+  for (size_t i = 0; i < (size_t)w * h; i++) {
+    const unsigned char* px = &img[i * bpp];
+    unsigned char r, g, b;
+    if (ctype == 0 || ctype == 4) r = g = b = px[0];
+    else if (ctype == 3) { const size_t k = (size_t)px[0] * 3; if (k + 2 >= plte.size()) return false; r = plte[k]; g = plte[k + 1]; b = plte[k + 2]; }
+    else { r = px[0]; g = px[step]; b = px[2 * step]; }
+    rgb[i * 3] = (float)r / 255.0f; rgb[i * 3 + 1] = (float)g / 255.0f; rgb[i * 3 + 2] = (float)b / 255.0f;
+  }
+  return true;
+}
+// imageio.rs:77-92 `read_image`: by extension.  PFM and PNG are read; TGA / HDR / EXR need codecs this build does not carry.
+static bool read_image_rgb(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
+  auto ends = [&](const char* e) { size_t n = std::strlen(e); return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0; };
+  if (ends(".pfm")) return read_pfm(fn, w, h, rgb);
+  if (ends(".png")) return read_png(fn, w, h, rgb);
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // API state machine (api.rs)
 namespace {
 
+// A material / texture parameter after lookup: a constant, or a row of the scene's texture table.
+struct TexRef { Rgb c{0, 0, 0}; float f = 0; int row = -1; };
 struct TextureParams {                                               // paramset.rs:349-467
   const ParamSet& geom; const ParamSet& mat;
-  const std::map<std::string, float>& ftex; const std::map<std::string, Rgb>& stex;
+  const std::map<std::string, int>& ftex; const std::map<std::string, int>& stex;   // name -> row of `table`
+  std::vector<rt_texture>* table;
   std::vector<std::string>* warn;
   float find_float(const std::string& n, float d) const { return geom.find_one_float(n, mat.find_one_float(n, d)); }
+  int32_t find_int(const std::string& n, int32_t d) const { return geom.find_one_int(n, mat.find_one_int(n, d)); }
   bool find_bool(const std::string& n, bool d) const { return geom.find_one_bool(n, mat.find_one_bool(n, d)); }
   std::string find_string(const std::string& n, const std::string& d) const { return geom.find_one_string(n, mat.find_one_string(n, d)); }
   Rgb find_spectrum(const std::string& n, Rgb d) const { return geom.find_one_spectrum(n, mat.find_one_spectrum(n, d)); }
+  Vec3 find_vector3(const std::string& n, Vec3 d) const { return geom.find_one_vector3(n, mat.find_one_vector3(n, d)); }
   std::string tex_name(const std::string& n) const { std::string nm = geom.find_texture(n); if (nm.empty()) nm = mat.find_texture(n); return nm; }
-  Rgb spectrum_texture(const std::string& n, Rgb def) const {        // :406-424
+  // a named texture: folded to its value when it is a ConstantTexture, else referenced by row
+  TexRef ref_of(int row) const {
+    const rt_texture& t = (*table)[(size_t)row];
+    TexRef r;
+    if (t.kind == RT_TEX_CONSTANT) { r.c = Rgb{t.value[0], t.value[1], t.value[2]}; r.f = t.value[0]; }
+    else r.row = row;
+    return r;
+  }
+  TexRef spectrum_texture(const std::string& n, Rgb def) const {     // :406-424
     std::string nm = tex_name(n);
     if (!nm.empty()) {
       auto it = stex.find(nm);
-      if (it != stex.end()) return it->second;
+      if (it != stex.end()) return ref_of(it->second);
       warn->push_back("Couldn't find spectrum texture " + nm + " for parameter " + n);
     }
-    return geom.find_one_spectrum(n, mat.find_one_spectrum(n, def));
+    TexRef r; r.c = geom.find_one_spectrum(n, mat.find_one_spectrum(n, def));
+    return r;
   }
-  float float_texture(const std::string& n, float def) const {       // :426-442
+  TexRef float_texture(const std::string& n, float def) const {      // :426-442
     std::string nm = tex_name(n);
     if (!nm.empty()) {
       auto it = ftex.find(nm);
-      if (it != ftex.end()) return it->second;
+      if (it != ftex.end()) return ref_of(it->second);
       warn->push_back("Couldn't find float texture " + nm + " for parameter " + n);
     }
-    return geom.find_one_float(n, mat.find_one_float(n, def));
+    TexRef r; r.f = geom.find_one_float(n, mat.find_one_float(n, def));
+    return r;
   }
-  bool float_texture_or_none(const std::string& n, float& out) const {   // :444-466
+  bool float_texture_or_none(const std::string& n, TexRef& out) const {   // :444-466
     std::string nm = tex_name(n);
     if (!nm.empty()) {
       auto it = ftex.find(nm);
-      if (it != ftex.end()) { out = it->second; return true; }
+      if (it != ftex.end()) { out = ref_of(it->second); return true; }
       warn->push_back("Couldn't find float texture " + nm + " for parameter " + n);
       return false;
     }
-    if (const auto* v = geom.find_float(n)) { out = v->at(0); return true; }
-    if (const auto* v = mat.find_float(n)) { out = v->at(0); return true; }
+    if (const auto* v = geom.find_float(n)) { out = TexRef(); out.f = v->at(0); return true; }
+    if (const auto* v = mat.find_float(n)) { out = TexRef(); out.f = v->at(0); return true; }
     return false;
+  }
+  // children of scale / mix / checkerboard textures are always rows: a constant gets its own ConstantTexture row
+  int child_row(const TexRef& r, bool is_float) const {
+    if (r.row >= 0) return r.row;
+    rt_texture t; std::memset(&t, 0, sizeof(t));
+    t.kind = RT_TEX_CONSTANT; t.is_float = is_float; t.tex1 = t.tex2 = t.amount = -1;
+    if (is_float) t.value[0] = t.value[1] = t.value[2] = r.f; else { t.value[0] = r.c.r; t.value[1] = r.c.g; t.value[2] = r.c.b; }
+    table->push_back(t);
+    return (int)table->size() - 1;
   }
 };
 
 struct GraphicsState {                                               // api.rs:313-371
-  std::map<std::string, float> float_textures;
-  std::map<std::string, Rgb> spectrum_textures;
+  std::map<std::string, int> float_textures;                         // name -> row of SceneStore::textures
+  std::map<std::string, int> spectrum_textures;
   ParamSet material_param; std::string material = "matte";
   std::map<std::string, int> named_material;                         // name -> material row
   std::string current_named_material;
@@ -290,9 +382,12 @@ struct Api {
   int make_material(const std::string& name_in, const TextureParams& mp) {   // api.rs:1141-1183 + material/*.rs create()
     std::string name = name_in;
     rt_material m; std::memset(&m, 0, sizeof(m));
-    auto put = [](float* d, Rgb c) { d[0] = c.r; d[1] = c.g; d[2] = c.b; };
-    float dummy;
-    if (mp.float_texture_or_none("bumpmap", dummy) || !mp.tex_name("bumpmap").empty()) throw ParseError("bump mapping is outside the GPU path's scope (SURVEY §2)");
+    // a parameter is a constant (folded into its field) or a texture row (tex[slot] = row + 1)
+    auto putS = [&m](float* d, int slot, const TexRef& r) { d[0] = r.c.r; d[1] = r.c.g; d[2] = r.c.b; m.tex[slot] = r.row + 1; };
+    auto putF = [&m](float& d, int slot, const TexRef& r) { d = r.f; m.tex[slot] = r.row + 1; };
+    auto opt_rough = [&](const char* pname, float& d, int slot) { TexRef r; if (!mp.float_texture_or_none(pname, r)) return 0; putF(d, slot, r); return 1; };
+    auto eta_or_index = [&]() { TexRef r; if (!mp.float_texture_or_none("eta", r)) r = mp.float_texture("index", 1.5f); putF(m.eta, RT_TS_ETA, r); };
+    auto bumpmap = [&]() { TexRef r; if (mp.float_texture_or_none("bumpmap", r)) m.tex[RT_TS_BUMP] = mp.child_row(r, true) + 1; };   // material/*.rs create(): get_float_texture_or_none("bumpmap")
     if (name == "disney" || name == "fourier")
       throw ParseError("Material \"" + name + "\" is not on the GPU hot path yet (SURVEY §8f)");
     if (name != "matte" && name != "plastic" && name != "glass" && name != "mirror" && name != "metal" && name != "uber" && name != "substrate" &&
@@ -302,39 +397,42 @@ struct Api {
     }
     m.remap_roughness = 1;
     if (name == "matte") {                                           // matte.rs:20-33
-      m.type = RT_MAT_MATTE; put(m.kd, mp.spectrum_texture("Kd", Rgb{0.5f, 0.5f, 0.5f})); m.sigma = mp.float_texture("sigma", 0.0f);
+      m.type = RT_MAT_MATTE; putS(m.kd, RT_TS_KD, mp.spectrum_texture("Kd", Rgb{0.5f, 0.5f, 0.5f})); putF(m.sigma, RT_TS_SIGMA, mp.float_texture("sigma", 0.0f));
+      bumpmap();
     } else if (name == "plastic") {                                  // plastic.rs:26-41
-      m.type = RT_MAT_PLASTIC; put(m.kd, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
-      m.roughness = mp.float_texture("roughness", 0.1f); m.remap_roughness = mp.find_bool("remaproughness", true);
+      m.type = RT_MAT_PLASTIC; putS(m.kd, RT_TS_KD, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); putS(m.ks, RT_TS_KS, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
+      putF(m.roughness, RT_TS_ROUGHNESS, mp.float_texture("roughness", 0.1f)); m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     } else if (name == "glass") {                                    // glass.rs:28-49
-      m.type = RT_MAT_GLASS; put(m.kr, mp.spectrum_texture("Kr", Rgb{1, 1, 1})); put(m.kt, mp.spectrum_texture("Kt", Rgb{1, 1, 1}));
-      float eta;
-      if (!mp.float_texture_or_none("eta", eta)) eta = mp.float_texture("index", 1.5f);
-      m.eta = eta; m.uroughness = mp.float_texture("uroughness", 0.0f); m.vroughness = mp.float_texture("vroughness", 0.0f);
+      m.type = RT_MAT_GLASS; putS(m.kr, RT_TS_KR, mp.spectrum_texture("Kr", Rgb{1, 1, 1})); putS(m.kt, RT_TS_KT, mp.spectrum_texture("Kt", Rgb{1, 1, 1}));
+      eta_or_index();
+      putF(m.uroughness, RT_TS_UROUGHNESS, mp.float_texture("uroughness", 0.0f)); putF(m.vroughness, RT_TS_VROUGHNESS, mp.float_texture("vroughness", 0.0f));
       m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     } else if (name == "uber") {                                     // uber.rs:32-57
       m.type = RT_MAT_UBER;
-      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
-      put(m.kr, mp.spectrum_texture("Kr", Rgb{0, 0, 0})); put(m.kt, mp.spectrum_texture("Kt", Rgb{0, 0, 0}));
-      m.roughness = mp.float_texture("roughness", 0.1f);
-      m.has_uroughness = mp.float_texture_or_none("uroughness", m.uroughness);
-      m.has_vroughness = mp.float_texture_or_none("vroughness", m.vroughness);
-      float eta;
-      if (!mp.float_texture_or_none("eta", eta)) eta = mp.float_texture("index", 1.5f);
-      m.eta = eta;
-      put(m.opacity, mp.spectrum_texture("opacity", Rgb{1, 1, 1}));
+      putS(m.kd, RT_TS_KD, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); putS(m.ks, RT_TS_KS, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
+      putS(m.kr, RT_TS_KR, mp.spectrum_texture("Kr", Rgb{0, 0, 0})); putS(m.kt, RT_TS_KT, mp.spectrum_texture("Kt", Rgb{0, 0, 0}));
+      putF(m.roughness, RT_TS_ROUGHNESS, mp.float_texture("roughness", 0.1f));
+      m.has_uroughness = opt_rough("uroughness", m.uroughness, RT_TS_UROUGHNESS);
+      m.has_vroughness = opt_rough("vroughness", m.vroughness, RT_TS_VROUGHNESS);
+      eta_or_index();
+      putS(m.opacity, RT_TS_OPACITY, mp.spectrum_texture("opacity", Rgb{1, 1, 1}));
       m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     } else if (name == "substrate") {                                // substrate.rs:23-38
       m.type = RT_MAT_SUBSTRATE;
-      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.5f, 0.5f, 0.5f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.5f, 0.5f, 0.5f}));
-      m.uroughness = mp.float_texture("uroughness", 0.1f); m.vroughness = mp.float_texture("vroughness", 0.1f);
+      putS(m.kd, RT_TS_KD, mp.spectrum_texture("Kd", Rgb{0.5f, 0.5f, 0.5f})); putS(m.ks, RT_TS_KS, mp.spectrum_texture("Ks", Rgb{0.5f, 0.5f, 0.5f}));
+      putF(m.uroughness, RT_TS_UROUGHNESS, mp.float_texture("uroughness", 0.1f)); putF(m.vroughness, RT_TS_VROUGHNESS, mp.float_texture("vroughness", 0.1f));
       m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     } else if (name == "translucent") {                              // translucent.rs:26-44
       m.type = RT_MAT_TRANSLUCENT;
-      put(m.kd, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); put(m.ks, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
-      put(m.reflect, mp.spectrum_texture("reflect", Rgb{0.5f, 0.5f, 0.5f})); put(m.transmit, mp.spectrum_texture("transmit", Rgb{0.5f, 0.5f, 0.5f}));
-      m.roughness = mp.float_texture("roughness", 0.1f);
+      putS(m.kd, RT_TS_KD, mp.spectrum_texture("Kd", Rgb{0.25f, 0.25f, 0.25f})); putS(m.ks, RT_TS_KS, mp.spectrum_texture("Ks", Rgb{0.25f, 0.25f, 0.25f}));
+      putS(m.reflect, RT_TS_REFLECT, mp.spectrum_texture("reflect", Rgb{0.5f, 0.5f, 0.5f})); putS(m.transmit, RT_TS_TRANSMIT, mp.spectrum_texture("transmit", Rgb{0.5f, 0.5f, 0.5f}));
+      putF(m.roughness, RT_TS_ROUGHNESS, mp.float_texture("roughness", 0.1f));
       m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     } else if (name == "mix") {                                      // api.rs:1165-1176 + mixmat.rs:20-31
       m.type = RT_MAT_MIX;
       const std::string n1 = mp.find_string("namedmaterial1", ""), n2 = mp.find_string("namedmaterial2", "");
@@ -345,23 +443,27 @@ struct Api {
         return make_material("matte", mp);
       };
       m.mix_a = child(n1); m.mix_b = child(n2);
-      put(m.amount, mp.spectrum_texture("amount", Rgb{0.5f, 0.5f, 0.5f}));
+      putS(m.amount, RT_TS_AMOUNT, mp.spectrum_texture("amount", Rgb{0.5f, 0.5f, 0.5f}));
     } else if (name == "mirror") {                                   // mirror.rs:20-26
-      m.type = RT_MAT_MIRROR; put(m.kr, mp.spectrum_texture("Kr", Rgb{0.9f, 0.9f, 0.9f}));
+      m.type = RT_MAT_MIRROR; putS(m.kr, RT_TS_KR, mp.spectrum_texture("Kr", Rgb{0.9f, 0.9f, 0.9f}));
+      bumpmap();
     } else {                                                         // metal.rs:24-46
       m.type = RT_MAT_METAL;
-      put(m.eta_rgb, mp.spectrum_texture("eta", Rgb{kCopperEtaRgb[0], kCopperEtaRgb[1], kCopperEtaRgb[2]}));
-      put(m.k_rgb, mp.spectrum_texture("k", Rgb{kCopperKRgb[0], kCopperKRgb[1], kCopperKRgb[2]}));
-      m.roughness = mp.float_texture("roughness", 0.01f);
-      m.has_uroughness = mp.float_texture_or_none("uroughness", m.uroughness);
-      m.has_vroughness = mp.float_texture_or_none("vroughness", m.vroughness);
+      putS(m.eta_rgb, RT_TS_ETA_RGB, mp.spectrum_texture("eta", Rgb{kCopperEtaRgb[0], kCopperEtaRgb[1], kCopperEtaRgb[2]}));
+      putS(m.k_rgb, RT_TS_K_RGB, mp.spectrum_texture("k", Rgb{kCopperKRgb[0], kCopperKRgb[1], kCopperKRgb[2]}));
+      putF(m.roughness, RT_TS_ROUGHNESS, mp.float_texture("roughness", 0.01f));
+      m.has_uroughness = opt_rough("uroughness", m.uroughness, RT_TS_UROUGHNESS);
+      m.has_vroughness = opt_rough("vroughness", m.vroughness, RT_TS_VROUGHNESS);
       m.remap_roughness = mp.find_bool("remaproughness", true);
+      bumpmap();
     }
+    for (int i = 0; i < RT_TS_COUNT; i++) if (m.tex[i] != 0) m.textured = 1;
+    if (m.type == RT_MAT_MIX && (out->store.materials[(size_t)m.mix_a].textured || out->store.materials[(size_t)m.mix_b].textured)) m.textured = 1;
     out->store.materials.push_back(m);
     return (int)out->store.materials.size() - 1;
   }
   int create_material(const ParamSet& shape_params) {                // api.rs:318-340
-    TextureParams mp{shape_params, gs.material_param, gs.float_textures, gs.spectrum_textures, &warn()};
+    TextureParams mp{shape_params, gs.material_param, gs.float_textures, gs.spectrum_textures, &out->store.textures, &warn()};
     if (!gs.current_named_material.empty()) {
       auto it = gs.named_material.find(gs.current_named_material);
       if (it != gs.named_material.end()) return it->second;
@@ -394,20 +496,103 @@ struct Api {
     if (pushed_transforms.empty()) { warn().push_back("Unmatched TransformEnd encountered. Ignoring it."); return; }
     ctm = pushed_transforms.back(); pushed_transforms.pop_back();
   }
-  void d_texture(const std::string& name, const std::string& typ, const std::string& cls, const ParamSet& ps) {   // api.rs:792-853
+  // UVMapping2D / PlanarMapping2D parameters (checkerboard.rs:55-79, uv.rs:24-43, imagemap.rs:99-110)
+  void texture_mapping(const TextureParams& tp, rt_texture& t, bool planar_ok, const char* cls) {
+    const std::string typ = tp.find_string("mapping", "uv");
+    t.mapping = RT_TEXMAP_UV; t.su = t.sv = 1.0f; t.du = t.dv = 0.0f;
+    if (typ == "uv") {
+      t.su = tp.find_float("uscale", 1.0f); t.sv = tp.find_float("vscale", 1.0f); t.du = tp.find_float("udelta", 0.0f); t.dv = tp.find_float("vdelta", 0.0f);
+    } else if (typ == "planar" && planar_ok) {
+      t.mapping = RT_TEXMAP_PLANAR;
+      Vec3 vs = tp.find_vector3("v1", v3(1, 0, 0)), vt = tp.find_vector3("v2", v3(0, 1, 0));
+      t.vs[0] = vs.x; t.vs[1] = vs.y; t.vs[2] = vs.z; t.vt[0] = vt.x; t.vt[1] = vt.y; t.vt[2] = vt.z;
+      t.du = tp.find_float("udelta", 0.0f); t.dv = tp.find_float("vdelta", 0.0f);
+    } else if (typ == "spherical" || typ == "cylindrical" || typ == "planar") {
+      throw ParseError(std::string("Texture \"") + cls + "\": mapping \"" + typ + "\" is unimplemented!() in the reference");
+    } else warn().push_back("2D texture mapping \"" + typ + "\" unknown.");
+  }
+  void d_texture(const std::string& name, const std::string& typ, const std::string& cls, const ParamSet& ps) {   // api.rs:791-846, 1201-1259
     need_world("Texture");
     check_notes(ps, "Texture");
     ParamSet empty;
-    TextureParams tp{ps, empty, gs.float_textures, gs.spectrum_textures, &warn()};
-    if (cls != "constant") throw ParseError("Texture class \"" + cls + "\" is outside the GPU path's scope (constant textures only, SURVEY §2)");
-    if (typ == "float") gs.float_textures[name] = tp.find_float("value", 1.0f);                     // texture/constant.rs:20-24
-    else if (typ == "color" || typ == "spectrum") gs.spectrum_textures[name] = tp.find_spectrum("value", Rgb{1, 1, 1});
-    else warn().push_back("Texture type \"" + typ + "\" unknown.");
+    TextureParams tp{ps, empty, gs.float_textures, gs.spectrum_textures, &out->store.textures, &warn()};
+    const bool is_float = typ == "float";
+    if (!is_float && typ != "color" && typ != "spectrum") { warn().push_back("Texture type \"" + typ + "\" unknown."); return; }
+    rt_texture t; std::memset(&t, 0, sizeof(t));
+    t.is_float = is_float; t.tex1 = t.tex2 = t.amount = -1;
+    auto childS = [&](const char* n, Rgb d) { return tp.child_row(tp.spectrum_texture(n, d), false); };
+    auto childF = [&](const char* n, float d) { return tp.child_row(tp.float_texture(n, d), true); };
+    if (cls == "constant") {                                         // texture/constant.rs:20-33
+      t.kind = RT_TEX_CONSTANT;
+      if (is_float) t.value[0] = t.value[1] = t.value[2] = tp.find_float("value", 1.0f);
+      else { Rgb v = tp.find_spectrum("value", Rgb{1, 1, 1}); t.value[0] = v.r; t.value[1] = v.g; t.value[2] = v.b; }
+    } else if (cls == "scale") {                                     // texture/scale.rs:29-43
+      t.kind = RT_TEX_SCALE;
+      if (is_float) { t.tex1 = childF("tex1", 1.0f); t.tex2 = childF("tex2", 1.0f); }
+      else { t.tex1 = childS("tex1", Rgb{1, 1, 1}); t.tex2 = childS("tex2", Rgb{1, 1, 1}); }
+    } else if (cls == "mix") {                                       // texture/mix.rs:33-51
+      t.kind = RT_TEX_MIX;
+      if (is_float) { t.tex1 = childF("tex1", 0.0f); t.tex2 = childF("tex2", 1.0f); }
+      else { t.tex1 = childS("tex1", Rgb{0, 0, 0}); t.tex2 = childS("tex2", Rgb{1, 1, 1}); }
+      t.amount = childF("amount", 0.5f);
+    } else if (cls == "imagemap") {                                  // texture/imagemap.rs:97-139, 160-205
+      t.kind = RT_TEX_IMAGEMAP;
+      texture_mapping(tp, t, false, "imagemap");
+      t.max_aniso = tp.find_float("maxanisotropy", 8.0f);
+      t.trilinear = tp.find_bool("trilinear", false);
+      const std::string wrap = tp.find_string("wrap", "repeat");
+      t.wrap = wrap == "black" ? RT_WRAP_BLACK : (wrap == "clamp" ? RT_WRAP_CLAMP : RT_WRAP_REPEAT);
+      const float scale = tp.find_float("scale", 1.0f);
+      std::string fn = tp.find_string("filename", "");
+      fn = fn.empty() ? fn : resolve_filename(fn, opt.search_dir);
+      auto ends = [&](const char* e) { size_t n = std::strlen(e); return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0; };
+      const bool gamma = tp.find_bool("gamma", ends(".tga") || ends(".png"));
+      int w = 0, h = 0; std::vector<float> rgb;
+      if (!read_image_rgb(fn, w, h, rgb)) {                          // imagemap.rs:62-69
+        warn().push_back("Could not open texture file " + fn + ". Using grey texture instead");
+        w = h = 1; rgb.assign(3, 0.18f);
+      }
+      for (int y = 0; y < h / 2; y++)                                // :51-58 flip in y
+        for (int x = 0; x < w * 3; x++) std::swap(rgb[(size_t)y * w * 3 + x], rgb[(size_t)(h - 1 - y) * w * 3 + x]);
+      auto inv_gamma = [](float v) { return v <= 0.04045f ? v / 12.92f : std::pow((v + 0.055f) * 1.0f / 1.055f, 2.4f); };   // spectrum.rs:379-385
+      std::vector<float> texels((size_t)w * h * (is_float ? 1 : 3));
+      for (size_t i = 0; i < (size_t)w * h; i++) {                   // :72-83
+        float c[3];
+        for (int k = 0; k < 3; k++) c[k] = scale * (gamma ? inv_gamma(rgb[i * 3 + k]) : rgb[i * 3 + k]);
+        if (is_float) texels[i] = 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2];   // Spectrum::y (spectrum.rs:149-152)
+        else { texels[i * 3] = c[0]; texels[i * 3 + 1] = c[1]; texels[i * 3 + 2] = c[2]; }
+      }
+      t.img_w = w; t.img_h = h; t.texels = out->store.keep(std::move(texels));
+    } else if (cls == "fbm") {                                       // texture/fbm.rs:26-37
+      t.kind = RT_TEX_FBM; t.w2t = to_ir(ctm);
+      t.omega = tp.find_float("omega", 0.5f); t.octaves = tp.find_int("octaves", 8);
+    } else if (cls == "uv" && !is_float) {                           // texture/uv.rs:22-46
+      t.kind = RT_TEX_UV;
+      texture_mapping(tp, t, false, "uv");
+    } else if (cls == "checkerboard" && !is_float) {                 // texture/checkerboard.rs:44-97
+      t.kind = RT_TEX_CHECKERBOARD;
+      const int dim = tp.find_int("dimension", 2);
+      if (dim != 2) throw ParseError(dim == 3 ? "3 dimensional checkerboard texture is unimplemented!() in the reference" : "checkerboard texture: unsupported dimension");
+      t.tex1 = childS("tex1", Rgb{1, 1, 1}); t.tex2 = childS("tex2", Rgb{0, 0, 0});
+      texture_mapping(tp, t, true, "checkerboard");
+      const std::string aa = tp.find_string("aamode", "closedform");
+      if (aa == "none") t.aa_none = 1;
+      else if (aa != "closedform") warn().push_back("Unknown aamethod \"" + aa + "\" found for CheckerboardTexture. Using closedform instead");
+    } else if (!is_float && (cls == "bilerp" || cls == "dots" || cls == "wrinkled" || cls == "marble" || cls == "windy" || cls == "ptex")) {
+      throw ParseError("Texture class \"" + cls + "\" is unimplemented!() in the reference (api.rs:1234-1253)");
+    } else {                                                         // api.rs:1217,1255: Err -> the texture is not registered
+      warn().push_back("Failed to create texture " + name + ": Unkown texture type " + cls);
+      return;
+    }
+    out->store.textures.push_back(t);
+    auto& reg = is_float ? gs.float_textures : gs.spectrum_textures;
+    if (reg.count(name)) warn().push_back("Texture \"" + name + "\" being redefined.");
+    reg[name] = (int)out->store.textures.size() - 1;
   }
   void d_make_named_material(const std::string& name, const ParamSet& ps) {   // api.rs:855-881
     check_notes(ps, "MakeNamedMaterial");
     ParamSet empty;
-    TextureParams mp{ps, empty, gs.float_textures, gs.spectrum_textures, &warn()};
+    TextureParams mp{ps, empty, gs.float_textures, gs.spectrum_textures, &out->store.textures, &warn()};
     std::string type = mp.find_string("type", "");
     if (type.empty()) throw ParseError("No parameter string \"type\" found in named_material");
     gs.named_material[name] = make_material(type, mp);

@@ -53,6 +53,7 @@ struct ParamSet {
   std::string find_one_string(const std::string& n, const std::string& d) const { auto* e = lookup(strings, n); return e ? e->values.at(0) : d; }
   Rgb find_one_spectrum(const std::string& n, Rgb d) const { auto* e = lookup(spectra, n); return e ? e->values.at(0) : d; }
   Vec3 find_one_point3(const std::string& n, Vec3 d) const { auto* e = lookup(point3s, n); return e ? e->values.at(0) : d; }
+  Vec3 find_one_vector3(const std::string& n, Vec3 d) const { auto* e = lookup(vector3s, n); return e ? e->values.at(0) : d; }
   std::string find_texture(const std::string& n) const { auto* e = lookup(textures, n); return e ? e->values.at(0) : std::string(); }
   const std::vector<float>* find_float(const std::string& n) const { auto* e = lookup(floats, n); return e ? &e->values : nullptr; }
   const std::vector<int32_t>* find_int(const std::string& n) const { auto* e = lookup(ints, n); return e ? &e->values : nullptr; }

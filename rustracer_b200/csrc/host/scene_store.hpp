@@ -12,6 +12,7 @@ struct SceneStore {
   std::vector<rt_area_light> area_lights;
   std::vector<rt_light> lights;
   std::vector<rt_material> materials;
+  std::vector<rt_texture> textures;
   // stable storage for per-shape arrays
   std::deque<std::vector<int32_t>> index_arrays;
   std::deque<std::vector<float>> float_arrays;
@@ -29,6 +30,7 @@ struct SceneStore {
     view.n_area_lights = (uint32_t)area_lights.size(); view.area_lights = area_lights.data();
     view.n_lights = (uint32_t)lights.size(); view.lights = lights.data();
     view.n_materials = (uint32_t)materials.size(); view.materials = materials.data();
+    view.n_textures = (uint32_t)textures.size(); view.textures = textures.data();
     return &view;
   }
   size_t n_primitives() const {

@@ -256,6 +256,122 @@ def balls(xres=1024, yres=768, spp=64, integrator=None, n_side=8, crop=None, mat
 
 
 # ------------------------------------------------------------------------------------------------
+# textures and bump mapping
+
+def write_pfm(path, img):
+    """img: (H, W, 3) or (H, W) float32, row 0 at the top (PFM stores rows bottom-to-top)."""
+    img = np.asarray(img, np.float32)
+    with open(path, "wb") as f:
+        f.write((b"PF" if img.ndim == 3 else b"Pf") + b"\n%d %d\n-1.0\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img[::-1]).tobytes())
+
+
+def write_png8(path, img):
+    """img: (H, W, 3) or (H, W) uint8; deflate-compressed, filter type 0 on even rows and 'sub' on odd rows."""
+    import struct
+    import zlib
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else 3
+    rows = img.reshape(h, w * ch)
+    raw = bytearray()
+    for y in range(h):
+        if y % 2 == 0:
+            raw += b"\x00" + rows[y].tobytes()
+        else:
+            d = rows[y].astype(np.int16)
+            d[ch:] -= rows[y, :-ch].astype(np.int16)
+            raw += b"\x01" + (d & 0xff).astype(np.uint8).tobytes()
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0 if ch == 1 else 2, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + chunk(b"IEND", b""))
+
+
+def texture_images(out_dir):
+    """The two harness textures: a 48x20 (non power-of-two) RGB PFM and a 16x16 greyscale PNG."""
+    os.makedirs(out_dir, exist_ok=True)
+    y, x = np.mgrid[0:20, 0:48].astype(np.float32)
+    rgb = np.stack([0.5 + 0.5 * np.sin(x * 0.4), 0.5 + 0.5 * np.cos(y * 0.7 + x * 0.1), ((x.astype(int) // 6 + y.astype(int) // 5) % 2) * 0.8 + 0.1], -1)
+    write_pfm(os.path.join(out_dir, "tex_rgb.pfm"), rgb.astype(np.float32))
+    y, x = np.mgrid[0:16, 0:16]
+    g = (127.5 + 127.5 * np.sin(x * 0.9) * np.cos(y * 0.6)).astype(np.uint8)
+    write_png8(os.path.join(out_dir, "tex_small.png"), g)
+
+
+_TEXTURES_PREAMBLE = """
+Texture "checks" "spectrum" "checkerboard" "float uscale" [8] "float vscale" [8] "rgb tex1" [0.8 0.8 0.8] "rgb tex2" [0.1 0.1 0.3]
+Texture "img" "spectrum" "imagemap" "string filename" "tex_rgb.pfm" "float uscale" [2] "float vscale" [2]
+Texture "imgtri" "spectrum" "imagemap" "string filename" "tex_rgb.pfm" "bool trilinear" "true" "string wrap" "clamp" "float scale" [0.9]
+Texture "png" "spectrum" "imagemap" "string filename" "tex_small.png" "string wrap" "black" "float maxanisotropy" [4]
+Texture "bumpf" "float" "fbm" "integer octaves" [4] "float omega" [0.6]
+Texture "bumpimg" "float" "imagemap" "string filename" "tex_small.png" "float scale" [0.05] "float uscale" [3] "float vscale" [3]
+Texture "fbms" "spectrum" "fbm" "integer octaves" [3]
+Texture "rough" "float" "mix" "float tex1" [0.02] "float tex2" [0.3] "texture amount" "bumpimg"
+Texture "uvt" "spectrum" "uv" "float uscale" [3] "float vscale" [2] "float udelta" [0.25]
+Texture "sc" "spectrum" "scale" "texture tex1" "checks" "texture tex2" "uvt"
+Texture "mx" "spectrum" "mix" "texture tex1" "img" "rgb tex2" [0.9 0.2 0.2] "float amount" [0.3]
+Texture "planar" "spectrum" "checkerboard" "string mapping" "planar" "vector v1" [0.5 0 0] "vector v2" [0 0 0.5] "rgb tex1" [0.6 0.6 0.55] "texture tex2" "fbms"
+Texture "ground_aa" "spectrum" "checkerboard" "float uscale" [24] "float vscale" [16] "string aamode" "none" "texture tex1" "png" "rgb tex2" [0.3 0.5 0.3]
+Texture "kconst" "spectrum" "constant" "rgb value" [0.4 0.5 0.6]
+Texture "fconst" "float" "constant" "float value" [0.2]
+MakeNamedMaterial "t_matte" "string type" "matte" "texture Kd" "checks"
+MakeNamedMaterial "t_plastic" "string type" "plastic" "texture Kd" "img" "texture roughness" "rough"
+MakeNamedMaterial "t_mix" "string type" "mix" "string namedmaterial1" "t_matte" "string namedmaterial2" "t_plastic" "texture amount" "checks"
+"""
+
+_MATERIALS_TEXTURED = [
+    'Material "matte" "texture Kd" "checks"',
+    'Material "plastic" "texture Kd" "img" "texture roughness" "rough" "rgb Ks" [0.3 0.3 0.3]',
+    'Material "matte" "texture Kd" "mx" "texture bumpmap" "bumpf" "float sigma" [20]',
+    'Material "glass" "texture bumpmap" "bumpimg"',
+    'Material "mirror" "texture Kr" "sc"',
+    'Material "uber" "texture Kd" "imgtri" "texture opacity" "checks" "rgb Kr" [0.1 0.1 0.1]',
+    'Material "metal" "texture roughness" "rough" "texture bumpmap" "bumpf"',
+    'Material "substrate" "texture Kd" "png" "texture uroughness" "fconst"',
+    'Material "translucent" "texture Kd" "uvt" "texture reflect" "kconst"',
+    'NamedMaterial "t_mix"',
+    'Material "matte" "rgb Kd" [{c}]',
+    'Material "plastic" "texture Kd" "fbms" "texture bumpmap" "bumpimg"',
+]
+
+
+def balls_textured(out_dir, xres=1024, yres=768, spp=64, integrator=None, n_side=5, crop=None, lens=False):
+    """The balls scene with textured materials (every texture class, both mappings, bump maps), a planar-mapped checkerboard
+    ground disk and a uv-mapped, image-textured triangle quad seen at a grazing angle (anisotropic EWA lookups).  Writes the
+    texture images into out_dir; parse with search_dir=out_dir."""
+    texture_images(out_dir)
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5]'
+    s = header(xres, yres, spp, integrator, 40, ([0, 5.5, -9.5], [0, 0.3, 0], [0, 1, 0]), crop)
+    if lens:
+        s = s.replace('"float fov" [40]', '"float fov" [40] "float lensradius" [0.05] "float focaldistance" [10]')
+    s += "WorldBegin\n" + _TEXTURES_PREAMBLE
+    s += 'LightSource "point" "rgb I" [220 220 220] "point from" [-6 9 -6]\n'
+    s += 'LightSource "infinite" "rgb L" [0.25 0.3 0.4]\n'
+    s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [12 12 12]\nTranslate 0 6 2\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "sphere" "float radius" [0.6]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "matte" "texture Kd" "planar"\nRotate -90 1 0 0\nShape "disk" "float radius" [20]\nAttributeEnd\n'
+    s += ('AttributeBegin\nMaterial "matte" "texture Kd" "ground_aa"\n'
+          'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-6 0.01 2  6 0.01 2  6 0.01 14  -6 0.01 14] "float uv" [0 0 1 0 1 1 0 1]\nAttributeEnd\n')
+    s += ('AttributeBegin\nMaterial "plastic" "texture Kd" "img" "texture bumpmap" "bumpimg"\nTranslate -4.5 1.2 4\nRotate 30 0 1 0\n'
+          'Shape "cylinder" "float radius" [0.7] "float zmin" [-1] "float zmax" [1]\nAttributeEnd\n')
+    rng = PCG32([7])
+    n = n_side * n_side
+    for i in range(n):
+        r = np.float32(0.4) + np.float32(0.2) * rng.f32()[0]
+        gx, gz = i % n_side, i // n_side
+        x = (gx - (n_side - 1) / 2) * 1.6 + float(rng.f32()[0] - 0.5) * 0.3
+        z = (gz - (n_side - 1) / 2) * 1.6 + float(rng.f32()[0] - 0.5) * 0.3
+        col = f"{0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f}"
+        s += "AttributeBegin\n" + _MATERIALS_TEXTURED[i % len(_MATERIALS_TEXTURED)].format(c=col) + f"\nTranslate {x:.5f} {float(r):.5f} {z:.5f}\nRotate {37 * i} 0.3 1 0.2\n"
+        s += f'Shape "sphere" "float radius" [{float(r):.5f}]\nAttributeEnd\n'
+    s += "WorldEnd\n"
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
 # SURVEY 8f rank 2: object instancing (ObjectBegin / ObjectEnd / ObjectInstance)
 
 def _inline_icosphere(level, radius=1.0):
