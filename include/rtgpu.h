@@ -18,6 +18,7 @@
 #define RTGPU_H
 #include <stddef.h>
 #include <stdint.h>
+#include "rt_scene.h"   /* rt_material / RT_TEX_* for the textured-material rows */
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -62,7 +63,29 @@ typedef struct rtgpu_instance {
 } rtgpu_instance;
 
 enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MAT_GLASS = 3, RTGPU_MAT_MIRROR = 4, RTGPU_MAT_NONE = 5,
-       RTGPU_MAT_LOBES = 6 };   /* uber / substrate / translucent / mix: the host lists the lobes (rtgpu_lobe rows) */
+       RTGPU_MAT_LOBES = 6,     /* uber / substrate / translucent / mix: the host lists the lobes (rtgpu_lobe rows) */
+       RTGPU_MAT_TEXTURED = 7 };/* some parameter is a non-constant texture, or there is a bump map: the device evaluates
+                                   rtgpu_scene_desc.texmats[row] at every hit (same row index as the material) and lists the lobes there */
+
+/* Texture row on the device (texture/\*.rs, mipmap.rs): rt_texture with the imagemap's MIP pyramid (MIPMap::new,
+ * mipmap.rs:65-180, built by the host) addressed inside rtgpu_scene_desc.tex_data.  tex_data[0..128) is the EWA weight
+ * table (mipmap.rs:35-45). */
+#define RTGPU_MAX_MIP_LEVELS 16
+typedef struct rtgpu_texture {
+  int32_t kind, is_float;      /* RT_TEX_* */
+  float value[3];
+  int32_t tex1, tex2, amount;  /* child rows */
+  int32_t mapping;             /* RT_TEXMAP_* */
+  float su, sv, du, dv; float vs[3], vt[3];
+  int32_t aa_none;
+  float w2t[16];               /* fbm: world_to_texture.m */
+  float omega; int32_t octaves;
+  int32_t wrap, trilinear; float max_aniso;
+  int32_t channels;            /* imagemap: 3 (spectrum) or 1 (float) floats per texel */
+  int32_t n_levels;
+  uint32_t level_offset[RTGPU_MAX_MIP_LEVELS];   /* first float of each level in tex_data, row-major u x v texels */
+  int32_t level_u[RTGPU_MAX_MIP_LEVELS], level_v[RTGPU_MAX_MIP_LEVELS];
+} rtgpu_texture;
 
 /* One BxDF of a material whose lobe list the host builds (constant textures make it a per-material constant):
  * material/{uber,substrate,translucent,mixmat}.rs.  kind = RTGPU_LOBE_*. */
@@ -129,6 +152,11 @@ typedef struct rtgpu_scene_desc {
   uint32_t n_quadrics;  const rtgpu_quadric* quadrics;
   uint32_t n_materials; const rtgpu_material* materials;
   uint32_t n_lobes;     const rtgpu_lobe* lobes;       /* lobe lists of the RTGPU_MAT_LOBES materials (may be 0 / NULL) */
+  /* textured materials (may be 0 / NULL): the neutral material rows (all of them, same indices as `materials`, so mix
+   * children resolve), the texture rows and their float pool */
+  uint32_t n_texmats;   const rt_material* texmats;
+  uint32_t n_textures;  const rtgpu_texture* textures;
+  uint32_t n_tex_floats; const float* tex_data;
   uint32_t n_instances; const rtgpu_instance* instances; /* object instances (may be 0 / NULL) */
   uint32_t n_lights;    const rtgpu_light* lights;
   uint32_t n_env_floats; const float* env_data;

@@ -105,6 +105,13 @@ class rtgpu_lobe(C.Structure):
                 ("eta_a", c_f), ("eta_b", c_f)]
 
 
+class rtgpu_texture(C.Structure):
+    _fields_ = [("kind", c_i32), ("is_float", c_i32), ("value", c_f * 3), ("tex1", c_i32), ("tex2", c_i32), ("amount", c_i32), ("mapping", c_i32),
+                ("su", c_f), ("sv", c_f), ("du", c_f), ("dv", c_f), ("vs", c_f * 3), ("vt", c_f * 3), ("aa_none", c_i32), ("w2t", c_f * 16),
+                ("omega", c_f), ("octaves", c_i32), ("wrap", c_i32), ("trilinear", c_i32), ("max_aniso", c_f), ("channels", c_i32), ("n_levels", c_i32),
+                ("level_offset", c_u32 * 16), ("level_u", c_i32 * 16), ("level_v", c_i32 * 16)]
+
+
 class rtgpu_instance(C.Structure):
     _fields_ = [("w2o", c_f * 12), ("o2w", c_f * 12), ("root_node", c_u32), ("first_slot", c_u32), ("lo", c_f * 3), ("hi", c_f * 3),
                 ("prim_number", c_u32), ("root_ref", c_u32)]
@@ -119,7 +126,9 @@ class rtgpu_light(C.Structure):
 class rtgpu_scene_desc(C.Structure):
     _fields_ = [("n_nodes", c_u32), ("node_lo", PF), ("node_hi", PF), ("n_prims", c_u32), ("prim_geom", PF), ("prim_info", PU32),
                 ("tri_n", PF), ("tri_s", PF), ("tri_uv", PF), ("n_quadrics", c_u32), ("quadrics", C.POINTER(rtgpu_quadric)),
-                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lobes", c_u32), ("lobes", C.POINTER(rtgpu_lobe)), ("n_instances", c_u32), ("instances", C.POINTER(rtgpu_instance)),
+                ("n_materials", c_u32), ("materials", C.POINTER(rtgpu_material)), ("n_lobes", c_u32), ("lobes", C.POINTER(rtgpu_lobe)),
+                ("n_texmats", c_u32), ("texmats", C.POINTER(rt_material)), ("n_textures", c_u32), ("textures", C.POINTER(rtgpu_texture)),
+                ("n_tex_floats", c_u32), ("tex_data", PF), ("n_instances", c_u32), ("instances", C.POINTER(rtgpu_instance)),
                 ("n_lights", c_u32), ("lights", C.POINTER(rtgpu_light)),
                 ("n_env_floats", c_u32), ("env_data", PF), ("world_lo", c_f * 3), ("world_hi", c_f * 3)]
 

@@ -329,6 +329,13 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if ((rc = upload(ctx, s->quadrics, (size_t)s->n_quadrics, &d.quadrics))) return rc;
   if ((rc = upload(ctx, s->materials, (size_t)s->n_materials, &d.materials))) return rc;
   if ((rc = upload(ctx, s->lobes, s->lobes ? (size_t)s->n_lobes : 0, &d.lobes))) return rc;
+  // textured materials (texture.cuh): neutral material rows, texture rows, MIP pyramids + EWA weight table
+  if (s->n_texmats && (!s->texmats || s->n_texmats != s->n_materials)) return fail(ctx, RTGPU_ERR_ARG, "texmats must mirror the material table");
+  if (s->n_texmats && (!s->tex_data || s->n_tex_floats < 128)) return fail(ctx, RTGPU_ERR_ARG, "texture pool missing");
+  if ((rc = upload(ctx, s->texmats, s->texmats ? (size_t)s->n_texmats : 0, &d.texmats))) return rc;
+  if ((rc = upload(ctx, s->textures, s->textures ? (size_t)s->n_textures : 0, &d.textures))) return rc;
+  if ((rc = upload(ctx, s->tex_data, s->tex_data ? (size_t)s->n_tex_floats : 0, &d.tex_data))) return rc;
+  d.n_textures = s->n_textures;
   if ((rc = upload(ctx, s->lights, (size_t)s->n_lights, &d.lights))) return rc;
   if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
   d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;

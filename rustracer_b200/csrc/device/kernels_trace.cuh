@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
       Ray ray = camera_ray(p.r2c, p.c2w, p.lens_radius, p.focal_distance, p_film, p_lens);
       store_ray(p.w.ray_o, p.w.ray_d, pos, ray, 0);
       p.w.beta[pos] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-      p.w.pstate[pos] = make_uint4(i, p.integrator == RTGPU_INTEGRATOR_PATH ? 0u : 1u, 0u, ss.d1 | (ss.d2 << 16));
+      // path: z bit 1 = "camera ray" (carries the ray differential); recursive: z = depth, w != 0 = camera ray
+      p.w.pstate[pos] = make_uint4(i, p.integrator == RTGPU_INTEGRATOR_PATH ? 0u : 1u, p.integrator == RTGPU_INTEGRATOR_PATH ? 2u : 0u, ss.d1 | (ss.d2 << 16));
       p.w.list[0][pos] = pos;
     }
   }

@@ -59,7 +59,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   WaveBuffers* w = ctx->wave;
   WaveView& v = w->v;
   if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
-      (v.hit_inst != nullptr || ctx->scene.n_instances == 0))
+      (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)))
     return 0;
   release(w);
   int rc = 0;
@@ -68,6 +68,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   A(hit_class, cap_items);
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
+  if (recursive && ctx->scene.texmats) { A(rdiff, (size_t)cap_items * 3); A(rdiff2, (size_t)cap_items * 3); }
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
   A(mi_o, cap_mis); A(mi_d, cap_mis); A(mi_c, cap_mis);
@@ -230,7 +231,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   // which material classes exist (skip empty shade launches)
   {
     const std::vector<rtgpu_material>& hm = ctx->h_materials;
-    auto queue_of = [](uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? (int)Q_LOBES : (int)Q_NONE); };
+    auto queue_of = [](uint32_t type) { return material_queue(type); };
     for (const rtgpu_material& m : hm) plan.mat_present[queue_of(m.type)] = true;
     plan.mat_present[Q_NONE] = true;     // primitives without a material row also land here
     bool any_none = false; for (const rtgpu_material& m : hm) any_none |= queue_of(m.type) == Q_NONE;

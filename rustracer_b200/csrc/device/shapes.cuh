@@ -22,6 +22,10 @@ struct DScene {
   const rtgpu_quadric* quadrics;
   const rtgpu_material* materials;
   const rtgpu_lobe* lobes;   // lobe lists of the RTGPU_MAT_LOBES materials (or null)
+  const rt_material* texmats;       // neutral material rows for the RTGPU_MAT_TEXTURED materials (or null): evaluated per hit
+  const rtgpu_texture* textures;     // texture rows (or null)
+  const float* tex_data;             // EWA weight table [0,128) + MIP pyramids
+  uint32_t n_textures;
   const rtgpu_instance* instances;   // object instances (or null); n_instances > 0 selects the instance-aware kernels
   uint32_t n_instances;
   const rtgpu_light* lights;
@@ -36,6 +40,15 @@ struct DScene {
 struct SurfHit {
   V3 p, p_error, n, wo;      // Interaction (n = geometric normal after orientation flips)
   V3 ns, dpdu_s;             // shading.n, shading.dpdu
+};
+// The rest of `SurfaceInteraction` that texture lookups and bump mapping read (interaction.rs:78-99); only the kernels that
+// shade textured materials ask for it.  dndu / dndv do not exist: every shape hands zeros to SurfaceInteraction::new
+// (mesh.rs:371-372) or goes through SurfaceInteraction::transform, which zeroes them (interaction.rs:168-169, :182-183).
+struct SurfTex {
+  P2 uv; V3 dpdu, dpdv;      // parametric position and partials
+  V3 dpdv_s;                 // shading.dpdv
+  bool flip;                 // shape.reverse_orientation ^ shape.transform_swaps_handedness
+  V3 dpdx, dpdy; float dudx, dvdx, dudy, dvdy;   // compute_differential (interaction.rs:245-314)
 };
 
 // ---- Triangle (shapes/mesh.rs) -----------------------------------------------------------------------
@@ -147,7 +160,7 @@ RT_DEV bool tri_hit_test_pre(const TriRay& tr, float t_max, V3 p0, V3 p1, V3 p2,
 }
 
 // Back half of Triangle::intersect (mesh.rs:321-425): the SurfaceInteraction of an accepted hit.
-RT_DEV void tri_surface(const DScene& sc, uint32_t slot, uint32_t flags, V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, V3 ray_d, SurfHit& out) {
+RT_DEV void tri_surface(const DScene& sc, uint32_t slot, uint32_t flags, V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, V3 ray_d, SurfHit& out, SurfTex* ex = nullptr) {
   V3 dpdu = v3(0, 0, 0), dpdv = v3(0, 0, 0);
   P2 uv0 = mk2(0.0f, 0.0f), uv1 = mk2(1.0f, 0.0f), uv2 = mk2(1.0f, 1.0f);                      // :199-210
   if ((flags & RTGPU_PRIMFLAG_HAS_UV) && sc.tri_uv) {
@@ -191,10 +204,15 @@ RT_DEV void tri_surface(const DScene& sc, uint32_t slot, uint32_t flags, V3 p0, 
   if (has_n) n = face_forward(n, ns);
   else if (flags & RTGPU_PRIMFLAG_FLIP) { n = -n; ns = n; }
   out.n = n; out.ns = ns; out.dpdu_s = ss;
+  if (ex) {
+    ex->uv = mk2(uv0.x * b0 + uv1.x * b1 + uv2.x * b2, uv0.y * b0 + uv1.y * b1 + uv2.y * b2);   // mesh.rs:352
+    ex->dpdu = dpdu; ex->dpdv = dpdv; ex->dpdv_s = ts; ex->flip = (flags & RTGPU_PRIMFLAG_FLIP) != 0;
+  }
 }
 
 // ---- interaction.rs:103-147 + :156-190 for quadrics: object-space hit -> world-space SurfHit ----------
-RT_DEV void quadric_surface(const rtgpu_quadric& q, V3 p_hit, V3 p_error, V3 neg_ray_d_obj, V3 dpdu, V3 dpdv, SurfHit& out) {
+RT_DEV void quadric_surface(const rtgpu_quadric& q, V3 p_hit, V3 p_error, V3 neg_ray_d_obj, V3 dpdu, V3 dpdv, SurfHit& out, float u = 0.0f, float v = 0.0f,
+                            SurfTex* ex = nullptr) {
   V3 n = normalize(cross(dpdu, dpdv));
   if (q.flags & RTGPU_PRIMFLAG_FLIP) n = n * -1.0f;
   V3 wo = normalize(normalize(neg_ray_d_obj));
@@ -205,10 +223,15 @@ RT_DEV void quadric_surface(const rtgpu_quadric& q, V3 p_hit, V3 p_error, V3 neg
   V3 ns = normalize(xf_normal(q.w2o, n));
   out.dpdu_s = xf_vector(q.o2w, dpdu);
   out.ns = face_forward(ns, out.n);
+  if (ex) {
+    ex->uv = mk2(u, v);
+    ex->dpdu = xf_vector(q.o2w, dpdu); ex->dpdv = xf_vector(q.o2w, dpdv); ex->dpdv_s = ex->dpdv;
+    ex->flip = (q.flags & RTGPU_PRIMFLAG_FLIP) != 0;
+  }
 }
 
 // Sphere::intersect (shapes/sphere.rs:71-203).  want_surface=false stops after t is known.
-RT_DEV bool sphere_intersect(const rtgpu_quadric& q, const Ray& ray, float& t_out, bool want_surface, SurfHit* out) {
+RT_DEV bool sphere_intersect(const rtgpu_quadric& q, const Ray& ray, float& t_out, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
   V3 o_err, d_err;
   Ray r = ray_transform(ray, q.w2o, o_err, d_err);
   EFloat ox = ef(r.o.x, o_err.x), oy = ef(r.o.y, o_err.y), oz = ef(r.o.z, o_err.z);
@@ -250,12 +273,12 @@ RT_DEV bool sphere_intersect(const rtgpu_quadric& q, const Ray& ray, float& t_ou
   V3 dpdu = v3(-q.phi_max * p_hit.y, q.phi_max * p_hit.x, 0.0f);
   V3 dpdv = (q.theta_max - q.theta_min) * v3(p_hit.z * cos_phi, p_hit.z * sin_phi, -radius * sinf(theta));
   V3 p_error = gamma_f(5) * vabs(p_hit);
-  quadric_surface(q, p_hit, p_error, -r.d, dpdu, dpdv, *out);
+  quadric_surface(q, p_hit, p_error, -r.d, dpdu, dpdv, *out, phi / q.phi_max, (theta - q.theta_min) / (q.theta_max - q.theta_min), ex);   // u, v: sphere.rs:141-148
   return true;
 }
 
 // Disk::intersect (shapes/disk.rs:65-120)
-RT_DEV bool disk_intersect(const rtgpu_quadric& q, const Ray& r, float& t_out, bool want_surface, SurfHit* out) {
+RT_DEV bool disk_intersect(const rtgpu_quadric& q, const Ray& r, float& t_out, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
   V3 oe, de;
   Ray ray = ray_transform(r, q.w2o, oe, de);
   if (ray.d.z == 0.0f) return false;
@@ -273,12 +296,13 @@ RT_DEV bool disk_intersect(const rtgpu_quadric& q, const Ray& r, float& t_out, b
   V3 dpdu = v3(-q.phi_max * p_hit.y, q.phi_max * p_hit.x, 0.0f);
   V3 dpdv = v3(p_hit.x, p_hit.y, 0.0f) * (q.radius - q.inner_radius) / r_hit;
   p_hit.z = q.height;
-  quadric_surface(q, p_hit, v3(0, 0, 0), -ray.d, dpdu, dpdv, *out);
+  const float one_minus_v = (r_hit - q.inner_radius) / (q.radius - q.inner_radius);              // disk.rs:89-92
+  quadric_surface(q, p_hit, v3(0, 0, 0), -ray.d, dpdu, dpdv, *out, phi / q.phi_max, 1.0f - one_minus_v, ex);
   return true;
 }
 
 // Cylinder::intersect / intersect_p (shapes/cylinder.rs:62-176 / :178-249)
-RT_DEV bool cylinder_intersect(const rtgpu_quadric& q, const Ray& r, float& t_out, bool want_surface, SurfHit* out) {
+RT_DEV bool cylinder_intersect(const rtgpu_quadric& q, const Ray& r, float& t_out, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
   V3 o_err, d_err;
   Ray ray = ray_transform(r, q.w2o, o_err, d_err);
   EFloat ox = ef(ray.o.x, o_err.x), oy = ef(ray.o.y, o_err.y);
@@ -316,19 +340,19 @@ RT_DEV bool cylinder_intersect(const rtgpu_quadric& q, const Ray& r, float& t_ou
   V3 dpdu = v3(-q.phi_max * p_hit.y, q.phi_max * p_hit.x, 0.0f);
   V3 dpdv = v3(0.0f, 0.0f, q.z_max - q.z_min);
   V3 p_error = gamma_f(3) * v3(fabsf(p_hit.x), fabsf(p_hit.y), 0.0f);
-  quadric_surface(q, p_hit, p_error, -ray.d, dpdu, dpdv, *out);
+  quadric_surface(q, p_hit, p_error, -ray.d, dpdu, dpdv, *out, phi / q.phi_max, (p_hit.z - q.z_min) / (q.z_max / q.z_min), ex);   // v as written in the reference (cylinder.rs:132)
   return true;
 }
 
-RT_DEV bool quadric_intersect(const rtgpu_quadric& q, const Ray& ray, float& t, bool want_surface, SurfHit* out) {
-  if (q.kind == RTGPU_PRIM_SPHERE) return sphere_intersect(q, ray, t, want_surface, out);
-  if (q.kind == RTGPU_PRIM_DISK) return disk_intersect(q, ray, t, want_surface, out);
-  return cylinder_intersect(q, ray, t, want_surface, out);
+RT_DEV bool quadric_intersect(const rtgpu_quadric& q, const Ray& ray, float& t, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
+  if (q.kind == RTGPU_PRIM_SPHERE) return sphere_intersect(q, ray, t, want_surface, out, ex);
+  if (q.kind == RTGPU_PRIM_DISK) return disk_intersect(q, ray, t, want_surface, out, ex);
+  return cylinder_intersect(q, ray, t, want_surface, out, ex);
 }
 
 // Shape::intersect on one ordered slot with the full surface record (GeometricPrimitive::intersect,
 // primitive.rs:45-51).  Used by the shading kernels on the final closest hit and by pdf_wi.
-RT_DEV bool slot_intersect_surface(const DScene& sc, uint32_t slot, const Ray& ray, float& t, SurfHit& out) {
+RT_DEV bool slot_intersect_surface(const DScene& sc, uint32_t slot, const Ray& ray, float& t, SurfHit& out, SurfTex* ex = nullptr) {
   float4 g0 = sc.geom[(size_t)slot * 3];
   uint32_t kind_bits = __float_as_uint(g0.w);
   if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) {
@@ -336,10 +360,10 @@ RT_DEV bool slot_intersect_surface(const DScene& sc, uint32_t slot, const Ray& r
     V3 p0 = v3(g0), p1 = v3(g1), p2 = v3(g2);
     float b0, b1, b2;
     if (!tri_hit_test(p0, p1, p2, ray, b0, b1, b2, t)) return false;
-    tri_surface(sc, slot, sc.info[slot].w, p0, p1, p2, b0, b1, b2, ray.d, out);
+    tri_surface(sc, slot, sc.info[slot].w, p0, p1, p2, b0, b1, b2, ray.d, out, ex);
     return true;
   }
-  return quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, true, &out);
+  return quadric_intersect(sc.quadrics[kind_bits >> 2], ray, t, true, &out, ex);
 }
 
 // ---- object instances: TransformedPrimitive (primitive.rs:79-118) -----------------------------------------------------
@@ -350,15 +374,16 @@ constexpr uint32_t kGeomLastBit = 1u, kGeomInstanceBit = 2u, kGeomClassShift = 2
 constexpr uint32_t kHitSlotBits = 29;
 constexpr int Q_MISS_CLASS = 7;
 // material queues of the path integrator (one shade launch per non-empty class)
-enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_LOBES, Q_MISS, Q_COUNT };   // Q_LOBES: uber / substrate / translucent / mix
+enum { Q_MATTE = 0, Q_PLASTIC, Q_METAL, Q_GLASS, Q_MIRROR, Q_NONE, Q_LOBES, Q_MISS, Q_COUNT };   // Q_LOBES: uber / substrate / translucent / mix, and every textured material
 // material type (rtgpu_material.type, or RTGPU_MAT_NONE for a primitive without material row) -> shade queue
-__host__ __device__ __forceinline__ int material_queue(uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : (type == RTGPU_MAT_LOBES ? Q_LOBES : Q_NONE); }
+__host__ __device__ __forceinline__ int material_queue(uint32_t type) { return type <= RTGPU_MAT_MIRROR ? (int)type : ((type == RTGPU_MAT_LOBES || type == RTGPU_MAT_TEXTURED) ? Q_LOBES : Q_NONE); }
 
 static_assert(Q_MISS == Q_MISS_CLASS && Q_COUNT <= 8, "the shade-queue id travels in three bits of the hit slot");
 // `primitive_to_world.inverse() * ray` (ray.rs:83-93): origin and direction only, no error offset, t_max kept
 RT_DEV Ray instance_ray(const rtgpu_instance& I, const Ray& ray) { return make_ray(xf_point_affine(I.w2o, ray.o), xf_vector(I.w2o, ray.d), ray.t_max); }
 // SurfaceInteraction::transform (interaction.rs:156-190) for the fields SurfHit keeps
-RT_DEV void instance_surface(const rtgpu_instance& I, const SurfHit& o, SurfHit& si) {
+RT_DEV void instance_surface(const rtgpu_instance& I, const SurfHit& o, SurfHit& si, SurfTex* ex = nullptr) {
+  if (ex) { ex->dpdu = xf_vector(I.o2w, ex->dpdu); ex->dpdv = xf_vector(I.o2w, ex->dpdv); ex->dpdv_s = xf_vector(I.o2w, ex->dpdv_s); }   // uv, shape kept
   si.p = xf_point_with_error<true>(I.o2w, o.p, o.p_error, si.p_error);
   si.wo = normalize(normalize(xf_vector(I.o2w, o.wo)));                          // `(t * wo).normalize()`, then Interaction::new normalises again
   si.n = normalize(xf_normal(I.w2o, o.n));
@@ -368,12 +393,12 @@ RT_DEV void instance_surface(const rtgpu_instance& I, const SurfHit& o, SurfHit&
 }
 // The surface record of a final closest hit: slot_intersect_surface, through the instance's transform when the hit lies
 // inside an object instance (inst = row of DScene::instances, or kNoInst).
-RT_DEV bool hit_surface(const DScene& sc, uint32_t slot, uint32_t inst, const Ray& ray, float& t, SurfHit& si) {
-  if (inst == kNoInst) return slot_intersect_surface(sc, slot, ray, t, si);
+RT_DEV bool hit_surface(const DScene& sc, uint32_t slot, uint32_t inst, const Ray& ray, float& t, SurfHit& si, SurfTex* ex = nullptr) {
+  if (inst == kNoInst) return slot_intersect_surface(sc, slot, ray, t, si, ex);
   const rtgpu_instance& I = sc.instances[inst];
   SurfHit o;
-  if (!slot_intersect_surface(sc, slot, instance_ray(I, ray), t, o)) return false;
-  instance_surface(I, o, si);
+  if (!slot_intersect_surface(sc, slot, instance_ray(I, ray), t, o, ex)) return false;
+  instance_surface(I, o, si, ex);
   return true;
 }
 

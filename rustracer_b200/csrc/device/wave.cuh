@@ -32,6 +32,7 @@ struct WaveView {            // device pointers, passed to kernels by value
   uint4* pstate;             // x = sample slot, y = bounces (path) | node id (recursive), z = flags | depth, w = d1 | d2 << 16
   // second item buffer (recursive integrators ping-pong between levels)
   float4 *ray_o2, *ray_d2; float4* beta2; uint4* pstate2;
+  float4 *rdiff, *rdiff2;    // ray differentials of the recursive integrators' items, 3 float4 each {rx_o, ry_o, rx_d, ry_d}; textured scenes only
   // camera samples
   float4* L;                 // rgb radiance accumulator, w = 1 if the sample exists
   float2* pfilm;

@@ -1,5 +1,6 @@
 // See scene_build.hpp.  Reference line numbers are relative to /root/reference/rustracer-core/src/.
 #include "scene_build.hpp"
+#include "../common/material_lobes.hpp"
 #include <stdexcept>
 
 namespace rth {
@@ -60,142 +61,35 @@ rtgpu_material prep_material(const rt_material& m) {
 
 // ---- lobe lists of UberMaterial / SubstrateMaterial / TranslucentMaterial / MixMaterial ------------------------------
 // With constant textures `compute_scattering_functions` adds the same BxDFs at every hit, so the host lists them once
-// per material (and per allow_multiple_lobes, which only a glass child of a mix looks at).
-struct Rgb3 { float v[3]; };
-inline Rgb3 rgb(const float* c) { return Rgb3{{c[0], c[1], c[2]}}; }
-inline Rgb3 clamp_rgb(Rgb3 c) { for (float& x : c.v) x = clampf(x, 0.0f, std::numeric_limits<float>::infinity()); return c; }   // Spectrum::clamp
-inline Rgb3 mul(Rgb3 a, Rgb3 b) { return Rgb3{{a.v[0] * b.v[0], a.v[1] * b.v[1], a.v[2] * b.v[2]}}; }
-inline Rgb3 one_minus(Rgb3 a) { return Rgb3{{1.0f - a.v[0], 1.0f - a.v[1], 1.0f - a.v[2]}}; }
-inline bool black(Rgb3 a) { return a.v[0] == 0.0f && a.v[1] == 0.0f && a.v[2] == 0.0f; }
-inline void put3(float* d, Rgb3 c) { d[0] = c.v[0]; d[1] = c.v[1]; d[2] = c.v[2]; }
-
-rtgpu_lobe new_lobe(uint32_t kind) {
-  rtgpu_lobe l; std::memset(&l, 0, sizeof(l));
-  l.kind = kind; l.fr_eta_i = l.fr_eta_t = 1.0f; l.eta_a = l.eta_b = 1.0f;
-  for (int i = 0; i < 3; i++) l.c_eta_t[i] = 1.0f;
-  return l;
-}
-void set_dielectric(rtgpu_lobe& l, float eta_i, float eta_t) { l.fr_kind = 1; l.fr_eta_i = eta_i; l.fr_eta_t = eta_t; }
-
-// Appends the BxDFs material `row` adds, in the reference's order; returns Bsdf::eta.
-float list_lobes(const rt_scene& in, int row, bool allow_multiple_lobes, std::vector<rtgpu_lobe>& out, int depth = 0) {
+// per material (and per allow_multiple_lobes, which only a glass child of a mix looks at).  The listing itself is
+// common/material_lobes.hpp, shared with the device (textured materials are listed there per hit).
+float list_lobes(const rt_scene& in, int row, bool allow_multiple_lobes, std::vector<rtgpu_lobe>& out) {
   if (row < 0 || (uint32_t)row >= in.n_materials) throw std::runtime_error("material row out of range");
-  if (depth > 2) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
+  rtgpu_lobe buf[rtml::kMaxLobes];
+  rtml::LobeList L{buf, 0, rtml::kOk};
+  auto children = [&in](int r, bool) -> rt_material {
+    if (r < 0 || (uint32_t)r >= in.n_materials) throw std::runtime_error("material row out of range");
+    return in.materials[r];
+  };
+  const float eta = rtml::list_lobes<0>(in.materials[row], allow_multiple_lobes, children, L);
+  if (L.error == rtml::kTooManyLobes) throw std::runtime_error("a material builds more than 8 BxDFs: the reference's BxDFHolder panics there (bsdf/mod.rs:41-52)");
+  if (L.error == rtml::kMixTooDeep) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
+  if (L.error == rtml::kNoBsdf) throw std::runtime_error("MixMaterial: a child material has no BSDF");
+  out.insert(out.end(), buf, buf + L.n);
+  return eta;
+}
+// Upper bound of the BxDFs a (textured) material can add at a hit, whatever its textures evaluate to.
+int max_lobes(const rt_scene& in, int row, int depth = 0) {
+  if (row < 0 || (uint32_t)row >= in.n_materials) throw std::runtime_error("material row out of range");
   const rt_material& m = in.materials[row];
   switch (m.type) {
-    case RT_MAT_UBER: {                                               // uber.rs:62-125
-      const float e = m.eta;
-      const Rgb3 op = clamp_rgb(rgb(m.opacity)), t = clamp_rgb(one_minus(op));
-      float eta = e;
-      if (!black(t)) {
-        eta = 1.0f;
-        rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_TRANS); put3(l.t, t); l.eta_a = 1.0f; l.eta_b = 1.0f; set_dielectric(l, 1.0f, 1.0f); out.push_back(l);
-      }
-      const Rgb3 kd = mul(op, clamp_rgb(rgb(m.kd)));
-      if (!black(kd)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, kd); out.push_back(l); }
-      const Rgb3 ks = mul(op, clamp_rgb(rgb(m.ks)));
-      if (!black(ks)) {
-        float ru = m.has_uroughness ? m.uroughness : m.roughness, rv = m.has_vroughness ? m.vroughness : m.roughness;
-        if (m.remap_roughness) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
-        rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, ks); set_dielectric(l, 1.0f, e); l.ax = ru; l.ay = rv; out.push_back(l);
-      }
-      const Rgb3 kr = mul(op, clamp_rgb(rgb(m.kr)));
-      if (!black(kr)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_REFL); put3(l.r, kr); set_dielectric(l, 1.0f, e); out.push_back(l); }
-      const Rgb3 kt = mul(op, clamp_rgb(rgb(m.kt)));
-      if (!black(kt)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_TRANS); put3(l.t, kt); l.eta_a = 1.0f; l.eta_b = e; set_dielectric(l, 1.0f, e); out.push_back(l); }
-      return eta;
-    }
-    case RT_MAT_SUBSTRATE: {                                          // substrate.rs:42-71
-      const Rgb3 d = clamp_rgb(rgb(m.kd)), s = clamp_rgb(rgb(m.ks));
-      if (!black(d) || !black(s)) {
-        float ru = m.uroughness, rv = m.vroughness;
-        if (m.remap_roughness) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
-        rtgpu_lobe l = new_lobe(RTGPU_LOBE_FRESNEL_BLEND); put3(l.r, s); put3(l.t, d); l.ax = ru; l.ay = rv; out.push_back(l);   // FresnelBlend::new(rs, rd, ..)
-      }
-      return 1.0f;
-    }
-    case RT_MAT_TRANSLUCENT: {                                        // translucent.rs:48-101
-      const float eta = 1.5f;
-      const Rgb3 r = clamp_rgb(rgb(m.reflect)), t = clamp_rgb(rgb(m.transmit));
-      if (!black(r) || !black(t)) {
-        const Rgb3 kd = clamp_rgb(rgb(m.kd));
-        if (!black(kd)) {
-          if (!black(r)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, mul(r, kd)); out.push_back(l); }
-          if (!black(t)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_T); put3(l.t, mul(t, kd)); out.push_back(l); }
-        }
-        const Rgb3 ks = clamp_rgb(rgb(m.ks));
-        if (!black(ks)) {
-          float rough = m.roughness;
-          if (m.remap_roughness) rough = roughness_to_alpha(rough);
-          if (!black(r)) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, mul(r, ks)); set_dielectric(l, 1.0f, eta); l.ax = l.ay = rough; out.push_back(l); }
-          if (!black(t)) {
-            rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_TRANS); put3(l.t, mul(t, ks)); l.eta_a = 1.0f; l.eta_b = eta; set_dielectric(l, 1.0f, eta); l.ax = l.ay = rough;
-            out.push_back(l);
-          }
-        }
-      }
-      return eta;
-    }
-    case RT_MAT_MIX: {                                                // mixmat.rs:34-64: ScaledBxDF(b, s1) for mat1's, ScaledBxDF(b, s2) for mat2's
-      const Rgb3 s1 = clamp_rgb(rgb(m.amount)), s2 = clamp_rgb(one_minus(s1));
-      const size_t first = out.size();
-      const float eta = list_lobes(in, m.mix_a, allow_multiple_lobes, out, depth + 1);   // the Bsdf object (eta, frame) stays mat1's
-      const size_t mid = out.size();
-      list_lobes(in, m.mix_b, allow_multiple_lobes, out, depth + 1);
-      for (size_t i = first; i < out.size(); i++) {
-        rtgpu_lobe& l = out[i];
-        if (l.n_scales >= 2) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
-        put3(l.scale[l.n_scales++], i < mid ? s1 : s2);
-      }
-      return eta;
-    }
-    // the five materials with their own shade kernels, as children of a mix
-    case RT_MAT_MATTE: {                                              // matte.rs:37-62
-      const rtgpu_material pm = prep_material(m);
-      if (!black(rgb(pm.kd))) {
-        rtgpu_lobe l = new_lobe(pm.use_oren_nayar ? RTGPU_LOBE_OREN_NAYAR : RTGPU_LOBE_LAMBERT_R); put3(l.r, rgb(pm.kd)); l.on_a = pm.oren_a; l.on_b = pm.oren_b;
-        out.push_back(l);
-      }
-      return 1.0f;
-    }
-    case RT_MAT_PLASTIC: {                                            // plastic.rs:45-74
-      const rtgpu_material pm = prep_material(m);
-      if (!black(rgb(pm.kd))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_LAMBERT_R); put3(l.r, rgb(pm.kd)); out.push_back(l); }
-      if (!black(rgb(pm.ks))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, rgb(pm.ks)); set_dielectric(l, 1.5f, 1.0f); l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l); }
-      return 1.0f;
-    }
-    case RT_MAT_METAL: {                                              // metal.rs:50-81
-      const rtgpu_material pm = prep_material(m);
-      rtgpu_lobe l = new_lobe(RTGPU_LOBE_MICRO_REFL); put3(l.r, Rgb3{{1, 1, 1}}); l.fr_kind = 2; put3(l.c_eta_t, rgb(pm.eta_rgb)); put3(l.c_k, rgb(pm.k_rgb));
-      l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
-      return 1.0f;
-    }
-    case RT_MAT_GLASS: {                                              // glass.rs:53-106
-      const rtgpu_material pm = prep_material(m);
-      const Rgb3 r = rgb(pm.kr), t = rgb(pm.kt);
-      if (!black(r) || !black(t)) {
-        if (pm.glass_specular && allow_multiple_lobes) {
-          rtgpu_lobe l = new_lobe(RTGPU_LOBE_FRESNEL_SPEC); put3(l.r, r); put3(l.t, t); l.eta_a = 1.0f; l.eta_b = pm.eta; out.push_back(l);
-        } else {
-          if (!black(r)) {
-            rtgpu_lobe l = new_lobe(pm.glass_specular ? RTGPU_LOBE_SPEC_REFL : RTGPU_LOBE_MICRO_REFL); put3(l.r, r); set_dielectric(l, 1.0f, pm.eta);
-            l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
-          }
-          if (!black(t)) {
-            rtgpu_lobe l = new_lobe(pm.glass_specular ? RTGPU_LOBE_SPEC_TRANS : RTGPU_LOBE_MICRO_TRANS);
-            put3(l.t, pm.glass_specular ? t : r);                     // the rough transmission lobe is built with Kr (glass.rs:97)
-            l.eta_a = 1.0f; l.eta_b = pm.eta; set_dielectric(l, 1.0f, pm.eta); l.ax = pm.alpha_u; l.ay = pm.alpha_v; out.push_back(l);
-          }
-        }
-      }
-      return pm.eta;
-    }
-    case RT_MAT_MIRROR: {                                             // mirror.rs:30-48
-      const rtgpu_material pm = prep_material(m);
-      if (!black(rgb(pm.kr))) { rtgpu_lobe l = new_lobe(RTGPU_LOBE_SPEC_REFL); put3(l.r, rgb(pm.kr)); l.fr_kind = 0; out.push_back(l); }
-      return 1.0f;
-    }
-    default: throw std::runtime_error("MixMaterial: a child material has no BSDF");
+    case RT_MAT_PLASTIC: case RT_MAT_GLASS: return 2;
+    case RT_MAT_UBER: return 5;
+    case RT_MAT_TRANSLUCENT: return 4;
+    case RT_MAT_MIX:
+      if (depth >= rtml::kMaxMixDepth) throw std::runtime_error("MixMaterial nested deeper than two levels is not supported");
+      return max_lobes(in, m.mix_a, depth + 1) + max_lobes(in, m.mix_b, depth + 1);
+    default: return 1;
   }
 }
 
@@ -524,10 +418,17 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   }
   for (uint32_t d = 0; d < in.n_objects; d++)                         // a one-primitive definition has no leaf node to mark its last slot
     if (dprims[d].size() == 1) { uint32_t u; std::memcpy(&u, &out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], 4); put_bits(&out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], u | 1u); }
+  bool any_textured = false;
   for (uint32_t i = 0; i < in.n_materials; i++) {
     rtgpu_material pm = prep_material(in.materials[i]);
     const int ty = in.materials[i].type;
-    if (ty == RT_MAT_UBER || ty == RT_MAT_SUBSTRATE || ty == RT_MAT_TRANSLUCENT || ty == RT_MAT_MIX) {
+    if (in.materials[i].textured) {                                   // evaluated per hit on the device (texture.cuh)
+      if (max_lobes(in, (int)i) > rtml::kMaxLobes)
+        throw std::runtime_error("a textured material can build more than 8 BxDFs: the reference's BxDFHolder panics there (bsdf/mod.rs:41-52)");
+      std::memset(&pm, 0, sizeof(pm));
+      pm.type = RTGPU_MAT_TEXTURED;
+      any_textured = true;
+    } else if (ty == RT_MAT_UBER || ty == RT_MAT_SUBSTRATE || ty == RT_MAT_TRANSLUCENT || ty == RT_MAT_MIX) {
       pm.type = RTGPU_MAT_LOBES;
       for (int allow = 0; allow < 2; allow++) {
         pm.lobe_first[allow] = (uint32_t)out.lobes.size();
@@ -539,6 +440,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
     }
     out.materials.push_back(pm);
   }
+  if (any_textured) build_textures(in, out.textures, out.tex_data);
   // 5. descriptor views
   rtgpu_scene_desc& d = out.desc;
   d.n_nodes = out.bvh.n_nodes; d.node_lo = out.bvh.node_lo.data(); d.node_hi = out.bvh.node_hi.data();
@@ -547,6 +449,9 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
   d.n_quadrics = (uint32_t)out.quadrics.size(); d.quadrics = out.quadrics.data();
   d.n_materials = (uint32_t)out.materials.size(); d.materials = out.materials.data();
   d.n_lobes = (uint32_t)out.lobes.size(); d.lobes = out.lobes.empty() ? nullptr : out.lobes.data();
+  d.n_texmats = any_textured ? in.n_materials : 0; d.texmats = any_textured ? in.materials : nullptr;
+  d.n_textures = (uint32_t)out.textures.size(); d.textures = out.textures.empty() ? nullptr : out.textures.data();
+  d.n_tex_floats = (uint32_t)out.tex_data.size(); d.tex_data = out.tex_data.empty() ? nullptr : out.tex_data.data();
   d.n_instances = (uint32_t)out.instances.size(); d.instances = out.instances.empty() ? nullptr : out.instances.data();
   d.n_lights = (uint32_t)out.lights.size(); d.lights = out.lights.data();
   d.n_env_floats = (uint32_t)out.env_data.size(); d.env_data = out.env_data.data();

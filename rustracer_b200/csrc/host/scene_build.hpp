@@ -19,6 +19,8 @@ struct FlatScene {
   std::vector<rtgpu_material> materials;
   std::vector<rtgpu_lobe> lobes;         // lobe lists of the RTGPU_MAT_LOBES materials
   std::vector<rtgpu_instance> instances; // object instances (TransformedPrimitive rows)
+  std::vector<rtgpu_texture> textures;   // texture rows + MIP pyramids (only when some material is textured)
+  std::vector<float> tex_data;
   std::vector<rtgpu_light> lights;
   std::vector<float> env_data;
   std::vector<uint32_t> slot_of_prim;    // prim_number -> slot
@@ -32,5 +34,7 @@ struct FlatScene {
 void flatten_scene(const rt_scene& in, int threads, FlatScene& out);
 // Film / camera / integrator / sampler part only (no geometry): fills out.render from `in`.
 void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd);
+// Texture rows for the device: copies the parameters and builds each imagemap's MIP pyramid (MIPMap::new) into `pool`.
+void build_textures(const rt_scene& in, std::vector<rtgpu_texture>& rows, std::vector<float>& pool);
 
 }  // namespace rth

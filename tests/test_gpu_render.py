@@ -34,12 +34,17 @@ def _cases(tmp):
     c["instanced_path"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=8)
     c["instanced_whitted"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "whitted" "integer maxdepth" [4]')
     c["instanced_ao"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [8]')
+    # every texture class, both 2-D mappings, bump maps, ray differentials (camera; specular chains in Whitted)
+    c["textured_path"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=8)
+    c["textured_path_lens"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, lens=True)
+    c["textured_whitted"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, integrator='Integrator "whitted" "integer maxdepth" [4]')
+    c["textured_direct"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, integrator='Integrator "directlighting" "integer maxdepth" [3] "string strategy" "one"')
     c["cornell_rr"] = lambda: scenes.cornell_box(xres=48, yres=48, spp=8, integrator='Integrator "path" "integer maxdepth" [12] "float rrthreshold" [1] "string lightsamplestrategy" "uniform"')
     return c
 
 
 NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr", "instanced_path", "instanced_whitted",
-                            "instanced_ao"]
+                            "instanced_ao", "textured_path", "textured_path_lens", "textured_whitted", "textured_direct"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -60,7 +65,10 @@ def test_li_and_image_match_oracle(dev, tmp_path, name):
     tol = 1e-4 * np.maximum(np.abs(ref), 1e-3) + 1e-6
     bad = (np.abs(got - ref) > tol).any(1)
     # a ulp in a transcendental can flip a discrete choice (light pick, lobe pick, roulette) on a rare sample
-    assert bad.mean() <= 2e-3, (bad.sum(), pix[bad][:3], ref[bad][:3], got[bad][:3])
+    # thin-lens + textures: the lens sample goes through sin / cos (concentric_sample_disk), so every camera ray differs from the
+    # oracle's by ulps and more samples land on the other side of a checkerboard edge / EWA weight-table step
+    bad_max, img_tol = (5e-3, 5e-4) if name == "textured_path_lens" else (2e-3, 1e-4)
+    assert bad.mean() <= bad_max, (bad.sum(), pix[bad][:3], ref[bad][:3], got[bad][:3])
     if name.endswith("_ao"):
         assert np.array_equal(got, ref)            # integer visibility counts: exact
     # whole image through rtgpu_render + film, and the reference's ray counters
@@ -68,7 +76,7 @@ def test_li_and_image_match_oracle(dev, tmp_path, name):
     film, rgb = dev.read_film(), dev.resolve_film()
     film_ref, rgb_ref, ost = o.render(sampler_kind=1, seed=7)
     assert np.array_equal(film[..., 3], film_ref[..., 3])                              # filter weights
-    assert np.abs(rgb - rgb_ref).sum() / np.abs(rgb_ref).sum() < 1e-4
+    assert np.abs(rgb - rgb_ref).sum() / np.abs(rgb_ref).sum() < img_tol
     assert st.camera_rays == ost.camera_rays
     assert abs(int(st.regular_rays) - int(ost.regular_rays)) <= 1e-3 * ost.regular_rays + 2
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 1e-3 * ost.shadow_rays + 2
