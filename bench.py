@@ -301,8 +301,15 @@ def run_ours(a):
         line["roofline"] = {"error": str(e)}
 
     if not a.no_cpu_baseline:
+        # In a fresh process: measured inside this one (CUDA context, torch thread pools, the clock sampler) the same CPU
+        # sample ran 2x slower than through `--impl reference` (profiles/r01h), which would flatter the GPU/CPU ratio.
         try:
-            line["cpu_baseline"] = {k: v for k, v in oracle_rate(sc, a, seconds=a.cpu_seconds).items() if k in ("value", "unit", "cores", "kind", "sample")}
+            import subprocess
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--spp-per-step", str(a.spp_per_step),
+                   "--level", str(a.level), "--xres", str(a.xres), "--yres", str(a.yres), "--cpu-seconds", str(a.cpu_seconds)]
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().splitlines()[-1]
+            line["cpu_baseline"] = json.loads(out)["cpu_baseline"]
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(line))

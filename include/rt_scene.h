@@ -79,7 +79,7 @@ typedef struct rt_light {
   int32_t shape;               /* RT_LIGHT_AREA: index into rt_scene.shapes */
 } rt_light;
 
-/* ---- textures (texture/*.rs, mipmap.rs) -------------------------------------------------------------
+/* ---- textures (texture/ and mipmap.rs of the reference) -------------------------------------------------------------
  * One row per texture object the front end creates: every `Texture` directive, plus one RT_TEX_CONSTANT row for each literal
  * (or defaulted) tex1 / tex2 / amount parameter of a scale / mix / checkerboard texture (paramset.rs:406-443 wraps those in a
  * ConstantTexture), so children are always rows.  `is_float` tells Texture<f32> from Texture<Spectrum>. */

@@ -67,7 +67,7 @@ enum { RTGPU_MAT_MATTE = 0, RTGPU_MAT_PLASTIC = 1, RTGPU_MAT_METAL = 2, RTGPU_MA
        RTGPU_MAT_TEXTURED = 7 };/* some parameter is a non-constant texture, or there is a bump map: the device evaluates
                                    rtgpu_scene_desc.texmats[row] at every hit (same row index as the material) and lists the lobes there */
 
-/* Texture row on the device (texture/\*.rs, mipmap.rs): rt_texture with the imagemap's MIP pyramid (MIPMap::new,
+/* Texture row on the device (texture/ and mipmap.rs of the reference): rt_texture with the imagemap's MIP pyramid (MIPMap::new,
  * mipmap.rs:65-180, built by the host) addressed inside rtgpu_scene_desc.tex_data.  tex_data[0..128) is the EWA weight
  * table (mipmap.rs:35-45). */
 #define RTGPU_MAX_MIP_LEVELS 16

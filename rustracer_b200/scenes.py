@@ -338,7 +338,7 @@ _MATERIALS_TEXTURED = [
 ]
 
 
-def balls_textured(out_dir, xres=1024, yres=768, spp=64, integrator=None, n_side=5, crop=None, lens=False):
+def balls_textured(out_dir, xres=1024, yres=768, spp=64, integrator=None, n_side=5, crop=None, lens=False, absolute_paths=False):
     """The balls scene with textured materials (every texture class, both mappings, bump maps), a planar-mapped checkerboard
     ground disk and a uv-mapped, image-textured triangle quad seen at a grazing angle (anisotropic EWA lookups).  Writes the
     texture images into out_dir; parse with search_dir=out_dir."""
@@ -348,7 +348,11 @@ def balls_textured(out_dir, xres=1024, yres=768, spp=64, integrator=None, n_side
     s = header(xres, yres, spp, integrator, 40, ([0, 5.5, -9.5], [0, 0.3, 0], [0, 1, 0]), crop)
     if lens:
         s = s.replace('"float fov" [40]', '"float fov" [40] "float lensradius" [0.05] "float focaldistance" [10]')
-    s += "WorldBegin\n" + _TEXTURES_PREAMBLE
+    pre = _TEXTURES_PREAMBLE
+    if absolute_paths:                                                # parse without a search directory
+        pre = pre.replace('"tex_rgb.pfm"', f'"{os.path.join(os.path.abspath(out_dir), "tex_rgb.pfm")}"').replace(
+            '"tex_small.png"', f'"{os.path.join(os.path.abspath(out_dir), "tex_small.png")}"')
+    s += "WorldBegin\n" + pre
     s += 'LightSource "point" "rgb I" [220 220 220] "point from" [-6 9 -6]\n'
     s += 'LightSource "infinite" "rgb L" [0.25 0.3 0.4]\n'
     s += 'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [12 12 12]\nTranslate 0 6 2\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "sphere" "float radius" [0.6]\nAttributeEnd\n'

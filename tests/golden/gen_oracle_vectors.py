@@ -18,6 +18,9 @@ sys.path.insert(0, ROOT)
 from oracle import binding as ob  # noqa: E402
 from rustracer_b200 import Scene, scenes  # noqa: E402
 
+import tempfile  # noqa: E402
+_TEX_DIR = os.path.join(tempfile.gettempdir(), "rustracer_b200_golden_textures")
+
 CASES = {
     "cornell_path": lambda: scenes.cornell_box(xres=64, yres=64, spp=8),
     "balls_path": lambda: scenes.balls(xres=96, yres=72, spp=8, integrator='Integrator "path" "integer maxdepth" [5]'),
@@ -29,6 +32,9 @@ CASES = {
     "balls_ext_path": lambda: scenes.balls_ext(xres=96, yres=72, spp=8, integrator='Integrator "path" "integer maxdepth" [5]'),
     "balls_ext_whitted": lambda: scenes.balls_ext(xres=96, yres=72, spp=8),
     "balls_ext_direct_all": lambda: scenes.balls_ext(xres=96, yres=72, spp=8, integrator='Integrator "directlighting" "string strategy" "all" "integer maxdepth" [5]'),
+    # textures + bump mapping (the texture images are regenerated next to the system temp directory)
+    "textured_path": lambda: scenes.balls_textured(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True),
+    "textured_whitted": lambda: scenes.balls_textured(_TEX_DIR, xres=96, yres=72, spp=8, integrator='Integrator "whitted" "integer maxdepth" [4]', absolute_paths=True),
 }
 N_RAYS, N_LI, SEED = 2000, 400, 11
 

@@ -34,17 +34,16 @@ def _cases(tmp):
     c["instanced_path"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=8)
     c["instanced_whitted"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "whitted" "integer maxdepth" [4]')
     c["instanced_ao"] = lambda: scenes.instanced_scene(xres=96, yres=72, spp=4, integrator='Integrator "ambientocclusion" "integer nsamples" [8]')
-    # every texture class, both 2-D mappings, bump maps, ray differentials (camera; specular chains in Whitted)
-    c["textured_path"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=8)
+    # every texture class, both 2-D mappings, bump maps, ray differentials (camera; specular chains in Whitted);
+    # textured_path and textured_whitted come with gen.CASES
     c["textured_path_lens"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, lens=True)
-    c["textured_whitted"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, integrator='Integrator "whitted" "integer maxdepth" [4]')
     c["textured_direct"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, integrator='Integrator "directlighting" "integer maxdepth" [3] "string strategy" "one"')
     c["cornell_rr"] = lambda: scenes.cornell_box(xres=48, yres=48, spp=8, integrator='Integrator "path" "integer maxdepth" [12] "float rrthreshold" [1] "string lightsamplestrategy" "uniform"')
     return c
 
 
 NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr", "instanced_path", "instanced_whitted",
-                            "instanced_ao", "textured_path", "textured_path_lens", "textured_whitted", "textured_direct"]
+                            "instanced_ao", "textured_path_lens", "textured_direct"]
 
 
 @pytest.mark.parametrize("name", NAMES)

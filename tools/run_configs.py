@@ -41,6 +41,7 @@ def gpu_render(dev, sc, spp_limit=None, label=""):
     dev.render(rd)                                   # warm-up (allocations, light grid)
     st = dev.render(rd)
     s = st.ms_total * 1e-3
+    gpu_render.last_stats = st
     return dict(label=label, ms=st.ms_total, spp_rendered=int(rd.sample_end - rd.sample_begin), spp_config=int(rd.spp), camera=int(st.camera_rays),
                 regular=int(st.regular_rays), shadow=int(st.shadow_rays), samples_per_s=st.camera_rays / s,
                 mrays_per_s=(st.regular_rays + st.shadow_rays) / s / 1e6, waves=int(st.waves), launches=int(st.kernel_launches))
@@ -75,6 +76,18 @@ def main():
             g = gpu_render(dev, sc, label=f"C2 balls {name} 1024x768 64spp")
             c = cpu_rate(sc, 64)
             record(f"c2_{name}", dict(gpu=g, cpu=c, speedup=g["samples_per_s"] / c["samples_per_s"]))
+    if "tex" in want:     # the textured balls scene (every texture class, bump maps), path and Whitted, 1024x768, 64 spp
+        for name, integ in (("path", None), ("whitted", 'Integrator "whitted" "integer maxdepth" [5]')):
+            sc = Scene.from_string(scenes.balls_textured(tmp, integrator=integ), search_dir=tmp)
+            dev.upload(sc)
+            dev.set_option("profile", 1)
+            g = gpu_render(dev, sc, label=f"textured balls {name} 1024x768 64spp")
+            st = gpu_render.last_stats
+            g.update(ms_closest=st.ms_closest, ms_anyhit=st.ms_anyhit, ms_shade=st.ms_shade, ms_other=st.ms_other)
+            dev.set_option("profile", 0)
+            g["unprofiled"] = gpu_render(dev, sc)
+            c = cpu_rate(sc, 64)
+            record(f"tex_{name}", dict(gpu=g, cpu=c, speedup=g["unprofiled"]["samples_per_s"] / c["samples_per_s"]))
     if "c3" in want:      # 1M-triangle field, AO (64 samples) and path spatial, 1920x1080, 256 spp
         for name, integ, spp_lim in (("path_spatial", None, 32), ("ao64", 'Integrator "ambientocclusion" "integer nsamples" [64]', 8)):
             sc = Scene.from_string(scenes.c3_scene(tmp, integrator=integ), search_dir=tmp)
