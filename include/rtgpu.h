@@ -221,6 +221,13 @@ int rtgpu_occluded_device(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uin
  * pointer): the N and T of the roofline's algorithmic bytes per ray; equal to the oracle's counts. */
 int rtgpu_intersect_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, rtgpu_hit* d_hits, uint32_t* d_stats);
 int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint8_t* d_occluded, uint32_t* d_stats);
+/* == BVH::new with the SAH split method (bvh/mod.rs:80-135; recursive_build :137-312; flatten_bvh :314-358) on the device:
+ * the same tree, node for node and slot for slot, as the reference builds on one CPU thread.  prim_bounds: 6 floats per
+ * primitive {min.xyz, max.xyz} in prim_number order (host pointer).  Outputs (host pointers): node_lo / node_hi with room for
+ * 2 * n_prims float4 each (the layout of rtgpu_scene_desc), ordered[n_prims] = slot -> prim_number, *n_nodes; build_ms (may be
+ * NULL) = device time from the first to the last kernel.  Needs no scene.  The signature is rthost.h's rth_bvh_builder. */
+int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, int max_prims_per_node, float* node_lo, float* node_hi, uint32_t* ordered,
+                    uint32_t* n_nodes, float* build_ms);
 /* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
  * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
  * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */

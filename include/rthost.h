@@ -33,6 +33,11 @@ const char* rth_integrator_name(rth_scene* s);
 
 /* Build the reference-identical SAH BVH and flatten everything for the device. threads <= 0: all cores. */
 int rth_flatten(rth_scene* s, int threads);
+/* Same, with the scene's top-level SAH BVH built by `builder` (e.g. rtgpu_build_bvh with its context as `user`) instead of the
+ * host builder; object definitions' trees and `splitmethod "middle"` stay on the host.  The tree must be the reference's. */
+typedef int (*rth_bvh_builder)(void* user, const float* prim_bounds, uint64_t n_prims, int max_prims_per_node, float* node_lo, float* node_hi,
+                               uint32_t* ordered, uint32_t* n_nodes, float* build_ms);
+int rth_flatten_with_builder(rth_scene* s, int threads, rth_bvh_builder builder, void* user);
 const rtgpu_scene_desc* rth_scene_desc(rth_scene* s);
 double rth_bvh_build_seconds(rth_scene* s);
 uint64_t rth_n_triangles(rth_scene* s);

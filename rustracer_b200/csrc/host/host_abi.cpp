@@ -46,6 +46,9 @@ const char* rth_integrator_name(rth_scene* s) { return s->parsed->integrator_nam
 int rth_flatten(rth_scene* s, int threads) {
   return guarded([&] { s->flat = FlatScene(); flatten_scene(s->parsed->store.view, threads, s->flat); s->flattened = true; });
 }
+int rth_flatten_with_builder(rth_scene* s, int threads, rth_bvh_builder builder, void* user) {
+  return guarded([&] { s->flat = FlatScene(); flatten_scene(s->parsed->store.view, threads, s->flat, builder, user); s->flattened = true; });
+}
 const rtgpu_scene_desc* rth_scene_desc(rth_scene* s) { return s->flattened ? &s->flat.desc : nullptr; }
 double rth_bvh_build_seconds(rth_scene* s) { return s->flat.bvh.build_seconds; }
 uint64_t rth_n_triangles(rth_scene* s) { return s->flat.n_triangles; }

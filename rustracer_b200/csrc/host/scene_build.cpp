@@ -169,7 +169,7 @@ void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd) {
   rd.seed = 0; rd.clear_film = 1; rd.wave_paths = 0;
 }
 
-void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
+void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhBuilder external_builder, void* builder_user) {
   // 1. primitives in Shape-directive order with world-space geometry and bounds
   // Shapes of an object definition (api.rs:951-957) form their own primitive list; an ObjectInstance is one primitive of
   // the scene's list, at the directive's place.
@@ -256,7 +256,22 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out) {
     bounds[pn] = b;
   }
   // 2b. same SAH BVH as the reference over the scene's primitive list
-  build_bvh(bounds, in.accel.max_node_prims, in.accel.split_method, threads, out.bvh);
+  if (external_builder && in.accel.split_method == RT_SPLIT_SAH && !bounds.empty()) {
+    const size_t nb = bounds.size();
+    std::vector<float> pb(nb * 6);
+    for (size_t i = 0; i < nb; i++) { pb[i * 6] = bounds[i].lo.x; pb[i * 6 + 1] = bounds[i].lo.y; pb[i * 6 + 2] = bounds[i].lo.z; pb[i * 6 + 3] = bounds[i].hi.x; pb[i * 6 + 4] = bounds[i].hi.y; pb[i * 6 + 5] = bounds[i].hi.z; }
+    out.bvh = FlatBvh();
+    out.bvh.node_lo.resize(nb * 8); out.bvh.node_hi.resize(nb * 8); out.bvh.ordered.resize(nb);
+    uint32_t n_nodes = 0; float ms = 0.0f;
+    const int rc = external_builder(builder_user, pb.data(), nb, std::max(0, (int)in.accel.max_node_prims), out.bvh.node_lo.data(), out.bvh.node_hi.data(), out.bvh.ordered.data(), &n_nodes, &ms);
+    if (rc != 0) throw std::runtime_error("external BVH builder failed (code " + std::to_string(rc) + ")");
+    out.bvh.n_nodes = n_nodes; out.bvh.node_lo.resize((size_t)n_nodes * 4); out.bvh.node_hi.resize((size_t)n_nodes * 4);
+    out.bvh.build_seconds = ms * 1e-3;
+    for (uint32_t i = 0; i < n_nodes; i++) {
+      uint32_t meta; std::memcpy(&meta, &out.bvh.node_hi[(size_t)i * 4 + 3], 4);
+      if (meta >> 2) { out.bvh.n_leaves++; out.bvh.max_leaf_prims = std::max(out.bvh.max_leaf_prims, meta >> 2); }
+    }
+  } else build_bvh(bounds, in.accel.max_node_prims, in.accel.split_method, threads, out.bvh);
   const size_t N0 = prims.size();
   // 2c. append the definitions' trees and slots to the same arrays with absolute indices
   std::vector<uint32_t> def_root_node(in.n_objects, 0xffffffffu), def_first_slot(in.n_objects, 0), def_first_pn(in.n_objects, 0);

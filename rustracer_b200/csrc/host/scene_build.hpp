@@ -31,7 +31,10 @@ struct FlatScene {
 };
 
 // threads: BVH build threads (<= 0: all).  Throws std::runtime_error on unsupported input.
-void flatten_scene(const rt_scene& in, int threads, FlatScene& out);
+// external_builder (may be null): builds the top-level SAH tree instead of build_bvh (include/rthost.h rth_bvh_builder).
+typedef int (*ExternalBvhBuilder)(void* user, const float* prim_bounds, uint64_t n_prims, int max_prims_per_node, float* node_lo, float* node_hi,
+                                  uint32_t* ordered, uint32_t* n_nodes, float* build_ms);
+void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhBuilder external_builder = nullptr, void* builder_user = nullptr);
 // Film / camera / integrator / sampler part only (no geometry): fills out.render from `in`.
 void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd);
 // Texture rows for the device: copies the parameters and builds each imagemap's MIP pyramid (MIPMap::new) into `pool`.

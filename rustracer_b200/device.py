@@ -44,6 +44,7 @@ def _lib():
     lib.rtgpu_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     lib.rtgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     lib.rtgpu_synchronize.argtypes = [vp]
+    lib.rtgpu_build_bvh.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     lib.rtgpu_launch_count.argtypes = [vp]
     lib.rtgpu_launch_count.restype = C.c_uint64
     lib._rtgpu_ready = True
@@ -85,6 +86,21 @@ class Device:
     def _check(self, rc):
         if rc != 0:
             raise DeviceError(f"{_STATUS.get(rc, rc)}: {self._lib.rtgpu_last_error(self._h).decode()}")
+
+    # ---- BVH construction (rtgpu_build_bvh) ------------------------------------------------------------
+    def bvh_builder(self):
+        """(function pointer, user pointer) for rth_flatten_with_builder: this context's rtgpu_build_bvh."""
+        return C.cast(self._lib.rtgpu_build_bvh, C.c_void_p), self._h
+
+    def build_bvh(self, prim_bounds, max_prims_per_node=4):
+        """== BVH::new (SAH) on the device.  prim_bounds: (n, 6) float32 {min, max}.  Returns dict(node_lo (m,4), node_hi (m,4), ordered (n,), ms)."""
+        b = np.ascontiguousarray(prim_bounds, np.float32).reshape(-1, 6)
+        n = b.shape[0]
+        lo, hi = np.zeros((2 * n, 4), np.float32), np.zeros((2 * n, 4), np.float32)
+        ordered = np.zeros(n, np.uint32)
+        m, ms = C.c_uint32(), C.c_float()
+        self._check(self._lib.rtgpu_build_bvh(self._h, b.ctypes.data, n, int(max_prims_per_node), lo.ctypes.data, hi.ctypes.data, ordered.ctypes.data, C.byref(m), C.byref(ms)))
+        return dict(node_lo=lo[: m.value].copy(), node_hi=hi[: m.value].copy(), ordered=ordered, ms=ms.value)
 
     # ---- scene -------------------------------------------------------------------------------------
     def upload(self, scene):

@@ -28,6 +28,7 @@ def _lib():
     lib.rth_integrator_name.argtypes = [C.c_void_p]
     lib.rth_integrator_name.restype = C.c_char_p
     lib.rth_flatten.argtypes = [C.c_void_p, C.c_int]
+    lib.rth_flatten_with_builder.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.rth_scene_desc.argtypes = [C.c_void_p]
     lib.rth_scene_desc.restype = C.POINTER(A.rtgpu_scene_desc)
     lib.rth_bvh_build_seconds.argtypes = [C.c_void_p]
@@ -98,9 +99,15 @@ class Scene:
     def integrator_name(self):
         return _lib().rth_integrator_name(self._h).decode()
 
-    def flatten(self, threads=0):
+    def flatten(self, threads=0, device=None):
+        """Build the SAH BVH and flatten.  device: a `Device` whose rtgpu_build_bvh builds the top-level tree (same tree)."""
         lib = _lib()
-        if lib.rth_flatten(self._h, threads) != 0:
+        if device is not None:
+            fn, user = device.bvh_builder()
+            rc = lib.rth_flatten_with_builder(self._h, threads, fn, user)
+        else:
+            rc = lib.rth_flatten(self._h, threads)
+        if rc != 0:
             raise SceneError(lib.rth_last_error().decode())
         self._flat = True
         return self
