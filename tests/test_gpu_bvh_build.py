@@ -47,13 +47,6 @@ def test_device_builder_reproduces_the_host_tree(dev, tmp_path, name):
 def test_degenerate_inputs(dev):
     """Coincident centroids (leaf whatever the count), duplicated boxes, a single primitive, two primitives in both orders."""
     rng = np.random.default_rng(2)
-    from rustracer_b200 import Scene, scenes
-
-    def host_tree(b, max_prims=4):
-        import ctypes as C
-        # the host builder through a scene of unit-less triangles is roundabout: compare against the device on scenes instead;
-        # here only structural properties are checked
-        return None
 
     for n in (1, 2, 3, 5, 33, 200):
         lo = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
@@ -80,4 +73,5 @@ def test_renders_identically_with_the_device_built_tree(dev, tmp_path):
     sc.flatten(device=dev)
     dev.upload(sc)
     dev.render(rd)
-    assert np.array_equal(a, dev.read_film())
+    b = dev.read_film()
+    assert np.array_equal(a[..., 3], b[..., 3]) and np.allclose(a, b, rtol=1e-5, atol=1e-6)   # same tree; float atomics reorder the sums
