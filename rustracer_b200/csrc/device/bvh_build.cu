@@ -107,40 +107,46 @@ __global__ void k_prepare(Nodes nd, Work w, uint32_t first, uint32_t count) {
     for (int d = 0; d < 3; d++) { w.bbox[((size_t)s * NB + b) * 6 + d] = fkey(FLT_MAX); w.bbox[((size_t)s * NB + b) * 6 + 3 + d] = fkey(-FLT_MAX); }
   }
 }
-// lanes of a warp that share `key` reduce with shuffles; the group leader issues the atomics
-__device__ __forceinline__ void group_min_max(unsigned group, int lane, int* dst_lo, int* dst_hi, float lo, float hi) {
-  // group = lanes with the same key (from __match_any_sync); butterfly over the whole warp restricted to the group
-  float mn = lo, mx = hi;
-  for (int off = 16; off > 0; off >>= 1) {
-    const float omn = __shfl_xor_sync(0xffffffffu, mn, off), omx = __shfl_xor_sync(0xffffffffu, mx, off);
-    if (group >> (lane ^ off) & 1u) { mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx; }
-  }
-  if (lane == __ffs(group) - 1) { atomicMin(dst_lo, fkey(mn)); atomicMax(dst_hi, fkey(mx)); }
+// Reductions into per-node (or per-bucket) min / max keys and counts.  Lanes of a warp that share a destination reduce with
+// __reduce_min/max/add_sync over their __match_any_sync group; when the whole block works on one node (the top levels, where a
+// single node spans millions of positions) the warps meet in shared memory first, so a block issues one global atomic per
+// destination instead of one per warp.
+__device__ __forceinline__ void group_min_max(unsigned group, bool leader, int* dst_lo, int* dst_hi, int klo, int khi) {
+  const int mn = __reduce_min_sync(group, klo), mx = __reduce_max_sync(group, khi);
+  if (leader) { atomicMin(dst_lo, mn); atomicMax(dst_hi, mx); }
 }
 // box and centroid bounds of every large node of the level (bvh/mod.rs:153-159, :170-174)
-__global__ void k_bounds(Nodes nd, Work w, uint32_t first, uint32_t count) {
+__global__ void __launch_bounds__(256) k_bounds(Nodes nd, Work w, uint32_t first, uint32_t count) {
+  __shared__ int sh[12];
+  __shared__ uint32_t sh_node;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t node = i < w.n ? w.node_of[i] : kNone;
   if (node != kNone && (node < first || node >= first + count || nd.bslot[node] == kNone)) node = kNone;
-  const int lane = threadIdx.x & 31;
-  const unsigned group = __match_any_sync(0xffffffffu, node);
-  // a butterfly restricted to a group is only a full reduction when the group is the whole warp; otherwise plain atomics
-  const bool whole = group == 0xffffffffu;
-  float b[6] = {0, 0, 0, 0, 0, 0}, c[3] = {0, 0, 0};
+  if (threadIdx.x == 0) sh_node = node;
+  if (threadIdx.x < 12) sh[threadIdx.x] = threadIdx.x % 6 < 3 ? fkey(FLT_MAX) : fkey(-FLT_MAX);   // {box lo, box hi, cbox lo, cbox hi}
+  __syncthreads();
+  const bool uniform = __syncthreads_and(node == sh_node || i >= w.n) && sh_node != kNone;
+  int kb[6] = {0, 0, 0, 0, 0, 0}, kc[3] = {0, 0, 0};
   if (node != kNone) {
     const uint32_t id = w.perm[i];
-    for (int d = 0; d < 6; d++) b[d] = w.bounds[6 * (size_t)id + d];
-    for (int d = 0; d < 3; d++) c[d] = 0.5f * b[d] + 0.5f * b[3 + d];
-  }
-  if (whole && node != kNone) {
     for (int d = 0; d < 3; d++) {
-      group_min_max(group, lane, &nd.box[6 * (size_t)node + d], &nd.box[6 * (size_t)node + 3 + d], b[d], b[3 + d]);
-      group_min_max(group, lane, &nd.cbox[6 * (size_t)node + d], &nd.cbox[6 * (size_t)node + 3 + d], c[d], c[d]);
+      const float lo = w.bounds[6 * (size_t)id + d], hi = w.bounds[6 * (size_t)id + 3 + d];
+      kb[d] = fkey(lo); kb[3 + d] = fkey(hi); kc[d] = fkey(0.5f * lo + 0.5f * hi);
     }
-  } else if (node != kNone) {
-    for (int d = 0; d < 3; d++) {
-      atomicMin(&nd.box[6 * (size_t)node + d], fkey(b[d])); atomicMax(&nd.box[6 * (size_t)node + 3 + d], fkey(b[3 + d]));
-      atomicMin(&nd.cbox[6 * (size_t)node + d], fkey(c[d])); atomicMax(&nd.cbox[6 * (size_t)node + 3 + d], fkey(c[d]));
+  }
+  const unsigned group = __match_any_sync(0xffffffffu, node);
+  const bool leader = (int)(threadIdx.x & 31) == __ffs(group) - 1 && node != kNone;
+  int* box = uniform ? sh : &nd.box[6 * (size_t)(node == kNone ? 0 : node)];
+  int* cbox = uniform ? sh + 6 : &nd.cbox[6 * (size_t)(node == kNone ? 0 : node)];
+  for (int d = 0; d < 3; d++) {
+    group_min_max(group, leader, &box[d], &box[3 + d], kb[d], kb[3 + d]);
+    group_min_max(group, leader, &cbox[d], &cbox[3 + d], kc[d], kc[d]);
+  }
+  if (uniform) {
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      int* dst = threadIdx.x < 6 ? &nd.box[6 * (size_t)sh_node + threadIdx.x] : &nd.cbox[6 * (size_t)sh_node + threadIdx.x - 6];
+      if (threadIdx.x % 6 < 3) atomicMin(dst, sh[threadIdx.x]); else atomicMax(dst, sh[threadIdx.x]);
     }
   }
 }
@@ -156,17 +162,42 @@ __global__ void k_choose_dim(Nodes nd, Work w, uint32_t first, uint32_t count) {
   nd.axis[node] = (uint8_t)dim;
   if (cl[dim] == ch[dim]) nd.state[node] = ST_LEAF;
 }
-__global__ void k_bucket(Nodes nd, Work w, uint32_t first, uint32_t count) {
+// bucket counts and bucket bounds (bvh/mod.rs:219-232)
+__global__ void __launch_bounds__(256) k_bucket(Nodes nd, Work w, uint32_t first, uint32_t count) {
+  __shared__ int sh_box[NB * 6];
+  __shared__ uint32_t sh_cnt[NB];
+  __shared__ uint32_t sh_node;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w.n) return;
-  const uint32_t node = w.node_of[i];
-  if (node == kNone || node < first || node >= first + count || nd.bslot[node] == kNone || nd.state[node] == ST_LEAF) return;
-  const int dim = nd.axis[node];
-  const uint32_t id = w.perm[i];
-  const int b = bucket_of(centroid(w.bounds, id, dim), funkey(nd.cbox[6 * (size_t)node + dim]), funkey(nd.cbox[6 * (size_t)node + 3 + dim]));
-  const size_t s = (size_t)nd.bslot[node] * NB + b;
-  atomicAdd(&w.bcount[s], 1u);
-  for (int d = 0; d < 3; d++) { atomicMin(&w.bbox[s * 6 + d], fkey(w.bounds[6 * (size_t)id + d])); atomicMax(&w.bbox[s * 6 + 3 + d], fkey(w.bounds[6 * (size_t)id + 3 + d])); }
+  uint32_t node = i < w.n ? w.node_of[i] : kNone;
+  if (node != kNone && (node < first || node >= first + count || nd.bslot[node] == kNone || nd.state[node] == ST_LEAF)) node = kNone;
+  if (threadIdx.x == 0) sh_node = node;
+  if (threadIdx.x < NB * 6) sh_box[threadIdx.x] = threadIdx.x % 6 < 3 ? fkey(FLT_MAX) : fkey(-FLT_MAX);
+  if (threadIdx.x < NB) sh_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const bool uniform = __syncthreads_and(node == sh_node || i >= w.n) && sh_node != kNone;
+  int b = 0, kb[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t dest = kNone;                                              // bucket row: bslot * NB + b
+  if (node != kNone) {
+    const int dim = nd.axis[node];
+    const uint32_t id = w.perm[i];
+    b = bucket_of(centroid(w.bounds, id, dim), funkey(nd.cbox[6 * (size_t)node + dim]), funkey(nd.cbox[6 * (size_t)node + 3 + dim]));
+    dest = nd.bslot[node] * NB + (uint32_t)b;
+    for (int d = 0; d < 6; d++) kb[d] = fkey(w.bounds[6 * (size_t)id + d]);
+  }
+  const unsigned group = __match_any_sync(0xffffffffu, dest);
+  const bool leader = (int)(threadIdx.x & 31) == __ffs(group) - 1 && node != kNone;
+  uint32_t* cnt = uniform ? &sh_cnt[b] : &w.bcount[dest == kNone ? 0 : dest];
+  int* box = uniform ? &sh_box[b * 6] : &w.bbox[(size_t)(dest == kNone ? 0 : dest) * 6];
+  if (leader) atomicAdd(cnt, (uint32_t)__popc(group));
+  for (int d = 0; d < 3; d++) group_min_max(group, leader, &box[d], &box[3 + d], kb[d], kb[3 + d]);
+  if (uniform) {
+    __syncthreads();
+    const size_t row = (size_t)nd.bslot[sh_node] * NB;
+    if (threadIdx.x < NB && sh_cnt[threadIdx.x]) atomicAdd(&w.bcount[row + threadIdx.x], sh_cnt[threadIdx.x]);
+    if (threadIdx.x < NB * 6 && sh_cnt[threadIdx.x / 6]) {
+      if (threadIdx.x % 6 < 3) atomicMin(&w.bbox[row * 6 + threadIdx.x], sh_box[threadIdx.x]); else atomicMax(&w.bbox[row * 6 + threadIdx.x], sh_box[threadIdx.x]);
+    }
+  }
 }
 // SAH split or leaf (bvh/mod.rs:234-286)
 __global__ void k_sah(Nodes nd, Work w, uint32_t first, uint32_t count) {

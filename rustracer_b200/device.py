@@ -104,7 +104,10 @@ class Device:
 
     # ---- scene -------------------------------------------------------------------------------------
     def upload(self, scene):
-        """scene: rustracer_b200.host.Scene (flattened on demand)."""
+        """scene: rustracer_b200.host.Scene.  Flattened on demand, the SAH BVH built on this device (rtgpu_build_bvh: the same
+        tree as the host builder's); a scene flattened beforehand is taken as it is."""
+        if not scene._flat:
+            scene.flatten(device=self)
         self._check(self._lib.rtgpu_upload_scene(self._h, scene.desc))
         self.scene = scene
         return self
