@@ -14,8 +14,10 @@
 
 #ifdef __CUDACC__
 #define RTML_HD __host__ __device__ __forceinline__
+#define RTML_LIST __host__ __device__ __noinline__      /* one function per mix depth: inlined, the nested listings multiply the code */
 #else
 #define RTML_HD inline
+#define RTML_LIST inline
 #endif
 
 namespace rtml {
@@ -59,7 +61,7 @@ RTML_HD void push(LobeList& L, const rtgpu_lobe& l) {
 // `children(row, first)` returns the evaluated material of a mix child (first = mat1, whose bump map stays on the caller's
 // surface; mat2 works on a clone, mixmat.rs:43-47).
 template <int DEPTH, class Children>
-RTML_HD float list_lobes(const rt_material& m, bool allow_multiple_lobes, Children& children, LobeList& L) {
+RTML_LIST float list_lobes(const rt_material& m, bool allow_multiple_lobes, Children& children, LobeList& L) {
   switch (m.type) {
     case RT_MAT_MATTE: {                                              // matte.rs:37-62 ; oren_nayar.rs:17-26 (sigma in degrees)
       const Rgb3 r = clamp_rgb(rgb(m.kd));

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int par
   float4* obeta = parity ? p.w.beta : p.w.beta2; uint4* ops = parity ? p.w.pstate : p.w.pstate2;
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
   const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t i = (TEX && p.w.item_order) ? p.w.item_order[k] : k;   // textured scenes: items in material order
     Ray ray = load_ray(ray_o, ray_d, i, nullptr);
     ray.t_max = inf_f();
     const HitRec h = p.w.hit[i];

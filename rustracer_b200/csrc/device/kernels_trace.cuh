@@ -206,6 +206,62 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t
   }
 }
 
+// ---- material sort of a shade queue (textured scenes) --------------------------------------------------------------------
+// The listed-lobes shade kernel and the recursive shade kernel evaluate textured materials with very different code per
+// material (texture graph, EWA loops, bump map, lobe list); unsorted, the warps of an SM wander through megabytes of code and
+// starve on instruction fetch (profiles/r01k: 95 % of the stall samples "no instruction").  A counting sort of the queue by
+// material row keeps neighbouring warps on the same material: histogram, exclusive scan, scatter.
+// Entry i of the queue is item `list ? list[i] : i`; its key is the material row of its hit (n_bins - 1: miss / no material).
+RT_DEV uint32_t matsort_key(const RenderParams& p, uint32_t item, uint32_t n_bins) {
+  const uint32_t hslot = p.w.hit[item].slot;
+  if (hslot == kMiss) return n_bins - 1u;
+  const uint32_t mrow = p.sc.info[hslot].y;
+  return mrow < n_bins - 1u ? mrow : n_bins - 1u;
+}
+__global__ void __launch_bounds__(256) k_matsort_hist(RenderParams p, const uint32_t* __restrict__ list, int count_idx, uint32_t* __restrict__ hist, uint32_t n_bins) {
+  const uint32_t n = p.w.counters[count_idx];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+    const uint32_t key = i < n ? matsort_key(p, list ? list[i] : i, n_bins) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (i < n && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+  }
+}
+__global__ void __launch_bounds__(256) k_matsort_scan(uint32_t* __restrict__ hist, uint32_t n_bins) {   // exclusive, in place, one block
+  __shared__ uint32_t warp_sums[8];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < n_bins; b0 += 256) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t v = i < n_bins ? hist[i] : 0;
+    uint32_t x = v;
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, off); if ((int)lane_id() >= off) x += y; }
+    if (lane_id() == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t before = carry;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += warp_sums[w];
+    if (i < n_bins) hist[i] = before + x - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = before + x;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_matsort_scatter(RenderParams p, const uint32_t* __restrict__ list, int count_idx, uint32_t* __restrict__ cursor, uint32_t n_bins,
+                                                         uint32_t* __restrict__ out) {
+  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t lane_lt = (1u << lane_id()) - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+    const uint32_t item = i < n ? (list ? list[i] : i) : 0u;
+    const uint32_t key = i < n ? matsort_key(p, item, n_bins) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (i < n && (int)lane_id() == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) out[base + (uint32_t)__popc(peers & lane_lt)] = item;
+  }
+}
+
 template <bool ATOMIC>
 struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;

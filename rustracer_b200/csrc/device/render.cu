@@ -59,7 +59,8 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   WaveBuffers* w = ctx->wave;
   WaveView& v = w->v;
   if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
-      (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)))
+      (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)) &&
+      (v.matsort_out != nullptr || !ctx->scene.texmats))
     return 0;
   release(w);
   int rc = 0;
@@ -69,6 +70,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   if (recursive && ctx->scene.texmats) { A(rdiff, (size_t)cap_items * 3); A(rdiff2, (size_t)cap_items * 3); }
+  if (ctx->scene.texmats) { A(matsort_hist, (size_t)ctx->scene.n_materials + 1); A(matsort_out, cap_items); }
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
   A(mi_o, cap_mis); A(mi_d, cap_mis); A(mi_c, cap_mis);
@@ -309,7 +311,14 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         if (plan.mat_present[Q_GLASS]) RT_LAUNCH(K_SHADE, launch_shade_path_3(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
         if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
-        if (plan.mat_present[Q_LOBES]) RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
+        if (plan.mat_present[Q_LOBES]) {
+          if (sc.texmats) {                                           // textured materials: keep neighbouring warps on one material (kernels_trace.cuh)
+            RT_LAUNCH(K_SHADE, launch_material_sort(p, p.w.matq[Q_LOBES], C_MATQ0 + Q_LOBES, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
+            ctx->launches += 2;
+            RenderParams ps = p; ps.w.matq[Q_LOBES] = p.w.matsort_out;
+            RT_LAUNCH(K_SHADE, launch_shade_path_6(ps, in, pblocks, ctx->stream));
+          } else RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
+        }
         if (sc.n_lights > 0) {
           RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, ctx->stream));
           if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, ctx->stream));
@@ -322,7 +331,12 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
         const int par = (int)(lvl & 1u);
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
-        RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
+        if (sc.texmats) {
+          RT_LAUNCH(K_SHADE, launch_material_sort(p, nullptr, C_LIVE0 + par, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
+          ctx->launches += 2;
+          RenderParams ps = p; ps.w.item_order = p.w.matsort_out;
+          RT_LAUNCH(K_SHADE, launch_shade_recursive(ps, par, pblocks, ctx->stream));
+        } else RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
         RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, ctx->stream));

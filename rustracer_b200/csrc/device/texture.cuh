@@ -254,8 +254,9 @@ static __device__ __noinline__ Spec tex_leaf(const rtgpu_texture* __restrict__ t
   }
 }
 // Texture<T>::evaluate; a float texture returns its value in all three channels.
+// (one real function per nesting level: inlined, the nine child call sites of a level would multiply into megabytes of code)
 template <int D>
-RT_DEV Spec tex_eval(const rtgpu_texture* __restrict__ textures, const float* __restrict__ pool, int row, const TexPoint& tp) {
+static __device__ __noinline__ Spec tex_eval(const rtgpu_texture* __restrict__ textures, const float* __restrict__ pool, int row, const TexPoint& tp) {
   const rtgpu_texture& t = textures[row];
   const int kind = t.kind;
   if (kind == RT_TEX_SCALE || kind == RT_TEX_MIX || kind == RT_TEX_CHECKERBOARD) {
@@ -290,25 +291,24 @@ RT_DEV Spec tex_eval(const rtgpu_texture* __restrict__ textures, const float* __
   }
   return tex_leaf(textures, pool, row, tp);
 }
-// One real function per shading kernel for the whole texture graph (the material evaluator calls it up to 18 times per hit)
-static __device__ __noinline__ Spec tex_evaluate(const rtgpu_texture* __restrict__ textures, const float* __restrict__ pool, int row, const TexPoint& tp) {
+RT_DEV Spec tex_evaluate(const rtgpu_texture* __restrict__ textures, const float* __restrict__ pool, int row, const TexPoint& tp) {
   return tex_eval<0>(textures, pool, row, tp);
 }
 
 // material/mod.rs:50-92 (dndu = dndv = 0: see SurfTex)
-RT_DEV void bump_map(const DScene& sc, int row, SurfHit& si, SurfTex& st) {
+static __device__ __noinline__ void bump_map(const rtgpu_texture* __restrict__ textures, const float* __restrict__ tex_data, int row, SurfHit& si, SurfTex& st) {
   const V3 zero_n = v3(0, 0, 0);
   TexPoint tp = tex_point(si, st);
   float du = 0.5f * (fabsf(st.dudx) + fabsf(st.dudy));
   if (du == 0.0f) du = 0.0005f;
   tp.p = si.p + du * si.dpdu_s; tp.uv = mk2(st.uv.x + du, st.uv.y + 0.0f);
-  const float u_displace = tex_evaluate(sc.textures, sc.tex_data, row, tp).r;
+  const float u_displace = tex_evaluate(textures, tex_data, row, tp).r;
   float dv = 0.5f * (fabsf(st.dvdx) + fabsf(st.dvdy));
   if (dv == 0.0f) dv = 0.0005f;
   tp.p = si.p + dv * st.dpdv_s; tp.uv = mk2(st.uv.x + 0.0f, st.uv.y + dv);
-  const float v_displace = tex_evaluate(sc.textures, sc.tex_data, row, tp).r;
+  const float v_displace = tex_evaluate(textures, tex_data, row, tp).r;
   tp.p = si.p; tp.uv = st.uv;
-  const float displace = tex_evaluate(sc.textures, sc.tex_data, row, tp).r;
+  const float displace = tex_evaluate(textures, tex_data, row, tp).r;
   const V3 dpdu = si.dpdu_s + (u_displace - displace) / du * si.ns + displace * zero_n;
   const V3 dpdv = st.dpdv_s + (v_displace - displace) / dv * si.ns + displace * zero_n;
   set_shading_geometry(si, st, dpdu, dpdv);
@@ -316,15 +316,16 @@ RT_DEV void bump_map(const DScene& sc, int row, SurfHit& si, SurfTex& st) {
 
 // The material row with every textured parameter evaluated at the hit (the `.evaluate(si)` calls of material/*.rs);
 // `apply_bump`: the material's bump map displaces the caller's shading geometry first.
-RT_DEV rt_material resolve_material(const DScene& sc, int row, SurfHit& si, SurfTex& st, bool apply_bump) {
-  rt_material m = sc.texmats[row];
-  if (!m.textured) return m;
-  if (apply_bump && m.type != RT_MAT_MIX && m.tex[RT_TS_BUMP]) bump_map(sc, m.tex[RT_TS_BUMP] - 1, si, st);
+static __device__ __noinline__ void resolve_material(const rt_material* __restrict__ texmats, const rtgpu_texture* __restrict__ textures, const float* __restrict__ tex_data,
+                                                    int row, SurfHit& si, SurfTex& st, bool apply_bump, rt_material& m) {
+  m = texmats[row];
+  if (!m.textured) return;
+  if (apply_bump && m.type != RT_MAT_MIX && m.tex[RT_TS_BUMP]) bump_map(textures, tex_data, m.tex[RT_TS_BUMP] - 1, si, st);
   const TexPoint tp = tex_point(si, st);
 #pragma unroll 1
   for (int slot = 0; slot < RT_TS_BUMP; slot++) {
     if (!m.tex[slot]) continue;
-    const Spec v = tex_evaluate(sc.textures, sc.tex_data, m.tex[slot] - 1, tp);
+    const Spec v = tex_evaluate(textures, tex_data, m.tex[slot] - 1, tp);
     float* d3 = nullptr; float* d1 = nullptr;
     switch (slot) {
       case RT_TS_KD: d3 = m.kd; break;           case RT_TS_KS: d3 = m.ks; break;             case RT_TS_KR: d3 = m.kr; break;
@@ -337,7 +338,6 @@ RT_DEV rt_material resolve_material(const DScene& sc, int row, SurfHit& si, Surf
     }
     if (d3) { d3[0] = v.r; d3[1] = v.g; d3[2] = v.b; } else *d1 = v.r;
   }
-  return m;
 }
 
 // Material::compute_scattering_functions for an RTGPU_MAT_TEXTURED material: differentials, bump map, parameter textures,
@@ -349,18 +349,27 @@ struct DeviceMixChildren {
   RT_DEV rt_material operator()(int row, bool first) {
     const bool apply = live && first;
     if (!first) live = false;
-    return resolve_material(sc, row, si, st, apply);
+    rt_material m;
+    resolve_material(sc.texmats, sc.textures, sc.tex_data, row, si, st, apply, m);
+    return m;
   }
 };
-RT_DEV void make_bsdf_textured(const DScene& sc, uint32_t row, SurfHit& si, SurfTex& st, const RayDiff& rd, bool allow_multiple_lobes, rtgpu_lobe* scratch,
-                               Bsdf& bsdf) {
-  compute_differential(si, st, rd);
-  const rt_material m = resolve_material(sc, (int)row, si, st, true);
+static __device__ __noinline__ float list_material_lobes(const DScene& sc, const rt_material& m, SurfHit& si, SurfTex& st, bool allow_multiple_lobes, rtgpu_lobe* scratch, int& n) {
   rtml::LobeList L{scratch, 0, rtml::kOk};
   DeviceMixChildren children{sc, si, st, true};
   const float eta = rtml::list_lobes<0>(m, allow_multiple_lobes, children, L);
+  n = L.n;
+  return eta;
+}
+RT_DEV void make_bsdf_textured(const DScene& sc, uint32_t row, SurfHit& si, SurfTex& st, const RayDiff& rd, bool allow_multiple_lobes, rtgpu_lobe* scratch,
+                               Bsdf& bsdf) {
+  compute_differential(si, st, rd);
+  rt_material m;
+  resolve_material(sc.texmats, sc.textures, sc.tex_data, (int)row, si, st, true, m);
+  int n;
+  const float eta = list_material_lobes(sc, m, si, st, allow_multiple_lobes, scratch, n);
   bsdf_init(bsdf, si, eta);
-  bsdf.g = scratch; bsdf.n = L.n;
+  bsdf.g = scratch; bsdf.n = n;
 }
 
 }  // namespace rt

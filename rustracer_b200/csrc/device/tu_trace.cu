@@ -34,6 +34,14 @@ void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blo
   else if (p.sc.n_instances) { if (atomic) k_trace_mis_engine<true, true><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false, true><<<blocks, 128, 0, s>>>(p); }
   else { if (atomic) k_trace_mis_engine<true, false><<<blocks, 128, 0, s>>>(p); else k_trace_mis_engine<false, false><<<blocks, 128, 0, s>>>(p); }
 }
+// Sorts the queue (list / count_idx; list == null: the items 0..n-1) by the material row of each item's hit into `out`.
+// hist: n_bins = n_materials + 1 counters.  Three launches + one memset, all on the stream.
+void launch_material_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* hist, uint32_t n_bins, uint32_t* out, unsigned blocks, cudaStream_t s) {
+  cudaMemsetAsync(hist, 0, sizeof(uint32_t) * n_bins, s);
+  k_matsort_hist<<<blocks, 256, 0, s>>>(p, list, count_idx, hist, n_bins);
+  k_matsort_scan<<<1, 256, 0, s>>>(hist, n_bins);
+  k_matsort_scatter<<<blocks, 256, 0, s>>>(p, list, count_idx, hist, n_bins, out);
+}
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s) {
