@@ -135,7 +135,8 @@ RT_DEV float fbm(V3 p, V3 dpdx, V3 dpdy, float omega, uint32_t max_octaves) {   
 }
 
 // ---- mipmap.rs: lookups --------------------------------------------------------------------------------------------------
-RT_DEV int mip_modulo(int a, int b) { const int r = a % b; return r < 0 ? r + b : r; }   // :455-462
+// :455-462 `modulo`: every pyramid level has power-of-two sides (MIPMap::new resamples first), so the non-negative remainder is a mask
+RT_DEV int mip_modulo(int a, int b) { return a & (b - 1); }
 RT_DEV Spec mip_texel(const rtgpu_texture& t, const float* __restrict__ pool, int level, int s, int tt) {   // :194-210
   const int u = t.level_u[level], v = t.level_v[level];
   if (t.wrap == RT_WRAP_REPEAT) { s = mip_modulo(s, u); tt = mip_modulo(tt, v); }

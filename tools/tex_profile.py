@@ -6,9 +6,18 @@ from rustracer_b200.device import Device
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 integ = None if len(sys.argv) < 3 or sys.argv[2] == "path" else 'Integrator "whitted" "integer maxdepth" [5]'
 tmp = tempfile.mkdtemp()
-sc = Scene.from_string(scenes.balls_textured(tmp, spp=spp, integrator=integ), search_dir=tmp)
+which = sys.argv[3] if len(sys.argv) > 3 else "textured"       # textured | ext (uber / substrate / translucent / mix, constant) | plain
+if integ is None:
+    integ = 'Integrator "path" "integer maxdepth" [5]'
+if which == "textured":
+    sc = Scene.from_string(scenes.balls_textured(tmp, spp=spp, integrator=integ), search_dir=tmp)
+elif which == "ext":
+    sc = Scene.from_string(scenes.balls_ext(spp=spp, integrator=integ))
+else:
+    sc = Scene.from_string(scenes.balls(spp=spp, integrator=integ))
 dev = Device(0).upload(sc)
 rd = sc.render_desc()
 dev.set_option("profile", 1)
 st = dev.render(rd)
-print("ms", st.ms_total, "closest", st.ms_closest, "anyhit", st.ms_anyhit, "shade", st.ms_shade, "camera", st.camera_rays)
+st = dev.render(rd)
+print(which, "ms", st.ms_total, "closest", st.ms_closest, "anyhit", st.ms_anyhit, "shade", st.ms_shade, "camera", st.camera_rays)
