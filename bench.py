@@ -31,6 +31,26 @@ METRIC = "path samples/s (C3: 1M-triangle field, PathIntegrator spatial, 1920x10
 UNIT = "samples/s"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Native libraries write to fd 1 behind Python's back (NCCL prints its version
+    banner there whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the line goes to a private
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,7 +174,7 @@ def run_reference(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mrays_per_s": float(np.mean([r["mrays_per_s"] for r in vals])) if vals else last["mrays_per_s"], "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(a):
@@ -312,13 +332,14 @@ def run_ours(a):
             line["cpu_baseline"] = json.loads(out)["cpu_baseline"]
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
     a = parse_args()
+    claim_stdout()
     import __graft_entry__ as g
     g.ensure_built()
     if a.impl == "reference":
