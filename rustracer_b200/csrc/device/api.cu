@@ -273,9 +273,27 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     const size_t nn = s->n_nodes;
     auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     auto fbits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
-    std::vector<uint32_t> interior_index(nn, 0);
+    // compact interior numbering: the top levels of the scene's tree first, breadth-first (the engine can stage them in shared
+    // memory, RT_ENGINE_TOP_NODES), then every other interior node in array (pre-order) order
+    std::vector<uint32_t> interior_index(nn, 0xffffffffu);
     uint32_t n_interior = 0;
-    for (size_t i = 0; i < nn; i++) if ((bits(s->node_hi[i * 4 + 3]) >> 2) == 0) interior_index[i] = n_interior++;
+    {
+      const uint32_t want_top = 255;
+      std::vector<size_t> level;
+      if (nn > 0 && (bits(s->node_hi[3]) >> 2) == 0) level.push_back(0);
+      while (!level.empty() && n_interior + level.size() <= want_top) {
+        std::vector<size_t> next;
+        for (size_t i : level) {
+          interior_index[i] = n_interior++;
+          const size_t L = i + 1, R = bits(s->node_lo[i * 4 + 3]);
+          if (L < nn && (bits(s->node_hi[L * 4 + 3]) >> 2) == 0) next.push_back(L);
+          if (R < nn && (bits(s->node_hi[R * 4 + 3]) >> 2) == 0) next.push_back(R);
+        }
+        level.swap(next);
+      }
+      d.n_top = n_interior < (uint32_t)RT_ENGINE_TOP_NODES ? n_interior : (uint32_t)RT_ENGINE_TOP_NODES;
+    }
+    for (size_t i = 0; i < nn; i++) if ((bits(s->node_hi[i * 4 + 3]) >> 2) == 0 && interior_index[i] == 0xffffffffu) interior_index[i] = n_interior++;
     auto ref_of = [&](size_t i) -> uint32_t {
       const uint32_t n_prims = bits(s->node_hi[i * 4 + 3]) >> 2;
       return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];

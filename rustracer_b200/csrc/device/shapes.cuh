@@ -5,6 +5,10 @@
 #include "dmath.cuh"
 #include "../../../include/rtgpu.h"
 
+#ifndef RT_ENGINE_TOP_NODES
+#define RT_ENGINE_TOP_NODES 0       // interior nodes of the top levels the traversal engine stages in shared memory (0: none; profiles/r01n)
+#endif
+
 namespace rt {
 
 // Device-resident scene (all pointers are device pointers).  Layout: DESIGN.md "Data layout in HBM".
@@ -13,6 +17,8 @@ struct DScene {
   const float4* wide;        // 4 float4 per INTERIOR node (compact numbering): {L.min, bits(ref L)}, {L.max, bits(ref R)},
                              //   {R.min, bits(axis)}, {R.max, 0}; ref = interior index, or 0x80000000 | first slot for a leaf
   uint32_t root_ref;         // ref of the root node
+  uint32_t n_top;            // interior nodes [0, n_top) are the top levels of the scene's tree in breadth-first order (staged in shared memory
+                             //   by the traversal engine when it is built with RT_ENGINE_TOP_NODES > 0)
   const float4* geom;        // 3 float4 per ordered slot: triangle v0,v1,v2 (w of v0 = bits(kind | quadric<<2),
                              //   w of v1 bit 0 = last primitive of its leaf)
   const uint4* info;         // per slot: prim_number, material row, light row (0xffffffff none), RTGPU_PRIMFLAG_*

@@ -102,6 +102,13 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
   // definition's tree share this one stack
   uint2 stack_l[(INST ? 2 * kStackSize + 1 : kStackSize) - RT_ENGINE_SMEM_DEPTH];
   const uint32_t tid = threadIdx.x;
+#if RT_ENGINE_TOP_NODES > 0
+  // top levels of the tree (breadth-first numbered at upload) staged in shared memory: every ray walks them
+  __shared__ float4 s_top[4 * RT_ENGINE_TOP_NODES];
+  const uint32_t n_top = sc.n_top;
+  for (uint32_t k = tid; k < 4u * n_top; k += blockDim.x) s_top[k] = __ldg(&wide[k]);
+  __syncthreads();
+#endif
   int sp = 0;
   bool queue_empty = n == 0;
   uint32_t negmask = 0;                     // bit k = dir_is_neg[k]
@@ -177,10 +184,17 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     if (m_l == 0u || __popc(m_n) >= node_threshold) {
       // ---- node step: one wide node = both children's slab tests ----------------------------------------------
       if (!(cur & kLeafBit)) {
-        const float4 a = __ldg(&wide[4 * (size_t)cur]);
-        const float4 b = __ldg(&wide[4 * (size_t)cur + 1]);
-        const float4 c = __ldg(&wide[4 * (size_t)cur + 2]);
-        const float4 d = __ldg(&wide[4 * (size_t)cur + 3]);
+        float4 a, b, c, d;
+#if RT_ENGINE_TOP_NODES > 0
+        if (cur < n_top) { a = s_top[4 * cur]; b = s_top[4 * cur + 1]; c = s_top[4 * cur + 2]; d = s_top[4 * cur + 3]; }
+        else
+#endif
+        {
+          a = __ldg(&wide[4 * (size_t)cur]);
+          b = __ldg(&wide[4 * (size_t)cur + 1]);
+          c = __ldg(&wide[4 * (size_t)cur + 2]);
+          d = __ldg(&wide[4 * (size_t)cur + 3]);
+        }
         float tl, trr;
         const bool hl = slab_interval_bf(a, b, ray.o, inv_dir, nx, ny, nz, ray.t_max, tl);
         const bool hr = slab_interval_bf(c, d, ray.o, inv_dir, nx, ny, nz, ray.t_max, trr);
