@@ -2,6 +2,7 @@
 #include "scene_build.hpp"
 #include "../common/material_lobes.hpp"
 #include <stdexcept>
+#include <thread>
 
 namespace rth {
 namespace {
@@ -91,6 +92,16 @@ int max_lobes(const rt_scene& in, int row, int depth = 0) {
       return max_lobes(in, m.mix_a, depth + 1) + max_lobes(in, m.mix_b, depth + 1);
     default: return 1;
   }
+}
+
+// Static split of [0, n) over the host threads for the per-primitive loops of the flattener (each index writes its own outputs).
+template <class F> void parallel_for(size_t n, int threads, F body) {
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads <= 1 || n < (size_t)1 << 16) { body((size_t)0, n); return; }
+  const size_t chunk = (n + (size_t)threads - 1) / (size_t)threads;
+  std::vector<std::thread> pool;
+  for (size_t b = 0; b < n; b += chunk) pool.emplace_back([=, &body]() { body(b, std::min(n, b + chunk)); });
+  for (auto& t : pool) t.join();
 }
 
 // sampling/distribution1d.rs:11-45
@@ -190,13 +201,19 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     if (s.kind == RT_SHAPE_TRIMESH) {
       std::vector<Vec3>& wp = world_p[si];
       wp.resize(s.n_vertices);
-      for (uint32_t i = 0; i < s.n_vertices; i++) wp[i] = xf_point(o2w.m, v3(s.P[3 * i], s.P[3 * i + 1], s.P[3 * i + 2]));   // mesh.rs:61
+      parallel_for(s.n_vertices, threads, [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; i++) wp[i] = xf_point(o2w.m, v3(s.P[3 * i], s.P[3 * i + 1], s.P[3 * i + 2]));   // mesh.rs:61
+      });
       any_n |= s.N != nullptr; any_s |= s.S != nullptr; any_uv |= s.uv != nullptr;
-      for (uint32_t t = 0; t < s.n_indices / 3; t++) {
-        Vec3 p0 = wp[s.indices[3 * t]], p1 = wp[s.indices[3 * t + 1]], p2 = wp[s.indices[3 * t + 2]];
-        Box3 b = box_of_points(p0, p1); b.grow(p2);                   // mesh.rs:603-608
-        P_.push_back(Prim{si, t}); B_.push_back(b);
-      }
+      const size_t first = P_.size(), nt = s.n_indices / 3;
+      P_.resize(first + nt); B_.resize(first + nt);
+      parallel_for(nt, threads, [&](size_t t0, size_t t1) {
+        for (size_t t = t0; t < t1; t++) {
+          Vec3 p0 = wp[s.indices[3 * t]], p1 = wp[s.indices[3 * t + 1]], p2 = wp[s.indices[3 * t + 2]];
+          Box3 b = box_of_points(p0, p1); b.grow(p2);                 // mesh.rs:603-608
+          P_[first + t] = Prim{si, (uint32_t)t}; B_[first + t] = b;
+        }
+      });
       out.n_triangles += s.n_indices / 3;
     } else {
       rtgpu_quadric q; std::memset(&q, 0, sizeof(q));
@@ -259,7 +276,9 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
   if (external_builder && in.accel.split_method == RT_SPLIT_SAH && !bounds.empty()) {
     const size_t nb = bounds.size();
     std::vector<float> pb(nb * 6);
-    for (size_t i = 0; i < nb; i++) { pb[i * 6] = bounds[i].lo.x; pb[i * 6 + 1] = bounds[i].lo.y; pb[i * 6 + 2] = bounds[i].lo.z; pb[i * 6 + 3] = bounds[i].hi.x; pb[i * 6 + 4] = bounds[i].hi.y; pb[i * 6 + 5] = bounds[i].hi.z; }
+    parallel_for(nb, threads, [&](size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; i++) { pb[i * 6] = bounds[i].lo.x; pb[i * 6 + 1] = bounds[i].lo.y; pb[i * 6 + 2] = bounds[i].lo.z; pb[i * 6 + 3] = bounds[i].hi.x; pb[i * 6 + 4] = bounds[i].hi.y; pb[i * 6 + 5] = bounds[i].hi.z; }
+    });
     out.bvh = FlatBvh();
     out.bvh.node_lo.resize(nb * 8); out.bvh.node_hi.resize(nb * 8); out.bvh.ordered.resize(nb);
     uint32_t n_nodes = 0; float ms = 0.0f;
@@ -398,7 +417,19 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
   if (any_n) out.tri_n.assign(N * 9, 0.0f);
   if (any_s) out.tri_s.assign(N * 9, 0.0f);
   if (any_uv) out.tri_uv.assign(N * 6, 0.0f);
-  for (size_t slot = 0; slot < N; slot++) {
+  std::vector<uint32_t> mesh_flags(in.n_shapes, 0);                   // per mesh: orientation flags (interaction.rs:119-122)
+  bool any_instance = false;
+  for (uint32_t si = 0; si < in.n_shapes; si++) {
+    const rt_shape& s = in.shapes[si];
+    any_instance |= s.kind == RT_SHAPE_INSTANCE;
+    if (s.kind != RT_SHAPE_TRIMESH) continue;
+    Xform o2w = from_ir(s.o2w);
+    if ((s.reverse_orientation != 0) ^ swaps_handedness(o2w.m)) mesh_flags[si] |= RTGPU_PRIMFLAG_FLIP;
+    if (s.reverse_orientation) mesh_flags[si] |= RTGPU_PRIMFLAG_REVERSE;
+  }
+  // every slot writes its own rows; only instance rows are numbered in slot order, so scenes with instances stay on one thread
+  parallel_for(N, any_instance ? 1 : threads, [&](size_t slot0, size_t slot1) {
+  for (size_t slot = slot0; slot < slot1; slot++) {
     uint32_t pn = out.bvh.ordered[slot];
     const Prim& pr = prim_of(pn);
     const rt_shape& s = in.shapes[pr.shape];
@@ -417,9 +448,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
       const int32_t* ix = &s.indices[3 * pr.local];
       for (int v = 0; v < 3; v++) { Vec3 p = world_p[pr.shape][ix[v]]; g[4 * v] = p.x; g[4 * v + 1] = p.y; g[4 * v + 2] = p.z; }
       put_bits(&g[3], RTGPU_PRIM_TRIANGLE);
-      Xform o2w = from_ir(s.o2w);
-      if ((s.reverse_orientation != 0) ^ swaps_handedness(o2w.m)) flags |= RTGPU_PRIMFLAG_FLIP;
-      if (s.reverse_orientation) flags |= RTGPU_PRIMFLAG_REVERSE;
+      flags = mesh_flags[pr.shape];
       if (s.N) { flags |= RTGPU_PRIMFLAG_HAS_N; for (int v = 0; v < 3; v++) for (int c = 0; c < 3; c++) out.tri_n[slot * 9 + v * 3 + c] = s.N[3 * ix[v] + c]; }
       if (s.S) { flags |= RTGPU_PRIMFLAG_HAS_S; for (int v = 0; v < 3; v++) for (int c = 0; c < 3; c++) out.tri_s[slot * 9 + v * 3 + c] = s.S[3 * ix[v] + c]; }
       if (s.uv) { flags |= RTGPU_PRIMFLAG_HAS_UV; for (int v = 0; v < 3; v++) for (int c = 0; c < 2; c++) out.tri_uv[slot * 6 + v * 2 + c] = s.uv[2 * ix[v] + c]; }
@@ -431,6 +460,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     uint32_t* info = &out.prim_info[slot * 4];
     info[0] = pn; info[1] = s.material >= 0 ? (uint32_t)s.material : 0xffffffffu; info[2] = (uint32_t)light_of_prim[pn]; info[3] = flags;
   }
+  });
   for (uint32_t d = 0; d < in.n_objects; d++)                         // a one-primitive definition has no leaf node to mark its last slot
     if (dprims[d].size() == 1) { uint32_t u; std::memcpy(&u, &out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], 4); put_bits(&out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], u | 1u); }
   bool any_textured = false;
