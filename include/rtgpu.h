@@ -229,6 +229,7 @@ int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t 
 int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, int max_prims_per_node, float* node_lo, float* node_hi, uint32_t* ordered,
                     uint32_t* n_nodes, float* build_ms);
 /* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
+ * "sort_items" (1 = rtgpu_render sorts the listed-lobes shade queue / the recursive integrators' items by material; default 1),
  * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
  * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);

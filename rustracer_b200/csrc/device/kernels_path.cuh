@@ -11,8 +11,11 @@ namespace rt {
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4      // resident 128-thread blocks per SM the path shade kernels are compiled for (register cap 128)
 #endif
+#ifndef RT_SHADE_MIN_BLOCKS_LOBES
+#define RT_SHADE_MIN_BLOCKS_LOBES 8   // the listed-lobes / textured kernel is instruction-fetch bound: more resident warps (64 registers) win 5-20 % (profiles/r01o)
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(128, RT_SHADE_MIN_BLOCKS) k_shade_path(RenderParams p, int parity) {
+__global__ void __launch_bounds__(128, MAT == Q_LOBES ? RT_SHADE_MIN_BLOCKS_LOBES : RT_SHADE_MIN_BLOCKS) k_shade_path(RenderParams p, int parity) {
   const uint32_t n = p.w.counters[C_MATQ0 + MAT];
   uint32_t* out_list = p.w.list[1 - parity];
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];

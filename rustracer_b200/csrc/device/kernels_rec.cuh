@@ -10,8 +10,11 @@ namespace rt {
 // camera sample; specular reflection / transmission spawn child items for the next level.
 // TEX: the scene has textured materials — every item carries its ray differential (integrator/mod.rs:64-83, :107-136) in
 // the rdiff buffers and textured materials are evaluated at the hit (texture.cuh); scenes without them run the lean variant.
+#ifndef RT_REC_MIN_BLOCKS
+#define RT_REC_MIN_BLOCKS 8          // 64 registers: 4 / 8 / 12 / 16 blocks per SM measured in profiles/r01o
+#endif
 template <bool TEX>
-__global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int parity) {
+__global__ void __launch_bounds__(128, RT_REC_MIN_BLOCKS) k_shade_recursive(RenderParams p, int parity) {
   const uint32_t n = p.w.counters[C_LIVE0 + parity];
   const float4* ray_o = parity ? p.w.ray_o2 : p.w.ray_o; const float4* ray_d = parity ? p.w.ray_d2 : p.w.ray_d;
   const float4* beta_in = parity ? p.w.beta2 : p.w.beta; const uint4* ps_in = parity ? p.w.pstate2 : p.w.pstate;
@@ -20,7 +23,7 @@ __global__ void __launch_bounds__(128) k_shade_recursive(RenderParams p, int par
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
   const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const uint32_t i = (TEX && p.w.item_order) ? p.w.item_order[k] : k;   // textured scenes: items in material order
+    const uint32_t i = p.w.item_order ? p.w.item_order[k] : k;           // items in material order (k_matsort_*)
     Ray ray = load_ray(ray_o, ray_d, i, nullptr);
     ray.t_max = inf_f();
     const HitRec h = p.w.hit[i];

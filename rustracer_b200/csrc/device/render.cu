@@ -60,7 +60,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   WaveView& v = w->v;
   if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
       (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)) &&
-      (v.matsort_out != nullptr || !ctx->scene.texmats))
+      v.matsort_out != nullptr && v.matsort_bins >= ctx->scene.n_materials + 1)
     return 0;
   release(w);
   int rc = 0;
@@ -70,7 +70,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   if (recursive && ctx->scene.texmats) { A(rdiff, (size_t)cap_items * 3); A(rdiff2, (size_t)cap_items * 3); }
-  if (ctx->scene.texmats) { A(matsort_hist, (size_t)ctx->scene.n_materials + 1); A(matsort_out, cap_items); }
+  A(matsort_hist, (size_t)ctx->scene.n_materials + 1); A(matsort_out, cap_items); v.matsort_bins = ctx->scene.n_materials + 1;
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
   A(mi_o, cap_mis); A(mi_d, cap_mis); A(mi_c, cap_mis);
@@ -312,7 +312,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
         if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_LOBES]) {
-          if (sc.texmats) {                                           // textured materials: keep neighbouring warps on one material (kernels_trace.cuh)
+          if (ctx->sort_items) {                                      // keep neighbouring warps on one material's lobe list / texture graph (kernels_trace.cuh)
             RT_LAUNCH(K_SHADE, launch_material_sort(p, p.w.matq[Q_LOBES], C_MATQ0 + Q_LOBES, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
             ctx->launches += 2;
             RenderParams ps = p; ps.w.matq[Q_LOBES] = p.w.matsort_out;
@@ -331,7 +331,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
         const int par = (int)(lvl & 1u);
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
-        if (sc.texmats) {
+        if (ctx->sort_items) {
           RT_LAUNCH(K_SHADE, launch_material_sort(p, nullptr, C_LIVE0 + par, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
           ctx->launches += 2;
           RenderParams ps = p; ps.w.item_order = p.w.matsort_out;

@@ -43,8 +43,9 @@ struct WaveView {            // device pointers, passed to kernels by value
   float4 *ma_o, *ma_d, *ma_c;          // MIS rays towards infinite lights, traced any-hit: c = rgb contribution if the ray escapes
   uint32_t* list[2];
   uint32_t* matq[Q_COUNT];
-  uint32_t *matsort_hist, *matsort_out;   // textured scenes: material sort of the listed-lobes queue / of the recursive items
-  const uint32_t* item_order;             // recursive integrators, textured scenes: processing order of the level's items (or null)
+  uint32_t *matsort_hist, *matsort_out;   // material sort of the listed-lobes queue (path) / of a level's items (recursive integrators)
+  uint32_t matsort_bins;
+  const uint32_t* item_order;             // recursive integrators: processing order of the level's items (or null)
   uint32_t* counters;
   unsigned long long* stats;
   uint32_t cap_items, cap_samples, cap_shadow, cap_mis;

@@ -18,6 +18,8 @@ else:
 dev = Device(0).upload(sc)
 rd = sc.render_desc()
 dev.set_option("profile", 1)
+if os.environ.get("RT_SORT_ITEMS"):
+    dev.set_option("sort_items", int(os.environ["RT_SORT_ITEMS"]))
 st = dev.render(rd)
 st = dev.render(rd)
 print(which, "ms", st.ms_total, "closest", st.ms_closest, "anyhit", st.ms_anyhit, "shade", st.ms_shade, "camera", st.camera_rays)
