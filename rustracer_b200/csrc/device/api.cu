@@ -240,6 +240,7 @@ int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_items") == 0) { ctx->sort_items = value; return RTGPU_OK; }
+  if (std::strcmp(name, "sort_bounce_rays") == 0) { ctx->sort_bounce_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "node_threshold") == 0) { ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK; }
   if (std::strcmp(name, "refill_threshold") == 0) { ctx->refill_threshold = value; ctx->scene.tune_refill_threshold = value; return RTGPU_OK; }
   if (std::strcmp(name, "simple_traversal") == 0) { ctx->simple_traversal = value; return RTGPU_OK; }

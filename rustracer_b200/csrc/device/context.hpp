@@ -38,6 +38,7 @@ struct rtgpu_ctx {
   int node_threshold = 12, refill_threshold = 16;   // trace_engine.cuh scheduling knobs
   int simple_traversal = 0;   // 1 = one-thread-one-ray reference walk everywhere (validation); 0 = persistent engine
   int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
+  int sort_bounce_rays = 0;   // rtgpu_render (path): bin the rays of bounces >= 1 by origin cell + direction octant before tracing (profiles/r01q)
   int sort_items = 1;   // rtgpu_render: counting sort of the listed-lobes queue / of the recursive integrators' items by material row
 };
 

@@ -262,6 +262,55 @@ __global__ void __launch_bounds__(256) k_matsort_scatter(RenderParams p, const u
   }
 }
 
+// ---- binning of a bounce's rays (option "sort_bounce_rays") ------------------------------------------------------------------
+// Same key as the batch API's ray binning (api.cu): Morton code of the origin's cell in a 32^3 grid over the world bounds, then
+// the direction octant.  A counting sort of the live list by that key before the closest-hit launch of a bounce.
+constexpr int kWaveCellBits = 5;
+constexpr int kWaveSortBins = 1 << (3 * kWaveCellBits + 3);
+struct WaveSortParams { float lo[3], inv_ext[3]; };
+RT_DEV uint32_t wave_spread3(uint32_t v) { v &= 0x3ffu; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u; return v; }
+RT_DEV uint32_t wave_ray_key(const float4 o, const float4 d, const WaveSortParams& sp) {
+  const float cells = (float)(1 << kWaveCellBits);
+  const int hi = (1 << kWaveCellBits) - 1;
+  const int cx = min(max(__float2int_rd((o.x - sp.lo[0]) * sp.inv_ext[0] * cells), 0), hi);
+  const int cy = min(max(__float2int_rd((o.y - sp.lo[1]) * sp.inv_ext[1] * cells), 0), hi);
+  const int cz = min(max(__float2int_rd((o.z - sp.lo[2]) * sp.inv_ext[2] * cells), 0), hi);
+  const uint32_t morton = wave_spread3((uint32_t)cx) | (wave_spread3((uint32_t)cy) << 1) | (wave_spread3((uint32_t)cz) << 2);
+  return (morton << 3) | (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+}
+__global__ void __launch_bounds__(256) k_raysort_hist(RenderParams p, const uint32_t* __restrict__ list, int count_idx, WaveSortParams sp, uint32_t* __restrict__ keys,
+                                                      uint32_t* __restrict__ hist) {
+  const uint32_t n = p.w.counters[count_idx];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = list[i];
+    const uint32_t k = wave_ray_key(p.w.ray_o[slot], p.w.ray_d[slot], sp);
+    keys[i] = k;
+    atomicAdd(&hist[k], 1u);
+  }
+}
+__global__ void __launch_bounds__(1024) k_raysort_scan(uint32_t* __restrict__ hist) {    // exclusive scan of kWaveSortBins counters, one block
+  __shared__ uint32_t partial[1024];
+  constexpr int per = kWaveSortBins / 1024;
+  const uint32_t base = threadIdx.x * per;
+  uint32_t sum = 0;
+  for (int i = 0; i < per; i++) sum += hist[base + i];
+  partial[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = threadIdx.x >= (uint32_t)off ? partial[threadIdx.x - off] : 0;
+    __syncthreads();
+    partial[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = partial[threadIdx.x] - sum;
+  for (int i = 0; i < per; i++) { const uint32_t c = hist[base + i]; hist[base + i] = run; run += c; }
+}
+__global__ void __launch_bounds__(256) k_raysort_scatter(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ offsets, uint32_t* __restrict__ out) {
+  const uint32_t n = p.w.counters[count_idx];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[atomicAdd(&offsets[keys[i]], 1u)] = list[i];
+}
+
 template <bool ATOMIC>
 struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;

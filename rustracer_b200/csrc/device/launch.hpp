@@ -14,6 +14,8 @@ void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx,
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s);
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s);
 void launch_material_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* hist, uint32_t n_bins, uint32_t* out, unsigned blocks, cudaStream_t s);
+uint32_t ray_sort_bins();
+void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* keys, uint32_t* hist, uint32_t* out, unsigned blocks, cudaStream_t s);
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s);
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s);

@@ -70,6 +70,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   if (recursive && ctx->scene.texmats) { A(rdiff, (size_t)cap_items * 3); A(rdiff2, (size_t)cap_items * 3); }
+  A(raysort_keys, cap_items); A(raysort_hist, (size_t)ray_sort_bins()); A(raysort_out, cap_items);
   A(matsort_hist, (size_t)ctx->scene.n_materials + 1); A(matsort_out, cap_items); v.matsort_bins = ctx->scene.n_materials + 1;
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
   A(sh_o, cap_shadow); A(sh_d, cap_shadow); A(sh_c, cap_shadow);
@@ -302,8 +303,14 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
       for (uint32_t b = 0; b < rounds; b++) {
         const int in = (int)(b & 1u);
-        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[in], C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
-        RT_LAUNCH(K_SHADE, launch_classify(p, p.w.list[in], C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, ctx->stream));
+        const uint32_t* live = p.w.list[in];
+        if (ctx->sort_bounce_rays && b >= 1) {                        // camera rays are coherent as generated
+          RT_LAUNCH(K_CLOSEST, launch_ray_sort(p, live, C_LIVE0 + in, p.w.raysort_keys, p.w.raysort_hist, p.w.raysort_out, pblocks / 2, ctx->stream));
+          ctx->launches += 2;
+          live = p.w.raysort_out;
+        }
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, live, C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_SHADE, launch_classify(p, live, C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
         if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));

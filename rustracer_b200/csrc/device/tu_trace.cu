@@ -42,6 +42,20 @@ void launch_material_sort(const RenderParams& p, const uint32_t* list, int count
   k_matsort_scan<<<1, 256, 0, s>>>(hist, n_bins);
   k_matsort_scatter<<<blocks, 256, 0, s>>>(p, list, count_idx, hist, n_bins, out);
 }
+// Sorts the live list of a bounce by (origin cell, direction octant) into `out`; keys: one uint32 per entry, hist: ray_sort_bins() counters.
+uint32_t ray_sort_bins() { return (uint32_t)kWaveSortBins; }
+void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* keys, uint32_t* hist, uint32_t* out, unsigned blocks, cudaStream_t s) {
+  WaveSortParams sp;
+  for (int k = 0; k < 3; k++) {
+    const float ext = p.sc.world_hi[k] - p.sc.world_lo[k];
+    sp.lo[k] = p.sc.world_lo[k] - 0.05f * ext;
+    sp.inv_ext[k] = ext > 0.0f ? 1.0f / (1.1f * ext) : 0.0f;
+  }
+  cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kWaveSortBins, s);
+  k_raysort_hist<<<blocks, 256, 0, s>>>(p, list, count_idx, sp, keys, hist);
+  k_raysort_scan<<<1, 1024, 0, s>>>(hist);
+  k_raysort_scatter<<<blocks, 256, 0, s>>>(p, list, count_idx, keys, hist, out);
+}
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s) {

@@ -40,11 +40,15 @@ def main():
             dev.set_option("refill_threshold", rt)
             dev.intersect_device(d_r, n, d_o)
             ms = min(dev.intersect_device(d_r, n, d_o) for _ in range(3))
-            dev.render(rd)
-            dev.set_option("profile", 1)
-            st = dev.render(rd)
-            dev.set_option("profile", 0)
-            print(f"{nt:8d} {rt:6d} | {n / ms / 1e3:9.1f} | {st.ms_total:7.2f} ({st.ms_closest:.2f}/{st.ms_anyhit:.2f}/{st.ms_shade:.2f})", flush=True)
+            for sb in ((0, 1) if os.environ.get("RT_TRY_SORT_BOUNCE") else (0,)):
+                dev.set_option("sort_bounce_rays", sb)
+                dev.render(rd)
+                dev.set_option("profile", 1)
+                st = dev.render(rd)
+                dev.set_option("profile", 0)
+                st2 = dev.render(rd)
+                print(f"{nt:8d} {rt:6d} | {n / ms / 1e3:9.1f} | {st.ms_total:7.2f} ({st.ms_closest:.2f}/{st.ms_anyhit:.2f}/{st.ms_shade:.2f})  sort_bounce_rays={sb} unprofiled {st2.ms_total:.2f} ms", flush=True)
+            dev.set_option("sort_bounce_rays", 0)
     if a.big:
         sc = Scene.from_string(scenes.c4_scene(tmp), search_dir=tmp)
         sc.flatten()
