@@ -258,11 +258,60 @@ static bool read_png(const std::string& fn, int& w, int& h, std::vector<float>& 
   }
   return true;
 }
-// imageio.rs:77-92 `read_image`: by extension.  PFM and PNG are read; TGA / HDR / EXR need codecs this build does not carry.
+// TGA reader (imageio.rs:94-113 handles .tga through the same `image::open(..).to_rgb8()`): true-colour (types 2 / 10, 24 or 32 bits)
+// and greyscale (types 3 / 11, 8 bits), raw or run-length encoded, either row order.  Rows top-to-bottom on return.
+static bool read_tga(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
+  FILE* f = std::fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  std::vector<unsigned char> d;
+  unsigned char buf[65536]; size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) d.insert(d.end(), buf, buf + n);
+  std::fclose(f);
+  if (d.size() < 18) return false;
+  const int id_len = d[0], cmap_type = d[1], type = d[2], bpp = d[16], desc = d[17];
+  w = d[12] | (d[13] << 8); h = d[14] | (d[15] << 8);
+  const bool grey = type == 3 || type == 11, rle = type == 10 || type == 11;
+  if (cmap_type != 0 || w <= 0 || h <= 0 || !(type == 2 || type == 3 || type == 10 || type == 11)) return false;
+  if ((grey && bpp != 8) || (!grey && bpp != 24 && bpp != 32)) return false;
+  const size_t px = (size_t)bpp / 8, total = (size_t)w * h;
+  std::vector<unsigned char> img(total * px);
+  size_t pos = 18 + (size_t)id_len, out = 0;
+  if (!rle) {
+    if (pos + total * px > d.size()) return false;
+    std::memcpy(img.data(), &d[pos], total * px);
+  } else {
+    while (out < total) {
+      if (pos >= d.size()) return false;
+      const int hdr = d[pos++], cnt = (hdr & 127) + 1;
+      if (out + (size_t)cnt > total) return false;
+      if (hdr & 128) {
+        if (pos + px > d.size()) return false;
+        for (int k = 0; k < cnt; k++) std::memcpy(&img[(out + k) * px], &d[pos], px);
+        pos += px;
+      } else {
+        if (pos + (size_t)cnt * px > d.size()) return false;
+        std::memcpy(&img[out * px], &d[pos], (size_t)cnt * px);
+        pos += (size_t)cnt * px;
+      }
+      out += (size_t)cnt;
+    }
+  }
+  const bool top_down = (desc & 0x20) != 0, right_left = (desc & 0x10) != 0;
+  rgb.resize(total * 3);
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    const unsigned char* p = &img[((size_t)(top_down ? y : h - 1 - y) * w + (size_t)(right_left ? w - 1 - x : x)) * px];
+    float* o = &rgb[((size_t)y * w + x) * 3];
+    if (grey) o[0] = o[1] = o[2] = (float)p[0] / 255.0f;
+    else { o[0] = (float)p[2] / 255.0f; o[1] = (float)p[1] / 255.0f; o[2] = (float)p[0] / 255.0f; }   // stored B, G, R
+  }
+  return true;
+}
+// imageio.rs:77-92 `read_image`: by extension.  PFM, PNG and TGA are read; HDR / EXR need codecs this build does not carry.
 static bool read_image_rgb(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
   auto ends = [&](const char* e) { size_t n = std::strlen(e); return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0; };
   if (ends(".pfm")) return read_pfm(fn, w, h, rgb);
   if (ends(".png")) return read_png(fn, w, h, rgb);
+  if (ends(".tga")) return read_tga(fn, w, h, rgb);
   return false;
 }
 

@@ -179,6 +179,23 @@ def test_png_reader_matches_the_generator(tmp_path):
     assert not sc.warnings
 
 
+def test_tga_reader(tmp_path):
+    rng = np.random.default_rng(4)
+    rgb = rng.integers(0, 256, (5, 6, 3), dtype=np.uint8)
+    hdr = bytes([0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 0, 5, 0, 24, 0])                     # raw true-colour, bottom-left origin
+    (tmp_path / "a.tga").write_bytes(hdr + rgb[::-1, :, ::-1].tobytes())
+    rle = bytearray([0, 0, 10, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 0, 5, 0, 24, 0x20])               # RLE, top-left origin
+    for y in range(5):
+        rle += bytes([0x80 | 1]) + bytes(rgb[y, 0, ::-1]) if (rgb[y, 0] == rgb[y, 1]).all() else bytes([1]) + rgb[y, 0:2, ::-1].tobytes()
+        rle += bytes([3]) + rgb[y, 2:6, ::-1].tobytes()
+    (tmp_path / "b.tga").write_bytes(bytes(rle))
+    for name in ("a.tga", "b.tga"):
+        sc = _scene(f'Texture "i" "spectrum" "imagemap" "string filename" "{name}" "bool gamma" "false"\n', search_dir=str(tmp_path))
+        t = sc.ir.textures[_row(sc, 5)]
+        assert (t.img_w, t.img_h) == (6, 5) and not sc.warnings
+        assert np.array_equal(np.ctypeslib.as_array(t.texels, shape=(5, 6, 3)), rgb[::-1].astype(np.float32) / np.float32(255))
+
+
 def test_front_end_texture_directive_semantics(tmp_path):
     sc = _scene('Texture "k" "spectrum" "constant" "rgb value" [0.1 0.2 0.3]\nTexture "f" "float" "constant" "float value" [0.7]\n'
                 'Texture "chk" "spectrum" "checkerboard"\nTexture "missing" "spectrum" "imagemap" "string filename" "nope.png"\n'
