@@ -25,5 +25,7 @@ for name, make in cases:
     if not same and lo_h.shape == lo_d.shape:
         bad = np.where((lo_h.view(np.uint32) != lo_d.view(np.uint32)).any(1) | (hi_h.view(np.uint32) != hi_d.view(np.uint32)).any(1))[0]
         print("   first differing nodes", bad[:5], lo_h[bad[:2]], lo_d[bad[:2]], hi_h[bad[:2]].view(np.uint32), hi_d[bad[:2]].view(np.uint32))
+    t0 = time.time(); dev.upload(sc); t_up = time.time() - t0
+    print(f"   rtgpu_upload_scene wall {t_up:.2f} s")
     print(f"{name}: prims {len(slot_h)} nodes host {lo_h.shape[0]} device {lo_d.shape[0]} identical={same}  host build {host_s*1e3:.1f} ms  device build (kernels) {dev_s*1e3:.2f} ms  "
           f"flatten wall host {t_host_flat:.2f} s device {t_dev_flat:.2f} s", flush=True)
