@@ -1,5 +1,7 @@
 // librtgpu.so — context, scene upload and the batched BVH::intersect / BVH::intersect_p entry points
 // (include/rtgpu.h).  Hand-written CUDA for sm_100a; compiled with -fmad=false.
+#include <atomic>
+#include <thread>
 #include "context.hpp"
 #include "trace_engine.cuh"
 #include <cstring>
@@ -176,6 +178,16 @@ static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_
 
 }  // namespace rt
 
+// Static split of [0, n) over the host threads for the per-node / per-slot staging loops of rtgpu_upload_scene.
+template <class F> static void parallel_for(size_t n, F body) {
+  int threads = (int)std::thread::hardware_concurrency();
+  if (threads <= 1 || n < ((size_t)1 << 16)) { body((size_t)0, n); return; }
+  const size_t chunk = (n + (size_t)threads - 1) / (size_t)threads;
+  std::vector<std::thread> pool;
+  for (size_t b = 0; b < n; b += chunk) pool.emplace_back([=, &body]() { body(b, std::min(n, b + chunk)); });
+  for (auto& t : pool) t.join();
+}
+
 template <class T> static int upload(rtgpu_ctx* ctx, const T* host, size_t count, const T** dev) {
   *dev = nullptr;
   if (count == 0 || host == nullptr) return 0;
@@ -259,10 +271,12 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   // interleave node_lo / node_hi into one 32-byte record per node (one DRAM sector per node visit)
   {
     std::vector<float> inter((size_t)s->n_nodes * 8);
-    for (size_t i = 0; i < s->n_nodes; i++) {
-      std::memcpy(&inter[i * 8], &s->node_lo[i * 4], 16);
-      std::memcpy(&inter[i * 8 + 4], &s->node_hi[i * 4], 16);
-    }
+    parallel_for(s->n_nodes, [&](size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; i++) {
+        std::memcpy(&inter[i * 8], &s->node_lo[i * 4], 16);
+        std::memcpy(&inter[i * 8 + 4], &s->node_hi[i * 4], 16);
+      }
+    });
     const float* p = nullptr;
     int rc = upload(ctx, inter.data(), inter.size(), &p); if (rc) return rc;
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `inter` dies at scope end
@@ -293,7 +307,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
         }
         level.swap(next);
       }
-      d.n_top = n_interior < (uint32_t)RT_ENGINE_TOP_NODES ? n_interior : (uint32_t)RT_ENGINE_TOP_NODES;
+      d.n_top = std::min<uint32_t>(n_interior, (uint32_t)RT_ENGINE_TOP_NODES);
     }
     for (size_t i = 0; i < nn; i++) if ((bits(s->node_hi[i * 4 + 3]) >> 2) == 0 && interior_index[i] == 0xffffffffu) interior_index[i] = n_interior++;
     auto ref_of = [&](size_t i) -> uint32_t {
@@ -305,24 +319,31 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     // shade-queue id of every slot's material in bits 2..4 of the second float4's w: the engine has that word in a register
     // when it records a hit, so classification needs no second look-up (hit slots are packed into 29 bits next to it)
     if (s->n_prims >= (1u << kHitSlotBits)) return fail(ctx, RTGPU_ERR_ARG, "more than 2^29 primitive slots");
-    for (size_t slot = 0; slot < s->n_prims; slot++) {
-      const uint32_t mrow = s->prim_info[slot * 4 + 1];
-      const uint32_t type = (mrow < s->n_materials && s->materials) ? s->materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
-      geom[slot * 12 + 7] = fbits(bits(geom[slot * 12 + 7]) | ((uint32_t)material_queue(type) << kGeomClassShift));
-    }
-    for (size_t i = 0; i < nn; i++) {
-      const uint32_t meta = bits(s->node_hi[i * 4 + 3]), n_prims = meta >> 2, off = bits(s->node_lo[i * 4 + 3]);
-      if (n_prims > 0) {
-        if ((size_t)off + n_prims > s->n_prims) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
-        geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | kGeomLastBit);
-        continue;
+    parallel_for(s->n_prims, [&](size_t s0, size_t s1) {
+      for (size_t slot = s0; slot < s1; slot++) {
+        const uint32_t mrow = s->prim_info[slot * 4 + 1];
+        const uint32_t type = (mrow < s->n_materials && s->materials) ? s->materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+        geom[slot * 12 + 7] = fbits(bits(geom[slot * 12 + 7]) | ((uint32_t)material_queue(type) << kGeomClassShift));
       }
-      const size_t L = i + 1, R = off;
-      if (L >= nn || R >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
-      float* w = &wide[(size_t)interior_index[i] * 16];
-      for (int k = 0; k < 3; k++) { w[k] = s->node_lo[L * 4 + k]; w[4 + k] = s->node_hi[L * 4 + k]; w[8 + k] = s->node_lo[R * 4 + k]; w[12 + k] = s->node_hi[R * 4 + k]; }
-      w[3] = fbits(ref_of(L)); w[7] = fbits(ref_of(R)); w[11] = fbits(meta & 3u); w[15] = 0.0f;
-    }
+    });
+    std::atomic<int> bad_nodes{0};                                    // every node writes its own wide record / its own leaf's last slot
+    parallel_for(nn, [&](size_t n0, size_t n1) {
+      for (size_t i = n0; i < n1; i++) {
+        const uint32_t meta = bits(s->node_hi[i * 4 + 3]), n_prims = meta >> 2, off = bits(s->node_lo[i * 4 + 3]);
+        if (n_prims > 0) {
+          if ((size_t)off + n_prims > s->n_prims) { bad_nodes = 1; continue; }
+          geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | kGeomLastBit);
+          continue;
+        }
+        const size_t L = i + 1, R = off;
+        if (L >= nn || R >= nn) { bad_nodes = 2; continue; }
+        float* w = &wide[(size_t)interior_index[i] * 16];
+        for (int k = 0; k < 3; k++) { w[k] = s->node_lo[L * 4 + k]; w[4 + k] = s->node_hi[L * 4 + k]; w[8 + k] = s->node_lo[R * 4 + k]; w[12 + k] = s->node_hi[R * 4 + k]; }
+        w[3] = fbits(ref_of(L)); w[7] = fbits(ref_of(R)); w[11] = fbits(meta & 3u); w[15] = 0.0f;
+      }
+    });
+    if (bad_nodes == 1) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
+    if (bad_nodes == 2) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
     d.root_ref = nn > 0 ? ref_of(0) : 0xffffffffu;
     // object instances: the engine's reference of each definition's root (a one-primitive definition is a one-slot leaf)
     if (s->n_instances && !s->instances) return fail(ctx, RTGPU_ERR_ARG, "instance table missing");
