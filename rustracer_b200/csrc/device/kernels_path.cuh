@@ -1,9 +1,6 @@
 // Material-sorted shading kernels of the path integrator (product code, sm_100a).
 #pragma once
 #include "shade_common.cuh"
-#if defined(RT_PATH_MAT) && RT_PATH_MAT == 6
-#include "texture.cuh"
-#endif
 
 namespace rt {
 
@@ -36,12 +33,7 @@ __global__ void __launch_bounds__(128, MAT == Q_LOBES ? RT_SHADE_MIN_BLOCKS_LOBE
       const uint2 sinf = p.w.sinfo[sample];
       SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = ps.w & 0xffffu; ss.d2 = ps.w >> 16; ss.da = 0;
       SurfHit si; float t_hit;
-#if defined(RT_PATH_MAT) && RT_PATH_MAT == 6
-      SurfTex st; rtgpu_lobe hit_lobes[rtml::kMaxLobes];
-      hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si, &st);
-#else
       hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
-#endif
       const uint4 info = p.sc.info[h.slot];
       Spec l_add = spec(0.0f);
       if ((bounces == 0 || specular_bounce) && info.z != kNoLight) l_add = beta * area_L(p.sc.lights[info.z], si.n, -ray.d);   // path.rs:127-131
@@ -54,17 +46,13 @@ __global__ void __launch_bounds__(128, MAT == Q_LOBES ? RT_SHADE_MIN_BLOCKS_LOBE
           alive = true;
         } else {
           Bsdf bsdf;
-#if defined(RT_PATH_MAT) && RT_PATH_MAT == 6
-          if (p.sc.materials[info.y].type == RTGPU_MAT_TEXTURED) {     // textures + bump map evaluated at this hit (texture.cuh)
-            RayDiff rd = no_diff();
-            if (ps.z & 2u) {                                           // still the ray k_raygen made: it has a differential (renderer.rs:110-111)
-              const float2 pf = p.w.pfilm[sample];
-              rd = camera_ray_diff(p.r2c, p.c2w, p.lens_radius, p.focal_distance, mk2(pf.x, pf.y), draw_2d(sinf.x, sinf.y, p.scfg, 1u), ray,
-                                   1.0f / sqrtf((float)p.scfg.spp));
-            }
-            make_bsdf_textured(p.sc, info.y, si, st, rd, true, hit_lobes, bsdf);
+          if (MAT == Q_LOBES && p.sc.materials[info.y].type == RTGPU_MAT_TEXTURED) {
+            // textures, bump map and lobe list were evaluated by the texture pass (kernels_tex.cuh): pick up the lobes and the bumped frame
+            const float4 f0 = p.w.tex_frame[2 * (size_t)slot], f1 = p.w.tex_frame[2 * (size_t)slot + 1];
+            si.ns = v3(f0.x, f0.y, f0.z); si.dpdu_s = v3(f1.x, f1.y, f1.z);
+            bsdf_init(bsdf, si, f0.w);
+            bsdf.g = p.w.tex_lobes + (size_t)slot * 8; bsdf.n = (int)__float_as_uint(f1.w);
           } else
-#endif
           make_bsdf(MAT == Q_LOBES ? (uint32_t)RTGPU_MAT_LOBES : (uint32_t)MAT, p.sc.materials[info.y], p.sc.lobes, si, true, bsdf);
           if (bsdf_num_components(bsdf, kBsdfNonSpecular) > 0 && p.sc.n_lights > 0) {   // path.rs:161-171 -> uniform_sample_one_light
             const Distrib dist = lookup_distrib(p, si.p);

@@ -32,6 +32,7 @@ void launch_shade_path_3(const RenderParams& p, int parity, unsigned blocks, cud
 void launch_shade_path_4(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
 void launch_shade_path_5(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
 void launch_shade_path_6(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);   // Q_LOBES
+void launch_eval_textured(const RenderParams& p, const uint32_t* list, unsigned blocks, cudaStream_t s);   // texture pass before launch_shade_path_6
 void launch_shade_recursive(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s);
 void launch_shade_ao(const RenderParams& p, unsigned blocks, cudaStream_t s);
 

@@ -60,7 +60,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   WaveView& v = w->v;
   if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
       (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)) &&
-      v.matsort_out != nullptr && v.matsort_bins >= ctx->scene.n_materials + 1)
+      v.matsort_out != nullptr && v.matsort_bins >= ctx->scene.n_materials + 1 && (v.tex_lobes != nullptr || recursive || !ctx->scene.texmats))
     return 0;
   release(w);
   int rc = 0;
@@ -70,6 +70,7 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
   if (recursive) { A(ray_o2, cap_items); A(ray_d2, cap_items); A(beta2, cap_items); A(pstate2, cap_items); }
   if (recursive && ctx->scene.texmats) { A(rdiff, (size_t)cap_items * 3); A(rdiff2, (size_t)cap_items * 3); }
+  if (!recursive && ctx->scene.texmats) { A(tex_lobes, (size_t)cap_items * 8); A(tex_frame, (size_t)cap_items * 2); }
   A(raysort_keys, cap_items); A(raysort_hist, (size_t)ray_sort_bins()); A(raysort_out, cap_items);
   A(matsort_hist, (size_t)ctx->scene.n_materials + 1); A(matsort_out, cap_items); v.matsort_bins = ctx->scene.n_materials + 1;
   A(L, cap_samples); A(pfilm, cap_samples); A(sinfo, cap_samples);
@@ -323,8 +324,12 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
             RT_LAUNCH(K_SHADE, launch_material_sort(p, p.w.matq[Q_LOBES], C_MATQ0 + Q_LOBES, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
             ctx->launches += 2;
             RenderParams ps = p; ps.w.matq[Q_LOBES] = p.w.matsort_out;
+            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(ps, ps.w.matq[Q_LOBES], pblocks, ctx->stream));
             RT_LAUNCH(K_SHADE, launch_shade_path_6(ps, in, pblocks, ctx->stream));
-          } else RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
+          } else {
+            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(p, p.w.matq[Q_LOBES], pblocks, ctx->stream));
+            RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
+          }
         }
         if (sc.n_lights > 0) {
           RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, ctx->stream));

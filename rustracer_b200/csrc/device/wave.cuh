@@ -45,6 +45,8 @@ struct WaveView {            // device pointers, passed to kernels by value
   uint32_t* matq[Q_COUNT];
   uint32_t *matsort_hist, *matsort_out;   // material sort of the listed-lobes queue (path) / of a level's items (recursive integrators)
   uint32_t matsort_bins;
+  rtgpu_lobe* tex_lobes;                  // path integrator, textured scenes: 8 lobe rows per item, written by k_eval_textured
+  float4* tex_frame;                      //   and 2 float4 per item: {bumped shading normal, Bsdf::eta}, {bumped shading dpdu, bits(lobe count)}
   uint32_t *raysort_keys, *raysort_hist, *raysort_out;   // option "sort_bounce_rays": binning of a bounce's rays before the closest-hit launch
   const uint32_t* item_order;             // recursive integrators: processing order of the level's items (or null)
   uint32_t* counters;
