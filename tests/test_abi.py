@@ -47,6 +47,22 @@ def test_struct_sizes_match_ctypes_mirror(native_libs):
     assert rd.tile_world == 1 and rd.sample_end == 4
 
 
+def test_every_ctypes_mirror_has_the_size_gcc_gives_the_header_struct(tmp_path):
+    """sizeof of every struct of include/rt_scene.h and include/rtgpu.h, from a C probe compiled here, against rustracer_b200/_abi.py."""
+    import subprocess
+    from rustracer_b200 import _abi as A
+    names = ["rt_transform", "rt_shape", "rt_area_light", "rt_light", "rt_texture", "rt_material", "rt_camera", "rt_film", "rt_sampler", "rt_integrator",
+             "rt_accel", "rt_scene", "rtgpu_ray", "rtgpu_hit", "rtgpu_quadric", "rtgpu_instance", "rtgpu_lobe", "rtgpu_texture", "rtgpu_material", "rtgpu_light",
+             "rtgpu_scene_desc", "rtgpu_render_desc", "rtgpu_stats"]
+    src = '#include <stdio.h>\n#include "rtgpu.h"\nint main(void) {\n' + "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n"
+    (tmp_path / "probe.c").write_text(src)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "probe"), str(tmp_path / "probe.c")], check=True)
+    out = subprocess.run([str(tmp_path / "probe")], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    wrong = {n: (int(sizes[n]), C.sizeof(getattr(A, n))) for n in names if int(sizes[n]) != C.sizeof(getattr(A, n))}
+    assert not wrong, wrong
+
+
 def test_no_gpu_means_loud_failure(native_libs):
     """The product path has no CPU fallback: without a CUDA device rtgpu_create fails and the binding raises."""
     import torch
