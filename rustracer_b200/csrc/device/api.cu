@@ -377,6 +377,11 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if ((rc = upload(ctx, s->textures, s->textures ? (size_t)s->n_textures : 0, &d.textures))) return rc;
   if ((rc = upload(ctx, s->tex_data, s->tex_data ? (size_t)s->n_tex_floats : 0, &d.tex_data))) return rc;
   d.n_textures = s->n_textures;
+  for (uint32_t i = 0; i < s->n_lights && s->lights; i++) {           // the env-map lookup wraps with a mask (lights.cuh env_texel)
+    const rtgpu_light& l = s->lights[i];
+    if (l.kind == RTGPU_LIGHT_INFINITE && (l.env_w == 0 || l.env_h == 0 || (l.env_w & (l.env_w - 1)) || (l.env_h & (l.env_h - 1))))
+      return fail(ctx, RTGPU_ERR_UNSUPPORTED, "infinite light: environment map sides must be powers of two (resample first, as MIPMap::new does)");
+  }
   if ((rc = upload(ctx, s->lights, (size_t)s->n_lights, &d.lights))) return rc;
   if ((rc = upload(ctx, s->env_data, (size_t)s->n_env_floats, &d.env))) return rc;
   d.n_nodes = s->n_nodes; d.n_prims = s->n_prims; d.n_quadrics = s->n_quadrics; d.n_materials = s->n_materials; d.n_lights = s->n_lights;

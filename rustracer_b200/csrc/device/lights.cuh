@@ -162,8 +162,7 @@ RT_DEV int dist1d_sample_discrete(const float* func, const float* cdf, int n, fl
 // ---- InfiniteAreaLight (light/infinite.rs) -------------------------------------------------------------------
 // MIPMap::lookup(st, 0.0) == level-0 bilinear with Repeat wrap on this path (mipmap.rs:227-245,285-309)
 RT_DEV Spec env_texel(const float* tex, int w, int h, int s, int t) {
-  int ss = s % w; if (ss < 0) ss += w;
-  int tt = t % h; if (tt < 0) tt += h;
+  const int ss = s & (w - 1), tt = t & (h - 1);                       // `modulo` (mipmap.rs:455-462): map sides are powers of two (checked by the host)
   const float* p = tex + ((size_t)tt * w + ss) * 3;
   return spec(p[0], p[1], p[2]);
 }

@@ -60,13 +60,17 @@ struct SurfTex {
 // ---- Triangle (shapes/mesh.rs) -----------------------------------------------------------------------
 // Front half shared by Triangle::intersect (:215-319) and Triangle::intersect_p (:428-536): returns the
 // barycentrics and t of an accepted hit.
+// Vector3::permute(kx, ky, kz) for the watertight test's cyclic choice kx = kz + 1, ky = kx + 1 (mesh.rs:229-238): a
+// rotation of the components selected by two predicates (six selects per vector instead of three dynamic index chains).
+RT_DEV V3 permute_cyclic(V3 v, int kz) {
+  const bool r1 = kz == 0, r2 = kz == 1;
+  return v3(r1 ? v.y : (r2 ? v.z : v.x), r1 ? v.z : (r2 ? v.x : v.y), r1 ? v.x : (r2 ? v.y : v.z));
+}
 RT_DEV bool tri_hit_test(V3 p0, V3 p1, V3 p2, const Ray& ray, float& b0, float& b1, float& b2, float& t) {
   V3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
   int kz = max_dimension(vabs(ray.d));
-  int kx = kz + 1; if (kx == 3) kx = 0;
-  int ky = kx + 1; if (ky == 3) ky = 0;
-  V3 d = permute(ray.d, kx, ky, kz);
-  p0t = permute(p0t, kx, ky, kz); p1t = permute(p1t, kx, ky, kz); p2t = permute(p2t, kx, ky, kz);
+  V3 d = permute_cyclic(ray.d, kz);                                   // kx = kz + 1, ky = kx + 1 (mod 3)
+  p0t = permute_cyclic(p0t, kz); p1t = permute_cyclic(p1t, kz); p2t = permute_cyclic(p2t, kz);
   float sx = -d.x / d.z, sy = -d.y / d.z, sz = 1.0f / d.z;
   p0t.x += sx * p0t.z; p0t.y += sy * p0t.z;
   p1t.x += sx * p1t.z; p1t.y += sy * p1t.z;
@@ -111,18 +115,12 @@ RT_DEV bool tri_hit_test(V3 p0, V3 p1, V3 p2, const Ray& ray, float& b0, float& 
 struct TriRay {
   V3 o; int kx, ky, kz; float sx, sy, sz;
 };
-// Vector3::permute(kx, ky, kz) for the watertight test's cyclic choice kx = kz + 1, ky = kx + 1 (mesh.rs:229-238): a
-// rotation of the components selected by two predicates (six selects per vector instead of three dynamic index chains).
-RT_DEV V3 permute_cyclic(V3 v, int kz) {
-  const bool r1 = kz == 0, r2 = kz == 1;
-  return v3(r1 ? v.y : (r2 ? v.z : v.x), r1 ? v.z : (r2 ? v.x : v.y), r1 ? v.x : (r2 ? v.y : v.z));
-}
 RT_DEV TriRay make_tri_ray(const Ray& ray) {
   TriRay tr; tr.o = ray.o;
   tr.kz = max_dimension(vabs(ray.d));
   tr.kx = tr.kz + 1; if (tr.kx == 3) tr.kx = 0;
   tr.ky = tr.kx + 1; if (tr.ky == 3) tr.ky = 0;
-  V3 d = permute(ray.d, tr.kx, tr.ky, tr.kz);
+  V3 d = permute_cyclic(ray.d, tr.kz);
   tr.sx = -d.x / d.z; tr.sy = -d.y / d.z; tr.sz = 1.0f / d.z;
   return tr;
 }
