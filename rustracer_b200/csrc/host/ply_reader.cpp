@@ -115,27 +115,68 @@ void read_ply(const std::string& filename, PlyMesh& out) {
       out.P.assign(e.count * 3, 0.0f);
       if (has_normals) out.N.assign(e.count * 3, 0.0f);
       if (has_texture) out.uv.assign(e.count * 2, 0.0f);
+      // where each property goes, decided once per element instead of once per vertex: 0-2 P, 3-5 N, 6-7 uv, -1 read and dropped
+      std::vector<int> dest(e.props.size(), -1);
+      for (size_t k = 0; k < e.props.size(); k++) {
+        const Prop& p = e.props[k];
+        if (p.is_list || p.type != S_F32) continue;                  // only ply::Property::Float is consumed (plymesh.rs:202-221)
+        const std::string& n = p.name;
+        if (n == "x") dest[k] = 0; else if (n == "y") dest[k] = 1; else if (n == "z") dest[k] = 2;
+        else if (has_normals && n == "nx") dest[k] = 3; else if (has_normals && n == "ny") dest[k] = 4; else if (has_normals && n == "nz") dest[k] = 5;
+        else if (has_texture && (n == "u" || n == "texture_u" || n == "s" || n == "texture_s")) dest[k] = 6;
+        else if (has_texture && (n == "v" || n == "t" || n == "texture_v" || n == "texture_t")) dest[k] = 7;
+      }
+      bool plain_f32 = r.fmt == 1;                                   // fast path: little-endian records of float32 scalars only
+      for (const Prop& p : e.props) plain_f32 = plain_f32 && !p.is_list && p.type == S_F32;
+      if (plain_f32) {
+        const size_t np = e.props.size(), stride = 4 * np;
+        if ((size_t)(r.end - r.p) < stride * e.count) throw ParseError("PLY: unexpected end of data");
+        for (size_t i = 0; i < e.count; i++, r.p += stride)
+          for (size_t k = 0; k < np; k++) {
+            const int d = dest[k];
+            if (d < 0) continue;
+            float fv; std::memcpy(&fv, r.p + 4 * k, 4);
+            if (d < 3) out.P[3 * i + d] = fv; else if (d < 6) out.N[3 * i + d - 3] = fv; else out.uv[2 * i + d - 6] = fv;
+          }
+        continue;
+      }
       for (size_t i = 0; i < e.count; i++) {
-        for (const Prop& p : e.props) {
-          if (p.is_list) { size_t n = (size_t)r.scalar(p.count_type); for (size_t k = 0; k < n; k++) r.scalar(p.type); continue; }
-          double v = r.scalar(p.type);
-          if (p.type != S_F32) continue;                             // only ply::Property::Float is consumed (plymesh.rs:202-221)
-          float fv = (float)v;
-          const std::string& n = p.name;
-          if (n == "x") out.P[3 * i] = fv; else if (n == "y") out.P[3 * i + 1] = fv; else if (n == "z") out.P[3 * i + 2] = fv;
-          else if (has_normals && n == "nx") out.N[3 * i] = fv; else if (has_normals && n == "ny") out.N[3 * i + 1] = fv; else if (has_normals && n == "nz") out.N[3 * i + 2] = fv;
-          else if (has_texture && (n == "u" || n == "texture_u" || n == "s" || n == "texture_s")) out.uv[2 * i] = fv;
-          else if (has_texture && (n == "v" || n == "t" || n == "texture_v" || n == "texture_t")) out.uv[2 * i + 1] = fv;
+        for (size_t k = 0; k < e.props.size(); k++) {
+          const Prop& p = e.props[k];
+          if (p.is_list) { size_t n = (size_t)r.scalar(p.count_type); for (size_t j = 0; j < n; j++) r.scalar(p.type); continue; }
+          const double v = r.scalar(p.type);
+          const int d = dest[k];
+          if (d < 0) continue;
+          const float fv = (float)v;
+          if (d < 3) out.P[3 * i + d] = fv; else if (d < 6) out.N[3 * i + d - 3] = fv; else out.uv[2 * i + d - 6] = fv;
         }
       }
     } else if (e.name == "face") {
       out.indices.reserve(e.count * 3);
+      std::vector<char> takes(e.props.size(), 0);
+      for (size_t k = 0; k < e.props.size(); k++)
+        takes[k] = e.props[k].is_list && e.props[k].name == "vertex_indices" && (e.props[k].type == S_I32 || e.props[k].type == S_U32);   // ListInt / ListUInt only (plymesh.rs:233-240)
+      if (r.fmt == 1 && e.props.size() == 1 && takes[0] && e.props[0].count_type == S_U8) {   // fast path: `list uchar int vertex_indices`, little-endian
+        for (size_t i = 0; i < e.count; i++) {
+          if (r.p >= r.end) throw ParseError("PLY: unexpected end of data");
+          const size_t n = *r.p++;
+          if ((size_t)(r.end - r.p) < 4 * n) throw ParseError("PLY: unexpected end of data");
+          if (n == 3 || n == 4) {
+            int32_t v[4]; std::memcpy(v, r.p, 4 * n);
+            out.indices.push_back(v[0]); out.indices.push_back(v[1]); out.indices.push_back(v[2]);
+            if (n == 4) { out.indices.push_back(v[3]); out.indices.push_back(v[0]); out.indices.push_back(v[2]); }
+          }
+          r.p += 4 * n;
+        }
+        continue;
+      }
       for (size_t i = 0; i < e.count; i++) {
         face.clear();
-        for (const Prop& p : e.props) {
+        for (size_t pk = 0; pk < e.props.size(); pk++) {
+          const Prop& p = e.props[pk];
           if (!p.is_list) { r.scalar(p.type); continue; }
           size_t n = (size_t)r.scalar(p.count_type);
-          bool take = p.name == "vertex_indices" && (p.type == S_I32 || p.type == S_U32);   // ListInt / ListUInt only (plymesh.rs:233-240)
+          const bool take = takes[pk] != 0;
           if (take) face.clear();
           for (size_t k = 0; k < n; k++) { double v = r.scalar(p.type); if (take) face.push_back((int32_t)(uint32_t)(int64_t)v); }
         }
