@@ -84,3 +84,47 @@ def test_middle_split_matches_or_rejects(native_libs):
         assert "middle" in str(e)
         return
     _compare(sc)
+
+
+def test_itertools_partition_has_the_closed_form_the_device_builder_uses():
+    """csrc/device/bvh_build.cu replaces itertools::partition (0.10.3: front scan for a failing element, back scan for a passing one,
+    swap — bvh/mod.rs:187,267 call it) by: with m passing elements, the k-th failing element of [0, m) in ascending order is exchanged
+    with the k-th passing element of [m, n) in descending order.  Checked here against the sequential algorithm on random inputs."""
+    rng = np.random.default_rng(9)
+
+    def sequential(items, pred):
+        a = list(items)
+        front, back, passed = 0, len(a), 0
+        while front < back:
+            if not pred(a[front]):
+                swapped = False
+                while front + 1 < back:
+                    back -= 1
+                    if pred(a[back]):
+                        a[front], a[back] = a[back], a[front]
+                        swapped = True
+                        break
+                if not swapped:
+                    return a, passed
+            passed += 1
+            front += 1
+        return a, passed
+
+    def closed_form(items, pred):
+        a = list(items)
+        ok = [pred(x) for x in a]
+        m = sum(ok)
+        fails = [i for i in range(m) if not ok[i]]                     # ascending
+        passes = [i for i in range(len(a) - 1, m - 1, -1) if ok[i]]    # descending
+        assert len(fails) == len(passes)
+        for i, j in zip(fails, passes):
+            a[i], a[j] = a[j], a[i]
+        return a, m
+
+    for n in list(range(0, 12)) + [33, 100, 257]:
+        for _ in range(40):
+            keys = rng.integers(0, 12, n)
+            thr = int(rng.integers(0, 12))
+            items = list(zip(keys.tolist(), range(n)))                 # (bucket, identity)
+            pred = lambda x: x[0] <= thr
+            assert sequential(items, pred) == closed_form(items, pred)
