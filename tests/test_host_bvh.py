@@ -128,3 +128,43 @@ def test_itertools_partition_has_the_closed_form_the_device_builder_uses():
             items = list(zip(keys.tolist(), range(n)))                 # (bucket, identity)
             pred = lambda x: x[0] <= thr
             assert sequential(items, pred) == closed_form(items, pred)
+
+
+def test_external_builder_hook_round_trips_the_host_tree(native_libs, tmp_path):
+    """rth_flatten_with_builder (the hook rtgpu_build_bvh plugs into): a builder that hands back the host builder's own tree must give
+    the same flattened scene; the primitive bounds it receives are the world bounds of the primitive list; a failing builder is an error."""
+    import ctypes as C
+    from rustracer_b200 import Scene, scenes
+    from rustracer_b200.host import _lib, SceneError
+    sc = Scene.from_string(scenes.c3_scene(str(tmp_path), level=1, xres=16, yres=16, spp=1), search_dir=str(tmp_path))
+    sc.flatten()
+    lo, hi = sc.nodes()
+    slot_of_prim = sc.slot_of_prim()
+    geom = sc.prim_geom().copy()
+    ordered = np.empty_like(slot_of_prim)
+    ordered[slot_of_prim] = np.arange(len(slot_of_prim), dtype=slot_of_prim.dtype)
+    seen = {}
+    BUILDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                          C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+
+    def builder(user, bounds, n, max_prims, node_lo, node_hi, out_ordered, n_nodes, ms):
+        seen["n"], seen["max_prims"] = n, max_prims
+        seen["bounds"] = np.ctypeslib.as_array(bounds, shape=(n, 6)).copy()
+        np.ctypeslib.as_array(node_lo, shape=(lo.shape[0], 4))[:] = lo
+        np.ctypeslib.as_array(node_hi, shape=(hi.shape[0], 4))[:] = hi
+        np.ctypeslib.as_array(out_ordered, shape=(n,))[:] = ordered
+        n_nodes[0] = lo.shape[0]
+        ms[0] = 1.5
+        return 0
+
+    cb = BUILDER(builder)
+    assert _lib().rth_flatten_with_builder(sc._h, 0, C.cast(cb, C.c_void_p), None) == 0
+    lo2, hi2 = sc.nodes()
+    assert np.array_equal(lo.view(np.uint32), lo2.view(np.uint32)) and np.array_equal(hi.view(np.uint32), hi2.view(np.uint32))
+    assert np.array_equal(sc.slot_of_prim(), slot_of_prim) and np.array_equal(sc.prim_geom(), geom)
+    assert seen["n"] == len(slot_of_prim) and seen["max_prims"] == 4 and abs(sc.bvh_build_seconds - 1.5e-3) < 1e-9
+    tri = geom[slot_of_prim].reshape(-1, 3, 4)[:, :, :3]                         # world-space vertices of primitive pn
+    assert np.array_equal(seen["bounds"][:, :3], tri.min(1)) and np.array_equal(seen["bounds"][:, 3:], tri.max(1))
+    fail = BUILDER(lambda *a: -4)
+    assert _lib().rth_flatten_with_builder(sc._h, 0, C.cast(fail, C.c_void_p), None) != 0
+    assert "external BVH builder failed" in _lib().rth_last_error().decode()
