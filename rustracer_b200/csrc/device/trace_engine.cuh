@@ -184,6 +184,10 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     if (m_l == 0u || __popc(m_n) >= node_threshold) {
       // ---- node step: one wide node = both children's slab tests ----------------------------------------------
       if (!(cur & kLeafBit)) {
+        // the stack top, read by every lane of the step while the node is in flight: a lane whose two children both miss takes it
+        // from here instead of running the pop loop on its own (profiles/r01r: the divergent pop was 8 % of the issue slots at 5 lanes)
+        const bool top_in_smem = sp > 0 && sp <= RT_ENGINE_SMEM_DEPTH;
+        const uint2 top = top_in_smem ? s_stack[sp - 1][tid] : make_uint2(kExitInstance, 0u);
         float4 a, b, c, d;
 #if RT_ENGINE_TOP_NODES > 0
         if (cur < n_top) { a = s_top[4 * cur]; b = s_top[4 * cur + 1]; c = s_top[4 * cur + 2]; d = s_top[4 * cur + 3]; }
@@ -221,6 +225,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
           }
           cur = first;
         } else if (hsecond) cur = second;
+        else if (top_in_smem && top.x != kExitInstance && (ANY || __uint_as_float(top.y) < ray.t_max)) { cur = top.x; --sp; }   // == the first iteration of the pop loop
         else RT_ENGINE_POP();
       }
     } else if ((cur & kLeafBit) != 0u && cur != kDoneRef) {
