@@ -11,13 +11,27 @@ namespace rt {
 #ifndef RT_SHADE_MIN_BLOCKS_LOBES
 #define RT_SHADE_MIN_BLOCKS_LOBES 8   // the listed-lobes / textured kernel is instruction-fetch bound: more resident warps (64 registers) win 5-20 % (profiles/r01o)
 #endif
+#ifndef RT_LOBES_THREADS
+#define RT_LOBES_THREADS 512         // block size of the listed-lobes kernel; its warps start every iteration together (below)
+#endif
+#ifndef RT_SHADE_THREADS
+#define RT_SHADE_THREADS 512         // block size of the per-material kernels; above 128 their warps also start every iteration together
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(128, MAT == Q_LOBES ? RT_SHADE_MIN_BLOCKS_LOBES : RT_SHADE_MIN_BLOCKS) k_shade_path(RenderParams p, int parity) {
+__global__ void __launch_bounds__(MAT == Q_LOBES ? RT_LOBES_THREADS : RT_SHADE_THREADS,
+                                  MAT == Q_LOBES ? RT_SHADE_MIN_BLOCKS_LOBES * 128 / RT_LOBES_THREADS : RT_SHADE_MIN_BLOCKS * 128 / RT_SHADE_THREADS)
+k_shade_path(RenderParams p, int parity) {
   const uint32_t n = p.w.counters[C_MATQ0 + MAT];
   uint32_t* out_list = p.w.list[1 - parity];
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
   const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;            // `max_ray_depth as u8` (path.rs:42)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+  // Block-uniform trip count.  The shade kernels run a long straight-line body and are (partly) instruction-fetch bound
+  // (profiles/r01l_SUMMARY.md): the 16 warps of a 512-thread block start every iteration together, so an instruction-cache line is
+  // fetched once per block instead of once per warp.  128 -> 512 threads with the barrier: listed lobes -20 %, textured -19 %, the
+  // per-material kernels -14 % on a five-material scene and unchanged on the all-matte C3 scene.
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    if (MAT == Q_LOBES || RT_SHADE_THREADS > 128) __syncthreads();
+    const uint32_t i = base + threadIdx.x;
     bool alive = false;
     uint32_t slot = 0;
     if (i < n) {

@@ -13,8 +13,11 @@ namespace rt {
 #ifndef RT_REC_MIN_BLOCKS
 #define RT_REC_MIN_BLOCKS 8          // 64 registers: 4 / 8 / 12 / 16 blocks per SM measured in profiles/r01o
 #endif
+#ifndef RT_REC_THREADS
+#define RT_REC_THREADS 512           // the warps of a block start every iteration together (instruction-cache reuse, see kernels_path.cuh)
+#endif
 template <bool TEX>
-__global__ void __launch_bounds__(128, RT_REC_MIN_BLOCKS) k_shade_recursive(RenderParams p, int parity) {
+__global__ void __launch_bounds__(RT_REC_THREADS, RT_REC_MIN_BLOCKS * 128 / RT_REC_THREADS) k_shade_recursive(RenderParams p, int parity) {
   const uint32_t n = p.w.counters[C_LIVE0 + parity];
   const float4* ray_o = parity ? p.w.ray_o2 : p.w.ray_o; const float4* ray_d = parity ? p.w.ray_d2 : p.w.ray_d;
   const float4* beta_in = parity ? p.w.beta2 : p.w.beta; const uint4* ps_in = parity ? p.w.pstate2 : p.w.pstate;
@@ -22,7 +25,10 @@ __global__ void __launch_bounds__(128, RT_REC_MIN_BLOCKS) k_shade_recursive(Rend
   float4* obeta = parity ? p.w.beta : p.w.beta2; uint4* ops = parity ? p.w.pstate : p.w.pstate2;
   uint32_t* out_count = &p.w.counters[C_LIVE0 + (1 - parity)];
   const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    __syncthreads();
+    const uint32_t k = base + threadIdx.x;
+    if (k >= n) continue;
     const uint32_t i = p.w.item_order ? p.w.item_order[k] : k;           // items in material order (k_matsort_*)
     Ray ray = load_ray(ray_o, ray_d, i, nullptr);
     ray.t_max = inf_f();

@@ -10,10 +10,16 @@
 
 namespace rt {
 
-__global__ void __launch_bounds__(128, 8) k_eval_textured(RenderParams p, const uint32_t* __restrict__ list) {
+#ifndef RT_TEX_THREADS
+#define RT_TEX_THREADS 512           // the warps of a block start every iteration together (instruction-cache reuse, see kernels_path.cuh)
+#endif
+__global__ void __launch_bounds__(RT_TEX_THREADS, 1024 / RT_TEX_THREADS) k_eval_textured(RenderParams p, const uint32_t* __restrict__ list) {
   const uint32_t n = p.w.counters[C_MATQ0 + Q_LOBES];
   const uint32_t max_depth = (uint32_t)p.max_depth & 0xffu;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    __syncthreads();
+    const uint32_t i = base + threadIdx.x;
+    if (i >= n) continue;
     const uint32_t slot = list[i];
     const HitRec h = p.w.hit[slot];
     const uint4 info = p.sc.info[h.slot];

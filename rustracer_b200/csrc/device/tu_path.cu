@@ -10,6 +10,7 @@
 
 namespace rt {
 void RT_CAT(launch_shade_path_, RT_PATH_MAT)(const RenderParams& p, int parity, unsigned blocks, cudaStream_t s) {
-  k_shade_path<RT_PATH_MAT><<<blocks, 128, 0, s>>>(p, parity);
+  constexpr unsigned threads = RT_PATH_MAT == 6 ? RT_LOBES_THREADS : RT_SHADE_THREADS;
+  k_shade_path<RT_PATH_MAT><<<blocks * 128 / threads, threads, 0, s>>>(p, parity);
 }
 }  // namespace rt
