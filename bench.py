@@ -195,6 +195,8 @@ def run_ours(a):
     sc = build_scene(a, tmp)
     sc.flatten()
     dev = Device(local).upload(sc)
+    for kv in filter(None, os.environ.get("RT_OPTIONS", "").split(",")):        # A/B runs: RT_OPTIONS=overlap_bounces=0,node_threshold=12
+        dev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     rd = sc.render_desc()
     rd.seed = 1
     spp = a.spp_per_step

@@ -220,6 +220,8 @@ int rtgpu_create(int device, rtgpu_ctx** out) {
   if (!ctx) return RTGPU_ERR_OOM;
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx; return RTGPU_ERR_CUDA;
   }
@@ -233,6 +235,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   if (!ctx) return RTGPU_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->side_stream);
   free_scene(ctx);
   rt::free_wave_buffers(ctx);
   if (ctx->film) cudaFree(ctx->film);
@@ -240,6 +243,8 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   if (ctx->scratch_hits) cudaFree(ctx->scratch_hits);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+  cudaStreamDestroy(ctx->side_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return RTGPU_OK;
@@ -252,6 +257,7 @@ int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_items") == 0) { ctx->sort_items = value; return RTGPU_OK; }
+  if (std::strcmp(name, "overlap_bounces") == 0) { ctx->overlap_bounces = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_bounce_rays") == 0) { ctx->sort_bounce_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "node_threshold") == 0) { ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK; }
   if (std::strcmp(name, "refill_threshold") == 0) { ctx->refill_threshold = value; ctx->scene.tune_refill_threshold = value; return RTGPU_OK; }

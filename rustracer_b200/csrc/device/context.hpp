@@ -1,4 +1,4 @@
-// Per-GPU context of librtgpu.so (product code).  One context owns one CUDA stream, the device copy of the
+// Per-GPU context of librtgpu.so (product code).  One context owns its CUDA streams (main + one side stream), the device copy of the
 // flattened scene, the film accumulator and the wavefront queues.
 #pragma once
 #include <cuda_runtime.h>
@@ -14,7 +14,9 @@ struct WaveBuffers;   // render.cu
 struct rtgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;        // path integrator: secondary traces of a bounce, beside the next closest-hit launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string error;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -39,6 +41,7 @@ struct rtgpu_ctx {
   int simple_traversal = 0;   // 1 = one-thread-one-ray reference walk everywhere (validation); 0 = persistent engine
   int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
   int sort_bounce_rays = 0;   // rtgpu_render (path): bin the rays of bounces >= 1 by origin cell + direction octant before tracing (profiles/r01q)
+  int overlap_bounces = 1;    // rtgpu_render (path): shadow / MIS traces of bounce b on a second stream, beside closest-hit + classify of bounce b + 1
   int sort_items = 1;   // rtgpu_render: counting sort of the listed-lobes queue / of the recursive integrators' items by material row
 };
 

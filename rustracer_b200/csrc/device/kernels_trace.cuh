@@ -436,20 +436,30 @@ __global__ void __launch_bounds__(128) k_shade_miss(RenderParams p) {
 }
 
 // End of a bounce: fold the queue sizes into the reference's ray counters and reset the per-bounce queues.
-__global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera) {
+// part bit 0: the live list, the material queues and the closest-hit cursor (what the next bounce's closest-hit launch needs);
+// part bit 1: the shadow / MIS queues and their cursors.  The path integrator runs the two halves on two streams
+// (render.cu: the secondary traces of bounce b overlap the closest-hit launch of bounce b + 1), hence the atomic adds.
+__global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera, int part) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint32_t* c = p.w.counters;
-  const uint32_t live = c[live_idx];
-  // MIS rays towards infinite lights travel in the shadow queue (shade_common.cuh) but are "regular" rays for the reference
-  p.w.stats[S_REGULAR] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis) + min(c[C_MIS_ANY], p.w.cap_mis) + c[C_MIS_SKIPPED];
-  p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
-  p.w.stats[S_CLOSEST_RAYS] += (unsigned long long)live + min(c[C_MIS], p.w.cap_mis);
-  p.w.stats[S_ANY_RAYS] += (unsigned long long)min(c[C_SHADOW], p.w.cap_shadow) + min(c[C_MIS_ANY], p.w.cap_mis);
-  if (count_camera) p.w.stats[S_CAMERA] += live;
   if (c[C_OVERFLOW]) p.w.stats[S_OVERFLOW] = 1;
-  c[live_idx] = 0;
-  for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;
-  c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MIS_ANY] = 0; c[C_MIS_SKIPPED] = 0; c[C_CUR_CLOSEST] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0; c[C_CUR_MISANY] = 0;
+  if (part & 1) {
+    const uint32_t live = c[live_idx];
+    atomicAdd(&p.w.stats[S_REGULAR], (unsigned long long)live);
+    atomicAdd(&p.w.stats[S_CLOSEST_RAYS], (unsigned long long)live);
+    if (count_camera) p.w.stats[S_CAMERA] += live;
+    c[live_idx] = 0;
+    for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;
+    c[C_CUR_CLOSEST] = 0;
+  }
+  if (part & 2) {
+    // MIS rays towards infinite lights travel in the shadow queue (shade_common.cuh) but are "regular" rays for the reference
+    atomicAdd(&p.w.stats[S_REGULAR], (unsigned long long)min(c[C_MIS], p.w.cap_mis) + min(c[C_MIS_ANY], p.w.cap_mis) + c[C_MIS_SKIPPED]);
+    p.w.stats[S_SHADOW] += min(c[C_SHADOW], p.w.cap_shadow);
+    atomicAdd(&p.w.stats[S_CLOSEST_RAYS], (unsigned long long)min(c[C_MIS], p.w.cap_mis));
+    p.w.stats[S_ANY_RAYS] += (unsigned long long)min(c[C_SHADOW], p.w.cap_shadow) + min(c[C_MIS_ANY], p.w.cap_mis);
+    c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MIS_ANY] = 0; c[C_MIS_SKIPPED] = 0; c[C_CUR_ANY] = 0; c[C_CUR_MIS] = 0; c[C_CUR_MISANY] = 0;
+  }
 }
 
 // ---- film (film.rs) -----------------------------------------------------------------------------------------------

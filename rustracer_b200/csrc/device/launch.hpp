@@ -17,7 +17,7 @@ void launch_material_sort(const RenderParams& p, const uint32_t* list, int count
 uint32_t ray_sort_bins();
 void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* keys, uint32_t* hist, uint32_t* out, unsigned blocks, cudaStream_t s);
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);
-void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s);
+void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, int part, cudaStream_t s);
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s);
 void launch_film_add(const FilmParams& f, const float4* L, const float2* pfilm, uint32_t n, cudaStream_t s);
 void launch_li_out(const float4* L, float ao_div, uint32_t n, float* out, cudaStream_t s);

@@ -302,7 +302,13 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     RT_LAUNCH(K_OTHER, launch_raygen(p, ctx->stream));
     if (rd->integrator == RTGPU_INTEGRATOR_PATH) {
       const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
-      for (uint32_t b = 0; b < rounds; b++) {
+      // Two streams: the shadow / MIS traces of bounce b (side stream, in the reference's order of additions to L) run beside the
+      // closest-hit launch and the classification of bounce b + 1; they join before anything of bounce b + 1 touches L or the
+      // shadow / MIS queues again.  The late bounces are short queues whose launches are bound by one warp's walk, not by the
+      // machine (profiles/r01z launch list).  Per-class timing (`profile`) and ray binning keep the single-stream order.
+      const bool overlap = ctx->overlap_bounces && !prof && !ctx->sort_bounce_rays && sc.n_lights > 0;
+      bool joined = true;
+      auto trace_closest = [&](uint32_t b) {
         const int in = (int)(b & 1u);
         const uint32_t* live = p.w.list[in];
         if (ctx->sort_bounce_rays && b >= 1) {                        // camera rays are coherent as generated
@@ -312,6 +318,11 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         }
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, live, C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
         RT_LAUNCH(K_SHADE, launch_classify(p, live, C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, ctx->stream));
+      };
+      for (uint32_t b = 0; b < rounds; b++) {
+        const int in = (int)(b & 1u);
+        if (b == 0 || !overlap) trace_closest(b);                     // overlap: bounce b >= 1 was traced beside the secondary rays of b - 1
+        if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
         RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
         if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
         if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));
@@ -331,13 +342,22 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
             RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
           }
         }
+        cudaStream_t sec = ctx->stream;
+        if (overlap) { sec = ctx->side_stream; cudaEventRecord(ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(sec, ctx->ev_fork, 0); }
         if (sc.n_lights > 0) {
-          RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, ctx->stream));
-          if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, ctx->stream));
-          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, ctx->stream));
+          RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, sec));
+          if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, sec));
+          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, sec));
         }
-        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, ctx->stream));
+        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 3, ctx->stream));
+        else {
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, 0, 2, sec));
+          cudaEventRecord(ctx->ev_join, sec); joined = false;
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 1, ctx->stream));
+          if (b + 1 < rounds) trace_closest(b + 1);
+        }
       }
+      if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
     } else if (plan.recursive) {
       const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
@@ -352,13 +372,13 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, ctx->stream));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, ctx->stream));
-        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, ctx->stream));
+        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 3, ctx->stream));
       }
     } else {
       RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
       RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));
       if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
-      RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, ctx->stream));
+      RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, 3, ctx->stream));
     }
     waves++;
     return check_cuda(ctx, cudaGetLastError(), "kernel launch");

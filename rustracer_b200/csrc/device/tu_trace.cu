@@ -57,7 +57,7 @@ void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx,
   k_raysort_scatter<<<blocks, 256, 0, s>>>(p, list, count_idx, keys, hist, out);
 }
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) { k_shade_miss<<<blocks, 128, 0, s>>>(p); }
-void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera); }
+void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, int part, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera, part); }
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s) {
   const size_t n_voxels = (size_t)nvx * nvy * nvz, total = n_voxels * sc.n_lights;
   k_lightgrid_contrib<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(sc, nvx, nvy, nvz, table);
