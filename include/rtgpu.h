@@ -230,6 +230,8 @@ int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, 
                     uint32_t* n_nodes, float* build_ms);
 /* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
  * "sort_items" (1 = rtgpu_render sorts the listed-lobes shade queue / the recursive integrators' items by material; default 1),
+ * "overlap_bounces" (path integrator: 0 = every launch on one stream; 1 = the shadow / MIS traces of bounce b on a second stream beside
+ *   the closest-hit launch of bounce b + 1; 2 = also the closest-hit MIS rays beside the any-hit MIS rays; default 2; results identical),
  * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
  * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);

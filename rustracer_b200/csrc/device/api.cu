@@ -221,6 +221,8 @@ int rtgpu_create(int device, rtgpu_ctx** out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx; return RTGPU_ERR_CUDA;
@@ -236,6 +238,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side_stream);
+  cudaStreamSynchronize(ctx->side_stream2);
   free_scene(ctx);
   rt::free_wave_buffers(ctx);
   if (ctx->film) cudaFree(ctx->film);
@@ -243,8 +246,8 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   if (ctx->scratch_hits) cudaFree(ctx->scratch_hits);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
-  cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
-  cudaStreamDestroy(ctx->side_stream);
+  cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2);
+  cudaStreamDestroy(ctx->side_stream); cudaStreamDestroy(ctx->side_stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return RTGPU_OK;

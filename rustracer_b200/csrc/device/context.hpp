@@ -14,9 +14,10 @@ struct WaveBuffers;   // render.cu
 struct rtgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream2 = nullptr;       // ... and the closest-hit MIS rays beside the any-hit MIS rays
   cudaStream_t side_stream = nullptr;        // path integrator: secondary traces of a bounce, beside the next closest-hit launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   std::string error;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -41,7 +42,8 @@ struct rtgpu_ctx {
   int simple_traversal = 0;   // 1 = one-thread-one-ray reference walk everywhere (validation); 0 = persistent engine
   int sort_rays = 1;    // batch API: bin rays by origin cell + direction octant before traversal
   int sort_bounce_rays = 0;   // rtgpu_render (path): bin the rays of bounces >= 1 by origin cell + direction octant before tracing (profiles/r01q)
-  int overlap_bounces = 1;    // rtgpu_render (path): shadow / MIS traces of bounce b on a second stream, beside closest-hit + classify of bounce b + 1
+  int overlap_bounces = 2;    // rtgpu_render (path): >= 1 shadow / MIS traces of bounce b on a second stream, beside closest-hit + classify of bounce b + 1;
+                              // 2: closest-hit MIS rays on a third stream beside the any-hit MIS rays
   int sort_items = 1;   // rtgpu_render: counting sort of the listed-lobes queue / of the recursive integrators' items by material row
 };
 

@@ -346,8 +346,14 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         if (overlap) { sec = ctx->side_stream; cudaEventRecord(ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(sec, ctx->ev_fork, 0); }
         if (sc.n_lights > 0) {
           RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, sec));
+          // The BSDF-sampled MIS ray of a vertex is either a closest-hit ray (area light chosen) or an any-hit ray (infinite light
+          // chosen), never both (uniform_sample_one_light, integrator/mod.rs:145-177): the two launches add to disjoint samples of L,
+          // after the light sample's shadow ray, so they may run side by side.
+          const bool third = overlap && has_infinite && ctx->overlap_bounces > 1;
+          if (third) { cudaEventRecord(ctx->ev_fork2, sec); cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_fork2, 0); }
           if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, sec));
-          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, sec));
+          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, third ? ctx->side_stream2 : sec));
+          if (third) { cudaEventRecord(ctx->ev_join2, ctx->side_stream2); cudaStreamWaitEvent(sec, ctx->ev_join2, 0); }
         }
         if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 3, ctx->stream));
         else {
