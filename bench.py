@@ -325,9 +325,10 @@ def run_ours(a):
     if not a.no_cpu_baseline:
         # In a fresh process: measured inside this one (CUDA context, torch thread pools, the clock sampler) the same CPU
         # sample ran 2x slower than through `--impl reference` (profiles/r01h), which would flatter the GPU/CPU ratio.
+        # One untimed pass first: a cold first pass was 2x slower once (profiles/r01zc_bench.json, 2.66 M against 4.90 M samples/s).
         try:
             import subprocess
-            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--spp-per-step", str(a.spp_per_step),
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--spp-per-step", str(a.spp_per_step),
                    "--level", str(a.level), "--xres", str(a.xres), "--yres", str(a.yres), "--cpu-seconds", str(a.cpu_seconds)]
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().splitlines()[-1]

@@ -366,20 +366,40 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
     } else if (plan.recursive) {
       const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
-      for (uint32_t lvl = 0; lvl < rounds; lvl++) {
+      // same two-stream schedule as the path integrator: the shadow / MIS traces of level l beside the closest-hit launch and the
+      // material sort of level l + 1 (these integrators add to L with atomics, so only the queues need the join)
+      const bool overlap = ctx->overlap_bounces && !prof;
+      bool joined = true;
+      auto trace_level = [&](uint32_t lvl) {
         const int par = (int)(lvl & 1u);
         RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
         if (ctx->sort_items) {
           RT_LAUNCH(K_SHADE, launch_material_sort(p, nullptr, C_LIVE0 + par, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
           ctx->launches += 2;
+        }
+      };
+      for (uint32_t lvl = 0; lvl < rounds; lvl++) {
+        const int par = (int)(lvl & 1u);
+        if (lvl == 0 || !overlap) trace_level(lvl);
+        if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
+        if (ctx->sort_items) {
           RenderParams ps = p; ps.w.item_order = p.w.matsort_out;
           RT_LAUNCH(K_SHADE, launch_shade_recursive(ps, par, pblocks, ctx->stream));
         } else RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
-        RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
-        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, ctx->stream));
-        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, ctx->stream));
-        RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 3, ctx->stream));
+        cudaStream_t sec = ctx->stream;
+        if (overlap) { sec = ctx->side_stream; cudaEventRecord(ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(sec, ctx->ev_fork, 0); }
+        RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, sec));
+        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, sec));
+        if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, sec));
+        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 3, ctx->stream));
+        else {
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, 0, 2, sec));
+          cudaEventRecord(ctx->ev_join, sec); joined = false;
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 1, ctx->stream));
+          if (lvl + 1 < rounds) trace_level(lvl + 1);
+        }
       }
+      if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
     } else {
       RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
       RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));

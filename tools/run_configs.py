@@ -55,6 +55,8 @@ def main():
     a = ap.parse_args()
     want = a.configs.split(",")
     dev = Device(0)
+    for kv in filter(None, os.environ.get("RT_OPTIONS", "").split(",")):        # A/B runs: RT_OPTIONS=overlap_bounces=0
+        dev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     tmp = tempfile.mkdtemp()
     res = {}
 
