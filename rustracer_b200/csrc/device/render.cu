@@ -183,7 +183,13 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   // default wave size (tools/wave_sweep.py on B200): the path integrator keeps gaining up to 16 M paths per wave (fewer, fuller
   // launches); the recursive integrators peak at 4 M items (their per-sample atomics and level queues stay L2-resident)
   const bool recursive_integrator = rd->integrator == RTGPU_INTEGRATOR_WHITTED || rd->integrator == RTGPU_INTEGRATOR_DIRECT;
-  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (recursive_integrator ? (1u << 22) : (1u << 24));
+  // Jobs of more than 16 M camera samples on untextured scenes take 32 M-path waves (~10 GB of queues at ~305 B per path): the short
+  // late-bounce launches are paid once per wave (profiles/r01zl_wave_sweep_large.log: C5 664 -> 688 M samples/s, C3 641 -> 652 M).
+  const uint64_t job_samples = d_explicit ? (uint64_t)n_explicit :
+      (uint64_t)std::max(0, rd->sample_bounds[2] - rd->sample_bounds[0]) * (uint64_t)std::max(0, rd->sample_bounds[3] - rd->sample_bounds[1]) *
+      (uint64_t)std::max(0, std::min(rd->spp, rd->sample_end) - std::max(0, rd->sample_begin)) / (uint64_t)std::max(1, rd->tile_world);
+  const uint32_t P_path = (rd->integrator == RTGPU_INTEGRATOR_PATH && !sc.texmats && job_samples > (1ull << 24)) ? (1u << 25) : (1u << 24);
+  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (recursive_integrator ? (1u << 22) : P_path);
   uint32_t cap_items = P, cap_samples = P, cap_shadow = P, cap_mis = P;
   uint32_t rays_per_item = 1;
   std::vector<uint32_t> nls;
