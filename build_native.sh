@@ -12,7 +12,7 @@ if [ "$1" != "device" ]; then
 fi
 if [ "$1" != "host" ]; then
   pids=()
-  for tu in api render tu_trace tu_rec tu_tex bvh_build; do
+  for tu in api render tu_trace tu_rec tu_tex tu_probe bvh_build; do
     nvcc $NVFLAGS -c $D/$tu.cu -o $OBJ/$tu.o > $OBJ/$tu.log 2>&1 & pids+=($!)
   done
   for m in 0 1 2 3 4 5 6; do

@@ -245,6 +245,18 @@ int rtgpu_render(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, rtgpu_stats* sta
 /* Radiance `li()` of individual samples {x, y, sample_index} (no film); host buffers; rgb = 3 floats each. */
 int rtgpu_li_samples(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const int32_t* pixels, size_t n, float* rgb);
 
+/* Probes of the shading code the render kernels run (host buffers; tests/test_gpu_pins.py).
+ * rtgpu_bsdf_probe: the Bsdf material `material_row` builds (Material::compute_scattering_functions, material/*.rs) on a canonical surface
+ *   (p = 0, n = +z, dpdu = +x), evaluated for n world-space triples wo[3], wi[3], u[2] with BxDFType `flags` (bsdf/bxdf.rs:8-16):
+ *   out[14] = { Bsdf::f rgb, Bsdf::pdf, then Bsdf::sample_f(wo, u): f rgb, wi xyz, pdf, sampled type, lobe count, Bsdf::eta }
+ *   (bsdf/mod.rs:94-251).  Textured materials are rejected (their lobes depend on the hit point).
+ * rtgpu_light_probe: light `light_row` seen from n reference points ref[6] = {p, n} with u[2] and a direction w[3]:
+ *   out[16] = { Light::sample_li: Li rgb, wi xyz, pdf, far end of the VisibilityTester xyz; Light::pdf_li(ref, w); Light::le(w) rgb;
+ *   Light::pdf_li(ref, wi); is_delta } (light/{point,distant,diffuse,infinite}.rs). */
+int rtgpu_bsdf_probe(rtgpu_ctx* ctx, uint32_t material_row, int allow_multiple_lobes, size_t n, const float* wo, const float* wi, const float* u, uint32_t flags,
+                     float* out);
+int rtgpu_light_probe(rtgpu_ctx* ctx, uint32_t light_row, size_t n, const float* ref, const float* u, const float* w, float* out);
+
 /* Film accumulators X,Y,Z,weight per cropped pixel (film.rs:38-43), row-major; host buffer of 4*W*H floats. */
 int rtgpu_read_film(rtgpu_ctx* ctx, float* xyzw);
 /* == Film::write_image arithmetic (film.rs:196-234): RGB = max(0, XYZ->RGB / weight) * scale; 3*W*H floats. */

@@ -77,6 +77,9 @@ def lib(native=False):
     l.orc_fresnel_blend_pdf.argtypes = [PF, PF, C.c_float, C.c_float]
     l.orc_fresnel_blend_pdf.restype = C.c_float
     l.orc_material_bsdf.argtypes = [C.c_void_p, C.c_int, C.c_int, PF, PF, PF, C.c_uint32, PF]
+    l.orc_bsdf_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, PF, PF, PF, C.c_uint32, PF]
+    l.orc_light_probe.argtypes = [C.c_void_p, C.c_int, C.c_uint64, PF, PF, PF, PF]
+    l.orc_light_env.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), PF, PF]
     l.orc_selftest.argtypes = [C.c_uint64, C.c_char_p, C.c_int]
     l.orc_texture_eval.argtypes = [C.c_void_p, C.c_int, PF, C.c_uint64, PF]
     l.orc_texture_mip_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), PF]
@@ -129,6 +132,36 @@ class OracleScene:
             raise RuntimeError(f"orc_material_bsdf: {rc} {self._l.orc_scene_error(self._h)}")
         return dict(f=out[0:3].copy(), pdf=float(out[3]), sf=out[4:7].copy(), swi=out[7:10].copy(), spdf=float(out[10]), sflags=int(out[11]),
                     n_lobes=int(out[12]), eta=float(out[13]))
+
+    def bsdf_probe(self, row, wo, wi, u, allow_multiple_lobes=True, flags=31):
+        """Batched material_bsdf: (n, 3) wo, wi and (n, 2) u -> dict of arrays (f, pdf, sf, swi, spdf, sflags, n_lobes, eta)."""
+        wo, wi, u = (np.ascontiguousarray(a, np.float32) for a in (wo, wi, u))
+        n = len(wo)
+        out = np.zeros((n, 14), np.float32)
+        rc = self._l.orc_bsdf_probe(self._h, row, 1 if allow_multiple_lobes else 0, n, _pf(wo), _pf(wi), _pf(u), flags, _pf(out))
+        if rc:
+            raise RuntimeError(f"orc_bsdf_probe: {rc} {self._l.orc_scene_error(self._h)}")
+        return dict(f=out[:, 0:3], pdf=out[:, 3], sf=out[:, 4:7], swi=out[:, 7:10], spdf=out[:, 10], sflags=out[:, 11].astype(np.int32),
+                    n_lobes=out[:, 12].astype(np.int32), eta=out[:, 13])
+
+    def light_probe(self, light, ref, u, w):
+        """Light row probed from reference points: ref (n, 6) {p, n}, u (n, 2), w (n, 3) -> dict(li, wi, pdf, p1, pdf_w, le_w, pdf_wi, delta)."""
+        ref, u, w = (np.ascontiguousarray(a, np.float32) for a in (ref, u, w))
+        n = len(ref)
+        out = np.zeros((n, 16), np.float32)
+        if self._l.orc_light_probe(self._h, light, n, _pf(ref), _pf(u), _pf(w), _pf(out)):
+            raise RuntimeError("orc_light_probe: bad light row")
+        return dict(li=out[:, 0:3], wi=out[:, 3:6], pdf=out[:, 6], p1=out[:, 7:10], pdf_w=out[:, 10], le_w=out[:, 11:14], pdf_wi=out[:, 14], delta=out[:, 15])
+
+    def light_env(self, light):
+        """Environment map of an infinite light after MIPMap::new: (texels (h, w, 3), distribution image (2h, 2w))."""
+        w, h = C.c_int32(), C.c_int32()
+        if self._l.orc_light_env(self._h, light, C.byref(w), C.byref(h), None, None):
+            raise RuntimeError("orc_light_env: not an infinite light")
+        tex = np.zeros((h.value, w.value, 3), np.float32)
+        func = np.zeros((2 * h.value, 2 * w.value), np.float32)
+        self._l.orc_light_env(self._h, light, C.byref(w), C.byref(h), _pf(tex), _pf(func))
+        return tex, func
 
     def texture_eval(self, row, points):
         """Texture row evaluated at explicit surface points: (n, 15) {uv, p, dpdx, dpdy, dudx, dvdx, dudy, dvdy} -> (n, 3)."""

@@ -99,7 +99,6 @@ orc_scene* orc_scene_create(const rt_scene* in) {
       else {
         L.l2w = to_transform(l.l2w); L.w2l = L.l2w.inverse(); L.n_samples = l.n_samples;
         if (l.env_w > 0 && l.env_h > 0 && l.env_rgb) {
-          if (!is_power_of_2(l.env_w) || !is_power_of_2(l.env_h)) { o->error = "environment map must have power-of-two dimensions"; return o; }
           L.env_w = l.env_w; L.env_h = l.env_h; L.texels.resize((size_t)l.env_w * l.env_h);
           for (size_t i = 0; i < L.texels.size(); i++) L.texels[i] = Spectrum(l.env_rgb[3 * i], l.env_rgb[3 * i + 1], l.env_rgb[3 * i + 2]) * L.I;   // infinite.rs:61
         } else { L.env_w = 1; L.env_h = 1; L.texels.assign(1, L.I); }
@@ -329,6 +328,49 @@ int orc_material_bsdf(orc_scene* s, int row, int allow_multiple_lobes, const flo
   b.sample_f(o, P2(u[0], u[1]), flags, sf, swi, spdf, sampled);
   out[4] = sf.r; out[5] = sf.g; out[6] = sf.b; out[7] = swi.x; out[8] = swi.y; out[9] = swi.z; out[10] = spdf; out[11] = (float)sampled;
   out[12] = (float)b.n; out[13] = b.eta;
+  return 0;
+}
+// Batched orc_material_bsdf: n triples (wo, wi, u) -> 14 floats each (same layout).  The independent pins (tests/test_pins_*.py:
+// pdf normalisation, chi-square of sample_f against pdf, white furnace, reciprocity) run on this and on the device's twin
+// rtgpu_bsdf_probe.
+int orc_bsdf_probe(orc_scene* s, int row, int allow_multiple_lobes, uint64_t n, const float* wo, const float* wi, const float* u, uint32_t flags, float* out) {
+  for (uint64_t i = 0; i < n; i++) {
+    int rc = orc_material_bsdf(s, row, allow_multiple_lobes, wo + 3 * i, wi + 3 * i, u + 2 * i, flags, out + 14 * i);
+    if (rc) return rc;
+  }
+  return 0;
+}
+// Light `light` (row of Scene::lights) probed from n reference points: ref = 6 floats each {p.xyz, n.xyz} (p_error = 0), u = 2 floats,
+// w = 3 floats (a direction for pdf_li / le).  out = 16 floats each:
+//   { Li.rgb, wi.xyz, pdf, p1.xyz (far end of the VisibilityTester), pdf_li(ref, w), le(w).rgb, pdf_li(ref, wi), is_delta }
+int orc_light_probe(orc_scene* s, int light, uint64_t n, const float* ref, const float* u, const float* w, float* out) {
+  if (light < 0 || (size_t)light >= s->scene.lights.size()) return -1;
+  const Light& L = s->scene.lights[(size_t)light];
+  for (uint64_t i = 0; i < n; i++) {
+    const float* r = ref + 6 * i;
+    Interaction it = Interaction::make(V3(r[0], r[1], r[2]), V3(0, 0, 0), V3(0, 0, 0), V3(r[3], r[4], r[5]));
+    V3 wi; float pdf; Interaction p1;
+    Spectrum li = L.sample_li(it, P2(u[2 * i], u[2 * i + 1]), wi, pdf, p1);
+    float* o = out + 16 * i;
+    o[0] = li.r; o[1] = li.g; o[2] = li.b; o[3] = wi.x; o[4] = wi.y; o[5] = wi.z; o[6] = pdf; o[7] = p1.p.x; o[8] = p1.p.y; o[9] = p1.p.z;
+    V3 ww(w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+    o[10] = L.pdf_li(it, ww);
+    Spectrum le = L.le(Ray(it.p, ww, INF));
+    o[11] = le.r; o[12] = le.g; o[13] = le.b;
+    o[14] = pdf > 0.0f ? L.pdf_li(it, wi) : 0.0f;
+    o[15] = L.is_delta() ? 1.0f : 0.0f;
+  }
+  return 0;
+}
+// The environment map of infinite light `light` as InfiniteAreaLight::new leaves it: level 0 of the MIP pyramid (w x h RGB texels,
+// already times L * scale) and the scalar image the Distribution2D is built from ((2w) x (2h)).  Sizes first (texels == NULL).
+int orc_light_env(orc_scene* s, int light, int32_t* w, int32_t* h, float* texels, float* func) {
+  if (light < 0 || (size_t)light >= s->scene.lights.size() || s->scene.lights[(size_t)light].kind != RT_LIGHT_INFINITE) return -1;
+  const Light& L = s->scene.lights[(size_t)light];
+  *w = L.l_map.res_x; *h = L.l_map.res_y;
+  if (texels) std::memcpy(texels, L.l_map.pyramid[0].d.data(), (size_t)L.l_map.res_x * L.l_map.res_y * 3 * sizeof(float));
+  if (func) for (size_t v = 0; v < L.distribution.cond.size(); v++)
+    std::memcpy(func + v * L.distribution.cond[v].func.size(), L.distribution.cond[v].func.data(), L.distribution.cond[v].func.size() * sizeof(float));
   return 0;
 }
 float orc_roughness_to_alpha(float r) { return TrowbridgeReitz::roughness_to_alpha(r); }

@@ -72,6 +72,7 @@ struct Light {                                                   // light/mod.rs
   int n_samples = 1;
   // infinite
   Transform l2w, w2l; int env_w = 1, env_h = 1; std::vector<Spectrum> texels; Distribution2D distribution;
+  MIPMap l_map;                                                  // infinite.rs:71-77: MIPMap::new(resolution, texels, false, 0.0, Repeat)
   // preprocess
   V3 w_center; float w_radius = 0;
 
@@ -79,43 +80,34 @@ struct Light {                                                   // light/mod.rs
   Spectrum L(const Interaction& si, V3 w) const {                // diffuse.rs:91-97
     return (two_sided || dot(si.n, w) > 0.0f) ? l_emit : Spectrum(0.0f);
   }
-  // mipmap.rs:201-225 texel with Repeat wrap ; :285-309 triangle (level 0 only on this path — Q31)
-  Spectrum texel(int64_t s, int64_t t) const {
-    auto modulo = [](int64_t a, int64_t b) { int64_t r = a % b; return r < 0 ? r + b : r; };
-    // level 0 is BlockedArray::new_from(res.x, res.y, data) indexed [(ss, tt)] = data[tt * u_size + ss]
-    return texels[(size_t)(modulo(t, env_h) * env_w + modulo(s, env_w))];
+  // MIPMap::lookup(st, width) (mipmap.rs:227-245) on the light's own pyramid: non-power-of-two maps were Lanczos-resampled
+  // by MIPMap::new (mipmap.rs:73-139), and width > 0 can select a coarser level (aspect ratios of 4:1 and beyond)
+  Spectrum map_lookup(P2 st, float width) const {
+    Texel t = l_map.lookup(st, width);
+    return Spectrum(t.c[0], t.c[1], t.c[2]);
   }
-  Spectrum lookup_level0(P2 st) const {
-    float s = st.x * (float)env_w - 0.5f, t = st.y * (float)env_h - 0.5f;
-    float fs = std::floor(s), ft = std::floor(t);
-    int64_t s0 = (int64_t)fs, t0 = (int64_t)ft;
-    float ds = s - fs, dt = t - ft;
-    return texel(s0, t0) * (1.0f - ds) * (1.0f - dt) + texel(s0, t0 + 1) * (1.0f - ds) * dt + texel(s0 + 1, t0) * ds * (1.0f - dt) +
-           texel(s0 + 1, t0 + 1) * ds * dt;
-  }
-  void init_infinite() {                                         // infinite.rs:46-113 (power-of-two maps; levels only matter via level 0)
-    int width = 2 * env_w, height = 2 * env_h;
+  void init_infinite() {                                         // infinite.rs:46-113
+    std::vector<float> rgb((size_t)env_w * env_h * 3);
+    for (size_t i = 0; i < texels.size(); i++) { rgb[3 * i] = texels[i].r; rgb[3 * i + 1] = texels[i].g; rgb[3 * i + 2] = texels[i].b; }
+    l_map.build(env_w, env_h, rgb.data(), 3, false, 0.0f, RT_WRAP_REPEAT);
+    int width = 2 * l_map.res_x, height = 2 * l_map.res_y;       // :80 (l_map.width() is the resampled resolution)
+    const float filter = 0.5f / fmin_((float)width, (float)height);
     std::vector<float> img((size_t)width * height);
     for (int v = 0; v < height; v++) {
       float vp = ((float)v + 0.5f) / (float)height;
       float sin_theta = std::sin(PI * ((float)v + 0.5f) / (float)height);
       for (int u = 0; u < width; u++) {
         float up = ((float)u + 0.5f) / (float)width;
-        img[(size_t)v * width + u] = lookup_for_distribution(P2(up, vp), 0.5f / fmin_((float)width, (float)height)).y() * sin_theta;
+        img[(size_t)v * width + u] = map_lookup(P2(up, vp), filter).y() * sin_theta;
       }
     }
     distribution.init(img.data(), width, height);
   }
-  // mipmap.rs:227-245 `lookup(st, width)` with width = 0.5/min(2W,2H): level = levels-1+log2(width)
-  // = log2(max/min) - 2 for power-of-two maps, i.e. < 0 (-> triangle(0)) for aspect <= 2:1 and == 0 with
-  // delta 0 (lerp(0,a,b) = a*1 + b*0 = a) for 4:1.  Maps with aspect > 4:1 or non-power-of-two sizes
-  // (Lanczos resample, mipmap.rs:73-139) are outside the oracle's scope and rejected at scene load.
-  Spectrum lookup_for_distribution(P2 st, float) const { return lookup_level0(st); }
   Spectrum le(const Ray& ray) const {                            // infinite.rs:210-219 ; light/mod.rs:92-94
     if (kind != RT_LIGHT_INFINITE) return Spectrum(0.0f);
     V3 w = normalize(w2l.vector(ray.d));
     P2 st(spherical_phi(w) * INV_PI * 0.5f, spherical_theta(w) * INV_PI);
-    return lookup_level0(st);
+    return map_lookup(st, 0.0f);
   }
   // returns Li; wi, pdf; p0/p1 of the VisibilityTester
   Spectrum sample_li(const Interaction& isect, P2 u, V3& wi, float& pdf, Interaction& p1) const {
@@ -149,7 +141,7 @@ struct Light {                                                   // light/mod.rs
         pdf = sin_t == 0.0f ? 0.0f : map_pdf / (2.0f * PI * PI * sin_t);
         V3 target = isect.p + wi * (2.0f * w_radius);
         p1 = Interaction::from_point(target);
-        return lookup_level0(uv);
+        return map_lookup(uv, 0.0f);
       }
     }
   }

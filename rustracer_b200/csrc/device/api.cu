@@ -262,8 +262,14 @@ int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (std::strcmp(name, "sort_items") == 0) { ctx->sort_items = value; return RTGPU_OK; }
   if (std::strcmp(name, "overlap_bounces") == 0) { ctx->overlap_bounces = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_bounce_rays") == 0) { ctx->sort_bounce_rays = value; return RTGPU_OK; }
-  if (std::strcmp(name, "node_threshold") == 0) { ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK; }
-  if (std::strcmp(name, "refill_threshold") == 0) { ctx->refill_threshold = value; ctx->scene.tune_refill_threshold = value; return RTGPU_OK; }
+  if (std::strcmp(name, "node_threshold") == 0) {
+    if (value < 0 || value > 32) return fail(ctx, RTGPU_ERR_ARG, "node_threshold must be in [0, 32]");
+    ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK;
+  }
+  if (std::strcmp(name, "refill_threshold") == 0) {           // <= 0 would enter the refill branch with no idle lane and spin
+    if (value < 1 || value > 32) return fail(ctx, RTGPU_ERR_ARG, "refill_threshold must be in [1, 32]");
+    ctx->refill_threshold = value; ctx->scene.tune_refill_threshold = value; return RTGPU_OK;
+  }
   if (std::strcmp(name, "simple_traversal") == 0) { ctx->simple_traversal = value; return RTGPU_OK; }
   if (std::strcmp(name, "profile") == 0) { ctx->profile = value; return RTGPU_OK; }
   if (std::strcmp(name, "count_traversal") == 0) { ctx->count_traversal = value; return RTGPU_OK; }

@@ -18,7 +18,7 @@ namespace rt {
 #endif
 template <bool TEX>
 __global__ void __launch_bounds__(RT_REC_THREADS, RT_REC_MIN_BLOCKS * 128 / RT_REC_THREADS) k_shade_recursive(RenderParams p, int parity) {
-  const uint32_t n = p.w.counters[C_LIVE0 + parity];
+  const uint32_t n = min(p.w.counters[C_LIVE0 + parity], p.w.cap_items);   // an overflowed level (the wave is discarded and split) must not read past its buffers
   const float4* ray_o = parity ? p.w.ray_o2 : p.w.ray_o; const float4* ray_d = parity ? p.w.ray_d2 : p.w.ray_d;
   const float4* beta_in = parity ? p.w.beta2 : p.w.beta; const uint4* ps_in = parity ? p.w.pstate2 : p.w.pstate;
   float4* oray_o = parity ? p.w.ray_o : p.w.ray_o2; float4* oray_d = parity ? p.w.ray_d : p.w.ray_d2;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(RT_REC_THREADS, RT_REC_MIN_BLOCKS * 128 / RT_R
 
 // ---- AmbientOcclusion::li (integrator/ao.rs:32-58) and Normal::li (normal.rs:20-34) ---------------------------
 __global__ void __launch_bounds__(128) k_shade_ao(RenderParams p) {
-  const uint32_t n = p.w.counters[C_LIVE0];
+  const uint32_t n = min(p.w.counters[C_LIVE0], p.w.cap_items);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = p.w.list[0][i];
     const HitRec h = p.w.hit[slot];

@@ -71,7 +71,7 @@ RT_DEV void flush_trav_stats(const RenderParams& p, const TravStats& st, int s_n
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_trace_closest(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                         const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   TravStats st; st.nodes = 0; st.prims = 0;
   while (true) {
     const uint32_t base = warp_fetch(&p.w.counters[C_CUR_CLOSEST]);
@@ -172,7 +172,7 @@ template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                                const uint32_t* __restrict__ list, int count_idx, HitRec* __restrict__ hits) {
   ClosestPolicy<INST> pol(ray_o, ray_d, list, hits, p.w.hit_inst, p.w.hit_class);
-  trace_engine<false, INST>(p.sc, &p.w.counters[C_CUR_CLOSEST], p.w.counters[count_idx], pol);
+  trace_engine<false, INST>(p.sc, &p.w.counters[C_CUR_CLOSEST], min(p.w.counters[count_idx], p.w.cap_items), pol);
 }
 
 // Material classification of the traced paths: appends each path to the queue of its hit material (or the miss queue)
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_eng
 // reads 5 bytes per path instead of chasing hit -> primitive info -> material row.
 template <bool FROM_CLASS>
 __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const HitRec* __restrict__ hits) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   const uint32_t lane = lane_id(), lane_lt = (1u << lane) - 1u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
     int q = -1; uint32_t slot = 0;
@@ -219,7 +219,7 @@ RT_DEV uint32_t matsort_key(const RenderParams& p, uint32_t item, uint32_t n_bin
   return mrow < n_bins - 1u ? mrow : n_bins - 1u;
 }
 __global__ void __launch_bounds__(256) k_matsort_hist(RenderParams p, const uint32_t* __restrict__ list, int count_idx, uint32_t* __restrict__ hist, uint32_t n_bins) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
     const uint32_t key = i < n ? matsort_key(p, list ? list[i] : i, n_bins) : 0xffffffffu;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_matsort_scan(uint32_t* __restrict__ his
 }
 __global__ void __launch_bounds__(256) k_matsort_scatter(RenderParams p, const uint32_t* __restrict__ list, int count_idx, uint32_t* __restrict__ cursor, uint32_t n_bins,
                                                          uint32_t* __restrict__ out) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   const uint32_t lane_lt = (1u << lane_id()) - 1u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
     const uint32_t item = i < n ? (list ? list[i] : i) : 0u;
@@ -280,7 +280,7 @@ RT_DEV uint32_t wave_ray_key(const float4 o, const float4 d, const WaveSortParam
 }
 __global__ void __launch_bounds__(256) k_raysort_hist(RenderParams p, const uint32_t* __restrict__ list, int count_idx, WaveSortParams sp, uint32_t* __restrict__ keys,
                                                       uint32_t* __restrict__ hist) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = list[i];
     const uint32_t k = wave_ray_key(p.w.ray_o[slot], p.w.ray_d[slot], sp);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(1024) k_raysort_scan(uint32_t* __restrict__ hi
 }
 __global__ void __launch_bounds__(256) k_raysort_scatter(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ offsets, uint32_t* __restrict__ out) {
-  const uint32_t n = p.w.counters[count_idx];
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[atomicAdd(&offsets[keys[i]], 1u)] = list[i];
 }
 
@@ -444,7 +444,7 @@ __global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera, in
   uint32_t* c = p.w.counters;
   if (c[C_OVERFLOW]) p.w.stats[S_OVERFLOW] = 1;
   if (part & 1) {
-    const uint32_t live = c[live_idx];
+    const uint32_t live = min(c[live_idx], p.w.cap_items);
     atomicAdd(&p.w.stats[S_REGULAR], (unsigned long long)live);
     atomicAdd(&p.w.stats[S_CLOSEST_RAYS], (unsigned long long)live);
     if (count_camera) p.w.stats[S_CAMERA] += live;

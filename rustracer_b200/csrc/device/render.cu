@@ -189,7 +189,8 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       (uint64_t)std::max(0, rd->sample_bounds[2] - rd->sample_bounds[0]) * (uint64_t)std::max(0, rd->sample_bounds[3] - rd->sample_bounds[1]) *
       (uint64_t)std::max(0, std::min(rd->spp, rd->sample_end) - std::max(0, rd->sample_begin)) / (uint64_t)std::max(1, rd->tile_world);
   const uint32_t P_path = (rd->integrator == RTGPU_INTEGRATOR_PATH && !sc.texmats && job_samples > (1ull << 24)) ? (1u << 25) : (1u << 24);
-  const uint32_t P = rd->wave_paths > 0 ? (uint32_t)rd->wave_paths : (recursive_integrator ? (1u << 22) : P_path);
+  // the smallest wave is one 16x16 tile of one sample index: 256 items, whatever the caller asks for
+  const uint32_t P = rd->wave_paths > 0 ? std::max(256u, (uint32_t)rd->wave_paths) : (recursive_integrator ? (1u << 22) : P_path);
   uint32_t cap_items = P, cap_samples = P, cap_shadow = P, cap_mis = P;
   uint32_t rays_per_item = 1;
   std::vector<uint32_t> nls;
@@ -303,6 +304,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     ctx->launches++; if ((kclass) == K_CLOSEST) n_closest_launches++; else if ((kclass) == K_ANYHIT) n_anyhit_launches++; } while (0)
 
   auto run_wave = [&](uint32_t n_items) -> int {
+    if (n_items > p.w.cap_samples || n_items > p.w.cap_items) return fail(ctx, RTGPU_ERR_ARG, "internal: wave larger than its buffers");
     p.n_items = n_items;
     RT_CUDA(ctx, cudaMemsetAsync(p.w.counters, 0, C_COUNT * sizeof(uint32_t), ctx->stream));
     RT_LAUNCH(K_OTHER, launch_raygen(p, ctx->stream));

@@ -145,7 +145,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
     const unsigned m_n = __ballot_sync(FULL, !(cur & kLeafBit));
     const unsigned m_l = __ballot_sync(FULL, (cur & kLeafBit) != 0u && cur != kDoneRef);
     const unsigned busy = m_n | m_l;
-    if (busy == 0u || (!queue_empty && 32 - __popc(busy) >= refill_threshold)) {
+    if (busy == 0u || (!queue_empty && busy != FULL && 32 - __popc(busy) >= refill_threshold)) {
       // ---- commit finished rays and pull new ones ----------------------------------------------------------
       if (pending) {
         HitRec hc = hit; uint32_t cls = (uint32_t)Q_MISS_CLASS;

@@ -185,7 +185,7 @@ static bool read_pfm(const std::string& fn, int& w, int& h, std::vector<float>& 
   FILE* f = std::fopen(fn.c_str(), "rb");
   if (!f) return false;
   char magic[3] = {0, 0, 0}; float scale = 0;
-  if (std::fscanf(f, "%2s %d %d %f", magic, &w, &h, &scale) != 4 || (magic[1] != 'F' && magic[1] != 'f') || w <= 0 || h <= 0) { std::fclose(f); return false; }
+  if (std::fscanf(f, "%2s %d %d %f", magic, &w, &h, &scale) != 4 || (magic[1] != 'F' && magic[1] != 'f') || w <= 0 || h <= 0 || w > 65536 || h > 65536) { std::fclose(f); return false; }
   std::fgetc(f);
   int nc = magic[1] == 'F' ? 3 : 1;
   std::vector<float> raw((size_t)w * h * nc);
@@ -193,6 +193,7 @@ static bool read_pfm(const std::string& fn, int& w, int& h, std::vector<float>& 
   std::fclose(f);
   if (got != raw.size()) return false;
   if (scale > 0) for (float& v : raw) { uint32_t u; std::memcpy(&u, &v, 4); u = __builtin_bswap32(u); std::memcpy(&v, &u, 4); }
+  if (std::fabs(scale) != 1.0f) for (float& v : raw) v *= std::fabs(scale);   // imageio.rs:231-233
   rgb.resize((size_t)w * h * 3);
   for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) for (int c = 0; c < 3; c++)
     rgb[((size_t)y * w + x) * 3 + c] = raw[((size_t)(h - 1 - y) * w + x) * nc + (nc == 3 ? c : 0)];
@@ -211,20 +212,27 @@ static bool read_png(const std::string& fn, int& w, int& h, std::vector<float>& 
   static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) return false;
   auto be32 = [&](size_t o) { return ((uint32_t)file[o] << 24) | ((uint32_t)file[o + 1] << 16) | ((uint32_t)file[o + 2] << 8) | (uint32_t)file[o + 3]; };
-  int depth = 0, ctype = 0, interlace = 0;
+  int depth = 0, ctype = 0, interlace = 0; bool have_ihdr = false;
+  w = h = 0;
   std::vector<unsigned char> idat, plte;
   for (size_t o = 8; o + 12 <= file.size();) {
     const uint32_t len = be32(o);
     if (o + 12 + len > file.size()) return false;
     const std::string type((const char*)&file[o + 4], 4);
     const unsigned char* d = &file[o + 8];
-    if (type == "IHDR") { w = (int)be32(o + 8); h = (int)be32(o + 12); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+    if (type == "IHDR") {
+      if (len != 13 || o != 8) return false;                          // IHDR is 13 bytes and comes first
+      const uint32_t uw = be32(o + 8), uh = be32(o + 12);
+      if (uw == 0 || uh == 0 || uw > 65536u || uh > 65536u) return false;   // keeps every size product below 2^35
+      w = (int)uw; h = (int)uh; depth = d[8]; ctype = d[9]; interlace = d[12]; have_ihdr = true;
+    }
+    else if (!have_ihdr) return false;
     else if (type == "PLTE") plte.assign(d, d + len);
     else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
     else if (type == "IEND") break;
     o += 12 + len;
   }
-  if (w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return false;
+  if (!have_ihdr || w <= 0 || h <= 0 || interlace != 0 || (depth != 8 && depth != 16) || (ctype == 3 && depth != 8)) return false;
   const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
   if (!channels) return false;
   const size_t bpp = (size_t)channels * depth / 8, stride = (size_t)w * bpp;
@@ -306,12 +314,79 @@ static bool read_tga(const std::string& fn, int& w, int& h, std::vector<float>& 
   }
   return true;
 }
+// Radiance .hdr reader (imageio.rs:115-132: `HdrDecoder::with_strictness(reader, false)` of the image crate, 0.24): "#?RADIANCE" /
+// "#?RGBE" signature, header lines up to an empty line, "-Y h +X w", then per scanline either new-style run-length encoding
+// (2 2 hi lo, four component planes) or flat RGBE quads (old-style runs with a 1 1 1 marker included).  A pixel (r, g, b, e) decodes to
+// c * 2^(e - 136), black when e == 0.  Rows top-to-bottom.
+static bool read_hdr(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
+  FILE* f = std::fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  std::vector<unsigned char> d;
+  unsigned char buf[65536]; size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) d.insert(d.end(), buf, buf + n);
+  std::fclose(f);
+  size_t pos = 0;
+  auto line = [&](std::string& out) { out.clear(); while (pos < d.size() && d[pos] != '\n') out.push_back((char)d[pos++]); if (pos >= d.size()) return false; pos++; return true; };
+  std::string ln;
+  if (!line(ln) || (ln.compare(0, 10, "#?RADIANCE") != 0 && ln.compare(0, 6, "#?RGBE") != 0)) return false;
+  while (true) { if (!line(ln)) return false; if (ln.empty()) break; }
+  if (!line(ln)) return false;
+  char sy = 0, sx = 0, ay = 0, ax = 0; int hh = 0, ww = 0;
+  if (std::sscanf(ln.c_str(), "%c%c %d %c%c %d", &sy, &ay, &hh, &sx, &ax, &ww) != 6 || sy != '-' || ay != 'Y' || sx != '+' || ax != 'X') return false;
+  if (ww <= 0 || hh <= 0 || ww > 65536 || hh > 65536) return false;
+  w = ww; h = hh;
+  std::vector<unsigned char> row((size_t)w * 4);
+  rgb.assign((size_t)w * h * 3, 0.0f);
+  for (int y = 0; y < h; y++) {
+    if (pos + 4 > d.size()) return false;
+    if (w >= 8 && w < 32768 && d[pos] == 2 && d[pos + 1] == 2 && (((int)d[pos + 2] << 8) | d[pos + 3]) == w) {
+      pos += 4;
+      for (int c = 0; c < 4; c++) {
+        int x = 0;
+        while (x < w) {
+          if (pos >= d.size()) return false;
+          int cnt = d[pos++];
+          if (cnt > 128) {                                            // run
+            cnt -= 128;
+            if (cnt == 0 || x + cnt > w || pos >= d.size()) return false;
+            const unsigned char v = d[pos++];
+            for (int k = 0; k < cnt; k++) row[(size_t)(x++) * 4 + c] = v;
+          } else {                                                    // literal
+            if (cnt == 0 || x + cnt > w || pos + (size_t)cnt > d.size()) return false;
+            for (int k = 0; k < cnt; k++) row[(size_t)(x++) * 4 + c] = d[pos++];
+          }
+        }
+      }
+    } else {                                                          // flat, with old-style run markers
+      int x = 0, shift = 0;
+      while (x < w) {
+        if (pos + 4 > d.size()) return false;
+        const unsigned char* q = &d[pos]; pos += 4;
+        if (q[0] == 1 && q[1] == 1 && q[2] == 1 && x > 0) {
+          const int cnt = (int)q[3] << shift;
+          if (x + cnt > w) return false;
+          for (int k = 0; k < cnt; k++) { std::memcpy(&row[(size_t)x * 4], &row[(size_t)(x - 1) * 4], 4); x++; }
+          shift += 8;
+        } else { std::memcpy(&row[(size_t)x * 4], q, 4); x++; shift = 0; }
+      }
+    }
+    for (int x = 0; x < w; x++) {
+      const unsigned char* q = &row[(size_t)x * 4];
+      float* o = &rgb[((size_t)y * w + x) * 3];
+      if (q[3] == 0) { o[0] = o[1] = o[2] = 0.0f; continue; }
+      const float e = std::exp2((float)q[3] - (128.0f + 8.0f));
+      o[0] = e * (float)q[0]; o[1] = e * (float)q[1]; o[2] = e * (float)q[2];
+    }
+  }
+  return true;
+}
 // imageio.rs:77-92 `read_image`: by extension.  PFM, PNG and TGA are read; HDR / EXR need codecs this build does not carry.
 static bool read_image_rgb(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
   auto ends = [&](const char* e) { size_t n = std::strlen(e); return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0; };
   if (ends(".pfm")) return read_pfm(fn, w, h, rgb);
   if (ends(".png")) return read_png(fn, w, h, rgb);
   if (ends(".tga")) return read_tga(fn, w, h, rgb);
+  if (ends(".hdr")) return read_hdr(fn, w, h, rgb);
   return false;
 }
 
@@ -671,10 +746,9 @@ struct Api {
       if (!mapname.empty()) {
         std::string fn = resolve_filename(mapname, opt.search_dir);
         int w, h; std::vector<float> rgb;
-        if (read_pfm(fn, w, h, rgb)) {
-          if ((w & (w - 1)) || (h & (h - 1))) throw ParseError("environment map " + fn + ": only power-of-two sizes are supported (the reference resamples others, mipmap.rs:73-139)");
+        if (read_image_rgb(fn, w, h, rgb)) {                          // infinite.rs:54-61: any format read_image knows, any size
           l.env_w = w; l.env_h = h; l.env_rgb = out->store.keep(std::move(rgb));
-        } else warn().push_back("Environment map " + fn + " for infinite light not found (PFM only)! Using constant texture instead.");   // infinite.rs:62-69
+        } else warn().push_back("Environment map " + fn + " for infinite light not found! Using constant texture instead.");   // infinite.rs:62-69
       }
     } else throw ParseError("Unsupported light type " + name);       // api.rs:509-512 -> Err -> parse failure
     out->store.lights.push_back(l);

@@ -109,6 +109,10 @@ void read_ply(const std::string& filename, PlyMesh& out) {
   }
   if (vertex_count == 0 || face_count == 0) return;                  // caller reports "invalid"
   Reader r{data.data() + pos, data.data() + data.size(), fmt};
+  // every vertex / face occupies at least one byte of the body (ASCII: a digit; binary: far more): a header count beyond the
+  // remaining file size is corrupt, and must not size an allocation
+  for (const Elem& e : elems)
+    if (e.count > data.size() - pos) throw ParseError("PLY file \"" + filename + "\": element count exceeds the file size");
   std::vector<int32_t> face;
   for (const Elem& e : elems) {
     if (e.name == "vertex") {

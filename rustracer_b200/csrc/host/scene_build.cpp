@@ -366,32 +366,52 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     else {                                                            // infinite.rs:46-113
       g.n_samples = (uint32_t)l.n_samples;
       for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { g.l2w[r * 3 + c] = l.l2w.m[r * 4 + c]; g.w2l[r * 3 + c] = l.l2w.m_inv[r * 4 + c]; }
-      int w = (l.env_w > 0 && l.env_h > 0 && l.env_rgb) ? l.env_w : 1, h = (l.env_w > 0 && l.env_h > 0 && l.env_rgb) ? l.env_h : 1;
-      if ((w & (w - 1)) || (h & (h - 1))) throw std::runtime_error("environment map sizes must be powers of two");
-      if (std::max(w, h) > 4 * std::min(w, h)) throw std::runtime_error("environment map aspect ratio above 4:1 needs the mip pyramid for its sampling image (mipmap.rs:227-245); unsupported");
+      // texels * power (infinite.rs:61 / :69), then MIPMap::new(resolution, texels, false, 0.0, Repeat) (:71-77): a map whose sides
+      // are not powers of two is Lanczos-resampled, and the pyramid's coarser levels serve the sampling image of very wide maps
+      const bool has_map = l.env_w > 0 && l.env_h > 0 && l.env_rgb;
+      const int rw = has_map ? l.env_w : 1, rh = has_map ? l.env_h : 1;
+      std::vector<float> scaled((size_t)rw * rh * 3);
+      for (size_t i = 0; i < (size_t)rw * rh; i++) for (int c = 0; c < 3; c++) scaled[3 * i + c] = (has_map ? l.env_rgb[3 * i + c] : 1.0f) * l.I[c];
+      const std::vector<MipLevel> pyr = build_mip_pyramid(rw, rh, 3, RT_WRAP_REPEAT, scaled.data());
+      const int w = pyr[0].u, h = pyr[0].v;
       g.env_w = (uint32_t)w; g.env_h = (uint32_t)h;
       std::vector<float>& E = out.env_data;
       g.env_texels = (uint32_t)E.size();
-      for (int i = 0; i < w * h; i++) for (int c = 0; c < 3; c++) E.push_back((l.env_rgb && l.env_w > 0 ? l.env_rgb[3 * i + c] : 1.0f) * l.I[c]);   // infinite.rs:61 / :69
-      const size_t tex0 = g.env_texels;
-      auto texel = [&](int64_t s, int64_t t, int c) {                 // mipmap.rs:201-225 (Repeat)
-        int64_t ss = s % w; if (ss < 0) ss += w;
-        int64_t tt = t % h; if (tt < 0) tt += h;
-        return out.env_data[tex0 + (size_t)(tt * w + ss) * 3 + c];
+      E.insert(E.end(), pyr[0].d.begin(), pyr[0].d.end());            // the device only ever looks up level 0 (width 0: le, sample_li)
+      auto triangle = [&](size_t level, float sx, float sy, float rgb[3]) {   // MIPMap::triangle (mipmap.rs:285-309), Repeat wrap (:201-225)
+        level = std::min(level, pyr.size() - 1);
+        const MipLevel& L = pyr[level];
+        auto texel = [&](int64_t s, int64_t t, int c) {
+          int64_t ss = s % L.u; if (ss < 0) ss += L.u;
+          int64_t tt = t % L.v; if (tt < 0) tt += L.v;
+          return L.d[(size_t)(tt * L.u + ss) * 3 + c];
+        };
+        const float s = sx * (float)L.u - 0.5f, t = sy * (float)L.v - 0.5f;
+        const float fs = std::floor(s), ft = std::floor(t);
+        const int64_t s0 = (int64_t)fs, t0 = (int64_t)ft;
+        const float ds = s - fs, dt = t - ft;
+        for (int c = 0; c < 3; c++)
+          rgb[c] = texel(s0, t0, c) * (1.0f - ds) * (1.0f - dt) + texel(s0, t0 + 1, c) * (1.0f - ds) * dt + texel(s0 + 1, t0, c) * ds * (1.0f - dt) + texel(s0 + 1, t0 + 1, c) * ds * dt;
       };
       const int W2 = 2 * w, H2 = 2 * h;
+      const float filter = 0.5f / std::min((float)W2, (float)H2);      // infinite.rs:81
+      const float n_levels_f = (float)pyr.size();
       std::vector<float> img((size_t)W2 * H2);
       for (int v = 0; v < H2; v++) {
         float vp = ((float)v + 0.5f) / (float)H2;
         float sin_theta = std::sin(kPi * ((float)v + 0.5f) / (float)H2);
         for (int u = 0; u < W2; u++) {
           float up = ((float)u + 0.5f) / (float)W2;
-          float s = up * (float)w - 0.5f, t = vp * (float)h - 0.5f;   // MIPMap::triangle, level 0 (mipmap.rs:285-309)
-          float fs = std::floor(s), ft = std::floor(t);
-          int64_t s0 = (int64_t)fs, t0 = (int64_t)ft;
-          float ds = s - fs, dt = t - ft, rgb[3];
-          for (int c = 0; c < 3; c++)
-            rgb[c] = texel(s0, t0, c) * (1.0f - ds) * (1.0f - dt) + texel(s0, t0 + 1, c) * (1.0f - ds) * dt + texel(s0 + 1, t0, c) * ds * (1.0f - dt) + texel(s0 + 1, t0 + 1, c) * ds * dt;
+          float rgb[3];
+          const float level = n_levels_f - 1.0f + std::log2(std::max(filter, 1e-8f));   // MIPMap::lookup (mipmap.rs:227-245)
+          if (level < 0.0f) triangle(0, up, vp, rgb);
+          else if (level >= n_levels_f - 1.0f) { for (int c = 0; c < 3; c++) rgb[c] = pyr.back().d[c]; }
+          else {
+            const float il = std::floor(level), delta = level - il;
+            float a[3], b2[3];
+            triangle((size_t)il, up, vp, a); triangle((size_t)il + 1, up, vp, b2);
+            for (int c = 0; c < 3; c++) rgb[c] = a[c] * (1.0f - delta) + b2[c] * delta;   // lerp (lib.rs:107-117)
+          }
           float y = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
           img[(size_t)v * W2 + u] = y * sin_theta;
         }

@@ -37,6 +37,9 @@ typedef int (*ExternalBvhBuilder)(void* user, const float* prim_bounds, uint64_t
 void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhBuilder external_builder = nullptr, void* builder_user = nullptr);
 // Film / camera / integrator / sampler part only (no geometry): fills out.render from `in`.
 void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd);
+// MIPMap::new (mipmap.rs:65-180): Lanczos resampling of non-power-of-two images + box-filtered levels through the wrap mode.
+struct MipLevel { int u = 0, v = 0; std::vector<float> d; };
+std::vector<MipLevel> build_mip_pyramid(int rx, int ry, int nc, int wrap, const float* texels);
 // Texture rows for the device: copies the parameters and builds each imagemap's MIP pyramid (MIPMap::new) into `pool`.
 void build_textures(const rt_scene& in, std::vector<rtgpu_texture>& rows, std::vector<float>& pool);
 

@@ -2,7 +2,9 @@
 // Restates MIPMap::new (rustracer-core/src/mipmap.rs:65-180): Lanczos resampling of non-power-of-two images to the next
 // powers of two, then the box-filtered pyramid through the wrap-mode texel lookup.  The filtering lookups themselves
 // (trilinear / EWA) run on the device (csrc/device/texture.cuh).
+#include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <stdexcept>
 #include "scene_build.hpp"
@@ -45,6 +47,59 @@ std::vector<ResampleWeight> resample_weights(size_t old_res, size_t new_res) {  
 
 }  // namespace
 
+// MIPMap::new (mipmap.rs:65-180): level 0 is the image itself, or its Lanczos resampling to the next powers of two; every further
+// level box-filters the previous one through the wrap-mode texel lookup.  `texels`: rx * ry * nc floats, row-major.
+std::vector<MipLevel> build_mip_pyramid(int rx, int ry, int nc, int wrap, const float* texels) {
+  std::vector<float> l0; int u0, v0;
+  if (!is_pow2(rx) || !is_pow2(ry)) {                                 // mipmap.rs:73-139
+    const int px = round_up_pow2(rx), py = round_up_pow2(ry);
+    l0.assign((size_t)px * py * nc, 0.0f);
+    const std::vector<ResampleWeight> sw = resample_weights((size_t)rx, (size_t)px);
+    for (int tt = 0; tt < ry; tt++)
+      for (int s = 0; s < px; s++)
+        for (int j = 0; j < 4; j++) {
+          const int64_t os = wrap_index(wrap, (int64_t)sw[s].first_texel + j, rx);
+          if (os >= 0 && os < rx)
+            for (int c = 0; c < nc; c++) l0[((size_t)tt * px + s) * nc + c] += texels[((size_t)tt * rx + (size_t)os) * nc + c] * sw[s].w[j];
+        }
+    const std::vector<ResampleWeight> tw = resample_weights((size_t)ry, (size_t)py);
+    std::vector<float> work((size_t)py * nc);
+    for (int s = 0; s < px; s++) {
+      std::fill(work.begin(), work.end(), 0.0f);
+      for (int tt = 0; tt < py; tt++)
+        for (int j = 0; j < 4; j++) {
+          const int64_t off = wrap_index(wrap, (int64_t)tw[tt].first_texel + j, ry);
+          if (off >= 0 && off < ry)
+            for (int c = 0; c < nc; c++) work[(size_t)tt * nc + c] += l0[((size_t)off * px + s) * nc + c] * tw[tt].w[j];
+        }
+      for (int tt = 0; tt < py; tt++)
+        for (int c = 0; c < nc; c++) { const float v = work[(size_t)tt * nc + c]; l0[((size_t)tt * px + s) * nc + c] = clampf(v, 0.0f, std::numeric_limits<float>::infinity()); }
+    }
+    u0 = px; v0 = py;
+  } else { l0.assign(texels, texels + (size_t)rx * ry * nc); u0 = rx; v0 = ry; }
+  const int n_levels = 1 + (int)std::log2((float)std::max(u0, v0));   // mipmap.rs:150
+  std::vector<MipLevel> out;
+  std::vector<float> prev = std::move(l0); int pu = u0, pv = v0;
+  for (int lv = 0; lv < n_levels; lv++) {
+    if (lv > 0) {                                                     // mipmap.rs:157-175
+      const int su = std::max(1, pu / 2), sv = std::max(1, pv / 2);
+      std::vector<float> cur((size_t)su * sv * nc);
+      auto texel = [&](int64_t s, int64_t tt, int c) -> float {       // MIPMap::texel (mipmap.rs:194-210)
+        if (wrap == RT_WRAP_REPEAT) { s = modulo(s, pu); tt = modulo(tt, pv); }
+        else if (wrap == RT_WRAP_CLAMP) { s = s < 0 ? 0 : (s > pu - 1 ? pu - 1 : s); tt = tt < 0 ? 0 : (tt > pv - 1 ? pv - 1 : tt); }
+        else if (s < 0 || s >= pu || tt < 0 || tt >= pv) return 0.0f;
+        return prev[((size_t)tt * pu + (size_t)s) * nc + c];
+      };
+      for (int tt = 0; tt < sv; tt++) for (int s = 0; s < su; s++) for (int c = 0; c < nc; c++)
+        cur[((size_t)tt * su + s) * nc + c] = (((texel(2 * s, 2 * tt, c) + texel(2 * s + 1, 2 * tt, c)) + texel(2 * s, 2 * tt + 1, c)) + texel(2 * s + 1, 2 * tt + 1, c)) * 0.25f;
+      prev = std::move(cur); pu = su; pv = sv;
+    }
+    MipLevel L; L.u = pu; L.v = pv; L.d = prev;
+    out.push_back(std::move(L));
+  }
+  return out;
+}
+
 void build_textures(const rt_scene& in, std::vector<rtgpu_texture>& rows, std::vector<float>& pool) {
   rows.clear(); pool.clear();
   pool.resize(128);                                                   // EWA weight table (mipmap.rs:35-45)
@@ -74,57 +129,15 @@ void build_textures(const rt_scene& in, std::vector<rtgpu_texture>& rows, std::v
     }
     if (t.kind == RT_TEX_IMAGEMAP) {
       const int nc = t.is_float ? 1 : 3;
-      const int rx = t.img_w, ry = t.img_h;
-      if (rx <= 0 || ry <= 0 || !t.texels) throw std::runtime_error("imagemap texture without texels");
+      if (t.img_w <= 0 || t.img_h <= 0 || !t.texels) throw std::runtime_error("imagemap texture without texels");
       o.channels = nc;
-      std::vector<float> l0; int u0, v0;
-      if (!is_pow2(rx) || !is_pow2(ry)) {                             // mipmap.rs:73-139
-        const int px = round_up_pow2(rx), py = round_up_pow2(ry);
-        l0.assign((size_t)px * py * nc, 0.0f);
-        const std::vector<ResampleWeight> sw = resample_weights((size_t)rx, (size_t)px);
-        for (int tt = 0; tt < ry; tt++)
-          for (int s = 0; s < px; s++)
-            for (int j = 0; j < 4; j++) {
-              const int64_t os = wrap_index(t.wrap, (int64_t)sw[s].first_texel + j, rx);
-              if (os >= 0 && os < rx)
-                for (int c = 0; c < nc; c++) l0[((size_t)tt * px + s) * nc + c] += t.texels[((size_t)tt * rx + (size_t)os) * nc + c] * sw[s].w[j];
-            }
-        const std::vector<ResampleWeight> tw = resample_weights((size_t)ry, (size_t)py);
-        std::vector<float> work((size_t)py * nc);
-        for (int s = 0; s < px; s++) {
-          std::fill(work.begin(), work.end(), 0.0f);
-          for (int tt = 0; tt < py; tt++)
-            for (int j = 0; j < 4; j++) {
-              const int64_t off = wrap_index(t.wrap, (int64_t)tw[tt].first_texel + j, ry);
-              if (off >= 0 && off < ry)
-                for (int c = 0; c < nc; c++) work[(size_t)tt * nc + c] += l0[((size_t)off * px + s) * nc + c] * tw[tt].w[j];
-            }
-          for (int tt = 0; tt < py; tt++)
-            for (int c = 0; c < nc; c++) { const float v = work[(size_t)tt * nc + c]; l0[((size_t)tt * px + s) * nc + c] = clampf(v, 0.0f, std::numeric_limits<float>::infinity()); }
-        }
-        u0 = px; v0 = py;
-      } else { l0.assign(t.texels, t.texels + (size_t)rx * ry * nc); u0 = rx; v0 = ry; }
-      const int n_levels = 1 + (int)std::log2((float)std::max(u0, v0));   // mipmap.rs:150
-      if (n_levels > RTGPU_MAX_MIP_LEVELS) throw std::runtime_error("imagemap texture larger than 32768 texels on a side");
-      o.n_levels = n_levels;
-      std::vector<float> prev = std::move(l0); int pu = u0, pv = v0;
-      for (int lv = 0; lv < n_levels; lv++) {
-        if (lv > 0) {                                                 // mipmap.rs:157-175
-          const int su = std::max(1, pu / 2), sv = std::max(1, pv / 2);
-          std::vector<float> cur((size_t)su * sv * nc);
-          auto texel = [&](int64_t s, int64_t tt, int c) -> float {   // MIPMap::texel (mipmap.rs:194-210)
-            if (t.wrap == RT_WRAP_REPEAT) { s = modulo(s, pu); tt = modulo(tt, pv); }
-            else if (t.wrap == RT_WRAP_CLAMP) { s = s < 0 ? 0 : (s > pu - 1 ? pu - 1 : s); tt = tt < 0 ? 0 : (tt > pv - 1 ? pv - 1 : tt); }
-            else if (s < 0 || s >= pu || tt < 0 || tt >= pv) return 0.0f;
-            return prev[((size_t)tt * pu + (size_t)s) * nc + c];
-          };
-          for (int tt = 0; tt < sv; tt++) for (int s = 0; s < su; s++) for (int c = 0; c < nc; c++)
-            cur[((size_t)tt * su + s) * nc + c] = (((texel(2 * s, 2 * tt, c) + texel(2 * s + 1, 2 * tt, c)) + texel(2 * s, 2 * tt + 1, c)) + texel(2 * s + 1, 2 * tt + 1, c)) * 0.25f;
-          prev = std::move(cur); pu = su; pv = sv;
-        }
-        if (pool.size() + prev.size() > 0xffffffffull) throw std::runtime_error("texture pool exceeds 4 Gi floats");
-        o.level_offset[lv] = (uint32_t)pool.size(); o.level_u[lv] = pu; o.level_v[lv] = pv;
-        pool.insert(pool.end(), prev.begin(), prev.end());
+      std::vector<MipLevel> levels = build_mip_pyramid(t.img_w, t.img_h, nc, t.wrap, t.texels);
+      if ((int)levels.size() > RTGPU_MAX_MIP_LEVELS) throw std::runtime_error("imagemap texture larger than 32768 texels on a side");
+      o.n_levels = (int)levels.size();
+      for (size_t lv = 0; lv < levels.size(); lv++) {
+        if (pool.size() + levels[lv].d.size() > 0xffffffffull) throw std::runtime_error("texture pool exceeds 4 Gi floats");
+        o.level_offset[lv] = (uint32_t)pool.size(); o.level_u[lv] = levels[lv].u; o.level_v[lv] = levels[lv].v;
+        pool.insert(pool.end(), levels[lv].d.begin(), levels[lv].d.end());
       }
     }
     rows.push_back(o);

@@ -45,6 +45,8 @@ def _lib():
     lib.rtgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     lib.rtgpu_synchronize.argtypes = [vp]
     lib.rtgpu_build_bvh.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    lib.rtgpu_bsdf_probe.argtypes = [vp, C.c_uint32, C.c_int, sz, vp, vp, vp, C.c_uint32, vp]
+    lib.rtgpu_light_probe.argtypes = [vp, C.c_uint32, sz, vp, vp, vp, vp]
     lib.rtgpu_launch_count.argtypes = [vp]
     lib.rtgpu_launch_count.restype = C.c_uint64
     lib._rtgpu_ready = True
@@ -194,6 +196,25 @@ class Device:
         finally:
             self.free(d_r), self.free(d_o), self.free(d_s)
         return dict(occluded=occ, nodes=st[:, 0].copy(), prims=st[:, 1].copy())
+
+    # ---- probes of the shading code (rtgpu_bsdf_probe / rtgpu_light_probe) ---------------------------------
+    def bsdf_probe(self, row, wo, wi, u, allow_multiple_lobes=True, flags=31):
+        """The Bsdf material `row` builds on a canonical surface (n = +z, dpdu = +x): (n, 3) wo, wi and (n, 2) u ->
+        dict of arrays (f, pdf, sf, swi, spdf, sflags, n_lobes, eta), the layout of the oracle's probe."""
+        wo, wi, u = (np.ascontiguousarray(a, np.float32) for a in (wo, wi, u))
+        n = len(wo)
+        out = np.zeros((n, 14), np.float32)
+        self._check(self._lib.rtgpu_bsdf_probe(self._h, row, 1 if allow_multiple_lobes else 0, n, wo.ctypes.data, wi.ctypes.data, u.ctypes.data, flags, out.ctypes.data))
+        return dict(f=out[:, 0:3], pdf=out[:, 3], sf=out[:, 4:7], swi=out[:, 7:10], spdf=out[:, 10], sflags=out[:, 11].astype(np.int32),
+                    n_lobes=out[:, 12].astype(np.int32), eta=out[:, 13])
+
+    def light_probe(self, light, ref, u, w):
+        """Light row probed from reference points: ref (n, 6) {p, n}, u (n, 2), w (n, 3) -> dict(li, wi, pdf, p1, pdf_w, le_w, pdf_wi, delta)."""
+        ref, u, w = (np.ascontiguousarray(a, np.float32) for a in (ref, u, w))
+        n = len(ref)
+        out = np.zeros((n, 16), np.float32)
+        self._check(self._lib.rtgpu_light_probe(self._h, light, n, ref.ctypes.data, u.ctypes.data, w.ctypes.data, out.ctypes.data))
+        return dict(li=out[:, 0:3], wi=out[:, 3:6], pdf=out[:, 6], p1=out[:, 7:10], pdf_w=out[:, 10], le_w=out[:, 11:14], pdf_wi=out[:, 14], delta=out[:, 15])
 
     # ---- camera / render / film -----------------------------------------------------------------------
     def generate_rays(self, rd, samples):

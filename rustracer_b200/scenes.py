@@ -290,6 +290,45 @@ def write_png8(path, img):
                 chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + chunk(b"IEND", b""))
 
 
+def write_hdr(path, img, rle=True):
+    """Radiance RGBE (.hdr), rows top-to-bottom ("-Y h +X w"); rle=True writes new-style run-length scanlines (needs 8 <= w < 32768).
+    Returns the image as a decoder sees it (RGBE quantisation applied), (H, W, 3) float32."""
+    img = np.asarray(img, np.float32)
+    h, w, _ = img.shape
+    m = img.max(-1)
+    e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0).astype(np.int32)       # m in [2^(e-1), 2^e)
+    scale = np.where(m > 1e-32, np.exp2((8 - e).astype(np.float32)), 0).astype(np.float32)
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    rgbe[..., :3] = np.clip(np.floor(img * scale[..., None]), 0, 255).astype(np.uint8)
+    rgbe[..., 3] = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        for y in range(h):
+            if not rle:
+                f.write(rgbe[y].tobytes())
+                continue
+            f.write(bytes([2, 2, w >> 8, w & 255]))
+            for c in range(4):
+                row = rgbe[y, :, c]
+                x = 0
+                while x < w:
+                    run = 1
+                    while x + run < w and run < 127 and row[x + run] == row[x]:
+                        run += 1
+                    if run >= 4:
+                        f.write(bytes([128 + run, int(row[x])]))
+                        x += run
+                    else:
+                        lit = 1
+                        while x + lit < w and lit < 128 and not (x + lit + 3 < w and row[x + lit] == row[x + lit + 1] == row[x + lit + 2] == row[x + lit + 3]):
+                            lit += 1
+                        f.write(bytes([lit]) + row[x:x + lit].tobytes())
+                        x += lit
+    dec = rgbe[..., :3].astype(np.float32) * np.exp2(rgbe[..., 3:4].astype(np.float32) - 136.0)
+    dec[rgbe[..., 3] == 0] = 0
+    return dec.astype(np.float32)
+
+
 def texture_images(out_dir):
     """The two harness textures: a 48x20 (non power-of-two) RGB PFM and a 16x16 greyscale PNG."""
     os.makedirs(out_dir, exist_ok=True)
@@ -371,6 +410,61 @@ def balls_textured(out_dir, xres=1024, yres=768, spp=64, integrator=None, n_side
         col = f"{0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f} {0.2 + 0.7 * float(rng.f32()[0]):.4f}"
         s += "AttributeBegin\n" + _MATERIALS_TEXTURED[i % len(_MATERIALS_TEXTURED)].format(c=col) + f"\nTranslate {x:.5f} {float(r):.5f} {z:.5f}\nRotate {37 * i} 0.3 1 0.2\n"
         s += f'Shape "sphere" "float radius" [{float(r):.5f}]\nAttributeEnd\n'
+    s += "WorldEnd\n"
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# every light class and every Shape::sample the lights call
+
+def env_map_image(w=32, h=16):
+    """Lat-long environment with strong contrast: a dim sky gradient, a warm horizon band and a small very bright 'sun' patch
+    (1000x the sky) — the importance sampling of infinite.rs:143-183 has to find it.  (h, w, 3) float32, row 0 = theta 0."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    sky = np.stack([0.05 + 0.02 * y / h, 0.08 + 0.03 * y / h, 0.15 + 0.1 * (1 - y / h)], -1)
+    band = np.exp(-((y - 0.55 * h) / (0.08 * h)) ** 2)[..., None] * np.array([0.6, 0.35, 0.15], np.float32)
+    img = (sky + band).astype(np.float32)
+    sy, sx = int(0.3 * h), int(0.7 * w)
+    img[sy:sy + max(1, h // 16), sx:sx + max(1, w // 16)] = np.array([60.0, 55.0, 45.0], np.float32)
+    return img
+
+
+def lights_zoo(out_dir, xres=96, yres=72, spp=8, integrator=None, env_size=(32, 16), env_name="env.pfm", absolute_paths=False, crop=None):
+    """Image-mapped infinite light under a rotated light_to_world (infinite.rs:46-219, distribution2d.rs, mipmap.rs:227-245),
+    a distant light (distant.rs:49-87), disk and cylinder area lights (disk.rs:138-154, cylinder.rs:259-278), a two-sided
+    and a one-sided triangle area light seen from both sides (diffuse.rs:91-97, mesh.rs:610-634), over matte / plastic / glass /
+    mirror / metal receivers.  Writes the environment map into out_dir; parse with search_dir=out_dir."""
+    os.makedirs(out_dir, exist_ok=True)
+    if env_name.endswith(".hdr"):
+        write_hdr(os.path.join(out_dir, env_name), env_map_image(*env_size))
+    else:
+        write_pfm(os.path.join(out_dir, env_name), env_map_image(*env_size))
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [5]'
+    s = header(xres, yres, spp, integrator, 42, ([0.5, 5.0, -10.5], [0, 1.0, 0], [0, 1, 0]), crop)
+    fn = os.path.join(os.path.abspath(out_dir), env_name) if absolute_paths else env_name
+    s += "WorldBegin\n"
+    s += ('AttributeBegin\nRotate -90 1 0 0\nRotate 35 0 0 1\nLightSource "infinite" "rgb L" [0.9 1.0 1.1] "rgb scale" [1.2 1.2 1.2] '
+          f'"string mapname" "{fn}" "integer samples" [2]\nAttributeEnd\n')
+    s += 'LightSource "distant" "rgb L" [1.6 1.5 1.3] "point from" [4 9 -3] "point to" [0 0 0]\n'
+    # disk light facing down, phimax-clipped annulus
+    s += ('AttributeBegin\nAreaLightSource "diffuse" "rgb L" [14 13 11] "integer samples" [2]\nMaterial "matte" "rgb Kd" [0 0 0]\nTranslate -3 4.5 0.5\nRotate 90 1 0 0\n'
+          'Shape "disk" "float radius" [0.9] "float innerradius" [0.25] "float phimax" [300]\nAttributeEnd\n')
+    # cylinder light lying along x (emits outwards), partial sweep
+    s += ('AttributeBegin\nAreaLightSource "diffuse" "rgb L" [9 10 12]\nMaterial "matte" "rgb Kd" [0 0 0]\nTranslate 3.2 2.6 1.5\nRotate 90 0 1 0\n'
+          'Shape "cylinder" "float radius" [0.3] "float z_min" [-1.1] "float z_max" [1.1] "float phi_max" [270]\nAttributeEnd\n')
+    # two-sided vertical triangle quad between two receivers; one-sided quad facing away from the camera (emits towards +z only)
+    s += ('AttributeBegin\nAreaLightSource "diffuse" "rgb L" [8 3 3] "bool twosided" "true"\nMaterial "matte" "rgb Kd" [0 0 0]\n'
+          + _quad([-0.6, 0.4, 1.0], [0.6, 0.4, 1.0], [0.6, 1.8, 1.0], [-0.6, 1.8, 1.0]) + 'AttributeEnd\n')
+    s += ('AttributeBegin\nAreaLightSource "diffuse" "rgb L" [3 8 3]\nMaterial "matte" "rgb Kd" [0 0 0]\n'
+          + _quad([1.6, 0.3, -1.5], [1.6, 1.5, -1.5], [2.8, 1.5, -1.5], [2.8, 0.3, -1.5]) + 'AttributeEnd\n')
+    s += 'AttributeBegin\nMaterial "matte" "rgb Kd" [0.55 0.55 0.5]\nRotate -90 1 0 0\nShape "disk" "float radius" [14]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "matte" "rgb Kd" [0.6 0.6 0.65]\n' + _quad([-7, 0, 5], [7, 0, 5], [7, 6, 5], [-7, 6, 5]) + 'AttributeEnd\n'
+    receivers = [('Material "matte" "rgb Kd" [0.7 0.3 0.25]', (-2.2, 0.7, -1.0), 0.7), ('Material "plastic" "rgb Kd" [0.2 0.4 0.7] "float roughness" [0.08]', (-0.3, 0.6, -2.2), 0.6),
+                 ('Material "glass" "float index" [1.5]', (1.2, 0.65, -3.0), 0.65), ('Material "mirror"', (2.6, 0.8, 3.0), 0.8),
+                 ('Material "metal" "float roughness" [0.1]', (-2.4, 0.75, 2.6), 0.75), ('Material "matte" "rgb Kd" [0.5 0.5 0.5] "float sigma" [25]', (0.0, 0.5, 2.8), 0.5)]
+    for mat, c, r in receivers:
+        s += f'AttributeBegin\n{mat}\nTranslate {c[0]} {c[1]} {c[2]}\nShape "sphere" "float radius" [{r}]\nAttributeEnd\n'
     s += "WorldEnd\n"
     return s
 

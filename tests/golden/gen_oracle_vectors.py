@@ -35,6 +35,15 @@ CASES = {
     # textures + bump mapping (the texture images are regenerated next to the system temp directory)
     "textured_path": lambda: scenes.balls_textured(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True),
     "textured_whitted": lambda: scenes.balls_textured(_TEX_DIR, xres=96, yres=72, spp=8, integrator='Integrator "whitted" "integer maxdepth" [4]', absolute_paths=True),
+    # image-mapped infinite light (rotated), distant light, disk / cylinder / two-sided triangle area lights
+    "lights_path": lambda: scenes.lights_zoo(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True),
+    "lights_path_uniform": lambda: scenes.lights_zoo(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True,
+                                                     integrator='Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "uniform"'),
+    "lights_direct_all": lambda: scenes.lights_zoo(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True,
+                                                   integrator='Integrator "directlighting" "string strategy" "all" "integer maxdepth" [5]'),
+    "lights_direct_one": lambda: scenes.lights_zoo(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True,
+                                                   integrator='Integrator "directlighting" "string strategy" "one" "integer maxdepth" [5]'),
+    "lights_whitted": lambda: scenes.lights_zoo(_TEX_DIR, xres=96, yres=72, spp=8, absolute_paths=True, integrator='Integrator "whitted" "integer maxdepth" [5]'),
 }
 N_RAYS, N_LI, SEED = 2000, 400, 11
 

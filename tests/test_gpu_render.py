@@ -38,15 +38,20 @@ def _cases(tmp):
     # textured_path and textured_whitted come with gen.CASES
     c["textured_path_lens"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, lens=True)
     c["textured_direct"] = lambda: scenes.balls_textured(str(tmp), xres=96, yres=72, spp=4, integrator='Integrator "directlighting" "integer maxdepth" [3] "string strategy" "one"')
+    # row a10 beyond gen.CASES: a non-power-of-two .hdr environment (Lanczos-resampled by MIPMap::new) and an 8:1 map whose sampling
+    # image comes from a coarser pyramid level (mipmap.rs:227-245 with width = 0.5 / min(2w, 2h))
+    c["lights_path_hdr"] = lambda: scenes.lights_zoo(str(tmp), xres=96, yres=72, spp=8, env_size=(40, 12), env_name="env.hdr")
+    c["lights_path_wide"] = lambda: scenes.lights_zoo(str(tmp), xres=96, yres=72, spp=8, env_size=(128, 16), env_name="env_wide.pfm")
     c["cornell_rr"] = lambda: scenes.cornell_box(xres=48, yres=48, spp=8, integrator='Integrator "path" "integer maxdepth" [12] "float rrthreshold" [1] "string lightsamplestrategy" "uniform"')
     return c
 
 
 NAMES = list(gen.CASES) + ["cornell_path_spatial", "balls_normal", "field_path_spatial", "field_ao", "cornell_rr", "instanced_path", "instanced_whitted",
-                            "instanced_ao", "textured_path_lens", "textured_direct"]
+                            "instanced_ao", "textured_path_lens", "textured_direct", "lights_path_hdr", "lights_path_wide"]
 
 
-@pytest.mark.parametrize("name", ["cornell_path_spatial", "field_path_spatial", "balls_path", "textured_path", "instanced_path", "balls_whitted", "textured_direct"])
+@pytest.mark.parametrize("name", ["cornell_path_spatial", "field_path_spatial", "balls_path", "textured_path", "instanced_path", "balls_whitted", "textured_direct",
+                                  "lights_path", "lights_direct_all"])
 def test_stream_overlap_keeps_every_sample(dev, tmp_path, name):
     """rtgpu option overlap_bounces (render.cu): the shadow / MIS traces of bounce b run on side streams beside the closest-hit launch of
     bounce b + 1.  The path integrator's additions to a sample's L keep the reference's order (path.rs:96-215, integrator/mod.rs:222-318),
