@@ -22,6 +22,6 @@ if [ "$1" != "host" ]; then
   for p in "${pids[@]}"; do wait $p || fail=1; done
   cat $OBJ/*.log
   [ $fail -eq 0 ] || { echo "nvcc failed"; exit 1; }
-  nvcc -shared -o rustracer_b200/lib/librtgpu${RT_LIB_VARIANT}.so $OBJ/*.o -lcudart
+  nvcc -shared -o rustracer_b200/lib/librtgpu${RT_LIB_VARIANT}.so $OBJ/*.o -lcudart -ldl
 fi
 wait

@@ -246,7 +246,7 @@ int rtgpu_render(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, rtgpu_stats* sta
 int rtgpu_li_samples(rtgpu_ctx* ctx, const rtgpu_render_desc* desc, const int32_t* pixels, size_t n, float* rgb);
 
 /* Probes of the shading code the render kernels run (host buffers; tests/test_gpu_pins.py).
- * rtgpu_bsdf_probe: the Bsdf material `material_row` builds (Material::compute_scattering_functions, material/*.rs) on a canonical surface
+ * rtgpu_bsdf_probe: the Bsdf material `material_row` builds (Material::compute_scattering_functions, material/ *.rs) on a canonical surface
  *   (p = 0, n = +z, dpdu = +x), evaluated for n world-space triples wo[3], wi[3], u[2] with BxDFType `flags` (bsdf/bxdf.rs:8-16):
  *   out[14] = { Bsdf::f rgb, Bsdf::pdf, then Bsdf::sample_f(wo, u): f rgb, wi xyz, pdf, sampled type, lobe count, Bsdf::eta }
  *   (bsdf/mod.rs:94-251).  Textured materials are rejected (their lobes depend on the hit point).
@@ -266,6 +266,17 @@ int rtgpu_resolve_film(rtgpu_ctx* ctx, float* rgb);
 int rtgpu_film_device_ptr(rtgpu_ctx* ctx, void** d_ptr, size_t* n_floats);
 /* Single-process multi-GPU: sum the films of ctxs[0..n) into ctxs[root] with peer copies + an add kernel. */
 int rtgpu_reduce_film(rtgpu_ctx** ctxs, int n, int root);
+
+/* Multi-process multi-GPU (one process and one context per GPU — SURVEY 8e): the film sum is ONE ncclReduce over NVLink / NVSwitch.
+ *   rank 0:      rtgpu_comm_unique_id(id)  -> ship the RTGPU_COMM_ID_BYTES to the other ranks by any means (file, socket, MPI, torch store)
+ *   every rank:  rtgpu_comm_init(ctx, id, rank, world);  rtgpu_render(... tile_rank = rank, tile_world = world ...);
+ *                rtgpu_reduce_film_nccl(ctx, root, NULL); then on the root: rtgpu_read_film / rtgpu_resolve_film
+ * NCCL is opened at run time (dlopen "libnccl.so.2"), so the library has no link-time dependency on it; RTGPU_ERR_UNSUPPORTED when absent. */
+#define RTGPU_COMM_ID_BYTES 128
+int rtgpu_comm_unique_id(void* id_out);
+int rtgpu_comm_init(rtgpu_ctx* ctx, const void* unique_id, int rank, int world);
+int rtgpu_reduce_film_nccl(rtgpu_ctx* ctx, int root, float* elapsed_ms /* may be NULL: CUDA-event time of the collective on this rank */);
+int rtgpu_comm_destroy(rtgpu_ctx* ctx);
 
 /* device memory helpers so FFI callers need no CUDA runtime binding */
 int rtgpu_malloc(rtgpu_ctx* ctx, size_t bytes, void** d_ptr);

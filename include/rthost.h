@@ -51,6 +51,11 @@ int rth_render_desc(rth_scene* s, rtgpu_render_desc* out);
 int rth_tokenize(const char* text, char* out, size_t out_len);
 int rth_param_header(const char* s, int* type_out, char* name_out, size_t name_len);
 
+/* The synthetic ray batches of the ray-batch microbenchmark, multi-threaded: ray i = PCG32 stream seed * 2^32 + first + i
+ * (rng.rs:5-52): origin uniform in the world bounds grown 5 %, direction uniform on the sphere with t_max = inf (closest-hit batch) or the
+ * segment to a second uniform point with t_max = 1 - 1e-4 (any_hit != 0).  rustracer_b200/scenes.py ray_batch is the definition. */
+int rth_ray_batch(uint64_t n, const float* world_lo, const float* world_hi, uint64_t seed, int any_hit, uint64_t first, rtgpu_ray* out);
+
 /* == imageio::write_image for .png (8-bit sRGB, spectrum.rs:52-66) and, for parity work, .pfm (raw float). */
 int rth_write_image(const char* path, const float* rgb, int width, int height);
 

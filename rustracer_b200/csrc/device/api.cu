@@ -239,6 +239,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side_stream);
   cudaStreamSynchronize(ctx->side_stream2);
+  rtgpu_comm_destroy(ctx);
   free_scene(ctx);
   rt::free_wave_buffers(ctx);
   if (ctx->film) cudaFree(ctx->film);

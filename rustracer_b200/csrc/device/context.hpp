@@ -44,6 +44,7 @@ struct rtgpu_ctx {
   int sort_bounce_rays = 0;   // rtgpu_render (path): bin the rays of bounces >= 1 by origin cell + direction octant before tracing (profiles/r01q)
   int overlap_bounces = 2;    // rtgpu_render (path): >= 1 shadow / MIS traces of bounce b on a second stream, beside closest-hit + classify of bounce b + 1;
                               // 2: closest-hit MIS rays on a third stream beside the any-hit MIS rays
+  void* comm = nullptr; int comm_rank = 0, comm_world = 1;   // ncclComm_t of rtgpu_comm_init (render.cu)
   int sort_items = 1;   // rtgpu_render: counting sort of the listed-lobes queue / of the recursive integrators' items by material row
 };
 

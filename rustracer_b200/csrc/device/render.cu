@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is opened at run time (rtgpu_comm_init), see NcclApi below
 
 using namespace rt;
 
@@ -601,6 +603,89 @@ int rtgpu_reduce_film(rtgpu_ctx** ctxs, int n, int root) {
     r->launches++;
   }
   RT_CUDA(r, cudaStreamSynchronize(r->stream));
+  return RTGPU_OK;
+}
+
+
+// ---- multi-process film reduce: one ncclReduce(sum) over NVLink (film.rs:177-194 is the merge it replaces) -----------
+// NCCL is opened with dlopen at the first rtgpu_comm_* call instead of being a link-time dependency: a host process that already
+// carries an NCCL (e.g. PyTorch's bundled libnccl.so.2) must keep exactly one copy, and a host without any (the Rust binary) gets the
+// system library.  Only entry points whose ABI is stable across NCCL 2.x are used.
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.handle || !api.error.empty()) return &api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+  if (!api.handle) { api.error = std::string("NCCL not found: ") + dlerror(); return &api; }
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+  api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.Reduce || !api.CommDestroy || !api.GetErrorString) { api.error = "NCCL library lacks an expected entry point"; api.handle = nullptr; }
+  return &api;
+}
+int nccl_fail(rtgpu_ctx* ctx, NcclApi* api, ncclResult_t r, const char* what) {
+  return fail(ctx, RTGPU_ERR_CUDA, std::string(what) + ": " + (api->GetErrorString ? api->GetErrorString(r) : "NCCL error"));
+}
+}  // namespace
+
+int rtgpu_comm_unique_id(void* id_out) {
+  static_assert(sizeof(ncclUniqueId) == RTGPU_COMM_ID_BYTES, "ncclUniqueId size");
+  if (!id_out) return RTGPU_ERR_ARG;
+  NcclApi* api = nccl_api();
+  if (!api->handle) return RTGPU_ERR_UNSUPPORTED;
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return RTGPU_ERR_CUDA;
+  std::memcpy(id_out, &id, sizeof(id));
+  return RTGPU_OK;
+}
+
+int rtgpu_comm_init(rtgpu_ctx* ctx, const void* unique_id, int rank, int world) {
+  if (!ctx || !unique_id || world < 1 || rank < 0 || rank >= world) return RTGPU_ERR_ARG;
+  NcclApi* api = nccl_api();
+  if (!api->handle) return fail(ctx, RTGPU_ERR_UNSUPPORTED, api->error);
+  if (ctx->comm) { api->CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
+  cudaSetDevice(ctx->device);
+  ncclUniqueId id; std::memcpy(&id, unique_id, sizeof(id));
+  ncclComm_t comm = nullptr;
+  const ncclResult_t r = api->CommInitRank(&comm, world, id, rank);
+  if (r != ncclSuccess) return nccl_fail(ctx, api, r, "ncclCommInitRank");
+  ctx->comm = comm; ctx->comm_rank = rank; ctx->comm_world = world;
+  return RTGPU_OK;
+}
+
+// The job's one collective: the raw accumulators (sum w*RGB, sum w per pixel — linear, film.rs:357-358) of every rank summed into
+// `root`, in place, on the context's stream; blocks until done.  With disjoint tile shares the other ranks contribute zeros.
+int rtgpu_reduce_film_nccl(rtgpu_ctx* ctx, int root, float* elapsed_ms) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, RTGPU_ERR_ARG, "no communicator: call rtgpu_comm_init first");
+  if (!ctx->film) return fail(ctx, RTGPU_ERR_ARG, "no film: call rtgpu_render first");
+  if (root < 0 || root >= ctx->comm_world) return fail(ctx, RTGPU_ERR_ARG, "root outside the communicator");
+  NcclApi* api = nccl_api();
+  cudaSetDevice(ctx->device);
+  if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const ncclResult_t r = api->Reduce(ctx->film, ctx->film, ctx->film_pixels * 4, ncclFloat, ncclSum, root, (ncclComm_t)ctx->comm, ctx->stream);
+  if (r != ncclSuccess) return nccl_fail(ctx, api, r, "ncclReduce");
+  if (elapsed_ms) RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (elapsed_ms) RT_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+  return RTGPU_OK;
+}
+
+int rtgpu_comm_destroy(rtgpu_ctx* ctx) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  if (ctx->comm) { NcclApi* api = nccl_api(); if (api->handle) api->CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
   return RTGPU_OK;
 }
 

@@ -2,8 +2,12 @@
 #include "../../../include/rthost.h"
 #include "pbrt_frontend.hpp"
 #include "scene_build.hpp"
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <string>
+#include <thread>
+#include <vector>
 
 using namespace rth;
 
@@ -98,6 +102,47 @@ static void png_chunk(FILE* f, const char* type, const std::vector<unsigned char
   std::fwrite(cb, 1, 4, f);
 }
 static float gamma_correct(float v) { return v <= 0.0031308f ? 12.92f * v : 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f; }   // spectrum.rs:387-393
+
+// SURVEY 8d C4 ray batches, the multi-threaded twin of rustracer_b200/scenes.py ray_batch (which defines them): ray i draws from the
+// PCG32 stream (rng.rs:5-52) `seed * 2^32 + i` — origin uniform in the world bounds grown 5 %, then either a uniform direction
+// (uniform_sample_sphere, sampling/mod.rs:14-20; t_max = inf) or the segment to a second uniform point (d = p1 - p0, t_max = 1 - 1e-4).
+int rth_ray_batch(uint64_t n, const float* world_lo, const float* world_hi, uint64_t seed, int any_hit, uint64_t first, rtgpu_ray* out) {
+  return guarded([&] {
+    float c[3], h[3];
+    for (int k = 0; k < 3; k++) { c[k] = (world_lo[k] + world_hi[k]) * 0.5f; h[k] = (world_hi[k] - world_lo[k]) * (float)(0.5 * 1.05); }
+    auto body = [&](uint64_t a, uint64_t b) {
+      for (uint64_t i = a; i < b; i++) {
+        const uint64_t idx = first + i;
+        uint64_t state = 0; const uint64_t inc = (((seed << 32) + idx) << 1) | 1u;        // RNG::set_sequence
+        auto u32 = [&]() { const uint64_t o = state; state = o * 0x5851F42D4C957F2Dull + inc;
+                           const uint32_t x = (uint32_t)(((o >> 18) ^ o) >> 27), r = (uint32_t)(o >> 59); return (x >> r) | (x << ((~r + 1u) & 31u)); };
+        u32(); state += 0x853C49E6748FEA9Bull; u32();
+        auto f32 = [&]() { const float v = (float)u32() * 2.3283064365386963e-10f; return v < 0.99999994f ? v : 0.99999994f; };
+        rtgpu_ray r;
+        float o[3];
+        for (int k = 0; k < 3; k++) o[k] = c[k] + (f32() * 2.0f - 1.0f) * h[k];
+        r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+        if (any_hit) {
+          float d[3];
+          for (int k = 0; k < 3; k++) { const float p1 = c[k] + (f32() * 2.0f - 1.0f) * h[k]; d[k] = p1 - o[k]; }
+          r.dx = d[0]; r.dy = d[1]; r.dz = d[2]; r.tmax = (float)(1.0 - 1e-4);
+        } else {
+          const float u0 = f32(), u1 = f32();
+          const float z = 1.0f - 2.0f * u0, rr = std::sqrt(std::max(1.0f - z * z, 0.0f)), phi = (float)(2.0 * 3.14159265358979323846) * u1;
+          r.dx = rr * std::cos(phi); r.dy = rr * std::sin(phi); r.dz = z; r.tmax = INFINITY;
+        }
+        r.tag = (uint32_t)(idx & 0xffffffffull);
+        out[i] = r;
+      }
+    };
+    unsigned threads = std::max(1u, std::thread::hardware_concurrency());
+    if (n < (1u << 16)) threads = 1;
+    const uint64_t chunk = (n + threads - 1) / threads;
+    std::vector<std::thread> pool;
+    for (uint64_t a = 0; a < n; a += chunk) pool.emplace_back(body, a, std::min(n, a + chunk));
+    for (auto& t : pool) t.join();
+  });
+}
 
 int rth_write_image(const char* path, const float* rgb, int width, int height) {
   return guarded([&] {

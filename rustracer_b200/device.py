@@ -47,6 +47,10 @@ def _lib():
     lib.rtgpu_build_bvh.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     lib.rtgpu_bsdf_probe.argtypes = [vp, C.c_uint32, C.c_int, sz, vp, vp, vp, C.c_uint32, vp]
     lib.rtgpu_light_probe.argtypes = [vp, C.c_uint32, sz, vp, vp, vp, vp]
+    lib.rtgpu_comm_unique_id.argtypes = [vp]
+    lib.rtgpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.rtgpu_reduce_film_nccl.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.rtgpu_comm_destroy.argtypes = [vp]
     lib.rtgpu_launch_count.argtypes = [vp]
     lib.rtgpu_launch_count.restype = C.c_uint64
     lib._rtgpu_ready = True
@@ -255,6 +259,25 @@ class Device:
         out = np.zeros((h, w, 3), np.float32)
         self._check(self._lib.rtgpu_resolve_film(self._h, out.ctypes.data))
         return out
+
+    # ---- multi-process film reduce (rtgpu_comm_* / rtgpu_reduce_film_nccl) ---------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        rc = _lib().rtgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise DeviceError(f"rtgpu_comm_unique_id: {_STATUS.get(rc, rc)}")
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        self._check(self._lib.rtgpu_comm_init(self._h, C.c_char_p(bytes(unique_id)), rank, world))
+
+    def reduce_film(self, root=0):
+        """One ncclReduce(sum) of the raw film accumulators into `root` (in place).  Returns the CUDA-event time of the collective (ms)."""
+        ms = C.c_float(0)
+        self._check(self._lib.rtgpu_reduce_film_nccl(self._h, root, C.byref(ms)))
+        return ms.value
 
     def film_device_array(self):
         """The raw film accumulator as a __cuda_array_interface__ object (for torch.as_tensor + NCCL reduce)."""

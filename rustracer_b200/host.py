@@ -40,6 +40,7 @@ def _lib():
     lib.rth_render_desc.argtypes = [C.c_void_p, C.POINTER(A.rtgpu_render_desc)]
     lib.rth_tokenize.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
     lib.rth_param_header.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+    lib.rth_ray_batch.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_int, C.c_uint64, C.c_void_p]
     lib.rth_write_image.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_int, C.c_int]
     lib._rth_ready = True
     return lib
@@ -180,3 +181,17 @@ def write_image(path, rgb):
     lib = _lib()
     if lib.rth_write_image(str(path).encode(), rgb.ctypes.data_as(C.POINTER(C.c_float)), w, h) != 0:
         raise SceneError(lib.rth_last_error().decode())
+
+
+def ray_batch(n, world_lo, world_hi, seed=5, any_hit=False, first=0, out=None):
+    """rth_ray_batch: the multi-threaded twin of scenes.ray_batch (SURVEY 8d C4).  Returns (n, 8) float32 {o, tmax, d, tag};
+    `out` may be a preallocated (n, 8) float32 array (e.g. the numpy view of a pinned buffer)."""
+    lo = np.ascontiguousarray(world_lo, np.float32)
+    hi = np.ascontiguousarray(world_hi, np.float32)
+    if out is None:
+        out = np.empty((n, 8), np.float32)
+    assert out.shape == (n, 8) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+    lib = _lib()
+    if lib.rth_ray_batch(n, lo.ctypes.data_as(C.POINTER(C.c_float)), hi.ctypes.data_as(C.POINTER(C.c_float)), seed, 1 if any_hit else 0, first, out.ctypes.data) != 0:
+        raise SceneError(lib.rth_last_error().decode())
+    return out
