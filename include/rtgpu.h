@@ -202,6 +202,8 @@ typedef struct rtgpu_stats {
   /* rays walked by the closest-hit kernels / by the any-hit kernels (MIS rays towards infinite lights are "regular" rays
    * for the reference's counters but are answered by an any-hit walk: they count here under anyhit_rays) */
   uint64_t closest_rays, anyhit_rays;
+  /* items handed to the shade kernels: path vertices incl. escaped rays (path), items of every level (whitted / directlighting), camera hits (ao) */
+  uint64_t shaded_items;
 } rtgpu_stats;
 
 int rtgpu_create(int device, rtgpu_ctx** out);
@@ -210,7 +212,8 @@ const char* rtgpu_last_error(rtgpu_ctx* ctx);
 
 int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* scene);
 
-/* == BVH::intersect / BVH::intersect_p over a batch; host buffers, H2D + kernel + D2H inside. */
+/* == BVH::intersect / BVH::intersect_p over a batch; host buffers, H2D + kernel + D2H inside, pipelined in 4 Mi-ray chunks (copy-in, traversal
+ * and copy-out of successive chunks overlap).  Buffers from rtgpu_host_alloc (page-locked) move at PCIe rate; pageable memory is accepted. */
 int rtgpu_intersect(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits);
 int rtgpu_occluded(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, uint8_t* occluded);
 /* Same, device-resident buffers (device pointers), asynchronous on the context's stream; elapsed_ms (may be NULL)
@@ -229,6 +232,7 @@ int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t 
 int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, int max_prims_per_node, float* node_lo, float* node_hi, uint32_t* ordered,
                     uint32_t* n_nodes, float* build_ms);
 /* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
+ * "sort_min_rays" (batches smaller than this skip the binning; default 32768),
  * "sort_items" (1 = rtgpu_render sorts the listed-lobes shade queue / the recursive integrators' items by material; default 1),
  * "overlap_bounces" (path integrator: 0 = every launch on one stream; 1 = the shadow / MIS traces of bounce b on a second stream beside
  *   the closest-hit launch of bounce b + 1; 2 = also the closest-hit MIS rays beside the any-hit MIS rays; default 2; results identical),
@@ -284,6 +288,9 @@ int rtgpu_free(rtgpu_ctx* ctx, void* d_ptr);
 int rtgpu_memcpy_h2d(rtgpu_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int rtgpu_memcpy_d2h(rtgpu_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int rtgpu_synchronize(rtgpu_ctx* ctx);
+/* page-locked host memory for the host-buffer entry points and the film read-back */
+int rtgpu_host_alloc(rtgpu_ctx* ctx, size_t bytes, void** h_ptr);
+int rtgpu_host_free(rtgpu_ctx* ctx, void* h_ptr);
 /* number of kernels launched by this context since creation (the bench's gpu_launches claim) */
 uint64_t rtgpu_launch_count(rtgpu_ctx* ctx);
 

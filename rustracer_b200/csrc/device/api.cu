@@ -47,22 +47,46 @@ __global__ void __launch_bounds__(256) k_sort_hist(const float4* __restrict__ ra
   keys[i] = k;
   atomicAdd(&hist[k], 1u);
 }
-// exclusive scan of kSortBins counters by one block of 1024 threads
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist) {
-  __shared__ uint32_t partial[1024];
-  constexpr int per = kSortBins / 1024;
-  uint32_t base = threadIdx.x * per, sum = 0;
-  for (int i = 0; i < per; i++) sum += hist[base + i];
-  partial[threadIdx.x] = sum;
+// exclusive scan of the kSortBins counters in three small launches (one block of 1024 threads walking all 262,144 bins took 431 us,
+// 20x the traversal of a 20 k-ray batch): per-segment sums, a scan of the kSortSegments sums by one block, then every segment's own scan
+constexpr int kSortSegment = 1024;                                   // bins per block
+constexpr int kSortSegments = kSortBins / kSortSegment;              // 256
+__global__ void __launch_bounds__(256) k_sort_scan_sums(const uint32_t* __restrict__ hist, uint32_t* __restrict__ sums) {
+  __shared__ uint32_t warp_sum[8];
+  const uint32_t base = blockIdx.x * kSortSegment;
+  uint32_t v = 0;
+  for (int i = threadIdx.x; i < kSortSegment; i += 256) v += hist[base + i];
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    uint32_t v = threadIdx.x >= off ? partial[threadIdx.x - off] : 0;
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += warp_sum[w]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(kSortSegments) k_sort_scan_top(uint32_t* __restrict__ sums) {   // exclusive scan of kSortSegments values, one block
+  __shared__ uint32_t tmp[kSortSegments];
+  const uint32_t own = sums[threadIdx.x];
+  tmp[threadIdx.x] = own;
+  __syncthreads();
+  for (int off = 1; off < kSortSegments; off <<= 1) {
+    const uint32_t v = (int)threadIdx.x >= off ? tmp[threadIdx.x - off] : 0;
     __syncthreads();
-    partial[threadIdx.x] += v;
+    tmp[threadIdx.x] += v;
     __syncthreads();
   }
-  uint32_t run = partial[threadIdx.x] - sum;
-  for (int i = 0; i < per; i++) { uint32_t c = hist[base + i]; hist[base + i] = run; run += c; }
+  sums[threadIdx.x] = tmp[threadIdx.x] - own;
+}
+__global__ void __launch_bounds__(256) k_sort_scan_segments(uint32_t* __restrict__ hist, const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t warp_sum[8];
+  const uint32_t base = blockIdx.x * kSortSegment + threadIdx.x * 4;   // 4 consecutive bins per thread
+  const uint4 c = *(const uint4*)&hist[base];
+  const uint32_t own = c.x + c.y + c.z + c.w;
+  uint32_t x = own;
+  for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, off); if ((int)(threadIdx.x & 31) >= off) x += y; }
+  if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+  __syncthreads();
+  uint32_t before = sums[blockIdx.x];
+  for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += warp_sum[w];
+  const uint32_t run = before + x - own;
+  *(uint4*)&hist[base] = make_uint4(run, run + c.x, run + c.x + c.y, run + c.x + c.y + c.z);
 }
 __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ offsets, uint32_t* __restrict__ perm) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,15 +163,15 @@ __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_anyhit_batch_engi
 }
 
 static int ensure_sort_scratch(rtgpu_ctx* ctx, size_t n, uint32_t** keys, uint32_t** perm, uint32_t** hist) {
-  // layout in one allocation: cursor[64] | hist[kSortBins] | keys[n] | perm[n]
-  size_t need = 256 + (size_t)kSortBins * 4 + n * 8;
+  // layout in one allocation: cursor[64] | hist[kSortBins] | segment sums[kSortSegments] | keys[n] | perm[n]
+  size_t need = 256 + (size_t)kSortBins * 4 + (size_t)kSortSegments * 4 + n * 8;
   if (ctx->scratch_n < need) {
     if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
     ctx->scratch_rays = nullptr; ctx->scratch_n = 0;
     RT_CUDA(ctx, cudaMalloc(&ctx->scratch_rays, need));
     ctx->scratch_n = need;
   }
-  *hist = (uint32_t*)ctx->scratch_rays + 64; *keys = *hist + kSortBins; *perm = *keys + n;
+  *hist = (uint32_t*)ctx->scratch_rays + 64; *keys = *hist + kSortBins + kSortSegments; *perm = *keys + n;
   return 0;
 }
 
@@ -157,7 +181,8 @@ static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_
   int rc = ensure_sort_scratch(ctx, n, &keys, &perm, &hist); if (rc) return rc;
   *cursor_out = (uint32_t*)ctx->scratch_rays;
   RT_CUDA(ctx, cudaMemsetAsync(*cursor_out, 0, 256, ctx->stream));
-  if (!ctx->sort_rays || n < 4096) return 0;
+  // below the break-even the binning costs more than the incoherent walk it avoids (profiles/r02b_small_batches.log)
+  if (!ctx->sort_rays || n < (size_t)ctx->sort_min_rays) return 0;
   SortParams sp;
   for (int k = 0; k < 3; k++) {
     float ext = ctx->scene.world_hi[k] - ctx->scene.world_lo[k];
@@ -168,9 +193,12 @@ static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_
   RT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)kSortBins * 4, ctx->stream));
   unsigned blocks = (unsigned)((n + 255) / 256);
   k_sort_hist<<<blocks, 256, 0, ctx->stream>>>((const float4*)d_rays, (uint32_t)n, sp, keys, hist);
-  k_sort_scan<<<1, 1024, 0, ctx->stream>>>(hist);
+  uint32_t* sums = hist + kSortBins;
+  k_sort_scan_sums<<<kSortSegments, 256, 0, ctx->stream>>>(hist, sums);
+  k_sort_scan_top<<<1, kSortSegments, 0, ctx->stream>>>(sums);
+  k_sort_scan_segments<<<kSortSegments, 256, 0, ctx->stream>>>(hist, sums);
   k_sort_scatter<<<blocks, 256, 0, ctx->stream>>>(keys, (uint32_t)n, hist, perm);
-  ctx->launches += 3;
+  ctx->launches += 5;
   RT_CUDA(ctx, cudaGetLastError());
   *perm_out = perm;
   return 0;
@@ -245,6 +273,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   if (ctx->film) cudaFree(ctx->film);
   if (ctx->scratch_rays) cudaFree(ctx->scratch_rays);
   if (ctx->scratch_hits) cudaFree(ctx->scratch_hits);
+  for (int k = 0; k < 2; k++) { if (ctx->batch_rays[k]) cudaFree(ctx->batch_rays[k]); if (ctx->batch_out[k]) cudaFree(ctx->batch_out[k]); for (int e = 0; e < 3; e++) if (ctx->batch_ev[k][e]) cudaEventDestroy(ctx->batch_ev[k][e]); }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2);
@@ -260,6 +289,7 @@ uint64_t rtgpu_launch_count(rtgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
+  if (std::strcmp(name, "sort_min_rays") == 0) { if (value < 0) return fail(ctx, RTGPU_ERR_ARG, "sort_min_rays must be >= 0"); ctx->sort_min_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_items") == 0) { ctx->sort_items = value; return RTGPU_OK; }
   if (std::strcmp(name, "overlap_bounces") == 0) { ctx->overlap_bounces = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_bounce_rays") == 0) { ctx->sort_bounce_rays = value; return RTGPU_OK; }
@@ -510,32 +540,70 @@ int rtgpu_occluded_device_stats(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t 
   return run_anyhit(ctx, d_rays, n, d_occluded, d_stats, nullptr);
 }
 
-// Host-buffer variants: H2D + kernel + D2H inside, chunked so any batch size fits.
+// Host-buffer variants: H2D + kernel + D2H inside (the reference-facing plugin call of the ray-batch config).  Chunks of 4 Mi rays go
+// through a three-stage pipeline on three streams — copy-in of chunk c + 1 (side stream), traversal of chunk c (main stream), copy-out of
+// chunk c - 1 (second side stream) — over two persistent device slots, so a large batch moves at the PCIe rate of its slower direction
+// instead of serialising copy, kernel and copy (round 1: 90 Mrays/s against 2 Grays/s on the device).  Pinned host memory
+// (rtgpu_host_alloc, or registered by the caller) is copied asynchronously at link rate; pageable memory works and is staged by the driver.
+static int ensure_batch_slots(rtgpu_ctx* ctx, size_t cap_rays) {
+  if (ctx->batch_cap >= cap_rays) return 0;
+  for (int k = 0; k < 2; k++) { if (ctx->batch_rays[k]) cudaFree(ctx->batch_rays[k]); if (ctx->batch_out[k]) cudaFree(ctx->batch_out[k]); ctx->batch_rays[k] = ctx->batch_out[k] = nullptr; }
+  ctx->batch_cap = 0;
+  for (int k = 0; k < 2; k++) {
+    RT_CUDA(ctx, cudaMalloc(&ctx->batch_rays[k], cap_rays * sizeof(rtgpu_ray)));
+    RT_CUDA(ctx, cudaMalloc(&ctx->batch_out[k], cap_rays * sizeof(rtgpu_hit)));
+    for (int e = 0; e < 3; e++) if (!ctx->batch_ev[k][e]) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->batch_ev[k][e], cudaEventDisableTiming));
+  }
+  ctx->batch_cap = cap_rays;
+  return 0;
+}
 static int host_batch(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits, uint8_t* occluded) {
   if (!ctx->has_scene) return fail(ctx, RTGPU_ERR_NO_SCENE, "no scene uploaded");
+  if (n == 0) return RTGPU_OK;
   cudaSetDevice(ctx->device);
-  const size_t chunk = (size_t)1 << 24;   // 16 Mi rays: 512 MiB of rays + 256 MiB of hits per chunk
-  void *d_rays = nullptr, *d_out = nullptr;
-  size_t cap = n < chunk ? n : chunk;
-  if (cap == 0) return RTGPU_OK;
-  RT_CUDA(ctx, cudaMalloc(&d_rays, cap * sizeof(rtgpu_ray)));
-  cudaError_t e = cudaMalloc(&d_out, cap * (hits ? sizeof(rtgpu_hit) : 1));
-  if (e != cudaSuccess) { cudaFree(d_rays); return check_cuda(ctx, e, "cudaMalloc"); }
-  int rc = RTGPU_OK;
-  for (size_t first = 0; first < n && rc == RTGPU_OK; first += cap) {
-    size_t m = n - first < cap ? n - first : cap;
-    e = cudaMemcpyAsync(d_rays, rays + first, m * sizeof(rtgpu_ray), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { rc = check_cuda(ctx, e, "cudaMemcpyAsync h2d"); break; }
-    if (hits) rc = run_closest(ctx, (const rtgpu_ray*)d_rays, m, (rtgpu_hit*)d_out, nullptr, nullptr);
-    else rc = run_anyhit(ctx, (const rtgpu_ray*)d_rays, m, (uint8_t*)d_out, nullptr, nullptr);
+  const size_t chunk = (size_t)1 << 22;
+  const size_t cap = n < chunk ? std::max<size_t>(n, 4096) : chunk;
+  int rc = ensure_batch_slots(ctx, cap); if (rc) return rc;
+  const size_t out_size = hits ? sizeof(rtgpu_hit) : 1;
+  cudaStream_t s_in = ctx->side_stream, s_run = ctx->stream, s_out = ctx->side_stream2;
+  enum { EV_IN = 0, EV_RUN = 1, EV_OUT = 2 };
+  size_t c = 0;
+  for (size_t first = 0; first < n; first += cap, c++) {
+    const int slot = (int)(c & 1);
+    const size_t m = std::min(cap, n - first);
+    if (c >= 2) RT_CUDA(ctx, cudaStreamWaitEvent(s_in, ctx->batch_ev[slot][EV_RUN], 0));          // the slot's previous rays have been traced
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->batch_rays[slot], rays + first, m * sizeof(rtgpu_ray), cudaMemcpyHostToDevice, s_in));
+    RT_CUDA(ctx, cudaEventRecord(ctx->batch_ev[slot][EV_IN], s_in));
+    RT_CUDA(ctx, cudaStreamWaitEvent(s_run, ctx->batch_ev[slot][EV_IN], 0));
+    if (c >= 2) RT_CUDA(ctx, cudaStreamWaitEvent(s_run, ctx->batch_ev[slot][EV_OUT], 0));         // the slot's previous results have left
+    if (hits) rc = run_closest(ctx, (const rtgpu_ray*)ctx->batch_rays[slot], m, (rtgpu_hit*)ctx->batch_out[slot], nullptr, nullptr);
+    else rc = run_anyhit(ctx, (const rtgpu_ray*)ctx->batch_rays[slot], m, (uint8_t*)ctx->batch_out[slot], nullptr, nullptr);
     if (rc) break;
-    if (hits) e = cudaMemcpyAsync(hits + first, d_out, m * sizeof(rtgpu_hit), cudaMemcpyDeviceToHost, ctx->stream);
-    else e = cudaMemcpyAsync(occluded + first, d_out, m, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = check_cuda(ctx, e, "cudaMemcpyAsync d2h");
+    RT_CUDA(ctx, cudaEventRecord(ctx->batch_ev[slot][EV_RUN], s_run));
+    RT_CUDA(ctx, cudaStreamWaitEvent(s_out, ctx->batch_ev[slot][EV_RUN], 0));
+    void* dst = hits ? (void*)(hits + first) : (void*)(occluded + first);
+    RT_CUDA(ctx, cudaMemcpyAsync(dst, ctx->batch_out[slot], m * out_size, cudaMemcpyDeviceToHost, s_out));
+    RT_CUDA(ctx, cudaEventRecord(ctx->batch_ev[slot][EV_OUT], s_out));
   }
-  cudaFree(d_rays); cudaFree(d_out);
-  return rc;
+  cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(s_run), e3 = cudaStreamSynchronize(s_out);
+  if (rc) return rc;
+  if (e1 != cudaSuccess) return check_cuda(ctx, e1, "copy-in stream");
+  if (e2 != cudaSuccess) return check_cuda(ctx, e2, "traversal stream");
+  if (e3 != cudaSuccess) return check_cuda(ctx, e3, "copy-out stream");
+  return RTGPU_OK;
+}
+// Pinned host memory for the host-buffer entry points (and the film read-back): page-locked, so copies run asynchronously at link rate.
+int rtgpu_host_alloc(rtgpu_ctx* ctx, size_t bytes, void** h_ptr) {
+  if (!ctx || !h_ptr) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaHostAlloc(h_ptr, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+  return RTGPU_OK;
+}
+int rtgpu_host_free(rtgpu_ctx* ctx, void* h_ptr) {
+  if (!ctx) return RTGPU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RT_CUDA(ctx, cudaFreeHost(h_ptr));
+  return RTGPU_OK;
 }
 int rtgpu_intersect(rtgpu_ctx* ctx, const rtgpu_ray* rays, size_t n, rtgpu_hit* hits) {
   if (!ctx || (n && (!rays || !hits))) return RTGPU_ERR_ARG;

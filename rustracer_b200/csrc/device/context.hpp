@@ -35,6 +35,10 @@ struct rtgpu_ctx {
   void* lightgrid = nullptr;
   // scratch for the batch API
   void* scratch_rays = nullptr; void* scratch_hits = nullptr; size_t scratch_n = 0;
+  // host-buffer batches (api.cu host_batch): two persistent device slots {rays, results} and their {copied-in, traced, copied-out} events
+  void* batch_rays[2] = {nullptr, nullptr}; void* batch_out[2] = {nullptr, nullptr}; size_t batch_cap = 0;
+  cudaEvent_t batch_ev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  int sort_min_rays = 32768;  // batch API: batches below this are traced in the caller's order
   int profile = 0;            // rtgpu_render: time every launch with CUDA events, per kernel class (rtgpu_stats.ms_*)
   int count_traversal = 0;    // rtgpu_render: count BVH nodes visited / primitives tested (rtgpu_stats.nodes_* / prims_*)
   std::vector<cudaEvent_t> event_pool;

@@ -447,6 +447,7 @@ __global__ void k_next_bounce(RenderParams p, int live_idx, int count_camera, in
     const uint32_t live = min(c[live_idx], p.w.cap_items);
     atomicAdd(&p.w.stats[S_REGULAR], (unsigned long long)live);
     atomicAdd(&p.w.stats[S_CLOSEST_RAYS], (unsigned long long)live);
+    p.w.stats[S_VERTICES] += live;                                    // items handed to the shade kernels (part 1 runs on one stream)
     if (count_camera) p.w.stats[S_CAMERA] += live;
     c[live_idx] = 0;
     for (int k = 0; k < Q_COUNT; k++) c[C_MATQ0 + k] = 0;

@@ -484,7 +484,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     stats->closest_launches = n_closest_launches; stats->anyhit_launches = n_anyhit_launches;
     stats->nodes_closest = hs[S_NODES_CLOSEST]; stats->prims_closest = hs[S_PRIMS_CLOSEST];
     stats->nodes_anyhit = hs[S_NODES_ANY]; stats->prims_anyhit = hs[S_PRIMS_ANY];
-    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS];
+    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS]; stats->shaded_items = hs[S_VERTICES];
     float acc[K_CLASSES] = {0, 0, 0, 0};
     for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b); acc[sp.cls] += ms; }
     stats->ms_closest = acc[K_CLOSEST]; stats->ms_anyhit = acc[K_ANYHIT]; stats->ms_shade = acc[K_SHADE]; stats->ms_other = acc[K_OTHER];

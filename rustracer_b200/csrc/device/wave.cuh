@@ -13,7 +13,7 @@ enum {
   C_LIVE0 = 0, C_LIVE1, C_MATQ0, C_SHADOW = C_MATQ0 + Q_COUNT, C_MIS, C_CUR_CLOSEST, C_CUR_ANY, C_CUR_MIS, C_OVERFLOW, C_MIS_ANY, C_MIS_SKIPPED, C_CUR_MISANY, C_COUNT = 32
 };
 // device statistics (uint64): the reference's counters (scene.rs:9-16, renderer.rs:17)
-enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_CLOSEST_RAYS, S_ANY_RAYS, S_COUNT = 10 };
+enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NODES_ANY, S_PRIMS_ANY, S_OVERFLOW, S_CLOSEST_RAYS, S_ANY_RAYS, S_VERTICES, S_COUNT = 11 };
 
 // Spatial / uniform light distribution tables (lightdistrib.rs).  Per voxel: func[n], cdf[n+1], func_int.
 struct LightGrid {

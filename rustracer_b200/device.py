@@ -44,6 +44,8 @@ def _lib():
     lib.rtgpu_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     lib.rtgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     lib.rtgpu_synchronize.argtypes = [vp]
+    lib.rtgpu_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.rtgpu_host_free.argtypes = [vp, vp]
     lib.rtgpu_build_bvh.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     lib.rtgpu_bsdf_probe.argtypes = [vp, C.c_uint32, C.c_int, sz, vp, vp, vp, C.c_uint32, vp]
     lib.rtgpu_light_probe.argtypes = [vp, C.c_uint32, sz, vp, vp, vp, vp]
@@ -80,6 +82,9 @@ class Device:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.rtgpu_host_free(self._h, p)
+            self._pinned = []
             self._lib.rtgpu_destroy(self._h)
             self._h = None
 
@@ -126,17 +131,22 @@ class Device:
         return int(self._lib.rtgpu_launch_count(self._h))
 
     # ---- batched BVH::intersect / intersect_p, host buffers -------------------------------------------
-    def intersect(self, rays):
+    def intersect(self, rays, out=None):
+        """== BVH::intersect over a host batch.  out: optional preallocated (n, 4) float32 array (then returned raw: {t, prim bits, b1, b2})."""
         rays = np.ascontiguousarray(rays, np.float32)
         n = rays.shape[0]
+        if out is not None:
+            self._check(self._lib.rtgpu_intersect(self._h, rays.ctypes.data, n, out.ctypes.data))
+            return out
         hits = np.zeros((n, 4), np.float32)
         self._check(self._lib.rtgpu_intersect(self._h, rays.ctypes.data, n, hits.ctypes.data))
         return dict(t=hits[:, 0].copy(), prim=hits[:, 1].copy().view(np.int32), b1=hits[:, 2].copy(), b2=hits[:, 3].copy())
 
-    def occluded(self, rays):
+    def occluded(self, rays, out=None):
         rays = np.ascontiguousarray(rays, np.float32)
         n = rays.shape[0]
-        out = np.zeros(n, np.uint8)
+        if out is None:
+            out = np.zeros(n, np.uint8)
         self._check(self._lib.rtgpu_occluded(self._h, rays.ctypes.data, n, out.ctypes.data))
         return out
 
@@ -156,6 +166,17 @@ class Device:
     def d2h(self, arr, dptr):
         assert arr.flags["C_CONTIGUOUS"]
         self._check(self._lib.rtgpu_memcpy_d2h(self._h, arr.ctypes.data, dptr, arr.nbytes))
+
+    def pinned_empty(self, shape, dtype=np.float32):
+        """numpy array over page-locked host memory (rtgpu_host_alloc): host-buffer batches and film read-backs move at PCIe rate.
+        The memory lives until the Device is closed."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(self._lib.rtgpu_host_alloc(self._h, n, C.byref(p)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p.value)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def synchronize(self):
         self._check(self._lib.rtgpu_synchronize(self._h))
