@@ -171,19 +171,25 @@ def count_triangles(sc):
 
 def oracle_rate(o, a, seconds=15.0, threads=0):
     """The oracle renderer (ZeroTwoSequence sampler, 16x16 tiles from a shared counter, all host threads) on a bounded sample of the
-    workload's step: every `stride`-th tile of the frame at spp_per_step spp.  o: the OracleScene (its SAH BVH is built once)."""
+    workload: every `stride`-th tile of the frame, each rendered the way renderer::render does it (renderer.rs:83-130) — ALL of the job's
+    samples of a pixel before the next pixel, one film merge under the mutex per tile.  (A sample of many tiles at few samples each made
+    the per-tile mutex traffic dominate on some runs: 2.6 M against 4.7-5.2 M samples/s, profiles/r02b_bench.json.)
+    o: the OracleScene (its SAH BVH is built once)."""
     from rustracer_b200 import _abi as A
-    samp = A.rt_sampler(spp=a.spp_per_step, dimensions=4)
-    # calibrate on a sparse subset, then size the real sample for ~`seconds`
+    job_spp = workload_config(a)["job_spp"]
+    samp = A.rt_sampler(spp=job_spp, dimensions=4)
     n_tiles = ((a.xres + 15) // 16) * ((a.yres + 15) // 16)
-    _, _, st = o.render(sampler=samp, sampler_kind=0, threads=threads, tile_stride=max(64, n_tiles // 64))
+    # calibrate on ~8 tiles per thread at an eighth of the samples, then size the real sample for ~`seconds` (at least 8 tiles per thread)
+    cal = A.rt_sampler(spp=max(1, job_spp // 8), dimensions=4)
+    _, _, st = o.render(sampler=cal, sampler_kind=0, threads=threads, tile_stride=max(1, n_tiles // (8 * max(1, os.cpu_count() or 1))))
     rate = st.camera_rays / max(st.seconds_tiles, 1e-6)
-    total = a.xres * a.yres * a.spp_per_step
-    stride = max(1, int(np.ceil(total / max(rate * seconds, 1.0))))
+    want_tiles = max(8 * int(st.threads), int(rate * seconds / (256.0 * job_spp)))
+    stride = max(1, n_tiles // want_tiles)
     _, _, st = o.render(sampler=samp, sampler_kind=0, threads=threads, tile_stride=stride)
     return {"value": st.camera_rays / st.seconds_tiles, "unit": UNIT, "cores": int(st.threads), "kind": "port",
-            "sample": f"every {stride}-th 16x16 tile of the {a.xres}x{a.yres} frame at {a.spp_per_step} spp: {st.camera_rays} camera paths in {st.seconds_tiles:.2f} s "
-                      f"(C++ restatement of rustracer's renderer, -O3 -march=native, ZeroTwoSequence sampler; the Rust binary cannot be built here)",
+            "sample": f"every {stride}-th 16x16 tile of the {a.xres}x{a.yres} frame at the job's {job_spp} spp (the reference's loop order: all samples of a tile, then the "
+                      f"next tile): {st.camera_rays} camera paths in {st.seconds_tiles:.2f} s (C++ restatement of rustracer's renderer, -O3 -march=native, ZeroTwoSequence "
+                      f"sampler; the Rust binary cannot be built here)",
             "mrays_per_s": (st.regular_rays + st.shadow_rays) / st.seconds_tiles / 1e6, "seconds": st.seconds_tiles, "camera_rays": int(st.camera_rays)}
 
 
@@ -455,12 +461,13 @@ def leg_c4(dev, a, tmp):
                 equal = int((ref["occluded"] == occ).sum())
                 res["check"] = {"rays": n, "equal": equal, "pct_equal": 100.0 * equal / n}
             else:
-                ref = o.intersect(rays, stats=False) if "stats" in o.intersect.__code__.co_varnames else o.intersect(rays)
+                ref = o.intersect(rays)
                 prim = hits[:, 1].view(np.int32)
                 same_id = ref["prim"] == prim
                 t_ref, t_got = ref["t"], hits[:, 0]
                 hit = ref["prim"] >= 0
-                t_ok = np.where(hit, np.abs(t_got - t_ref) <= 1e-5 * np.abs(t_ref), ~np.isfinite(t_got) | (prim < 0))
+                with np.errstate(invalid="ignore"):
+                    t_ok = np.where(hit, np.abs(t_got - t_ref) <= 1e-5 * np.abs(t_ref), prim < 0)
                 res["check"] = {"rays": n, "ids_equal": int(same_id.sum()), "pct_ids_equal": 100.0 * float(same_id.mean()),
                                 "t_bit_equal": int((t_ref[hit] == t_got[hit]).sum()), "pct_t_within_1e-5": 100.0 * float(t_ok.mean()), "hits": int(hit.sum())}
             res["check"]["oracle_seconds"] = time.perf_counter() - t0

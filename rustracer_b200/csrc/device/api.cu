@@ -335,6 +335,44 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     const size_t nn = s->n_nodes;
     auto bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
     auto fbits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+#if RT_ENGINE_WIDE4
+    // Collapsed nodes (trace_engine.cuh): one record per interior node at EVEN depth below the root of its tree — the scene's tree and
+    // every object definition's — numbered in pre-order; it holds the children's children (a leaf child stands for itself).
+    auto is_leaf = [&](size_t i) { return (bits(s->node_hi[i * 4 + 3]) >> 2) != 0; };
+    std::vector<uint32_t> interior_index(nn, 0xffffffffu);
+    uint32_t n_interior = 0;
+    std::vector<size_t> roots;
+    if (nn > 0) roots.push_back(0);
+    for (uint32_t k = 0; k < s->n_instances && s->instances; k++) if (s->instances[k].root_node != 0xffffffffu && s->instances[k].root_node < nn) roots.push_back(s->instances[k].root_node);
+    {
+      std::vector<size_t> todo;
+      for (size_t r : roots) {
+        if (is_leaf(r) || interior_index[r] != 0xffffffffu) continue;
+        todo.push_back(r);
+        while (!todo.empty()) {
+          const size_t i = todo.back(); todo.pop_back();
+          if (interior_index[i] != 0xffffffffu) continue;
+          interior_index[i] = n_interior++;
+          const size_t kids[2] = {i + 1, (size_t)bits(s->node_lo[i * 4 + 3])};
+          size_t grand[4]; int ng = 0;
+          for (size_t c : kids) {
+            if (c >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
+            if (is_leaf(c)) continue;
+            const size_t g0 = c + 1, g1 = bits(s->node_lo[c * 4 + 3]);
+            if (g0 >= nn || g1 >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
+            grand[ng++] = g0; grand[ng++] = g1;
+          }
+          for (int k = ng - 1; k >= 0; k--) if (!is_leaf(grand[k])) todo.push_back(grand[k]);   // pre-order: the first grandchild's subtree follows its parent
+        }
+      }
+      d.n_top = 0;
+    }
+    auto ref_of = [&](size_t i) -> uint32_t {
+      const uint32_t n_prims = bits(s->node_hi[i * 4 + 3]) >> 2;
+      return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];
+    };
+    std::vector<float> wide((size_t)n_interior * 32, 0.0f);
+#else
     // compact interior numbering: the top levels of the scene's tree first, breadth-first (the engine can stage them in shared
     // memory, RT_ENGINE_TOP_NODES), then every other interior node in array (pre-order) order
     std::vector<uint32_t> interior_index(nn, 0xffffffffu);
@@ -361,6 +399,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
       return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];
     };
     std::vector<float> wide((size_t)n_interior * 16, 0.0f);
+#endif
     std::vector<float> geom(s->prim_geom, s->prim_geom + (size_t)s->n_prims * 12);
     // shade-queue id of every slot's material in bits 2..4 of the second float4's w: the engine has that word in a register
     // when it records a hit, so classification needs no second look-up (hit slots are packed into 29 bits next to it)
@@ -381,11 +420,34 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
           geom[((size_t)off + n_prims - 1) * 12 + 7] = fbits(bits(geom[((size_t)off + n_prims - 1) * 12 + 7]) | kGeomLastBit);
           continue;
         }
+#if RT_ENGINE_WIDE4
+        if (interior_index[i] == 0xffffffffu) continue;                // an interior node of odd depth: absorbed by its parent's record
+        float* w = &wide[(size_t)interior_index[i] * 32];
+        const size_t kids[2] = {i + 1, (size_t)off};
+        uint32_t axes = meta & 3u, refs[4];
+        for (int c = 0; c < 2; c++) {
+          const size_t k = kids[c];
+          size_t e[2]; int ne;
+          if ((bits(s->node_hi[k * 4 + 3]) >> 2) != 0) { e[0] = k; ne = 1; }
+          else { e[0] = k + 1; e[1] = bits(s->node_lo[k * 4 + 3]); ne = 2; axes |= (bits(s->node_hi[k * 4 + 3]) & 3u) << (2 + 2 * c); }
+          for (int j = 0; j < 2; j++) {
+            const int slot = 2 * c + j;
+            float* lo = w + 8 * slot; float* hi = lo + 4;
+            if (j < ne) {
+              for (int x = 0; x < 3; x++) { lo[x] = s->node_lo[e[j] * 4 + x]; hi[x] = s->node_hi[e[j] * 4 + x]; }
+              refs[slot] = ref_of(e[j]);
+            } else refs[slot] = 0xffffffffu;
+          }
+        }
+        // w components of the eight float4: ref c0, ref c1, axes, ref c2, ref c3, -, -, -
+        w[3] = fbits(refs[0]); w[7] = fbits(refs[1]); w[11] = fbits(axes); w[15] = fbits(refs[2]); w[19] = fbits(refs[3]);
+#else
         const size_t L = i + 1, R = off;
         if (L >= nn || R >= nn) { bad_nodes = 2; continue; }
         float* w = &wide[(size_t)interior_index[i] * 16];
         for (int k = 0; k < 3; k++) { w[k] = s->node_lo[L * 4 + k]; w[4 + k] = s->node_hi[L * 4 + k]; w[8 + k] = s->node_lo[R * 4 + k]; w[12 + k] = s->node_hi[R * 4 + k]; }
         w[3] = fbits(ref_of(L)); w[7] = fbits(ref_of(R)); w[11] = fbits(meta & 3u); w[15] = 0.0f;
+#endif
       }
     });
     if (bad_nodes == 1) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");

@@ -5,6 +5,9 @@
 #include "dmath.cuh"
 #include "../../../include/rtgpu.h"
 
+#ifndef RT_ENGINE_WIDE4
+#define RT_ENGINE_WIDE4 1           // 1: the traversal engine walks 128-byte nodes that hold the FOUR grandchildren of a binary node (two levels of the
+#endif                              //    reference's tree collapsed, visit order preserved: trace_engine.cuh); 0: 64-byte nodes with the two children
 #ifndef RT_ENGINE_TOP_NODES
 #define RT_ENGINE_TOP_NODES 0       // interior nodes of the top levels the traversal engine stages in shared memory (0: none; profiles/r01n)
 #endif
@@ -14,8 +17,12 @@ namespace rt {
 // Device-resident scene (all pointers are device pointers).  Layout: DESIGN.md "Data layout in HBM".
 struct DScene {
   const float4* nodes;       // 2 float4 per LinearBVHNode: {min.xyz, bits(offset)}, {max.xyz, bits(n_prims<<2 | axis)}
-  const float4* wide;        // 4 float4 per INTERIOR node (compact numbering): {L.min, bits(ref L)}, {L.max, bits(ref R)},
-                             //   {R.min, bits(axis)}, {R.max, 0}; ref = interior index, or 0x80000000 | first slot for a leaf
+  const float4* wide;        // RT_ENGINE_WIDE4 == 0: 4 float4 per INTERIOR node (compact numbering): {L.min, bits(ref L)}, {L.max, bits(ref R)},
+                             //   {R.min, bits(axis)}, {R.max, 0}; ref = interior index, or 0x80000000 | first slot for a leaf.
+                             // RT_ENGINE_WIDE4 == 1: 8 float4 per interior node of EVEN depth below its tree's root (compact numbering), children
+                             //   c0, c1 = the left child's children (or the left child itself + an empty entry when it is a leaf), c2, c3 likewise
+                             //   for the right child: {c0.min, ref c0}, {c0.max, ref c1}, {c1.min, bits(axis | axisL << 2 | axisR << 4)},
+                             //   {c1.max, ref c2}, {c2.min, ref c3}, {c2.max, 0}, {c3.min, 0}, {c3.max, 0}; an empty entry has ref 0xffffffff
   uint32_t root_ref;         // ref of the root node
   uint32_t n_top;            // interior nodes [0, n_top) are the top levels of the scene's tree in breadth-first order (staged in shared memory
                              //   by the traversal engine when it is built with RT_ENGINE_TOP_NODES > 0)

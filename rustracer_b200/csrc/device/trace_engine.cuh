@@ -5,7 +5,13 @@
 // wins at equal t.  What changes is how the 32 lanes of a warp share the work (profiles/r01a: the one-thread-one-ray loop
 // ran with 5.5 of 32 lanes active):
 //   * wide nodes: one 64-byte record per interior node holds BOTH children's boxes, so one fetch feeds two slab tests
-//     and children that miss are never pushed.  A pushed child keeps its entry distance; it is re-checked against the
+//     and children that miss are never pushed.  With RT_ENGINE_WIDE4 (default) two levels of the reference's binary tree are
+//     collapsed into one 128-byte record with the boxes of the four grandchildren c0..c3 and the three split axes: the step
+//     tests all four and visits them in the order the binary near-first rule would reach them (the near child's near and far
+//     grandchild, then the far child's), so the sequence of leaves a ray visits is the reference's.  The skipped intermediate
+//     node needs no test of its own: Bounds3::intersect_p_fast is monotone in the box (every product (plane - o) * inv_dir
+//     rounds monotonically, NaN compares false on both sides alike), so a grandchild that passes implies its parent passes
+//     at the same t_max.  47 node steps per ray become ~26 dependent fetches (profiles/r02c).  A pushed child keeps its entry distance; it is re-checked against the
 //     ray's current t_max when popped, which is exactly the test the reference performs at that moment (its slab test
 //     depends on t_max only through the final `tmin < t_max`).
 //   * scheduled while-while: each round the warp runs ONE node step for the lanes standing on an interior node, as long
@@ -100,7 +106,12 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
   __shared__ uint2 s_stack[RT_ENGINE_SMEM_DEPTH][128];
   // capacity: the reference's 64 entries per tree (bvh/mod.rs:372); with instances the scene's tree, the exit marker and the
   // definition's tree share this one stack
-  uint2 stack_l[(INST ? 2 * kStackSize + 1 : kStackSize) - RT_ENGINE_SMEM_DEPTH];
+#if RT_ENGINE_WIDE4
+  constexpr int kTreeStack = (kStackSize / 2) * 3;   // up to three postponed grandchildren per collapsed pair of levels
+#else
+  constexpr int kTreeStack = kStackSize;
+#endif
+  uint2 stack_l[(INST ? 2 * kTreeStack + 1 : kTreeStack) - RT_ENGINE_SMEM_DEPTH];
   const uint32_t tid = threadIdx.x;
 #if RT_ENGINE_TOP_NODES > 0
   // top levels of the tree (breadth-first numbered at upload) staged in shared memory: every ray walks them
@@ -188,6 +199,35 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         // from here instead of running the pop loop on its own (profiles/r01r: the divergent pop was 8 % of the issue slots at 5 lanes)
         const bool top_in_smem = sp > 0 && sp <= RT_ENGINE_SMEM_DEPTH;
         const uint2 top = top_in_smem ? s_stack[sp - 1][tid] : make_uint2(kExitInstance, 0u);
+#if RT_ENGINE_WIDE4
+        const float4* __restrict__ nd = wide + 8 * (size_t)cur;
+        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+        const float4 q4 = __ldg(nd + 4), q5 = __ldg(nd + 5), q6 = __ldg(nd + 6), q7 = __ldg(nd + 7);
+        const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w), axes = __float_as_uint(q2.w), r2 = __float_as_uint(q3.w), r3 = __float_as_uint(q4.w);
+        float t0, t1, t2, t3;
+        const bool h0 = slab_interval_bf(q0, q1, ray.o, inv_dir, nx, ny, nz, ray.t_max, t0);
+        const bool h1 = slab_interval_bf(q2, q3, ray.o, inv_dir, nx, ny, nz, ray.t_max, t1) & (r1 != kDoneRef);
+        const bool h2 = slab_interval_bf(q4, q5, ray.o, inv_dir, nx, ny, nz, ray.t_max, t2);
+        const bool h3 = slab_interval_bf(q6, q7, ray.o, inv_dir, nx, ny, nz, ray.t_max, t3) & (r3 != kDoneRef);
+        // bvh/mod.rs:408-421 at the binary node and at each of its children: the second child first when the ray is negative along the split axis
+        const bool negA = ((negmask >> (axes & 3u)) & 1u) != 0u, negL = ((negmask >> ((axes >> 2) & 3u)) & 1u) != 0u, negR = ((negmask >> ((axes >> 4) & 3u)) & 1u) != 0u;
+        const uint32_t la_r = negL ? r1 : r0, lb_r = negL ? r0 : r1, ra_r = negR ? r3 : r2, rb_r = negR ? r2 : r3;
+        const float la_t = negL ? t1 : t0, lb_t = negL ? t0 : t1, ra_t = negR ? t3 : t2, rb_t = negR ? t2 : t3;
+        const bool la_h = negL ? h1 : h0, lb_h = negL ? h0 : h1, ra_h = negR ? h3 : h2, rb_h = negR ? h2 : h3;
+        const uint32_t e0r = negA ? ra_r : la_r, e1r = negA ? rb_r : lb_r, e2r = negA ? la_r : ra_r, e3r = negA ? lb_r : rb_r;
+        const float e1t = negA ? rb_t : lb_t, e2t = negA ? la_t : ra_t, e3t = negA ? lb_t : rb_t;
+        const bool e0h = negA ? ra_h : la_h, e1h = negA ? rb_h : lb_h, e2h = negA ? la_h : ra_h, e3h = negA ? lb_h : rb_h;
+        // the first entry that passes is visited now; the others wait on the stack, nearest on top, each with its entry distance
+        if (e3h & (e0h | e1h | e2h)) RT_ENGINE_PUSH(make_uint2(e3r, __float_as_uint(e3t)));
+        if (e2h & (e0h | e1h)) RT_ENGINE_PUSH(make_uint2(e2r, __float_as_uint(e2t)));
+        if (e1h & e0h) RT_ENGINE_PUSH(make_uint2(e1r, __float_as_uint(e1t)));
+        if (e0h) cur = e0r;
+        else if (e1h) cur = e1r;
+        else if (e2h) cur = e2r;
+        else if (e3h) cur = e3r;
+        else if (top_in_smem && top.x != kExitInstance && (ANY || __uint_as_float(top.y) < ray.t_max)) { cur = top.x; --sp; }   // == the first iteration of the pop loop
+        else RT_ENGINE_POP();
+#else
         float4 a, b, c, d;
 #if RT_ENGINE_TOP_NODES > 0
         if (cur < n_top) { a = s_top[4 * cur]; b = s_top[4 * cur + 1]; c = s_top[4 * cur + 2]; d = s_top[4 * cur + 3]; }
@@ -227,6 +267,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         } else if (hsecond) cur = second;
         else if (top_in_smem && top.x != kExitInstance && (ANY || __uint_as_float(top.y) < ray.t_max)) { cur = top.x; --sp; }   // == the first iteration of the pop loop
         else RT_ENGINE_POP();
+#endif
       }
     } else if ((cur & kLeafBit) != 0u && cur != kDoneRef) {
       // ---- leaf step: every primitive of the leaf, in slot order (bvh/mod.rs:392-396) ---------------------------

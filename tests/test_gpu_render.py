@@ -158,6 +158,25 @@ def test_filters_crop_and_wave_splitting(dev):
     assert np.allclose(imgs[0], imgs[2], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("pixel_filter", ['PixelFilter "mitchell"', 'PixelFilter "mitchell" "float xwidth" [1.5] "float ywidth" [2.5] "float B" [0.2] "float C" [0.4]',
+                                          'PixelFilter "triangle"', 'PixelFilter "triangle" "float xwidth" [1.25] "float ywidth" [0.75]'])
+def test_mitchell_and_triangle_filters(dev, pixel_filter):
+    """filter/mitchell.rs (negative lobes: weights and weighted sums can be negative) and filter/triangle.rs through the film's 16x16
+    weight table (film.rs:92-102, :298-361): filter weights bit-equal, image within fp32 summation noise of the oracle's."""
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.balls(xres=80, yres=60, spp=4, integrator='Integrator "path" "integer maxdepth" [4]').replace('PixelFilter "box"', pixel_filter))
+    dev.upload(sc)
+    o = ob.OracleScene(sc.ir_ptr)
+    film_ref, rgb_ref, _ = o.render(sampler_kind=1, seed=5)
+    rd = sc.render_desc()
+    rd.seed = 5
+    dev.render(rd)
+    film, rgb = dev.read_film(), dev.resolve_film()
+    assert np.allclose(film[..., 3], film_ref[..., 3], rtol=2e-5, atol=1e-5)          # sums of up to ~100 table weights per pixel, atomics order
+    assert np.abs(rgb - rgb_ref).sum() / np.abs(rgb_ref).sum() < 2e-4
+
+
 def test_recursive_wave_overflow_splits(dev):
     """Whitted / DirectLighting waves are sized for the expected growth of the ray tree; a wave that overflows its queues
     is discarded and split.  A tiny wave_paths forces overflows: image and counters must equal the roomy render's."""
@@ -174,6 +193,51 @@ def test_recursive_wave_overflow_splits(dev):
         assert st1.waves > st0.waves
         assert (st1.camera_rays, st1.regular_rays, st1.shadow_rays) == (st0.camera_rays, st0.regular_rays, st0.shadow_rays)
         assert np.allclose(img0, img1, rtol=2e-5, atol=1e-6)
+
+
+def test_recursive_overflow_at_production_wave_size(dev):
+    """a level queue that overflows by far more than its capacity at a realistic wave size.  Every reader of the live
+    count clamps it to the queue's capacity (kernels_trace.cuh, kernels_rec.cuh), so the overflowed levels stay inside their buffers, the
+    wave is discarded and split, and the result equals the roomy render's.  maxdepth 8 on the glass / mirror balls doubles the items per
+    level; 2^18 items per wave leave room for ~1.3 levels of growth."""
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.balls(xres=640, yres=480, spp=4, integrator='Integrator "whitted" "integer maxdepth" [8]'))
+    dev.upload(sc)
+    rd = sc.render_desc()
+    st0 = dev.render(rd)
+    img0 = dev.resolve_film()
+    rd.wave_paths = 1 << 18
+    st1 = dev.render(rd)
+    img1 = dev.resolve_film()
+    assert st1.waves > st0.waves
+    assert (st1.camera_rays, st1.regular_rays, st1.shadow_rays) == (st0.camera_rays, st0.regular_rays, st0.shadow_rays)
+    assert np.allclose(img0, img1, rtol=2e-5, atol=1e-6)
+    # the next call on the context still works (no sticky CUDA error from an out-of-bounds access)
+    dev.render(rd)
+
+
+def test_wave_paths_below_one_tile_is_clamped(dev):
+    """wave_paths in [1, 255] is raised to one 16x16 tile instead of writing 256 items into smaller buffers."""
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.cornell_box(xres=32, yres=32, spp=2))
+    dev.upload(sc)
+    rd = sc.render_desc()
+    dev.render(rd)
+    img0 = dev.resolve_film()
+    for wp in (1, 100, 255):
+        rd.wave_paths = wp
+        dev.render(rd)
+        assert np.allclose(dev.resolve_film(), img0, rtol=1e-5, atol=1e-6)
+
+
+def test_engine_options_are_range_checked(dev):
+    """refill_threshold <= 0 would spin the traversal engine forever."""
+    from rustracer_b200.device import DeviceError
+    for name, bad in (("refill_threshold", 0), ("refill_threshold", 33), ("node_threshold", -1), ("node_threshold", 40)):
+        with pytest.raises(DeviceError):
+            dev.set_option(name, bad)
+    dev.set_option("refill_threshold", 16)
+    dev.set_option("node_threshold", 12)
 
 
 def test_sample_ranges_accumulate(dev):
