@@ -204,6 +204,7 @@ typedef struct rtgpu_stats {
   uint64_t closest_rays, anyhit_rays;
   /* items handed to the shade kernels: path vertices incl. escaped rays (path), items of every level (whitted / directlighting), camera hits (ao) */
   uint64_t shaded_items;
+  uint64_t lightgrid_rows;     /* sparse spatial light distribution: voxels that hold a distribution so far (0 in dense mode) */
 } rtgpu_stats;
 
 int rtgpu_create(int device, rtgpu_ctx** out);
@@ -233,9 +234,13 @@ int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, 
                     uint32_t* n_nodes, float* build_ms);
 /* Tunables: "sort_rays" (1 = bin batch rays by origin cell + direction octant before traversal; default 1),
  * "sort_min_rays" (batches smaller than this skip the binning; default 32768),
+ * "lightgrid_dense_mib" / "lightgrid_sparse_mib" (SpatialLightDistribution, lightdistrib.rs:59-296: the per-voxel tables are built for every voxel up
+ *   front while they fit the first budget [2048 MiB], else on demand for the voxels path vertices fall into, within the second budget [8192 MiB]),
  * "sort_items" (1 = rtgpu_render sorts the listed-lobes shade queue / the recursive integrators' items by material; default 1),
  * "overlap_bounces" (path integrator: 0 = every launch on one stream; 1 = the shadow / MIS traces of bounce b on a second stream beside
  *   the closest-hit launch of bounce b + 1; 2 = also the closest-hit MIS rays beside the any-hit MIS rays; default 2; results identical),
+ * "waves_in_flight" (path integrator: 2 = two waves at a time on two stream groups with two sets of wave buffers, so the first bounces of one
+ *   wave run under the short late-bounce launches of the other; 1 = one after the other; default 2; samples identical),
  * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
  * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);

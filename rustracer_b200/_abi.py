@@ -147,4 +147,4 @@ class rtgpu_stats(C.Structure):
                 ("ms_total", c_f), ("ms_closest", c_f), ("ms_anyhit", c_f), ("ms_shade", c_f), ("ms_other", c_f),
                 ("closest_launches", c_u64), ("anyhit_launches", c_u64),
                 ("nodes_closest", c_u64), ("prims_closest", c_u64), ("nodes_anyhit", c_u64), ("prims_anyhit", c_u64),
-                ("closest_rays", c_u64), ("anyhit_rays", c_u64), ("shaded_items", c_u64)]
+                ("closest_rays", c_u64), ("anyhit_rays", c_u64), ("shaded_items", c_u64), ("lightgrid_rows", c_u64)]

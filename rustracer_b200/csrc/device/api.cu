@@ -252,6 +252,11 @@ int rtgpu_create(int device, rtgpu_ctx** out) {
       cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->side_stream_b, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream2_b, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork_b, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join_b, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork2_b, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join2_b, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_group_b, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx; return RTGPU_ERR_CUDA;
   }
@@ -267,6 +272,7 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->side_stream);
   cudaStreamSynchronize(ctx->side_stream2);
+  cudaStreamSynchronize(ctx->stream_b); cudaStreamSynchronize(ctx->side_stream_b); cudaStreamSynchronize(ctx->side_stream2_b);
   rtgpu_comm_destroy(ctx);
   free_scene(ctx);
   rt::free_wave_buffers(ctx);
@@ -278,6 +284,8 @@ int rtgpu_destroy(rtgpu_ctx* ctx) {
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_join2);
   cudaStreamDestroy(ctx->side_stream); cudaStreamDestroy(ctx->side_stream2);
+  cudaEventDestroy(ctx->ev_fork_b); cudaEventDestroy(ctx->ev_join_b); cudaEventDestroy(ctx->ev_fork2_b); cudaEventDestroy(ctx->ev_join2_b); cudaEventDestroy(ctx->ev_group_b);
+  cudaStreamDestroy(ctx->stream_b); cudaStreamDestroy(ctx->side_stream_b); cudaStreamDestroy(ctx->side_stream2_b);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return RTGPU_OK;
@@ -290,6 +298,13 @@ int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return RTGPU_ERR_ARG;
   if (std::strcmp(name, "sort_rays") == 0) { ctx->sort_rays = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_min_rays") == 0) { if (value < 0) return fail(ctx, RTGPU_ERR_ARG, "sort_min_rays must be >= 0"); ctx->sort_min_rays = value; return RTGPU_OK; }
+  if (std::strcmp(name, "lightgrid_dense_mib") == 0 || std::strcmp(name, "lightgrid_sparse_mib") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(ctx, RTGPU_ERR_ARG, "light grid budgets are in MiB, 0 .. 2^20");
+    (name[10] == 'd' ? ctx->lightgrid_dense_mib : ctx->lightgrid_sparse_mib) = value;
+    rt::free_lightgrid(ctx);                                           // rebuilt in the new mode by the next render
+    return RTGPU_OK;
+  }
+  if (std::strcmp(name, "waves_in_flight") == 0) { if (value < 1 || value > 2) return fail(ctx, RTGPU_ERR_ARG, "waves_in_flight must be 1 or 2"); ctx->waves_in_flight = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_items") == 0) { ctx->sort_items = value; return RTGPU_OK; }
   if (std::strcmp(name, "overlap_bounces") == 0) { ctx->overlap_bounces = value; return RTGPU_OK; }
   if (std::strcmp(name, "sort_bounce_rays") == 0) { ctx->sort_bounce_rays = value; return RTGPU_OK; }

@@ -18,6 +18,10 @@ struct rtgpu_ctx {
   cudaStream_t side_stream = nullptr;        // path integrator: secondary traces of a bounce, beside the next closest-hit launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  // second stream group: the path integrator keeps two waves in flight (render.cu), each on its own three streams
+  cudaStream_t stream_b = nullptr, side_stream_b = nullptr, side_stream2_b = nullptr;
+  cudaEvent_t ev_fork_b = nullptr, ev_join_b = nullptr, ev_fork2_b = nullptr, ev_join2_b = nullptr, ev_group_b = nullptr;
+  int waves_in_flight = 2;
   std::string error;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -49,6 +53,8 @@ struct rtgpu_ctx {
   int overlap_bounces = 2;    // rtgpu_render (path): >= 1 shadow / MIS traces of bounce b on a second stream, beside closest-hit + classify of bounce b + 1;
                               // 2: closest-hit MIS rays on a third stream beside the any-hit MIS rays
   void* comm = nullptr; int comm_rank = 0, comm_world = 1;   // ncclComm_t of rtgpu_comm_init (render.cu)
+  int lightgrid_dense_mib = 2048;    // spatial light distribution: dense voxel table up to this size, sparse (rows on demand) beyond
+  int lightgrid_sparse_mib = 8192;   // budget of the sparse table
   int sort_items = 1;   // rtgpu_render: counting sort of the listed-lobes queue / of the recursive integrators' items by material row
 };
 

@@ -364,14 +364,9 @@ __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_mis_engine(
 }
 
 // compute_distribution (lightdistrib.rs:101-179), first half: one thread per (voxel, light) accumulates the
-// 128 Halton-point estimates sequentially, in the reference's order.
-__global__ void __launch_bounds__(128) k_lightgrid_contrib(DScene sc, int nvx, int nvy, int nvz, float* __restrict__ table) {
-  const int n = (int)sc.n_lights;
-  const size_t total = (size_t)nvx * nvy * nvz * n;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % n);
-  const size_t voxel = idx / n;
+// 128 Halton-point estimates sequentially, in the reference's order.  Dense mode: every voxel of the grid, row = voxel.
+// Sparse mode (`list` non-null): the {voxel, row} pairs k_lightgrid_mark claimed for this bounce, count read from the device.
+RT_DEV float lightgrid_contrib(const DScene& sc, int nvx, int nvy, int nvz, size_t voxel, int j) {
   const int pz = (int)(voxel % nvz), py = (int)((voxel / nvz) % nvy), px = (int)(voxel / ((size_t)nvz * nvy));
   const float lo[3] = {sc.world_lo[0], sc.world_lo[1], sc.world_lo[2]}, hi[3] = {sc.world_hi[0], sc.world_hi[1], sc.world_hi[2]};
   const int pi[3] = {px, py, pz}, nv[3] = {nvx, nvy, nvz};
@@ -392,26 +387,65 @@ __global__ void __launch_bounds__(128) k_lightgrid_contrib(DScene sc, int nvx, i
     Spec li = light_sample_li(sc, light, intr, u, wi, pdf, p1);
     if (pdf > 0.0f) contrib += lum(li) / pdf;
   }
-  table[voxel * (size_t)(2 * n + 2) + j] = contrib;
+  return contrib;
+}
+__global__ void __launch_bounds__(128) k_lightgrid_contrib(DScene sc, int nvx, int nvy, int nvz, float* __restrict__ table, const uint32_t* __restrict__ list,
+                                                            const uint32_t* __restrict__ grid_counters) {
+  const int n = (int)sc.n_lights;
+  const size_t n_rows = list ? (size_t)grid_counters[G_NEW] : (size_t)nvx * nvy * nvz;
+  const size_t total = n_rows * n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % n);
+    const size_t k = idx / n;
+    const size_t voxel = list ? (size_t)list[2 * k] : k, row = list ? (size_t)list[2 * k + 1] : k;
+    table[row * (size_t)(2 * n + 2) + j] = lightgrid_contrib(sc, nvx, nvy, nvz, voxel, j);
+  }
 }
 // second half: floor at 0.1 % of the average, then Distribution1D::new (distribution1d.rs:11-45)
-__global__ void __launch_bounds__(128) k_lightgrid_build(int n, size_t n_voxels, float* __restrict__ table) {
-  const size_t voxel = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (voxel >= n_voxels) return;
-  float* func = table + voxel * (size_t)(2 * n + 2);
-  float* cdf = func + n;
-  float sum = 0.0f;
-  for (int j = 0; j < n; j++) sum += func[j];
-  const float avg = sum / (float)(128ull * (unsigned long long)n);
-  const float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
-  for (int j = 0; j < n; j++) func[j] = fmaxf(func[j], min_contrib);
-  cdf[0] = 0.0f;
-  for (int i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + func[i - 1] / (float)n;
-  const float func_int = cdf[n];
-  if (func_int == 0.0f) for (int i = 1; i < n + 1; i++) cdf[i] = (float)i / (float)n;
-  else for (int i = 1; i < n + 1; i++) cdf[i] /= func_int;
-  func[2 * n + 1] = func_int;
+__global__ void __launch_bounds__(128) k_lightgrid_build(int n, size_t n_voxels, float* __restrict__ table, const uint32_t* __restrict__ list,
+                                                          const uint32_t* __restrict__ grid_counters) {
+  const size_t n_rows = list ? (size_t)grid_counters[G_NEW] : n_voxels;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_rows; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = list ? (size_t)list[2 * k + 1] : k;
+    float* func = table + row * (size_t)(2 * n + 2);
+    float* cdf = func + n;
+    float sum = 0.0f;
+    for (int j = 0; j < n; j++) sum += func[j];
+    const float avg = sum / (float)(128ull * (unsigned long long)n);
+    const float min_contrib = avg > 0.0f ? 0.001f * avg : 1.0f;
+    for (int j = 0; j < n; j++) func[j] = fmaxf(func[j], min_contrib);
+    cdf[0] = 0.0f;
+    for (int i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + func[i - 1] / (float)n;
+    const float func_int = cdf[n];
+    if (func_int == 0.0f) for (int i = 1; i < n + 1; i++) cdf[i] = (float)i / (float)n;
+    else for (int i = 1; i < n + 1; i++) cdf[i] /= func_int;
+    func[2 * n + 1] = func_int;
+  }
 }
+// Sparse mode, before a bounce is shaded: every hit point of the bounce's live list claims the row of its voxel if the voxel has none
+// yet (the device-side counterpart of the reference's lazy insert under compare-and-swap, lightdistrib.rs:221-296).  The point is the
+// one the shade kernel will look up (hit_surface's p), so the voxel is the same.
+__global__ void __launch_bounds__(256) k_lightgrid_mark(RenderParams p, const uint32_t* __restrict__ list, int count_idx) {
+  const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = list ? list[i] : i;
+    const HitRec h = p.w.hit[slot];
+    if (h.slot == kMiss) continue;
+    Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
+    ray.t_max = inf_f();
+    SurfHit si; float t_hit;
+    hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
+    const size_t voxel = grid_voxel(p.sc, p.grid, si.p);
+    if (p.grid.slots[voxel] != -1) continue;
+    if (atomicCAS(&p.grid.slots[voxel], -1, -2) != -1) continue;      // somebody else claims it
+    const uint32_t row = atomicAdd(&p.grid.grid_counters[G_ROWS], 1u);
+    if (row >= p.grid.cap_rows) { p.grid.grid_counters[G_OVERFLOW] = 1; p.grid.slots[voxel] = 0; continue; }
+    const uint32_t k = atomicAdd(&p.grid.grid_counters[G_NEW], 1u);
+    p.grid.new_voxels[2 * (size_t)k] = (uint32_t)voxel; p.grid.new_voxels[2 * (size_t)k + 1] = row;
+    p.grid.slots[voxel] = (int)row;                                   // read by the shade kernels, which run after the rows are built
+  }
+}
+__global__ void k_lightgrid_new_done(uint32_t* grid_counters) { if (threadIdx.x == 0 && blockIdx.x == 0) grid_counters[G_NEW] = 0; }
 
 // Escaped paths: emission of the infinite lights, then the path ends (path.rs:127-141).
 __global__ void __launch_bounds__(128) k_shade_miss(RenderParams p) {

@@ -19,6 +19,7 @@ void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx,
 void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s);
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, int part, cudaStream_t s);
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s);
+void launch_lightgrid_bounce(const RenderParams& p, const uint32_t* list, int count_idx, float* table, unsigned blocks, cudaStream_t s);
 void launch_film_add(const FilmParams& f, const float4* L, const float2* pfilm, uint32_t n, cudaStream_t s);
 void launch_li_out(const float4* L, float ao_div, uint32_t n, float* out, cudaStream_t s);
 void launch_film_xyz(const float4* film, size_t n, float4* out, cudaStream_t s);

@@ -15,9 +15,13 @@ using namespace rt;
 struct WaveBuffers {
   WaveView v{};
   std::vector<void*> allocs;
+  WaveView v2{};                    // second set of wave buffers: two waves of the path integrator in flight (run_render)
+  std::vector<void*> allocs2;
   bool recursive = false;
   float* uniform_table = nullptr; int uniform_n = 0;          // UniformLightDistribution
   float* grid_table = nullptr; int grid_nv[3] = {0, 0, 0}; int grid_n = 0; bool grid_valid = false;
+  // sparse mode of the spatial light distribution (wave.cuh LightGrid): voxel -> row map, the rows claimed per bounce, counters
+  int* grid_slots = nullptr; uint32_t* grid_new = nullptr; uint32_t* grid_counters = nullptr; uint32_t grid_cap_rows = 0;
   uint32_t* n_light_samples = nullptr; uint32_t n_light_samples_cap = 0;
   float4* film_tmp = nullptr; size_t film_tmp_n = 0;
   unsigned long long* stats_backup = nullptr;
@@ -25,16 +29,18 @@ struct WaveBuffers {
 
 namespace rt {
 
-static void release(WaveBuffers* w) {
-  for (void* p : w->allocs) cudaFree(p);
-  w->allocs.clear();
-  w->v = WaveView{};
+static void release(WaveBuffers* w, int set = -1) {
+  if (set != 1) { for (void* p : w->allocs) cudaFree(p); w->allocs.clear(); w->v = WaveView{}; }
+  if (set != 0) { for (void* p : w->allocs2) cudaFree(p); w->allocs2.clear(); w->v2 = WaveView{}; }
 }
 void free_wave_buffers(rtgpu_ctx* ctx) {
   if (!ctx->wave) return;
   release(ctx->wave);
   if (ctx->wave->uniform_table) cudaFree(ctx->wave->uniform_table);
   if (ctx->wave->grid_table) cudaFree(ctx->wave->grid_table);
+  if (ctx->wave->grid_slots) cudaFree(ctx->wave->grid_slots);
+  if (ctx->wave->grid_new) cudaFree(ctx->wave->grid_new);
+  if (ctx->wave->grid_counters) cudaFree(ctx->wave->grid_counters);
   if (ctx->wave->n_light_samples) cudaFree(ctx->wave->n_light_samples);
   if (ctx->wave->film_tmp) cudaFree(ctx->wave->film_tmp);
   delete ctx->wave;
@@ -45,28 +51,33 @@ void free_lightgrid(rtgpu_ctx* ctx) {
   WaveBuffers* w = ctx->wave;
   if (w->uniform_table) { cudaFree(w->uniform_table); w->uniform_table = nullptr; w->uniform_n = 0; }
   if (w->grid_table) { cudaFree(w->grid_table); w->grid_table = nullptr; }
+  if (w->grid_slots) { cudaFree(w->grid_slots); w->grid_slots = nullptr; }
+  if (w->grid_new) { cudaFree(w->grid_new); w->grid_new = nullptr; }
+  if (w->grid_counters) { cudaFree(w->grid_counters); w->grid_counters = nullptr; }
+  w->grid_cap_rows = 0;
   w->grid_valid = false;
 }
 
-template <class T> static int dalloc(rtgpu_ctx* ctx, WaveBuffers* w, T** out, size_t count) {
+template <class T> static int dalloc(rtgpu_ctx* ctx, std::vector<void*>& allocs, T** out, size_t count) {
   void* p = nullptr;
   RT_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-  w->allocs.push_back(p);
+  allocs.push_back(p);
   *out = (T*)p;
   return 0;
 }
 
-static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples, uint32_t cap_shadow, uint32_t cap_mis, bool recursive) {
+static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples, uint32_t cap_shadow, uint32_t cap_mis, bool recursive, int set = 0) {
   if (!ctx->wave) ctx->wave = new WaveBuffers();
   WaveBuffers* w = ctx->wave;
-  WaveView& v = w->v;
+  WaveView& v = set ? w->v2 : w->v;
+  std::vector<void*>& allocs = set ? w->allocs2 : w->allocs;
   if (v.cap_items >= cap_items && v.cap_samples >= cap_samples && v.cap_shadow >= cap_shadow && v.cap_mis >= cap_mis && (w->recursive || !recursive) && v.counters &&
       (v.hit_inst != nullptr || ctx->scene.n_instances == 0) && (v.rdiff != nullptr || !(recursive && ctx->scene.texmats)) &&
       v.matsort_out != nullptr && v.matsort_bins >= ctx->scene.n_materials + 1 && (v.tex_lobes != nullptr || recursive || !ctx->scene.texmats))
     return 0;
-  release(w);
+  release(w, set);
   int rc = 0;
-#define A(field, n) if ((rc = dalloc(ctx, w, &v.field, (n)))) return rc
+#define A(field, n) if ((rc = dalloc(ctx, allocs, &v.field, (n)))) return rc
   A(ray_o, cap_items); A(ray_d, cap_items); A(hit, cap_items); A(beta, cap_items); A(pstate, cap_items);
   A(hit_class, cap_items);
   if (ctx->scene.n_instances) A(hit_inst, cap_items);
@@ -83,9 +94,9 @@ static int ensure_wave(rtgpu_ctx* ctx, uint32_t cap_items, uint32_t cap_samples,
   for (int k = 0; k < Q_COUNT; k++) A(matq[k], cap_items);
   A(counters, C_COUNT); A(stats, S_COUNT);
 #undef A
-  if ((rc = dalloc(ctx, w, &w->stats_backup, (size_t)S_COUNT))) return rc;
+  if (!set && (rc = dalloc(ctx, allocs, &w->stats_backup, (size_t)S_COUNT))) return rc;
   v.cap_items = cap_items; v.cap_samples = cap_samples; v.cap_shadow = cap_shadow; v.cap_mis = cap_mis;
-  w->recursive = recursive;
+  if (!set) w->recursive = recursive;
   return 0;
 }
 
@@ -128,14 +139,35 @@ static int ensure_light_grid(rtgpu_ctx* ctx) {
     n_voxels *= (size_t)w->grid_nv[k];
   }
   const int n = (int)sc.n_lights;
-  const size_t floats = n_voxels * (size_t)(2 * n + 2);
-  if (floats * sizeof(float) > ((size_t)16 << 30))
-    return fail(ctx, RTGPU_ERR_UNSUPPORTED, "spatial light distribution: dense voxel table would exceed 16 GiB; use lightsamplestrategy \"uniform\"");
+  const size_t row_floats = (size_t)(2 * n + 2);
+  const size_t floats = n_voxels * row_floats;
   if (w->grid_table) { cudaFree(w->grid_table); w->grid_table = nullptr; }
-  RT_CUDA(ctx, cudaMalloc((void**)&w->grid_table, floats * sizeof(float)));
-  launch_lightgrid(sc, w->grid_nv[0], w->grid_nv[1], w->grid_nv[2], w->grid_table, ctx->stream);
-  ctx->launches += 2;
-  RT_CUDA(ctx, cudaGetLastError());
+  if (w->grid_slots) { cudaFree(w->grid_slots); w->grid_slots = nullptr; }
+  if (w->grid_new) { cudaFree(w->grid_new); w->grid_new = nullptr; }
+  if (w->grid_counters) { cudaFree(w->grid_counters); w->grid_counters = nullptr; }
+  w->grid_cap_rows = 0;
+  const size_t dense_limit = (size_t)ctx->lightgrid_dense_mib << 20;
+  if (floats * sizeof(float) <= dense_limit) {
+    // few lights: every voxel's distribution up front (dense prepass, same per-voxel values as the reference's lazily filled table)
+    RT_CUDA(ctx, cudaMalloc((void**)&w->grid_table, floats * sizeof(float)));
+    launch_lightgrid(sc, w->grid_nv[0], w->grid_nv[1], w->grid_nv[2], w->grid_table, ctx->stream);
+    ctx->launches += 2;
+    RT_CUDA(ctx, cudaGetLastError());
+  } else {
+    // many lights (an emissive mesh): only the voxels path vertices fall into get a row, claimed and built bounce by bounce
+    // (k_lightgrid_mark), as the reference's hash table fills on demand (lightdistrib.rs:221-296)
+    const size_t budget = (size_t)ctx->lightgrid_sparse_mib << 20;
+    const size_t rows = std::min<size_t>(n_voxels, budget / (row_floats * sizeof(float)));
+    if (rows < 64) return fail(ctx, RTGPU_ERR_UNSUPPORTED, "spatial light distribution: one voxel's table over all lights does not fit the budget 64 times; "
+                                                            "raise option lightgrid_sparse_mib or use lightsamplestrategy \"uniform\"");
+    RT_CUDA(ctx, cudaMalloc((void**)&w->grid_table, rows * row_floats * sizeof(float)));
+    RT_CUDA(ctx, cudaMalloc((void**)&w->grid_slots, n_voxels * sizeof(int)));
+    RT_CUDA(ctx, cudaMalloc((void**)&w->grid_new, rows * 2 * sizeof(uint32_t)));
+    RT_CUDA(ctx, cudaMalloc((void**)&w->grid_counters, 4 * sizeof(uint32_t)));
+    RT_CUDA(ctx, cudaMemsetAsync(w->grid_slots, 0xff, n_voxels * sizeof(int), ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(w->grid_counters, 0, 4 * sizeof(uint32_t), ctx->stream));
+    w->grid_cap_rows = (uint32_t)rows;
+  }
   w->grid_n = n; w->grid_valid = true;
   return 0;
 }
@@ -230,6 +262,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     } else {
       rc = ensure_light_grid(ctx); if (rc) return rc;
       p.grid.table = wb->grid_table; for (int k = 0; k < 3; k++) p.grid.nv[k] = wb->grid_nv[k]; p.grid.n_lights = wb->grid_n;
+      p.grid.slots = wb->grid_slots; p.grid.new_voxels = wb->grid_new; p.grid.grid_counters = wb->grid_counters; p.grid.cap_rows = wb->grid_cap_rows;
     }
   }
   if (!nls.empty()) {
@@ -305,11 +338,14 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     else { call; } \
     ctx->launches++; if ((kclass) == K_CLOSEST) n_closest_launches++; else if ((kclass) == K_ANYHIT) n_anyhit_launches++; } while (0)
 
-  auto run_wave = [&](uint32_t n_items) -> int {
+  struct StreamGroup { cudaStream_t main, side, side2; cudaEvent_t fork, join, fork2, join2; };
+  const StreamGroup groups[2] = {{ctx->stream, ctx->side_stream, ctx->side_stream2, ctx->ev_fork, ctx->ev_join, ctx->ev_fork2, ctx->ev_join2},
+                                 {ctx->stream_b, ctx->side_stream_b, ctx->side_stream2_b, ctx->ev_fork_b, ctx->ev_join_b, ctx->ev_fork2_b, ctx->ev_join2_b}};
+  auto run_wave = [&](RenderParams& p, uint32_t n_items, const StreamGroup& G) -> int {
     if (n_items > p.w.cap_samples || n_items > p.w.cap_items) return fail(ctx, RTGPU_ERR_ARG, "internal: wave larger than its buffers");
     p.n_items = n_items;
-    RT_CUDA(ctx, cudaMemsetAsync(p.w.counters, 0, C_COUNT * sizeof(uint32_t), ctx->stream));
-    RT_LAUNCH(K_OTHER, launch_raygen(p, ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(p.w.counters, 0, C_COUNT * sizeof(uint32_t), G.main));
+    RT_LAUNCH(K_OTHER, launch_raygen(p, G.main));
     if (rd->integrator == RTGPU_INTEGRATOR_PATH) {
       const uint32_t rounds = max_depth + 1 + (uint32_t)plan.extra_rounds;
       // Two streams: the shadow / MIS traces of bounce b (side stream, in the reference's order of additions to L) run beside the
@@ -322,58 +358,62 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         const int in = (int)(b & 1u);
         const uint32_t* live = p.w.list[in];
         if (ctx->sort_bounce_rays && b >= 1) {                        // camera rays are coherent as generated
-          RT_LAUNCH(K_CLOSEST, launch_ray_sort(p, live, C_LIVE0 + in, p.w.raysort_keys, p.w.raysort_hist, p.w.raysort_out, pblocks / 2, ctx->stream));
+          RT_LAUNCH(K_CLOSEST, launch_ray_sort(p, live, C_LIVE0 + in, p.w.raysort_keys, p.w.raysort_hist, p.w.raysort_out, pblocks / 2, G.main));
           ctx->launches += 2;
           live = p.w.raysort_out;
         }
-        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, live, C_LIVE0 + in, p.w.hit, pblocks, ctx->stream));
-        RT_LAUNCH(K_SHADE, launch_classify(p, live, C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, ctx->stream));
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, live, C_LIVE0 + in, p.w.hit, pblocks, G.main));
+        RT_LAUNCH(K_SHADE, launch_classify(p, live, C_LIVE0 + in, p.w.hit, tstats == TRACE_ENGINE, pblocks / 2, G.main));
       };
       for (uint32_t b = 0; b < rounds; b++) {
         const int in = (int)(b & 1u);
         if (b == 0 || !overlap) trace_closest(b);                     // overlap: bounce b >= 1 was traced beside the secondary rays of b - 1
-        if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
-        RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, ctx->stream));
-        if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, ctx->stream));
-        if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, ctx->stream));
-        if (plan.mat_present[Q_METAL]) RT_LAUNCH(K_SHADE, launch_shade_path_2(p, in, pblocks, ctx->stream));
-        if (plan.mat_present[Q_GLASS]) RT_LAUNCH(K_SHADE, launch_shade_path_3(p, in, pblocks, ctx->stream));
-        if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, ctx->stream));
-        if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, ctx->stream));
+        if (!joined) { cudaStreamWaitEvent(G.main, G.join, 0); joined = true; }
+        if (p.grid.slots && b < max_depth) {                            // sparse light grid: rows for the voxels this bounce's vertices fall into
+          RT_LAUNCH(K_SHADE, launch_lightgrid_bounce(p, p.w.list[in], C_LIVE0 + in, wb->grid_table, pblocks, G.main));
+          ctx->launches += 3;
+        }
+        RT_LAUNCH(K_SHADE, launch_shade_miss(p, pblocks, G.main));
+        if (plan.mat_present[Q_MATTE]) RT_LAUNCH(K_SHADE, launch_shade_path_0(p, in, pblocks, G.main));
+        if (plan.mat_present[Q_PLASTIC]) RT_LAUNCH(K_SHADE, launch_shade_path_1(p, in, pblocks, G.main));
+        if (plan.mat_present[Q_METAL]) RT_LAUNCH(K_SHADE, launch_shade_path_2(p, in, pblocks, G.main));
+        if (plan.mat_present[Q_GLASS]) RT_LAUNCH(K_SHADE, launch_shade_path_3(p, in, pblocks, G.main));
+        if (plan.mat_present[Q_MIRROR]) RT_LAUNCH(K_SHADE, launch_shade_path_4(p, in, pblocks, G.main));
+        if (plan.extra_rounds) RT_LAUNCH(K_SHADE, launch_shade_path_5(p, in, pblocks, G.main));
         if (plan.mat_present[Q_LOBES]) {
           if (ctx->sort_items) {                                      // keep neighbouring warps on one material's lobe list / texture graph (kernels_trace.cuh)
-            RT_LAUNCH(K_SHADE, launch_material_sort(p, p.w.matq[Q_LOBES], C_MATQ0 + Q_LOBES, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
+            RT_LAUNCH(K_SHADE, launch_material_sort(p, p.w.matq[Q_LOBES], C_MATQ0 + Q_LOBES, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, G.main));
             ctx->launches += 2;
             RenderParams ps = p; ps.w.matq[Q_LOBES] = p.w.matsort_out;
-            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(ps, ps.w.matq[Q_LOBES], pblocks, ctx->stream));
-            RT_LAUNCH(K_SHADE, launch_shade_path_6(ps, in, pblocks, ctx->stream));
+            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(ps, ps.w.matq[Q_LOBES], pblocks, G.main));
+            RT_LAUNCH(K_SHADE, launch_shade_path_6(ps, in, pblocks, G.main));
           } else {
-            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(p, p.w.matq[Q_LOBES], pblocks, ctx->stream));
-            RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, ctx->stream));
+            if (sc.texmats) RT_LAUNCH(K_SHADE, launch_eval_textured(p, p.w.matq[Q_LOBES], pblocks, G.main));
+            RT_LAUNCH(K_SHADE, launch_shade_path_6(p, in, pblocks, G.main));
           }
         }
-        cudaStream_t sec = ctx->stream;
-        if (overlap) { sec = ctx->side_stream; cudaEventRecord(ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(sec, ctx->ev_fork, 0); }
+        cudaStream_t sec = G.main;
+        if (overlap) { sec = G.side; cudaEventRecord(G.fork, G.main); cudaStreamWaitEvent(sec, G.fork, 0); }
         if (sc.n_lights > 0) {
           RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 0, pblocks, sec));
           // The BSDF-sampled MIS ray of a vertex is either a closest-hit ray (area light chosen) or an any-hit ray (infinite light
           // chosen), never both (uniform_sample_one_light, integrator/mod.rs:145-177): the two launches add to disjoint samples of L,
           // after the light sample's shadow ray, so they may run side by side.
           const bool third = overlap && has_infinite && ctx->overlap_bounces > 1;
-          if (third) { cudaEventRecord(ctx->ev_fork2, sec); cudaStreamWaitEvent(ctx->side_stream2, ctx->ev_fork2, 0); }
+          if (third) { cudaEventRecord(G.fork2, sec); cudaStreamWaitEvent(G.side2, G.fork2, 0); }
           if (has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(false, tstats, p, 1, pblocks, sec));
-          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, third ? ctx->side_stream2 : sec));
-          if (third) { cudaEventRecord(ctx->ev_join2, ctx->side_stream2); cudaStreamWaitEvent(sec, ctx->ev_join2, 0); }
+          RT_LAUNCH(K_CLOSEST, launch_trace_mis(false, tstats, p, pblocks, third ? G.side2 : sec));
+          if (third) { cudaEventRecord(G.join2, G.side2); cudaStreamWaitEvent(sec, G.join2, 0); }
         }
-        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 3, ctx->stream));
+        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 3, G.main));
         else {
           RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, 0, 2, sec));
-          cudaEventRecord(ctx->ev_join, sec); joined = false;
-          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 1, ctx->stream));
+          cudaEventRecord(G.join, sec); joined = false;
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + in, b == 0 ? 1 : 0, 1, G.main));
           if (b + 1 < rounds) trace_closest(b + 1);
         }
       }
-      if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
+      if (!joined) { cudaStreamWaitEvent(G.main, G.join, 0); joined = true; }
     } else if (plan.recursive) {
       const uint32_t rounds = std::max(1u, max_depth) + (uint32_t)plan.extra_rounds;
       // same two-stream schedule as the path integrator: the shadow / MIS traces of level l beside the closest-hit launch and the
@@ -382,39 +422,39 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       bool joined = true;
       auto trace_level = [&](uint32_t lvl) {
         const int par = (int)(lvl & 1u);
-        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, ctx->stream));
+        RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, par ? p.w.ray_o2 : p.w.ray_o, par ? p.w.ray_d2 : p.w.ray_d, nullptr, C_LIVE0 + par, p.w.hit, pblocks, G.main));
         if (ctx->sort_items) {
-          RT_LAUNCH(K_SHADE, launch_material_sort(p, nullptr, C_LIVE0 + par, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, ctx->stream));
+          RT_LAUNCH(K_SHADE, launch_material_sort(p, nullptr, C_LIVE0 + par, p.w.matsort_hist, sc.n_materials + 1u, p.w.matsort_out, pblocks / 2, G.main));
           ctx->launches += 2;
         }
       };
       for (uint32_t lvl = 0; lvl < rounds; lvl++) {
         const int par = (int)(lvl & 1u);
         if (lvl == 0 || !overlap) trace_level(lvl);
-        if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
+        if (!joined) { cudaStreamWaitEvent(G.main, G.join, 0); joined = true; }
         if (ctx->sort_items) {
           RenderParams ps = p; ps.w.item_order = p.w.matsort_out;
-          RT_LAUNCH(K_SHADE, launch_shade_recursive(ps, par, pblocks, ctx->stream));
-        } else RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, ctx->stream));
-        cudaStream_t sec = ctx->stream;
-        if (overlap) { sec = ctx->side_stream; cudaEventRecord(ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(sec, ctx->ev_fork, 0); }
+          RT_LAUNCH(K_SHADE, launch_shade_recursive(ps, par, pblocks, G.main));
+        } else RT_LAUNCH(K_SHADE, launch_shade_recursive(p, par, pblocks, G.main));
+        cudaStream_t sec = G.main;
+        if (overlap) { sec = G.side; cudaEventRecord(G.fork, G.main); cudaStreamWaitEvent(sec, G.fork, 0); }
         RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, sec));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT && has_infinite) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 1, pblocks, sec));
         if (rd->integrator == RTGPU_INTEGRATOR_DIRECT) RT_LAUNCH(K_CLOSEST, launch_trace_mis(true, tstats, p, pblocks, sec));
-        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 3, ctx->stream));
+        if (!overlap) RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 3, G.main));
         else {
           RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, 0, 2, sec));
-          cudaEventRecord(ctx->ev_join, sec); joined = false;
-          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 1, ctx->stream));
+          cudaEventRecord(G.join, sec); joined = false;
+          RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0 + par, lvl == 0 ? 1 : 0, 1, G.main));
           if (lvl + 1 < rounds) trace_level(lvl + 1);
         }
       }
-      if (!joined) { cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0); joined = true; }
+      if (!joined) { cudaStreamWaitEvent(G.main, G.join, 0); joined = true; }
     } else {
-      RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, ctx->stream));
-      RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, ctx->stream));
-      if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, ctx->stream));
-      RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, 3, ctx->stream));
+      RT_LAUNCH(K_CLOSEST, launch_trace_closest(tstats, p, p.w.ray_o, p.w.ray_d, p.w.list[0], C_LIVE0, p.w.hit, pblocks, G.main));
+      RT_LAUNCH(K_SHADE, launch_shade_ao(p, pblocks, G.main));
+      if (rd->integrator == RTGPU_INTEGRATOR_AO) RT_LAUNCH(K_ANYHIT, launch_trace_shadow(true, tstats, p, 0, pblocks, G.main));
+      RT_LAUNCH(K_OTHER, launch_next_bounce(p, C_LIVE0, 1, 3, G.main));
     }
     waves++;
     return check_cuda(ctx, cudaGetLastError(), "kernel launch");
@@ -442,40 +482,96 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
         fwd.push_back(Chunk{t0, std::min(tiles_per_wave, my_tiles - t0), s0, (int)std::min<long long>(samples_per_wave, s_end - s0)});
     work.assign(fwd.rbegin(), fwd.rend());                  // processed from the back
   }
+  // Two waves in flight (path integrator): wave k runs on stream group k & 1 with its own set of wave buffers, so the head of wave k + 1
+  // (ray generation, the big first-bounce launches) fills the SMs under the tail of wave k, whose late-bounce launches are short queues
+  // bound by one warp's walk.  Waves are independent: each adds its samples to the film with atomics (k_film_add).
+  const bool two_sets = rd->integrator == RTGPU_INTEGRATOR_PATH && !d_explicit && !prof && !p.grid.slots && ctx->waves_in_flight > 1 && work.size() > 1 &&
+                        !ctx->count_traversal;
+  RenderParams p2 = p;
+  if (two_sets) {
+    rc = ensure_wave(ctx, cap_items, cap_samples, cap_shadow, cap_mis, false, 1); if (rc) return rc;
+    p2.w = wb->v2;
+    p2.w.cap_items = cap_items; p2.w.cap_samples = cap_samples; p2.w.cap_shadow = cap_shadow; p2.w.cap_mis = cap_mis;
+    RT_CUDA(ctx, cudaStreamWaitEvent(groups[1].main, ctx->ev0, 0));    // after the film clear and the light tables
+    RT_CUDA(ctx, cudaMemsetAsync(p2.w.stats, 0, S_COUNT * sizeof(unsigned long long), groups[1].main));
+  }
+  // Processing order and stream group of every wave.  With two sets the waves alternate between the groups, and the second group's
+  // first wave is cut in two halves, one run first and one last: the groups then stay half a wave apart, so the short late-bounce launches
+  // of one group's wave meet the long first-bounce launches of the other's instead of its tail.
+  std::vector<int> group_of(work.size(), 0);                          // indexed like `work` (processed from the back)
+  if (two_sets) {
+    std::vector<Chunk> order(work.rbegin(), work.rend());
+    Chunk h1 = order[1], h2 = order[1];
+    const bool by_samples = !d_explicit && order[1].sn >= 2, by_tiles = order[1].an >= 2;
+    if (by_samples) { h1.sn = order[1].sn / 2; h2.s0 = order[1].s0 + h1.sn; h2.sn = order[1].sn - h1.sn; }
+    else if (by_tiles) { h1.an = order[1].an / 2; h2.a0 = order[1].a0 + h1.an; h2.an = order[1].an - h1.an; }
+    std::vector<Chunk> seq; std::vector<int> grp;
+    for (size_t k = 0; k < order.size(); k++) {
+      if (k == 1 && (by_samples || by_tiles)) { seq.push_back(h1); grp.push_back(1); continue; }
+      seq.push_back(order[k]); grp.push_back((int)(k & 1u));
+    }
+    if (by_samples || by_tiles) { seq.push_back(h2); grp.push_back(1); }
+    work.assign(seq.rbegin(), seq.rend());
+    group_of.assign(grp.rbegin(), grp.rend());
+  }
   while (!work.empty()) {
     const Chunk c = work.back();
     work.pop_back();
+    const int g = group_of.empty() ? 0 : group_of.back();
+    if (!group_of.empty()) group_of.pop_back();
+    RenderParams& pw = g ? p2 : p;
+    const StreamGroup& G = groups[g];
     uint32_t n_items;
-    if (d_explicit) { p.explicit_pixels = d_explicit + 3 * c.a0; n_items = (uint32_t)c.an; }
-    else { p.tile_first = (int)c.a0; p.n_tiles = (int)c.an; p.sample_first = c.s0; p.n_samples = c.sn; n_items = (uint32_t)(c.an * 256 * c.sn); }
-    if (plan.recursive) RT_CUDA(ctx, cudaMemcpyAsync(wb->stats_backup, p.w.stats, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
-    rc = run_wave(n_items); if (rc) return rc;
+    if (d_explicit) { pw.explicit_pixels = d_explicit + 3 * c.a0; n_items = (uint32_t)c.an; }
+    else { pw.tile_first = (int)c.a0; pw.n_tiles = (int)c.an; pw.sample_first = c.s0; pw.n_samples = c.sn; n_items = (uint32_t)(c.an * 256 * c.sn); }
+    if (plan.recursive) RT_CUDA(ctx, cudaMemcpyAsync(wb->stats_backup, pw.w.stats, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, G.main));
+    rc = run_wave(pw, n_items, G); if (rc) return rc;
     if (plan.recursive) {
       unsigned long long over = 0;
-      RT_CUDA(ctx, cudaMemcpyAsync(&over, p.w.stats + S_OVERFLOW, sizeof(over), cudaMemcpyDeviceToHost, ctx->stream));
-      RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      RT_CUDA(ctx, cudaMemcpyAsync(&over, pw.w.stats + S_OVERFLOW, sizeof(over), cudaMemcpyDeviceToHost, G.main));
+      RT_CUDA(ctx, cudaStreamSynchronize(G.main));
       if (over) {
-        RT_CUDA(ctx, cudaMemcpyAsync(p.w.stats, wb->stats_backup, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(pw.w.stats, wb->stats_backup, S_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, G.main));
         if (d_explicit ? c.an < 2 : (c.sn < 2 && c.an < 2))
           return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed on a minimal wave; raise wave_paths or lower the light sample counts");
         Chunk lo = c, hi = c;
         if (!d_explicit && c.sn >= 2) { lo.sn = c.sn / 2; hi.s0 = c.s0 + lo.sn; hi.sn = c.sn - lo.sn; }
         else { lo.an = c.an / 2; hi.a0 = c.a0 + lo.an; hi.an = c.an - lo.an; }
         work.push_back(hi); work.push_back(lo);
+        group_of.push_back(0); group_of.push_back(0);
         splits++;
         continue;
       }
     }
-    if (d_explicit) RT_LAUNCH(K_OTHER, launch_li_out(p.w.L, fp.ao_div, n_items, d_li_out + 3 * c.a0, ctx->stream));
-    else RT_LAUNCH(K_OTHER, launch_film_add(fp, p.w.L, p.w.pfilm, n_items, ctx->stream));
+    if (d_explicit) RT_LAUNCH(K_OTHER, launch_li_out(pw.w.L, fp.ao_div, n_items, d_li_out + 3 * c.a0, G.main));
+    else RT_LAUNCH(K_OTHER, launch_film_add(fp, pw.w.L, pw.w.pfilm, n_items, G.main));
+  }
+  if (two_sets) {                                                      // the second group joins the main stream before the end event
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_group_b, groups[1].main));
+    RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_group_b, 0));
   }
   RT_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   RT_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
   RT_CUDA(ctx, cudaGetLastError());
   unsigned long long hs[S_COUNT];
   RT_CUDA(ctx, cudaMemcpy(hs, p.w.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+  if (two_sets) {
+    unsigned long long hs2[S_COUNT];
+    RT_CUDA(ctx, cudaMemcpy(hs2, p2.w.stats, sizeof(hs2), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < S_COUNT; k++) hs[k] += hs2[k];
+  }
   (void)splits;
   if (hs[S_OVERFLOW]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; raise wave_paths or lower the light sample counts");
+  if (p.grid.slots) {
+    uint32_t gc[4];
+    RT_CUDA(ctx, cudaMemcpy(gc, p.grid.grid_counters, sizeof(gc), cudaMemcpyDeviceToHost));
+    if (gc[G_OVERFLOW]) {
+      free_lightgrid(ctx);                                             // the film holds samples shaded with a wrong distribution: the caller must not use it
+      return fail(ctx, RTGPU_ERR_UNSUPPORTED, "spatial light distribution: more occupied voxels than the sparse table holds; raise option lightgrid_sparse_mib "
+                                               "or use lightsamplestrategy \"uniform\"");
+    }
+    if (stats) stats->lightgrid_rows = gc[G_ROWS];
+  }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->camera_rays = hs[S_CAMERA]; stats->regular_rays = hs[S_REGULAR]; stats->shadow_rays = hs[S_SHADOW];
@@ -484,7 +580,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     stats->closest_launches = n_closest_launches; stats->anyhit_launches = n_anyhit_launches;
     stats->nodes_closest = hs[S_NODES_CLOSEST]; stats->prims_closest = hs[S_PRIMS_CLOSEST];
     stats->nodes_anyhit = hs[S_NODES_ANY]; stats->prims_anyhit = hs[S_PRIMS_ANY];
-    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS]; stats->shaded_items = hs[S_VERTICES];
+    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS]; stats->shaded_items = hs[S_VERTICES]; stats->lightgrid_rows = 0;
     float acc[K_CLASSES] = {0, 0, 0, 0};
     for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b); acc[sp.cls] += ms; }
     stats->ms_closest = acc[K_CLOSEST]; stats->ms_anyhit = acc[K_ANYHIT]; stats->ms_shade = acc[K_SHADE]; stats->ms_other = acc[K_OTHER];

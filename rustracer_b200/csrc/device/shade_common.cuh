@@ -26,19 +26,24 @@ RT_DEV Ray camera_ray(const float* r2c, const float* c2w, float lens_radius, flo
 
 // ---- light distributions (lightdistrib.rs) ---------------------------------------------------------------------
 struct Distrib { const float* func; const float* cdf; float func_int; int n; };
+// voxel of a point (SpatialLightDistribution::lookup, lightdistrib.rs:183-201)
+RT_DEV size_t grid_voxel(const DScene& sc, const LightGrid& g, V3 pt) {
+  const float* lo = sc.world_lo; const float* hi = sc.world_hi;
+  float ox = pt.x - lo[0], oy = pt.y - lo[1], oz = pt.z - lo[2];      // Bounds3::offset (bounds.rs:177-190)
+  if (hi[0] > lo[0]) ox /= hi[0] - lo[0];
+  if (hi[1] > lo[1]) oy /= hi[1] - lo[1];
+  if (hi[2] > lo[2]) oz /= hi[2] - lo[2];
+  const int px = min(max(f2i32(ox * (float)g.nv[0]), 0), g.nv[0] - 1);
+  const int py = min(max(f2i32(oy * (float)g.nv[1]), 0), g.nv[1] - 1);
+  const int pz = min(max(f2i32(oz * (float)g.nv[2]), 0), g.nv[2] - 1);
+  return ((size_t)px * g.nv[1] + py) * g.nv[2] + pz;
+}
 RT_DEV Distrib lookup_distrib(const RenderParams& p, V3 pt) {
   const LightGrid& g = p.grid;
   size_t voxel = 0;
-  if (g.nv[0] > 0) {                                                  // SpatialLightDistribution::lookup :183-201
-    const float* lo = p.sc.world_lo; const float* hi = p.sc.world_hi;
-    float ox = pt.x - lo[0], oy = pt.y - lo[1], oz = pt.z - lo[2];    // Bounds3::offset (bounds.rs:177-190)
-    if (hi[0] > lo[0]) ox /= hi[0] - lo[0];
-    if (hi[1] > lo[1]) oy /= hi[1] - lo[1];
-    if (hi[2] > lo[2]) oz /= hi[2] - lo[2];
-    int px = min(max(f2i32(ox * (float)g.nv[0]), 0), g.nv[0] - 1);
-    int py = min(max(f2i32(oy * (float)g.nv[1]), 0), g.nv[1] - 1);
-    int pz = min(max(f2i32(oz * (float)g.nv[2]), 0), g.nv[2] - 1);
-    voxel = ((size_t)px * g.nv[1] + py) * g.nv[2] + pz;
+  if (g.nv[0] > 0) {
+    voxel = grid_voxel(p.sc, g, pt);
+    if (g.slots) voxel = (size_t)max(g.slots[voxel], 0);             // sparse mode: the row k_lightgrid_mark claimed for this voxel before the bounce was shaded
   }
   const int n = g.n_lights;
   const float* base = g.table + voxel * (size_t)(2 * n + 2);

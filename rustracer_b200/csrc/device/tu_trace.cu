@@ -1,6 +1,7 @@
 // Translation unit: ray generation, queue traversal, bounce bookkeeping, film and light-grid kernels.
 #include "kernels_trace.cuh"
 #include "launch.hpp"
+#include <algorithm>
 
 namespace rt {
 
@@ -60,8 +61,15 @@ void launch_shade_miss(const RenderParams& p, unsigned blocks, cudaStream_t s) {
 void launch_next_bounce(const RenderParams& p, int live_idx, int count_camera, int part, cudaStream_t s) { k_next_bounce<<<1, 32, 0, s>>>(p, live_idx, count_camera, part); }
 void launch_lightgrid(const DScene& sc, int nvx, int nvy, int nvz, float* table, cudaStream_t s) {
   const size_t n_voxels = (size_t)nvx * nvy * nvz, total = n_voxels * sc.n_lights;
-  k_lightgrid_contrib<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(sc, nvx, nvy, nvz, table);
-  k_lightgrid_build<<<(unsigned)((n_voxels + 127) / 128), 128, 0, s>>>((int)sc.n_lights, n_voxels, table);
+  k_lightgrid_contrib<<<(unsigned)std::min<size_t>((total + 127) / 128, (size_t)1 << 30), 128, 0, s>>>(sc, nvx, nvy, nvz, table, nullptr, nullptr);
+  k_lightgrid_build<<<(unsigned)((n_voxels + 127) / 128), 128, 0, s>>>((int)sc.n_lights, n_voxels, table, nullptr, nullptr);
+}
+// Sparse light grid, before shading a bounce: claim rows for the new voxels of the bounce's hit points and build them (4 launches).
+void launch_lightgrid_bounce(const RenderParams& p, const uint32_t* list, int count_idx, float* table, unsigned blocks, cudaStream_t s) {
+  k_lightgrid_mark<<<blocks, 256, 0, s>>>(p, list, count_idx);
+  k_lightgrid_contrib<<<blocks * 2, 128, 0, s>>>(p.sc, p.grid.nv[0], p.grid.nv[1], p.grid.nv[2], table, p.grid.new_voxels, p.grid.grid_counters);
+  k_lightgrid_build<<<blocks / 2, 128, 0, s>>>((int)p.sc.n_lights, 0, table, p.grid.new_voxels, p.grid.grid_counters);
+  k_lightgrid_new_done<<<1, 32, 0, s>>>(p.grid.grid_counters);
 }
 void launch_film_add(const FilmParams& f, const float4* L, const float2* pfilm, uint32_t n, cudaStream_t s) { k_film_add<<<(n + 255) / 256, 256, 0, s>>>(f, L, pfilm, n); }
 void launch_li_out(const float4* L, float ao_div, uint32_t n, float* out, cudaStream_t s) { k_li_out<<<(n + 255) / 256, 256, 0, s>>>(L, ao_div, n, out); }

@@ -17,10 +17,18 @@ enum { S_CAMERA = 0, S_REGULAR, S_SHADOW, S_NODES_CLOSEST, S_PRIMS_CLOSEST, S_NO
 
 // Spatial / uniform light distribution tables (lightdistrib.rs).  Per voxel: func[n], cdf[n+1], func_int.
 struct LightGrid {
-  const float* table;        // dense voxel table, or the single uniform distribution when nv = {0,0,0}
+  const float* table;        // voxel table (dense: row = voxel; sparse: row = slots[voxel]), or the single uniform distribution when nv = {0,0,0}
   int nv[3];
   int n_lights;
+  // Sparse mode (many lights: the dense table would not fit).  Like the reference's hash table (lightdistrib.rs:201-296) only the voxels
+  // that path vertices actually fall into get a distribution: k_lightgrid_mark claims a row for every new voxel among a bounce's hit
+  // points, k_lightgrid_contrib / _build fill the new rows, all before the bounce is shaded.  Rows live as long as the scene.
+  int* slots;                // per voxel: row, -1 = not requested yet, -2 = being claimed; null in dense mode
+  uint32_t* new_voxels;      // the rows claimed by the current bounce: {voxel, row} pairs
+  uint32_t* grid_counters;   // [0] rows in use, [1] entries of new_voxels, [2] overflow flag
+  uint32_t cap_rows;
 };
+enum { G_ROWS = 0, G_NEW = 1, G_OVERFLOW = 2 };
 
 struct WaveView {            // device pointers, passed to kernels by value
   // items (path: item slot == sample slot)

@@ -380,13 +380,136 @@ static bool read_hdr(const std::string& fn, int& w, int& h, std::vector<float>& 
   }
   return true;
 }
-// imageio.rs:77-92 `read_image`: by extension.  PFM, PNG and TGA are read; HDR / EXR need codecs this build does not carry.
+// OpenEXR reader (imageio.rs:134-160: `exr::prelude::read_first_rgba_layer_from_file`): single-part scan-line files with R, G, B channels
+// (A and any other channel ignored) of type HALF, FLOAT or UINT, compression NONE / RLE / ZIPS / ZIP, data window == display window,
+// increasing or decreasing line order.  Tiled, multi-part and deep files and the PIZ / PXR24 / B44 / DWA codecs are not read (the
+// caller then takes the reference's "not found" path).  Rows top-to-bottom.
+static float half_to_float(uint16_t hbits) {
+  const uint32_t sign = (uint32_t)(hbits >> 15) << 31, exp = (hbits >> 10) & 31u, man = hbits & 1023u;
+  uint32_t out;
+  if (exp == 0) {
+    if (man == 0) out = sign;
+    else { int e = -1; uint32_t m = man; do { e++; m <<= 1; } while (!(m & 1024u)); out = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 1023u) << 13); }
+  } else if (exp == 31) out = sign | 0x7f800000u | (man << 13);
+  else out = sign | ((exp + 127 - 15) << 23) | (man << 13);
+  float f; std::memcpy(&f, &out, 4); return f;
+}
+static bool read_exr(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
+  FILE* f = std::fopen(fn.c_str(), "rb");
+  if (!f) return false;
+  std::vector<unsigned char> d;
+  unsigned char buf[65536]; size_t n;
+  while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) d.insert(d.end(), buf, buf + n);
+  std::fclose(f);
+  auto u32 = [&](size_t o) { return (uint32_t)d[o] | ((uint32_t)d[o + 1] << 8) | ((uint32_t)d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24); };
+  auto u64 = [&](size_t o) { return (uint64_t)u32(o) | ((uint64_t)u32(o + 4) << 32); };
+  if (d.size() < 8 || u32(0) != 20000630u) return false;
+  const uint32_t version = u32(4);
+  if ((version & 0xffu) != 2 || (version & 0x1a00u)) return false;     // tiled, deep or multi-part
+  size_t pos = 8;
+  struct Chan { std::string name; int type; };
+  std::vector<Chan> chans;
+  int compression = -1, line_order = 0; int32_t dw[4] = {0, 0, -1, -1}, disp[4] = {0, 0, -1, -1};
+  while (true) {
+    std::string name, type;
+    while (pos < d.size() && d[pos]) name.push_back((char)d[pos++]);
+    if (pos >= d.size()) return false;
+    pos++;
+    if (name.empty()) break;
+    while (pos < d.size() && d[pos]) type.push_back((char)d[pos++]);
+    pos++;
+    if (pos + 4 > d.size()) return false;
+    const uint32_t size = u32(pos); pos += 4;
+    if (pos + size > d.size()) return false;
+    if (name == "channels" && type == "chlist") {
+      size_t q = pos;
+      while (q < pos + size && d[q]) {
+        Chan c;
+        while (q < pos + size && d[q]) c.name.push_back((char)d[q++]);
+        q++;
+        if (q + 16 > pos + size) return false;
+        c.type = (int)u32(q);
+        if (u32(q + 8) != 1 || u32(q + 12) != 1) return false;          // sub-sampled channels
+        q += 16;
+        chans.push_back(c);
+      }
+    } else if (name == "compression" && size == 1) compression = d[pos];
+    else if (name == "lineOrder" && size == 1) line_order = d[pos];
+    else if (name == "dataWindow" && size == 16) for (int k = 0; k < 4; k++) dw[k] = (int32_t)u32(pos + 4 * k);
+    else if (name == "displayWindow" && size == 16) for (int k = 0; k < 4; k++) disp[k] = (int32_t)u32(pos + 4 * k);
+    pos += size;
+  }
+  if (compression < 0 || compression > 3 || line_order > 1) return false;
+  for (int k = 0; k < 4; k++) if (dw[k] != disp[k]) return false;
+  const int64_t W = (int64_t)dw[2] - dw[0] + 1, H = (int64_t)dw[3] - dw[1] + 1;
+  if (W <= 0 || H <= 0 || W > 65536 || H > 65536) return false;
+  int ci[3] = {-1, -1, -1};
+  std::vector<size_t> chan_off(chans.size()); size_t line_bytes = 0;
+  for (size_t k = 0; k < chans.size(); k++) {
+    if (chans[k].type < 0 || chans[k].type > 2) return false;
+    chan_off[k] = line_bytes; line_bytes += (size_t)W * (chans[k].type == 1 ? 2 : 4);
+    if (chans[k].name == "R") ci[0] = (int)k; else if (chans[k].name == "G") ci[1] = (int)k; else if (chans[k].name == "B") ci[2] = (int)k;
+  }
+  if (ci[0] < 0 || ci[1] < 0 || ci[2] < 0) return false;
+  const int lines_per_block = compression == 3 ? 16 : 1;
+  const size_t n_blocks = (size_t)((H + lines_per_block - 1) / lines_per_block);
+  if (pos + 8 * n_blocks > d.size()) return false;
+  w = (int)W; h = (int)H;
+  rgb.assign((size_t)W * H * 3, 0.0f);
+  std::vector<unsigned char> raw, tmp;
+  for (size_t b = 0; b < n_blocks; b++) {
+    const uint64_t off = u64(pos + 8 * b);
+    if (off + 8 > d.size()) return false;
+    const int32_t y0 = (int32_t)u32(off); const uint32_t csize = u32(off + 4);
+    if (off + 8 + csize > d.size() || y0 < dw[1] || y0 > dw[3]) return false;
+    const int lines = (int)std::min<int64_t>(lines_per_block, (int64_t)dw[3] - y0 + 1);
+    const size_t usize = line_bytes * (size_t)lines;
+    const unsigned char* src = &d[off + 8];
+    raw.resize(usize);
+    if (compression == 0 || csize >= usize) { if (csize != usize) return false; std::memcpy(raw.data(), src, usize); }
+    else {
+      tmp.resize(usize);
+      if (compression == 1) {                                         // RLE: n < 0 -> -n literal bytes; n >= 0 -> the next byte n + 1 times
+        size_t i = 0, o = 0;
+        while (i < csize) {
+          const int c = (signed char)src[i++];
+          if (c < 0) { const size_t m = (size_t)(-c); if (i + m > csize || o + m > usize) return false; std::memcpy(&tmp[o], &src[i], m); i += m; o += m; }
+          else { const size_t m = (size_t)c + 1; if (i >= csize || o + m > usize) return false; std::memset(&tmp[o], src[i++], m); o += m; }
+        }
+        if (o != usize) return false;
+      } else {
+        uLongf len = (uLongf)usize;
+        if (uncompress(tmp.data(), &len, src, (uLong)csize) != Z_OK || len != usize) return false;
+      }
+      for (size_t i = 1; i < usize; i++) tmp[i] = (unsigned char)(tmp[i - 1] + tmp[i] - 128);   // predictor
+      const size_t half = (usize + 1) / 2;                            // de-interleave: first half = even bytes, second half = odd bytes
+      for (size_t i = 0; i < usize; i++) raw[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+    }
+    for (int l = 0; l < lines; l++) {
+      const int64_t y = (int64_t)y0 - dw[1] + l;
+      for (int c = 0; c < 3; c++) {
+        const unsigned char* q = &raw[(size_t)l * line_bytes + chan_off[(size_t)ci[c]]];
+        const int type = chans[(size_t)ci[c]].type;
+        for (int64_t x = 0; x < W; x++) {
+          float v;
+          if (type == 1) { uint16_t hb; std::memcpy(&hb, q + 2 * x, 2); v = half_to_float(hb); }
+          else if (type == 2) std::memcpy(&v, q + 4 * x, 4);
+          else { uint32_t u; std::memcpy(&u, q + 4 * x, 4); v = (float)u; }
+          rgb[((size_t)y * W + (size_t)x) * 3 + c] = v;
+        }
+      }
+    }
+  }
+  return true;
+}
+// imageio.rs:77-92 `read_image`: by extension.  PFM, PNG, TGA, Radiance HDR and scan-line OpenEXR (NONE / RLE / ZIPS / ZIP) are read.
 static bool read_image_rgb(const std::string& fn, int& w, int& h, std::vector<float>& rgb) {
   auto ends = [&](const char* e) { size_t n = std::strlen(e); return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0; };
   if (ends(".pfm")) return read_pfm(fn, w, h, rgb);
   if (ends(".png")) return read_png(fn, w, h, rgb);
   if (ends(".tga")) return read_tga(fn, w, h, rgb);
   if (ends(".hdr")) return read_hdr(fn, w, h, rgb);
+  if (ends(".exr")) return read_exr(fn, w, h, rgb);
   return false;
 }
 

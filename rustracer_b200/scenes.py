@@ -329,6 +329,68 @@ def write_hdr(path, img, rle=True):
     return dec.astype(np.float32)
 
 
+def write_exr(path, img, pixel_type="half", compression="zip", decreasing_y=False):
+    """Single-part scan-line OpenEXR with channels B, G, R (alphabetical, as the format requires): pixel_type "half" | "float",
+    compression "none" | "rle" | "zips" | "zip".  Returns the image as a reader sees it (half rounding applied), (H, W, 3) float32."""
+    import struct
+    import zlib
+    img = np.asarray(img, np.float32)
+    h, w, _ = img.shape
+    dt = np.float16 if pixel_type == "half" else np.float32
+    code = {"none": 0, "rle": 1, "zips": 2, "zip": 3}[compression]
+    lines_per_block = 16 if code == 3 else 1
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+    chlist = b"".join(n.encode() + b"\0" + struct.pack("<iBxxxii", 1 if pixel_type == "half" else 2, 0, 1, 1) for n in ("B", "G", "R")) + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    hdr = (struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([code])) + attr("dataWindow", "box2i", box) +
+           attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", bytes([1 if decreasing_y else 0])) + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) +
+           attr("screenWindowCenter", "v2f", struct.pack("<ff", 0, 0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+
+    def rle(b):
+        out, i = bytearray(), 0
+        while i < len(b):
+            run = 1
+            while i + run < len(b) and run < 127 and b[i + run] == b[i]:
+                run += 1
+            if run >= 3:
+                out += bytes([run - 1, b[i]])
+                i += run
+            else:
+                j = i
+                while j < len(b) and j - i < 127 and not (j + 2 < len(b) and b[j] == b[j + 1] == b[j + 2]):
+                    j += 1
+                out += bytes([(256 - (j - i)) & 255]) + bytes(b[i:j])
+                i = j
+        return bytes(out)
+    blocks = []
+    for y0 in range(0, h, lines_per_block):
+        rows = img[y0:y0 + lines_per_block]
+        raw = b"".join(rows[l, :, c].astype(dt).tobytes() for l in range(rows.shape[0]) for c in (2, 1, 0))
+        data = raw
+        if code:
+            a = np.frombuffer(raw, np.uint8)
+            t = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)
+            t[1:] = (t[1:] - t[:-1] + 128 + 256) & 255
+            pre = t.astype(np.uint8).tobytes()
+            comp = rle(pre) if code == 1 else zlib.compress(pre, 6)
+            data = comp if len(comp) < len(raw) else raw
+        blocks.append((y0, data))
+    if decreasing_y:
+        blocks = blocks[::-1]
+    table_pos = len(hdr)
+    pos = table_pos + 8 * len(blocks)
+    offsets = {}
+    body = bytearray()
+    for y0, data in blocks:
+        offsets[y0] = pos + len(body)
+        body += struct.pack("<ii", y0, len(data)) + data
+    with open(path, "wb") as f:
+        f.write(hdr + b"".join(struct.pack("<Q", offsets[y0]) for y0 in sorted(offsets)) + bytes(body))
+    return img.astype(dt).astype(np.float32)
+
+
 def texture_images(out_dir):
     """The two harness textures: a 48x20 (non power-of-two) RGB PFM and a 16x16 greyscale PNG."""
     os.makedirs(out_dir, exist_ok=True)
@@ -437,6 +499,8 @@ def lights_zoo(out_dir, xres=96, yres=72, spp=8, integrator=None, env_size=(32, 
     os.makedirs(out_dir, exist_ok=True)
     if env_name.endswith(".hdr"):
         write_hdr(os.path.join(out_dir, env_name), env_map_image(*env_size))
+    elif env_name.endswith(".exr"):
+        write_exr(os.path.join(out_dir, env_name), env_map_image(*env_size))
     else:
         write_pfm(os.path.join(out_dir, env_name), env_map_image(*env_size))
     if integrator is None:
@@ -465,6 +529,26 @@ def lights_zoo(out_dir, xres=96, yres=72, spp=8, integrator=None, env_size=(32, 
                  ('Material "metal" "float roughness" [0.1]', (-2.4, 0.75, 2.6), 0.75), ('Material "matte" "rgb Kd" [0.5 0.5 0.5] "float sigma" [25]', (0.0, 0.5, 2.8), 0.5)]
     for mat, c, r in receivers:
         s += f'AttributeBegin\n{mat}\nTranslate {c[0]} {c[1]} {c[2]}\nShape "sphere" "float radius" [{r}]\nAttributeEnd\n'
+    s += "WorldEnd\n"
+    return s
+
+
+def emissive_mesh_scene(out_dir, level=5, xres=64, yres=48, spp=4, integrator=None):
+    """Many-light scene: an emissive icosphere mesh (20 * 4^level triangle lights; level 5 = 20,480) above a ground quad with a matte,
+    a plastic and a mirror ball — SpatialLightDistribution (lightdistrib.rs:59-296) over thousands of lights, where only the voxels
+    that path vertices fall into can hold a distribution."""
+    os.makedirs(out_dir, exist_ok=True)
+    v, f = icosphere(level)
+    write_ply(os.path.join(out_dir, f"emitter_{level}.ply"), v * 0.8 + np.array([0.0, 3.2, 0.5]), f)
+    if integrator is None:
+        integrator = 'Integrator "path" "integer maxdepth" [4] "string lightsamplestrategy" "spatial"'
+    s = header(xres, yres, spp, integrator, 40, ([0, 3.0, -9.0], [0, 1.2, 0], [0, 1, 0]))
+    s += "WorldBegin\n"
+    s += f'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [6 5.5 5]\nMaterial "matte" "rgb Kd" [0 0 0]\nShape "plymesh" "string filename" "emitter_{level}.ply"\nAttributeEnd\n'
+    s += 'Material "matte" "rgb Kd" [0.55 0.55 0.5]\n' + _quad([-8, 0, -8], [8, 0, -8], [8, 0, 8], [-8, 0, 8])
+    s += 'AttributeBegin\nMaterial "matte" "rgb Kd" [0.7 0.3 0.25]\nTranslate -2 0.8 0\nShape "sphere" "float radius" [0.8]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "plastic" "rgb Kd" [0.2 0.4 0.7] "float roughness" [0.1]\nTranslate 0 0.7 -1.5\nShape "sphere" "float radius" [0.7]\nAttributeEnd\n'
+    s += 'AttributeBegin\nMaterial "mirror"\nTranslate 2 0.9 0.5\nShape "sphere" "float radius" [0.9]\nAttributeEnd\n'
     s += "WorldEnd\n"
     return s
 

@@ -212,3 +212,26 @@ def test_hdr_reader_decodes_rgbe(native_libs, tmp_path):
         tex, _ = ob.OracleScene(sc.ir_ptr).light_env(0)
         assert np.array_equal(tex, want)
         assert np.abs(want - img).max() / img.max() < 1 / 128
+
+
+@pytest.mark.parametrize("pixel_type,compression,decreasing", [("half", "zip", False), ("float", "zip", True), ("half", "none", False), ("float", "zips", False),
+                                                               ("half", "rle", True)])
+def test_exr_reader(native_libs, tmp_path, pixel_type, compression, decreasing):
+    """read_image_exr (imageio.rs:134-160) restated for scan-line files: HALF / FLOAT channels, NONE / RLE / ZIPS / ZIP blocks, both line
+    orders; 40 x 21 pixels so the last ZIP block is short.  Checked through the environment light, which keeps the texels unfiltered
+    when the size is a power of two — so a 64 x 32 copy is compared bit for bit and the odd size through its resampled mean."""
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, scenes
+    for size in ((64, 32), (40, 21)):
+        img = scenes.env_map_image(*size)
+        want = scenes.write_exr(str(tmp_path / "env.exr"), img, pixel_type=pixel_type, compression=compression, decreasing_y=decreasing)
+        txt = scenes.lights_zoo(str(tmp_path), xres=16, yres=16, spp=1, env_name="unused.pfm").replace("unused.pfm", "env.exr")
+        txt = txt.replace('"rgb L" [0.9 1.0 1.1] "rgb scale" [1.2 1.2 1.2]', '"rgb L" [1 1 1]')
+        sc = Scene.from_string(txt, search_dir=str(tmp_path))
+        assert sc.warnings == []
+        sc.flatten()
+        tex, _ = ob.OracleScene(sc.ir_ptr).light_env(0)
+        if size == (64, 32):
+            assert np.array_equal(tex, want)
+        else:
+            assert tex.shape == (32, 64, 3) and abs(tex.mean() - want.mean()) / want.mean() < 0.05
