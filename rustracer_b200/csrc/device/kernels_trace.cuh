@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
               x >= p.pixel_bounds[0] && x < p.pixel_bounds[2] && y >= p.pixel_bounds[1] && y < p.pixel_bounds[3];   // renderer.rs:103-105
     }
   }
-  const uint32_t pos = warp_append(&p.w.counters[C_LIVE0], valid);
+  // queue positions for the valid items: one global atomic per block (a 32 M-sample wave issued 1 M same-address atomics per warp-level
+  // append, which bounded the kernel: 61 ps per sample against 17 ps for its 100 bytes of traffic, profiles/r02f_launches_c5.csv)
+  const uint32_t pos = block_append(&p.w.counters[C_LIVE0], valid);
   if (i < p.n_items) {
     SamplerState ss; ss.ph = pixel_hash(x, y, p.seed); ss.s = s; ss.d1 = 0; ss.d2 = 0; ss.da = 0;
     P2 u = ss.get_2d(p.scfg);
@@ -180,29 +182,50 @@ __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_eng
 // distinct class and warp via match_any) instead of seven ballot rounds inside every refill of the traversal engine.
 // FROM_CLASS: the engine left each hit's queue id in hit_class (it rides in the hit slot's geometry record), so the pass
 // reads 5 bytes per path instead of chasing hit -> primitive info -> material row.
+// Queue positions are claimed per BLOCK: every thread classifies kClassifyPerThread paths, the block counts each class in shared
+// memory and issues one global atomic per class for all of them (with one atomic per class and warp the eight counters took 17 M
+// same-address atomics per C5 step and the pass ran at 32 ps per path instead of ~3: profiles/r02f_launches_c5.csv).
+constexpr int kClassifyPerThread = 8;
 template <bool FROM_CLASS>
 __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t* __restrict__ list, int count_idx, const HitRec* __restrict__ hits) {
+  __shared__ uint32_t s_count[Q_COUNT], s_base[Q_COUNT];
   const uint32_t n = min(p.w.counters[count_idx], p.w.cap_items);   // a level queue that overflowed keeps counting past its capacity
   const uint32_t lane = lane_id(), lane_lt = (1u << lane) - 1u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31u) & ~31u); i += gridDim.x * blockDim.x) {
-    int q = -1; uint32_t slot = 0;
-    if (i < n) {
-      slot = list ? list[i] : i;
-      const uint32_t hslot = FROM_CLASS ? 0u : hits[slot].slot;
-      if (FROM_CLASS) q = (int)p.w.hit_class[slot];
-      else if (hslot == kMiss) q = Q_MISS;
-      else {
-        const uint32_t mrow = p.sc.info[hslot].y;
-        const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
-        q = material_queue(type);
+  const uint32_t tile = 256u * kClassifyPerThread;
+  for (uint32_t base = blockIdx.x * tile; base < n; base += gridDim.x * tile) {
+    if (threadIdx.x < Q_COUNT) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    int q[kClassifyPerThread]; uint32_t slot[kClassifyPerThread], off[kClassifyPerThread];
+#pragma unroll
+    for (int k = 0; k < kClassifyPerThread; k++) {
+      const uint32_t i = base + (uint32_t)k * 256u + threadIdx.x;
+      q[k] = -1; slot[k] = 0; off[k] = 0;
+      if (i < n) {
+        slot[k] = list ? list[i] : i;
+        if (FROM_CLASS) q[k] = (int)p.w.hit_class[slot[k]];
+        else {
+          const uint32_t hslot = hits[slot[k]].slot;
+          if (hslot == kMiss) q[k] = Q_MISS;
+          else {
+            const uint32_t mrow = p.sc.info[hslot].y;
+            const uint32_t type = mrow < p.sc.n_materials ? p.sc.materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
+            q[k] = material_queue(type);
+          }
+        }
       }
+      const unsigned peers = __match_any_sync(0xffffffffu, q[k]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t wbase = 0;
+      if (q[k] >= 0 && (int)lane == leader) wbase = atomicAdd(&s_count[q[k]], (uint32_t)__popc(peers));   // shared-memory atomic
+      wbase = __shfl_sync(0xffffffffu, wbase, leader);
+      off[k] = wbase + (uint32_t)__popc(peers & lane_lt);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, q);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (q >= 0 && (int)lane == leader) base = atomicAdd(&p.w.counters[C_MATQ0 + q], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (q >= 0) p.w.matq[q][base + (uint32_t)__popc(peers & lane_lt)] = slot;
+    __syncthreads();
+    if (threadIdx.x < Q_COUNT && s_count[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&p.w.counters[C_MATQ0 + threadIdx.x], s_count[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kClassifyPerThread; k++) if (q[k] >= 0) p.w.matq[q[k]][s_base[q[k]] + off[k]] = slot[k];
+    __syncthreads();
   }
 }
 

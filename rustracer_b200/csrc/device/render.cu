@@ -562,6 +562,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   }
   (void)splits;
   if (hs[S_OVERFLOW]) return fail(ctx, RTGPU_ERR_QUEUE_OVERFLOW, "a wavefront queue overflowed; raise wave_paths or lower the light sample counts");
+  uint64_t grid_rows = 0;
   if (p.grid.slots) {
     uint32_t gc[4];
     RT_CUDA(ctx, cudaMemcpy(gc, p.grid.grid_counters, sizeof(gc), cudaMemcpyDeviceToHost));
@@ -570,7 +571,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
       return fail(ctx, RTGPU_ERR_UNSUPPORTED, "spatial light distribution: more occupied voxels than the sparse table holds; raise option lightgrid_sparse_mib "
                                                "or use lightsamplestrategy \"uniform\"");
     }
-    if (stats) stats->lightgrid_rows = gc[G_ROWS];
+    grid_rows = gc[G_ROWS];
   }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
@@ -580,7 +581,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
     stats->closest_launches = n_closest_launches; stats->anyhit_launches = n_anyhit_launches;
     stats->nodes_closest = hs[S_NODES_CLOSEST]; stats->prims_closest = hs[S_PRIMS_CLOSEST];
     stats->nodes_anyhit = hs[S_NODES_ANY]; stats->prims_anyhit = hs[S_PRIMS_ANY];
-    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS]; stats->shaded_items = hs[S_VERTICES]; stats->lightgrid_rows = 0;
+    stats->closest_rays = hs[S_CLOSEST_RAYS]; stats->anyhit_rays = hs[S_ANY_RAYS]; stats->shaded_items = hs[S_VERTICES]; stats->lightgrid_rows = grid_rows;
     float acc[K_CLASSES] = {0, 0, 0, 0};
     for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b); acc[sp.cls] += ms; }
     stats->ms_closest = acc[K_CLOSEST]; stats->ms_anyhit = acc[K_ANYHIT]; stats->ms_shade = acc[K_SHADE]; stats->ms_other = acc[K_OTHER];

@@ -34,10 +34,20 @@ namespace rt {
 #ifndef RT_ENGINE_PREFETCH
 #define RT_ENGINE_PREFETCH 0        // 1 / 2: prefetch a pushed subtree's record into L1 / L2 (measured: see profiles/)
 #endif
+#ifndef RT_ENGINE_LDG256
+#define RT_ENGINE_LDG256 1          // collapsed nodes are fetched with four 256-bit loads instead of eight 128-bit ones
+#endif
 #ifndef RT_ENGINE_SMEM_DEPTH
 #define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
 #endif
 RT_DEV uint32_t lane_id_() { return threadIdx.x & 31u; }
+// One 256-bit read-only load (sm_100: LDG.E.256.CONSTANT) of two consecutive float4; p must be 32-byte aligned.  The engine is bound
+// by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 89 % of peak with 128-bit loads, profiles/r02f): a lane's node costs one
+// wavefront per load instruction, so half as many instructions per node are half as many wavefronts.
+RT_DEV void ldg256(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDoneRef = 0xffffffffu;        // (a leaf ref never has all 31 payload bits set: slots < 2^31 - 1)
 constexpr uint32_t kHitSlotMask = (1u << kHitSlotBits) - 1u;   // inside the engine a hit slot carries its shade-queue id in the top 3 bits
@@ -201,8 +211,13 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         const uint2 top = top_in_smem ? s_stack[sp - 1][tid] : make_uint2(kExitInstance, 0u);
 #if RT_ENGINE_WIDE4
         const float4* __restrict__ nd = wide + 8 * (size_t)cur;
-        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-        const float4 q4 = __ldg(nd + 4), q5 = __ldg(nd + 5), q6 = __ldg(nd + 6), q7 = __ldg(nd + 7);
+        float4 q0, q1, q2, q3, q4, q5, q6, q7;
+#if RT_ENGINE_LDG256
+        ldg256(nd, q0, q1); ldg256(nd + 2, q2, q3); ldg256(nd + 4, q4, q5); ldg256(nd + 6, q6, q7);
+#else
+        q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
+        q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); q6 = __ldg(nd + 6); q7 = __ldg(nd + 7);
+#endif
         const uint32_t r0 = __float_as_uint(q0.w), r1 = __float_as_uint(q1.w), axes = __float_as_uint(q2.w), r2 = __float_as_uint(q3.w), r3 = __float_as_uint(q4.w);
         float t0, t1, t2, t3;
         const bool h0 = slab_interval_bf(q0, q1, ray.o, inv_dir, nx, ny, nz, ray.t_max, t0);

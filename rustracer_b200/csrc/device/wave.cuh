@@ -95,6 +95,26 @@ RT_DEV uint32_t warp_append(uint32_t* counter, bool pred) {
   base = __shfl_sync(mask, base, leader);
   return base + (uint32_t)__popc(mask & ((1u << lane_id()) - 1u));
 }
+// Append to a device queue: one atomicAdd per BLOCK.  Every thread of the block must call it (it synchronises); blockDim.x <= 1024.
+RT_DEV uint32_t block_append(uint32_t* counter, bool pred) {
+  __shared__ uint32_t s_warp_count[32];
+  __shared__ uint32_t s_block_base;
+  const unsigned mask = __ballot_sync(0xffffffffu, pred);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+  if (lane == 0) s_warp_count[warp] = (uint32_t)__popc(mask);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t c = lane < n_warps ? s_warp_count[lane] : 0u;
+    uint32_t x = c;                                                  // inclusive scan of the warp counts
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, off); if ((int)lane >= off) x += y; }
+    if (lane == 31) s_block_base = x ? atomicAdd(counter, x) : 0u;
+    if (lane < n_warps) s_warp_count[lane] = x - c;                  // exclusive offset of each warp
+  }
+  __syncthreads();
+  const uint32_t pos = s_block_base + s_warp_count[warp] + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+  __syncthreads();                                                   // the shared words are reused by the next call
+  return pred ? pos : 0xffffffffu;
+}
 // Next packet of 32 queue entries for a persistent warp (atomic cursor).
 RT_DEV uint32_t warp_fetch(uint32_t* cursor) {
   uint32_t base = 0;
