@@ -286,10 +286,10 @@ def render_roofline(dev, step_desc, reps, traffic_key, full_defaults):
     achieved = bytes_step / t_closest / 1e9
     tr = traffic_entry(traffic_key) if full_defaults else {}
     launches_per_step = acc["launches"] / reps
-    roof = {"bound": tr.get("bound", "hbm"), "kernel": "k_trace_closest_engine + k_trace_mis_engine (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "limited_by": tr.get("limited_by"), "kernel": "k_trace_closest_engine + k_trace_mis_engine (closest-hit BVH traversal)", "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
             "traffic": tr.get("dram_bytes_per_launch"), "l2_bytes_per_launch": tr.get("l2_bytes_per_launch"), "l2_frac": tr.get("l2_frac"),
-            "traffic_source": tr.get("source"),
+            "l1_frac": tr.get("l1_frac"), "dram_frac": tr.get("dram_frac"), "traffic_source": tr.get("source"),
             "algorithmic_bytes_per_launch": bytes_step / max(1.0, launches_per_step), "algorithmic_bytes_per_step": bytes_step, "rays_per_step": int(n_rays),
             "nodes_per_ray": stc.nodes_closest / max(1, n_rays), "prims_per_ray": stc.prims_closest / max(1, n_rays),
             "launches_per_step": launches_per_step, "avg_launch_ms": acc["closest"] / max(1, acc["launches"]),
@@ -445,9 +445,11 @@ def leg_c4(dev, a, tmp):
         res = {"mrays_per_s_device": n / (ms * 1e-3) / 1e6, "ms_device": ms, "mrays_per_s_host_buffers": n / t_host / 1e6, "seconds_host_buffers": t_host,
                "h2d_bytes": n * 32, "d2h_bytes": n * (1 if any_hit else 16), "host_memory": "pinned (rtgpu_host_alloc)",
                "nodes_per_ray": nodes, "prims_per_ray": prims, "algorithmic_bytes_per_ray": bytes_ray,
-               "roofline": {"bound": "hbm", "kernel": "k_anyhit_batch_engine" if any_hit else "k_closest_batch_engine", "achieved": n * bytes_ray / (ms * 1e-3) / 1e9,
+               "roofline": {"bound": "hbm", "limited_by": tr.get("limited_by"), "kernel": "k_anyhit_batch_engine" if any_hit else "k_closest_batch_engine",
+                            "achieved": n * bytes_ray / (ms * 1e-3) / 1e9,
                             "peak": peak, "unit": "GB/s", "frac": n * bytes_ray / (ms * 1e-3) / 1e9 / peak, "traffic": tr.get("dram_bytes_per_launch"),
-                            "l2_bytes_per_launch": tr.get("l2_bytes_per_launch"), "traffic_source": tr.get("source"),
+                            "algorithmic_bytes_per_launch": (1 << 24) * bytes_ray, "l2_bytes_per_launch": tr.get("l2_bytes_per_launch"), "l2_frac": tr.get("l2_frac"),
+                            "l1_frac": tr.get("l1_frac"), "dram_frac": tr.get("dram_frac"), "traffic_source": tr.get("source"),
                             "note": "includes the ray binning (k_sort_*) inside the timed launches"}}
         # every ray against the oracle (all host threads)
         if not a.no_cpu_baseline:

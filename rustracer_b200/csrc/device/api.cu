@@ -1,5 +1,6 @@
 // librtgpu.so — context, scene upload and the batched BVH::intersect / BVH::intersect_p entry points
 // (include/rtgpu.h).  Hand-written CUDA for sm_100a; compiled with -fmad=false.
+#define RT_QUADRIC_INLINE 1   // shapes.cuh: quadric tests inlined (hot on sphere / disk / cylinder scenes)
 #include <atomic>
 #include <thread>
 #include "context.hpp"

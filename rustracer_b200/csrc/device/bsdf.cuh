@@ -98,6 +98,23 @@ enum { FR_NOOP = 0, FR_DIELECTRIC = 1, FR_CONDUCTOR = 2 };
 enum { LOBE_LAMBERT_R = 0, LOBE_OREN_NAYAR, LOBE_SPEC_REFL, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_MICRO_REFL, LOBE_MICRO_TRANS,
        LOBE_LAMBERT_T, LOBE_FRESNEL_BLEND };
 
+// Lobe kinds and lobe counts a translation unit can meet (bit k = LOBE_* kind k).  The per-material path kernels (tu_path.cu) narrow
+// them: their `switch (kind)` dispatch then drops the other lobes' code — the matte kernel carried 61 k SASS instructions of which a
+// warp ever executed 4.9 k (profiles/r02f_ncu_full_shade_c3_raw.csv: 877 KB never executed, 18 % "no instruction" stalls).
+#ifndef RT_LOBE_KINDS
+#define RT_LOBE_KINDS 0x1ffu
+#endif
+#ifndef RT_MAX_BUILT_LOBES
+#define RT_MAX_BUILT_LOBES 8
+#endif
+// RT_LOBE_OFF(K...) as the first statement of a `case`: a compile-time test, so the optimiser deletes the case of a kind this TU never meets
+#define RT_LOBE_ON(K) (((RT_LOBE_KINDS) >> (K)) & 1u)
+#define RT_LOBE_OFF1(A) if (!RT_LOBE_ON(A)) __builtin_unreachable();
+#define RT_LOBE_OFF2(A, B) if (!(RT_LOBE_ON(A) | RT_LOBE_ON(B))) __builtin_unreachable();
+#define RT_LOBE_OFF3(A, B, C) if (!(RT_LOBE_ON(A) | RT_LOBE_ON(B) | RT_LOBE_ON(C))) __builtin_unreachable();
+RT_DEV int lobe_kind_known(int kind) { return kind; }
+RT_DEV int lobe_count_known(int n) { if (n > RT_MAX_BUILT_LOBES) __builtin_unreachable(); return n; }
+
 struct Lobe {
   int kind;
   Spec r, t;                        // FresnelBlend: rs in r, rd in t
@@ -187,10 +204,10 @@ RT_DEV bool lobe_matches(int kind, uint32_t flags) { uint32_t t = lobe_type(kind
 
 RT_DEV float pow5(float v) { return (v * v) * (v * v) * v; }                     // fresnel.rs:414-417
 RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
-  switch (l.kind) {
-    case LOBE_LAMBERT_R: return l.r * kInvPi;                                    // lambertian.rs:19-21
-    case LOBE_LAMBERT_T: return l.t * kInvPi;                                    // lambertian.rs:39-41
-    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:358-375 (rs = r, rd = t)
+  switch (lobe_kind_known(l.kind)) {
+    case LOBE_LAMBERT_R: RT_LOBE_OFF1(LOBE_LAMBERT_R) return l.r * kInvPi;                                    // lambertian.rs:19-21
+    case LOBE_LAMBERT_T: RT_LOBE_OFF1(LOBE_LAMBERT_T) return l.t * kInvPi;                                    // lambertian.rs:39-41
+    case LOBE_FRESNEL_BLEND: { RT_LOBE_OFF1(LOBE_FRESNEL_BLEND)                   // fresnel.rs:358-375 (rs = r, rd = t)
       Spec diffuse = (28.0f / (23.0f * kPi)) * l.t * (spec(1.0f) - l.r) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
                      (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo)));
       V3 wh = wi + wo;
@@ -200,7 +217,7 @@ RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
       Spec specular = tr_d(l.ax, l.ay, wh) / (4.0f * fabsf(dot(wi, wh)) * fmaxf(abs_cos_theta(wi), abs_cos_theta(wo))) * schlick;
       return diffuse + specular;
     }
-    case LOBE_OREN_NAYAR: {                                                      // oren_nayar.rs:30-52
+    case LOBE_OREN_NAYAR: { RT_LOBE_OFF1(LOBE_OREN_NAYAR)                        // oren_nayar.rs:30-52
       float sti = sin_theta(wi), sto = sin_theta(wo);
       float max_cos = 0.0f;
       if (sti > 1e-4f && sto > 1e-4f) {
@@ -212,7 +229,7 @@ RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
       else { sin_alpha = sti; tan_beta = sto / abs_cos_theta(wo); }
       return l.r * kInvPi * (l.on_a + l.on_b * max_cos * sin_alpha * tan_beta);
     }
-    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:36-53
+    case LOBE_MICRO_REFL: { RT_LOBE_OFF1(LOBE_MICRO_REFL)                        // microfacet.rs:36-53
       float cto = abs_cos_theta(wo), cti = abs_cos_theta(wi);
       V3 wh = wi + wo;
       if (cto == 0.0f || cti == 0.0f) return spec(0.0f);
@@ -221,7 +238,7 @@ RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
       Spec F = fresnel_evaluate(l, dot(wi, wh));
       return l.r * tr_d(l.ax, l.ay, wh) * tr_g(l.ax, l.ay, wo, wi) * F / (4.0f * cti * cto);
     }
-    case LOBE_MICRO_TRANS: {                                                     // microfacet.rs:125-169
+    case LOBE_MICRO_TRANS: { RT_LOBE_OFF1(LOBE_MICRO_TRANS)                      // microfacet.rs:125-169
       if (same_hemisphere(wo, wi)) return spec(0.0f);
       float cto = cos_theta(wo), cti = cos_theta(wi);
       if (cto == 0.0f || cti == 0.0f) return spec(0.0f);
@@ -239,21 +256,22 @@ RT_DEV Spec lobe_f_inner(const Lobe& l, V3 wo, V3 wi) {
   }
 }
 RT_DEV float lobe_pdf_inner(const Lobe& l, V3 wo, V3 wi) {
-  switch (l.kind) {
+  switch (lobe_kind_known(l.kind)) {
     case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T:              // bxdf.rs:38-44 (LambertianTransmission keeps the default)
+      RT_LOBE_OFF3(LOBE_LAMBERT_R, LOBE_OREN_NAYAR, LOBE_LAMBERT_T)
       return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * kInvPi : 0.0f;
-    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:377-385
+    case LOBE_FRESNEL_BLEND: { RT_LOBE_OFF1(LOBE_FRESNEL_BLEND)                   // fresnel.rs:377-385
       if (!same_hemisphere(wo, wi)) return 0.0f;
       V3 wh = normalize(wo + wi);
       float pdf_wh = tr_pdf(l.ax, l.ay, wo, wh);
       return 0.5f * (abs_cos_theta(wi) * kInvPi + pdf_wh / (4.0f * dot(wo, wh)));
     }
-    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:87-94
+    case LOBE_MICRO_REFL: { RT_LOBE_OFF1(LOBE_MICRO_REFL)                        // microfacet.rs:87-94
       if (!same_hemisphere(wo, wi)) return 0.0f;
       V3 wh = normalize(wo + wi);
       return tr_pdf(l.ax, l.ay, wo, wh) / (4.0f * dot(wo, wh));
     }
-    case LOBE_MICRO_TRANS: {                                                     // microfacet.rs:207-222
+    case LOBE_MICRO_TRANS: { RT_LOBE_OFF1(LOBE_MICRO_TRANS)                      // microfacet.rs:207-222
       if (same_hemisphere(wo, wi)) return 0.0f;
       float eta = cos_theta(wo) > 0.0f ? l.eta_b / l.eta_a : l.eta_a / l.eta_b;
       V3 wh = normalize(wo + wi * eta);
@@ -266,8 +284,8 @@ RT_DEV float lobe_pdf_inner(const Lobe& l, V3 wo, V3 wi) {
 }
 // `sampled` is the BxdfType the lobe reports (bxdf.rs:18-25: the default sample_f reports EMPTY)
 RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi, float& pdf_out, uint32_t& sampled) {
-  switch (l.kind) {
-    case LOBE_FRESNEL_BLEND: {                                                   // fresnel.rs:387-407
+  switch (lobe_kind_known(l.kind)) {
+    case LOBE_FRESNEL_BLEND: { RT_LOBE_OFF1(LOBE_FRESNEL_BLEND)                   // fresnel.rs:387-407
       sampled = lobe_type(l.kind);
       if (u.x < 0.5f) {
         u.x = fminf(2.0f * u.x, kOneMinusEpsilon);
@@ -282,19 +300,19 @@ RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi,
       f_out = lobe_f_inner(l, wo, wi); pdf_out = lobe_pdf_inner(l, wo, wi);
       return;
     }
-    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T: {            // bxdf.rs:18-25: the hemisphere of wo, also for LambertianTransmission
+    case LOBE_LAMBERT_R: case LOBE_OREN_NAYAR: case LOBE_LAMBERT_T: { RT_LOBE_OFF3(LOBE_LAMBERT_R, LOBE_OREN_NAYAR, LOBE_LAMBERT_T)   // bxdf.rs:18-25: the hemisphere of wo, also for LambertianTransmission
       wi = cosine_sample_hemisphere(u);
       if (wo.z < 0.0f) wi.z *= -1.0f;
       pdf_out = lobe_pdf_inner(l, wo, wi); f_out = lobe_f_inner(l, wo, wi); sampled = 0;
       return;
     }
-    case LOBE_SPEC_REFL: {                                                       // fresnel.rs:159-164
+    case LOBE_SPEC_REFL: { RT_LOBE_OFF1(LOBE_SPEC_REFL)                          // fresnel.rs:159-164
       wi = v3(-wo.x, -wo.y, wo.z);
       f_out = fresnel_evaluate(l, cos_theta(wi)) * l.r / abs_cos_theta(wi);
       pdf_out = 1.0f; sampled = lobe_type(l.kind);
       return;
     }
-    case LOBE_SPEC_TRANS: {                                                      // fresnel.rs:203-230
+    case LOBE_SPEC_TRANS: { RT_LOBE_OFF1(LOBE_SPEC_TRANS)                        // fresnel.rs:203-230
       bool entering = cos_theta(wo) > 0.0f;
       float ei = entering ? l.eta_a : l.eta_b, et = entering ? l.eta_b : l.eta_a;
       V3 w;
@@ -306,7 +324,7 @@ RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi,
       } else { f_out = spec(1.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; }
       return;
     }
-    case LOBE_FRESNEL_SPEC: {                                                    // fresnel.rs:273-322
+    case LOBE_FRESNEL_SPEC: { RT_LOBE_OFF1(LOBE_FRESNEL_SPEC)                    // fresnel.rs:273-322
       float fr = fr_dielectric(cos_theta(wo), l.eta_a, l.eta_b);
       if (u.x < fr) {
         wi = v3(-wo.x, -wo.y, wo.z);
@@ -324,7 +342,7 @@ RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi,
       }
       return;
     }
-    case LOBE_MICRO_REFL: {                                                      // microfacet.rs:61-85
+    case LOBE_MICRO_REFL: { RT_LOBE_OFF1(LOBE_MICRO_REFL)                        // microfacet.rs:61-85
       sampled = lobe_type(l.kind);
       if (wo.z == 0.0f) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
       V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
@@ -334,7 +352,7 @@ RT_DEV void lobe_sample_f_inner(const Lobe& l, V3 wo, P2 u, Spec& f_out, V3& wi,
       f_out = lobe_f_inner(l, wo, wi);
       return;
     }
-    default: {                                                                   // LOBE_MICRO_TRANS microfacet.rs:177-205
+    default: { RT_LOBE_OFF1(LOBE_MICRO_TRANS)                                    // LOBE_MICRO_TRANS microfacet.rs:177-205
       sampled = lobe_type(l.kind);
       if (wo.z == 0.0f) { f_out = spec(0.0f); wi = v3(0, 0, 0); pdf_out = 0.0f; return; }
       V3 wh = tr_sample_wh(l.ax, l.ay, wo, u);
@@ -407,7 +425,7 @@ RT_DEV V3 local_to_world(const Bsdf& b, V3 v) {                                 
 }
 RT_DEV int bsdf_num_components(const Bsdf& b, uint32_t flags) {                  // :265-268
   int c = 0;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) c++;
+  for (int i = 0; i < lobe_count_known(b.n); i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) c++;
   return c;
 }
 RT_DEV Spec bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {            // :94-112
@@ -415,7 +433,7 @@ RT_DEV Spec bsdf_f(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {           
   if (wo.z == 0.0f) return spec(0.0f);
   bool refl = dot(wi_w, b.ng) * dot(wo_w, b.ng) > 0.0f;
   Spec c = spec(0.0f);
-  for (int i = 0; i < b.n; i++) {
+  for (int i = 0; i < lobe_count_known(b.n); i++) {
     const int kind = bsdf_lobe_kind(b, i);
     uint32_t t = lobe_type(kind);
     if (lobe_matches(kind, flags) && ((refl && (t & BSDF_REFLECTION)) || (!refl && (t & BSDF_TRANSMISSION)))) c = c + lobe_f(b, i, wo, wi);
@@ -428,13 +446,13 @@ RT_DEV float bsdf_pdf(const Bsdf& b, V3 wo_w, V3 wi_w, uint32_t flags) {        
   if (wo.z == 0.0f) return 0.0f;
   V3 wi = world_to_local(b, wi_w);
   int matched = 0; float p = 0.0f;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) { matched++; p += lobe_pdf(b, i, wo, wi); }
+  for (int i = 0; i < lobe_count_known(b.n); i++) if (lobe_matches(bsdf_lobe_kind(b, i), flags)) { matched++; p += lobe_pdf(b, i, wo, wi); }
   return matched == 0 ? 0.0f : p / (float)matched;
 }
 // the lobes built in place: the matching lobes are listed once (kernels that never see host-listed lobes use this form)
 RT_DEV void bsdf_sample_f_built(const Bsdf& b, V3 wo_w, P2 u, uint32_t flags, Spec& f_out, V3& wi_w, float& pdf_out, uint32_t& sampled) {   // :138-251
-  int m[kMaxLobes]; int nm = 0;
-  for (int i = 0; i < b.n; i++) if (lobe_matches(b.lobes[i].kind, flags)) m[nm++] = i;
+  int m[RT_MAX_BUILT_LOBES]; int nm = 0;
+  for (int i = 0; i < lobe_count_known(b.n); i++) if (lobe_matches(b.lobes[i].kind, flags)) m[nm++] = i;
   if (nm == 0) { f_out = spec(0.0f); wi_w = v3(0, 0, 0); pdf_out = 0.0f; sampled = 0; return; }
   int comp = (int)min(f2u32(floorf(u.x * (float)nm)), (uint32_t)(nm - 1));
   const Lobe& bxdf = b.lobes[m[comp]];

@@ -69,13 +69,15 @@ RT_DEV void cylinder_sample(const rtgpu_quadric& q, P2 u, Inter& it, float& pdf)
   it.n = n;
   pdf = 1.0f / q.area;
 }
-RT_DEV void shape_sample(const DScene& sc, uint32_t slot, float area, P2 u, Inter& it, float& pdf) {
-  const uint32_t kind_bits = __float_as_uint(sc.geom[(size_t)slot * 3].w);
-  if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) { tri_sample(sc, slot, area, u, it, pdf); return; }
-  const rtgpu_quadric& q = sc.quadrics[kind_bits >> 2];
+static __device__ __noinline__ void quadric_sample(const rtgpu_quadric& q, P2 u, Inter& it, float& pdf) {   // out of line: cold on triangle scenes
   if (q.kind == RTGPU_PRIM_SPHERE) sphere_sample(q, u, it, pdf);
   else if (q.kind == RTGPU_PRIM_DISK) disk_sample(q, u, it, pdf);
   else cylinder_sample(q, u, it, pdf);
+}
+RT_DEV void shape_sample(const DScene& sc, uint32_t slot, float area, P2 u, Inter& it, float& pdf) {
+  const uint32_t kind_bits = __float_as_uint(sc.geom[(size_t)slot * 3].w);
+  if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) { tri_sample(sc, slot, area, u, it, pdf); return; }
+  quadric_sample(sc.quadrics[kind_bits >> 2], u, it, pdf);
 }
 // Shape::sample_si default (shapes/mod.rs:39-53): area pdf -> solid angle
 RT_DEV void area_to_solid_angle(const Inter& ref, const Inter& it, float& pdf, bool check_inf_inside) {
@@ -88,10 +90,8 @@ RT_DEV void area_to_solid_angle(const Inter& ref, const Inter& it, float& pdf, b
   }
 }
 // Shape::sample_si (default) and Sphere::sample_si (sphere.rs:245-308)
-RT_DEV void shape_sample_si(const DScene& sc, uint32_t slot, float area, const Inter& ref, P2 u, Inter& it, float& pdf) {
-  const uint32_t kind_bits = __float_as_uint(sc.geom[(size_t)slot * 3].w);
-  if ((kind_bits & 3u) == RTGPU_PRIM_SPHERE) {
-    const rtgpu_quadric& q = sc.quadrics[kind_bits >> 2];
+static __device__ __noinline__ void sphere_sample_si(const rtgpu_quadric& q, const Inter& ref, P2 u, Inter& it, float& pdf) {
+  {
     const float radius = q.radius;
     V3 p_center = xf_point(q.o2w, v3(0, 0, 0));
     V3 p_origin = offset_ray_origin(ref.p, ref.p_error, ref.n, p_center - ref.p);
@@ -121,6 +121,10 @@ RT_DEV void shape_sample_si(const DScene& sc, uint32_t slot, float area, const I
     pdf = 1.0f / (2.0f * kPi * (1.0f - cos_theta_max));
     return;
   }
+}
+RT_DEV void shape_sample_si(const DScene& sc, uint32_t slot, float area, const Inter& ref, P2 u, Inter& it, float& pdf) {
+  const uint32_t kind_bits = __float_as_uint(sc.geom[(size_t)slot * 3].w);
+  if ((kind_bits & 3u) == RTGPU_PRIM_SPHERE) { sphere_sample_si(sc.quadrics[kind_bits >> 2], ref, u, it, pdf); return; }
   shape_sample(sc, slot, area, u, it, pdf);
   area_to_solid_angle(ref, it, pdf, true);
 }

@@ -355,7 +355,16 @@ RT_DEV bool cylinder_intersect(const rtgpu_quadric& q, const Ray& r, float& t_ou
   return true;
 }
 
+// A real function, not inlined: the three quadric tests (EFloat intervals, f64 discriminants, phi / z clipping, partials) are thousands of
+// instructions, used to be inlined two or three times into every kernel that can meet a quadric, and are cold on triangle scenes
+// (profiles/r02f: 877 KB of the matte shade kernel's 978 KB of SASS never executed).
+// Translation units whose kernels run it on their hot path for quadric scenes (the traversal engine, the recursive integrators: C2 lost
+// 9 % to the call) define RT_QUADRIC_INLINE; the per-material path kernels take the call.
+#ifdef RT_QUADRIC_INLINE
 RT_DEV bool quadric_intersect(const rtgpu_quadric& q, const Ray& ray, float& t, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
+#else
+static __device__ __noinline__ bool quadric_intersect(const rtgpu_quadric& q, const Ray& ray, float& t, bool want_surface, SurfHit* out, SurfTex* ex = nullptr) {
+#endif
   if (q.kind == RTGPU_PRIM_SPHERE) return sphere_intersect(q, ray, t, want_surface, out, ex);
   if (q.kind == RTGPU_PRIM_DISK) return disk_intersect(q, ray, t, want_surface, out, ex);
   return cylinder_intersect(q, ray, t, want_surface, out, ex);

@@ -1,4 +1,5 @@
 // Translation unit: Whitted / DirectLighting / AmbientOcclusion / Normal shading kernels.
+#define RT_QUADRIC_INLINE 1   // shapes.cuh: quadric tests inlined (hot on sphere / disk / cylinder scenes)
 #include "kernels_rec.cuh"
 #include "launch.hpp"
 

@@ -1,4 +1,5 @@
 // Translation unit: ray generation, queue traversal, bounce bookkeeping, film and light-grid kernels.
+#define RT_QUADRIC_INLINE 1   // shapes.cuh: quadric tests inlined (hot on sphere / disk / cylinder scenes)
 #include "kernels_trace.cuh"
 #include "launch.hpp"
 #include <algorithm>
