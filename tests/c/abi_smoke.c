@@ -70,6 +70,7 @@ static int film_sane(const float* film, size_t n_pix, int expect_spp) {
 
 int main(int argc, char** argv) {
   const int world = argc > 1 ? atoi(argv[1]) : 1;
+  alarm(240);   /* a wedged collective must not hold the test box: SIGALRM ends the process (alarms are not inherited across fork: the child arms its own) */
   rtgpu_ctx* ctx = NULL;
   float* film = NULL; size_t n_pix = 0;
   if (world <= 1) {
@@ -96,6 +97,7 @@ int main(int argc, char** argv) {
   if (child < 0) return 31;
   unsigned char id[RTGPU_COMM_ID_BYTES];
   if (child == 0) {
+    alarm(240);
     close(fd[1]);
     if (read(fd[0], id, sizeof(id)) != (ssize_t)sizeof(id)) return 32;
     int rc = render_share(1, 1, 2, id, &film, &n_pix, &ctx);
@@ -106,6 +108,9 @@ int main(int argc, char** argv) {
   if (rtgpu_comm_unique_id(id) != 0) { fprintf(stderr, "no NCCL\n"); return 33; }
   if (write(fd[1], id, sizeof(id)) != (ssize_t)sizeof(id)) return 34;
   int rc = render_share(0, 0, 2, id, &film, &n_pix, &ctx);
+  /* both ranks tear the communicator down at the same point of the job (ncclCommDestroy may wait for its peers): the child does it in
+     rtgpu_destroy right after its render_share, so the parent must not sit in waitpid with its own communicator still open */
+  if (!rc) rtgpu_comm_destroy(ctx);
   int status = 0;
   waitpid(child, &status, 0);
   if (rc || !WIFEXITED(status) || WEXITSTATUS(status) != 0) { fprintf(stderr, "rank failed: %d / %d\n", rc, status); return 35; }
