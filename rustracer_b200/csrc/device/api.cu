@@ -182,7 +182,7 @@ static int build_perm(rtgpu_ctx* ctx, const rtgpu_ray* d_rays, size_t n, uint32_
   int rc = ensure_sort_scratch(ctx, n, &keys, &perm, &hist); if (rc) return rc;
   *cursor_out = (uint32_t*)ctx->scratch_rays;
   RT_CUDA(ctx, cudaMemsetAsync(*cursor_out, 0, 256, ctx->stream));
-  // below the break-even the binning costs more than the incoherent walk it avoids (profiles/r02b_small_batches.log)
+  // below the break-even the binning costs more than the incoherent walk it avoids (profiles/r02m_small_batches.log)
   if (!ctx->sort_rays || n < (size_t)ctx->sort_min_rays) return 0;
   SortParams sp;
   for (int k = 0; k < 3; k++) {

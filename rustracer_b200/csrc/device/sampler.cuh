@@ -22,10 +22,15 @@ RT_DEV uint32_t cmj_permute(uint32_t i, uint32_t l, uint32_t p) {
     i ^= (i & w) >> 1; i *= 1 | p >> 27; i *= 0x6935fa69u; i ^= (i & w) >> 11; i *= 0x74dcb303u; i ^= (i & w) >> 2;
     i *= 0x9e501cc3u; i ^= (i & w) >> 2; i *= 0xc860a3dfu; i &= w; i ^= i >> 5;
   } while (i >= l);
-  return (i + p) % l;
+  return (l & w) == 0 ? ((i + p) & w) : (i + p) % l;     // l a power of two (02sequence rounds spp up): the modulo is a mask
 }
 // Sobol' dimension 2 generator (lowdiscrepancy.rs:141-174): column i = c[i-1] ^ (c[i-1] >> 1), c[0] = 1 << 31
-RT_DEV uint32_t sobol1_eval(uint32_t idx) { uint32_t v = 0, c = 0x80000000u; while (idx) { if (idx & 1) v ^= c; c ^= c >> 1; idx >>= 1; } return v; }
+// In bit-reversed order the columns are (1 + x)^i over GF(2), so the product is the substitution x -> x + 1 in the polynomial whose
+// coefficients are the bits of idx: five butterfly steps ((x + 1)^(2^k) = x^(2^k) + 1) instead of one iteration per bit of idx.
+RT_DEV uint32_t sobol1_eval(uint32_t idx) {
+  idx ^= (idx >> 1) & 0x55555555u; idx ^= (idx >> 2) & 0x33333333u; idx ^= (idx >> 4) & 0x0f0f0f0fu; idx ^= (idx >> 8) & 0x00ff00ffu; idx ^= idx >> 16;
+  return __brev(idx);
+}
 RT_DEV float u32_to_unit(uint32_t v) { return fminf((float)v * kU32ToUnit, kOneMinusEpsilon); }     // lowdiscrepancy.rs:16, rng.rs:42-44
 
 RT_DEV uint32_t pixel_hash(int x, int y, uint64_t seed) {

@@ -37,6 +37,9 @@ namespace rt {
 #ifndef RT_ENGINE_LDG256
 #define RT_ENGINE_LDG256 1          // collapsed nodes are fetched with four 256-bit loads instead of eight 128-bit ones
 #endif
+#ifndef RT_ENGINE_ANY_FIXED_ORDER
+#define RT_ENGINE_ANY_FIXED_ORDER 0 // 1: any-hit walks visit a collapsed node's children in storage order (the occlusion answer is order-independent)
+#endif
 #ifndef RT_ENGINE_SMEM_DEPTH
 #define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
 #endif
@@ -224,8 +227,17 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         const bool h1 = slab_interval_bf(q2, q3, ray.o, inv_dir, nx, ny, nz, ray.t_max, t1) & (r1 != kDoneRef);
         const bool h2 = slab_interval_bf(q4, q5, ray.o, inv_dir, nx, ny, nz, ray.t_max, t2);
         const bool h3 = slab_interval_bf(q6, q7, ray.o, inv_dir, nx, ny, nz, ray.t_max, t3) & (r3 != kDoneRef);
+#if RT_ENGINE_ANY_FIXED_ORDER
+        // intersect_p answers "is anything in the way": the answer does not depend on the order the subtrees are searched in (no t_max
+        // shrinks during an any-hit walk, so the set of leaves that can be reached is the same), and the near-first permutation below is a
+        // tenth of the node step's instructions.  Any-hit walks therefore take the children in storage order.
+        const bool fixed_order = ANY;
+#else
+        const bool fixed_order = false;
+#endif
         // bvh/mod.rs:408-421 at the binary node and at each of its children: the second child first when the ray is negative along the split axis
-        const bool negA = ((negmask >> (axes & 3u)) & 1u) != 0u, negL = ((negmask >> ((axes >> 2) & 3u)) & 1u) != 0u, negR = ((negmask >> ((axes >> 4) & 3u)) & 1u) != 0u;
+        const bool negA = !fixed_order && ((negmask >> (axes & 3u)) & 1u) != 0u, negL = !fixed_order && ((negmask >> ((axes >> 2) & 3u)) & 1u) != 0u,
+                   negR = !fixed_order && ((negmask >> ((axes >> 4) & 3u)) & 1u) != 0u;
         const uint32_t la_r = negL ? r1 : r0, lb_r = negL ? r0 : r1, ra_r = negR ? r3 : r2, rb_r = negR ? r2 : r3;
         const float la_t = negL ? t1 : t0, lb_t = negL ? t0 : t1, ra_t = negR ? t3 : t2, rb_t = negR ? t2 : t3;
         const bool la_h = negL ? h1 : h0, lb_h = negL ? h0 : h1, ra_h = negR ? h3 : h2, rb_h = negR ? h2 : h3;
