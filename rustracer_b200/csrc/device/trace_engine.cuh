@@ -38,7 +38,7 @@ namespace rt {
 #define RT_ENGINE_LDG256 1          // collapsed nodes are fetched with four 256-bit loads instead of eight 128-bit ones
 #endif
 #ifndef RT_ENGINE_ANY_FIXED_ORDER
-#define RT_ENGINE_ANY_FIXED_ORDER 0 // 1: any-hit walks visit a collapsed node's children in storage order (the occlusion answer is order-independent)
+#define RT_ENGINE_ANY_FIXED_ORDER 1 // 1: any-hit walks visit a collapsed node's children in storage order (the occlusion answer is order-independent; profiles/r02n: C3 +3.6 %, AO +12 %)
 #endif
 #ifndef RT_ENGINE_SMEM_DEPTH
 #define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
