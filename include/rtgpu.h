@@ -183,7 +183,9 @@ typedef struct rtgpu_render_desc {
   float lens_radius, focal_distance;
   float filter_radius[2]; float filter_table[256];    /* film.rs:92-102 */
   float max_sample_luminance, scale;
-  /* work partition (multi-GPU): 16x16 tiles t with t % tile_world == tile_rank, samples [sample_begin, sample_end) */
+  /* work partition (multi-GPU): 16x16 tiles t with t % tile_world == tile_rank, samples [sample_begin, sample_end).  Tile t is the tile of
+     row t / tiles_x whose column is (t % tiles_x + row) % tiles_x, tiles_x = tiles per row of the sample bounds: every tile belongs to
+     exactly one rank, and a rank's share runs diagonally through the frame whatever tiles_x % tile_world is */
   int32_t tile_rank, tile_world;
   int32_t sample_begin, sample_end;
   uint64_t seed;

@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
       const uint32_t j = i / per_sample, rem = i - j * per_sample;
       const uint32_t tile_ord = (uint32_t)p.tile_first + rem / 256u, pix = rem & 255u;
       const uint32_t tile = (uint32_t)p.tile_rank + tile_ord * (uint32_t)p.tile_world;
-      const int tx = (int)(tile % (uint32_t)p.tiles_x), ty = (int)(tile / (uint32_t)p.tiles_x);
+      // tile number -> tile of the frame: row ty, column rotated by ty.  With a tile count per row that is a multiple of the rank count
+      // (3840 / 16 = 240 columns over 8 ranks) the plain row-major numbering would hand every rank the same columns of every row —
+      // vertical stripes, whose work follows the scene's layout (profiles/r02o: the slowest of 8 ranks 2 % behind); rotated, the stripes run diagonally
+      const int ty = (int)(tile / (uint32_t)p.tiles_x), tx = (int)((tile % (uint32_t)p.tiles_x + (uint32_t)ty) % (uint32_t)p.tiles_x);
       x = p.sample_bounds[0] + tx * 16 + (int)(pix & 15u);
       y = p.sample_bounds[1] + ty * 16 + (int)(pix >> 4);
       s = (uint32_t)p.sample_first + j;

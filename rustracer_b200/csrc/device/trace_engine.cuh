@@ -38,7 +38,7 @@ namespace rt {
 #define RT_ENGINE_LDG256 1          // collapsed nodes are fetched with four 256-bit loads instead of eight 128-bit ones
 #endif
 #ifndef RT_ENGINE_ANY_FIXED_ORDER
-#define RT_ENGINE_ANY_FIXED_ORDER 1 // 1: any-hit walks visit a collapsed node's children in storage order (the occlusion answer is order-independent; profiles/r02n: C3 +3.6 %, AO +12 %)
+#define RT_ENGINE_ANY_FIXED_ORDER 1 // 1: any-hit walks visit a collapsed node's children in storage order (2: near pair first, storage order inside a pair) (the occlusion answer is order-independent; profiles/r02n: C3 +3.6 %, AO +12 %)
 #endif
 #ifndef RT_ENGINE_SMEM_DEPTH
 #define RT_ENGINE_SMEM_DEPTH 8      // traversal-stack entries per lane kept in shared memory; deeper entries go to local memory
@@ -236,7 +236,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         const bool fixed_order = false;
 #endif
         // bvh/mod.rs:408-421 at the binary node and at each of its children: the second child first when the ray is negative along the split axis
-        const bool negA = !fixed_order && ((negmask >> (axes & 3u)) & 1u) != 0u, negL = !fixed_order && ((negmask >> ((axes >> 2) & 3u)) & 1u) != 0u,
+        const bool negA = (!fixed_order || RT_ENGINE_ANY_FIXED_ORDER == 2) && ((negmask >> (axes & 3u)) & 1u) != 0u, negL = !fixed_order && ((negmask >> ((axes >> 2) & 3u)) & 1u) != 0u,
                    negR = !fixed_order && ((negmask >> ((axes >> 4) & 3u)) & 1u) != 0u;
         const uint32_t la_r = negL ? r1 : r0, lb_r = negL ? r0 : r1, ra_r = negR ? r3 : r2, rb_r = negR ? r2 : r3;
         const float la_t = negL ? t1 : t0, lb_t = negL ? t0 : t1, ra_t = negR ? t3 : t2, rb_t = negR ? t2 : t3;
