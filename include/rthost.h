@@ -56,7 +56,8 @@ int rth_param_header(const char* s, int* type_out, char* name_out, size_t name_l
  * segment to a second uniform point with t_max = 1 - 1e-4 (any_hit != 0).  rustracer_b200/scenes.py ray_batch is the definition. */
 int rth_ray_batch(uint64_t n, const float* world_lo, const float* world_hi, uint64_t seed, int any_hit, uint64_t first, rtgpu_ray* out);
 
-/* == imageio::write_image for .png (8-bit sRGB, spectrum.rs:52-66) and, for parity work, .pfm (raw float). */
+/* == imageio::write_image (imageio.rs:35-92): .png (8-bit sRGB, spectrum.rs:52-66) and .exr (32-bit float R, G, B scan lines, ZIP blocks);
+ * for parity work also .pfm (raw float).  Any other extension fails with the reference's "Unsupported file format". */
 int rth_write_image(const char* path, const float* rgb, int width, int height);
 
 #ifdef __cplusplus

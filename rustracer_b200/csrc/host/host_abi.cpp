@@ -2,6 +2,7 @@
 #include "../../../include/rthost.h"
 #include "pbrt_frontend.hpp"
 #include "scene_build.hpp"
+#include <zlib.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -184,7 +185,56 @@ int rth_write_image(const char* path, const float* rgb, int width, int height) {
       z.push_back((unsigned char)(ad >> 24)); z.push_back((unsigned char)(ad >> 16)); z.push_back((unsigned char)(ad >> 8)); z.push_back((unsigned char)ad);
       png_chunk(f, "IDAT", z);
       png_chunk(f, "IEND", {});
-    } else { std::fclose(f); throw std::runtime_error("Unsupported file format"); }   // imageio.rs:47-49 (.exr is out of scope here)
+    } else if (ends(".exr")) {                                        // imageio.rs:75-92: 32-bit float R, G, B scan lines (here ZIP blocks of 16 lines)
+      std::vector<unsigned char> hd;
+      auto put32 = [](std::vector<unsigned char>& v, uint32_t x) { for (int k = 0; k < 4; k++) v.push_back((unsigned char)(x >> (8 * k))); };
+      auto put64 = [](std::vector<unsigned char>& v, uint64_t x) { for (int k = 0; k < 8; k++) v.push_back((unsigned char)(x >> (8 * k))); };
+      auto putf = [&](std::vector<unsigned char>& v, float x) { uint32_t u; std::memcpy(&u, &x, 4); put32(v, u); };
+      auto puts0 = [](std::vector<unsigned char>& v, const char* t) { while (*t) v.push_back((unsigned char)*t++); v.push_back(0); };
+      auto attr = [&](const char* name, const char* type, const std::vector<unsigned char>& data) { puts0(hd, name); puts0(hd, type); put32(hd, (uint32_t)data.size()); hd.insert(hd.end(), data.begin(), data.end()); };
+      put32(hd, 20000630u); put32(hd, 2u);
+      std::vector<unsigned char> a;
+      for (const char* c : {"B", "G", "R"}) { puts0(a, c); put32(a, 2u); put32(a, 0u); put32(a, 1u); put32(a, 1u); }   // FLOAT, pLinear 0, sampling 1 x 1; channels in alphabetical order
+      a.push_back(0);
+      attr("channels", "chlist", a);
+      attr("compression", "compression", {3});
+      a.clear(); put32(a, 0u); put32(a, 0u); put32(a, (uint32_t)(width - 1)); put32(a, (uint32_t)(height - 1));
+      attr("dataWindow", "box2i", a); attr("displayWindow", "box2i", a);
+      attr("lineOrder", "lineOrder", {0});
+      a.clear(); putf(a, 1.0f); attr("pixelAspectRatio", "float", a);
+      a.clear(); putf(a, 0.0f); putf(a, 0.0f); attr("screenWindowCenter", "v2f", a);
+      a.clear(); putf(a, 1.0f); attr("screenWindowWidth", "float", a);
+      hd.push_back(0);
+      const int lines_per_block = 16;
+      const size_t n_blocks = ((size_t)std::max(height, 0) + lines_per_block - 1) / lines_per_block, line_bytes = (size_t)width * 12;
+      std::vector<std::vector<unsigned char>> blocks(n_blocks);
+      std::vector<unsigned char> raw, tmp;
+      for (size_t b = 0; b < n_blocks; b++) {
+        const int y0 = (int)b * lines_per_block, lines = std::min(lines_per_block, height - y0);
+        const size_t n = line_bytes * (size_t)lines;
+        raw.resize(n); tmp.resize(n);
+        for (int l = 0; l < lines; l++)
+          for (int c = 0; c < 3; c++)                                   // B, G, R planes of the line
+            for (int x = 0; x < width; x++) std::memcpy(&raw[(size_t)l * line_bytes + ((size_t)c * width + x) * 4], &rgb[((size_t)(y0 + l) * width + x) * 3 + (2 - c)], 4);
+        size_t e = 0, o = (n + 1) / 2;                                  // even bytes first, odd bytes second, then the byte-difference predictor
+        for (size_t i = 0; i < n; i++) { if (i & 1) tmp[o++] = raw[i]; else tmp[e++] = raw[i]; }
+        unsigned char prev = n ? tmp[0] : 0;
+        for (size_t i = 1; i < n; i++) { const unsigned char cur = tmp[i]; tmp[i] = (unsigned char)(cur - prev + 128); prev = cur; }
+        uLongf len = compressBound((uLong)n);
+        std::vector<unsigned char>& out = blocks[b];
+        out.resize(len);
+        if (compress2(out.data(), &len, tmp.data(), (uLong)n, 6) != Z_OK || len >= n) out = raw;   // a block that does not shrink is stored as it is
+        else out.resize(len);
+      }
+      uint64_t off = hd.size() + 8 * n_blocks;
+      for (size_t b = 0; b < n_blocks; b++) { put64(hd, off); off += 8 + blocks[b].size(); }
+      std::fwrite(hd.data(), 1, hd.size(), f);
+      for (size_t b = 0; b < n_blocks; b++) {
+        std::vector<unsigned char> bh; put32(bh, (uint32_t)(b * lines_per_block)); put32(bh, (uint32_t)blocks[b].size());
+        std::fwrite(bh.data(), 1, 8, f);
+        std::fwrite(blocks[b].data(), 1, blocks[b].size(), f);
+      }
+    } else { std::fclose(f); throw std::runtime_error("Unsupported file format"); }   // imageio.rs:47-49
     std::fclose(f);
   });
 }

@@ -175,7 +175,7 @@ def param_header(s):
 
 
 def write_image(path, rgb):
-    """rgb: (H, W, 3) float32 linear; .png (8-bit sRGB) or .pfm."""
+    """rgb: (H, W, 3) float32 linear; .png (8-bit sRGB), .exr (32-bit float scan lines, ZIP) as imageio.rs:35-92 writes, or .pfm."""
     rgb = np.ascontiguousarray(rgb, dtype=np.float32)
     h, w, _ = rgb.shape
     lib = _lib()

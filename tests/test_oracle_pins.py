@@ -235,3 +235,34 @@ def test_exr_reader(native_libs, tmp_path, pixel_type, compression, decreasing):
             assert np.array_equal(tex, want)
         else:
             assert tex.shape == (32, 64, 3) and abs(tex.mean() - want.mean()) / want.mean() < 0.05
+
+
+def test_exr_writer_round_trip(native_libs, tmp_path):
+    """write_image_exr (imageio.rs:75-92: f32 R, G, B): rth_write_image("*.exr") writes scan-line ZIP blocks; read back through the front end's
+    reader as an environment map (64 x 32 stays unfiltered), bit for bit — incompressible noise exercises the stored-block path, 21 lines the
+    short last block."""
+    import zlib
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, host, scenes
+    rng = np.random.default_rng(3)
+    for img in (scenes.env_map_image(64, 32).astype(np.float32), rng.random((32, 64, 3)).astype(np.float32)):
+        host.write_image(str(tmp_path / "env.exr"), img)
+        txt = scenes.lights_zoo(str(tmp_path), xres=16, yres=16, spp=1, env_name="unused.pfm").replace("unused.pfm", "env.exr")
+        txt = txt.replace('"rgb L" [0.9 1.0 1.1] "rgb scale" [1.2 1.2 1.2]', '"rgb L" [1 1 1]')
+        sc = Scene.from_string(txt, search_dir=str(tmp_path))
+        assert sc.warnings == []
+        sc.flatten()
+        tex, _ = ob.OracleScene(sc.ir_ptr).light_env(0)
+        assert np.array_equal(tex, img)
+    # header as the format defines it: magic, version 2 single-part scan lines, channels B G R of type FLOAT, ZIP, one offset per 16 lines
+    img = scenes.env_map_image(40, 21).astype(np.float32)
+    host.write_image(str(tmp_path / "odd.exr"), img)
+    d = open(tmp_path / "odd.exr", "rb").read()
+    assert d[:8] == (20000630).to_bytes(4, "little") + (2).to_bytes(4, "little")
+    assert b"channels\0chlist\0" in d and b"B\0\x02\0\0\0" in d and b"compression\0compression\0\x01\0\0\0\x03" in d
+    end = d.index(b"screenWindowWidth\0float\0") + len(b"screenWindowWidth\0float\0") + 8 + 1
+    offs = np.frombuffer(d[end:end + 16], "<u8")
+    assert offs[0] == end + 16
+    y0, size = np.frombuffer(d[int(offs[1]):int(offs[1]) + 8], "<i4")
+    assert y0 == 16 and int(offs[1]) + 8 + size == len(d)
+    assert len(zlib.decompress(d[int(offs[1]) + 8:])) == 5 * 40 * 12          # the short last block: 21 - 16 lines of three float planes
