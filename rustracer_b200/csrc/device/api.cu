@@ -135,8 +135,9 @@ struct BatchClosestPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst, uint32_t) {
+  RT_DEV void commit(uint32_t, const HitRec& h, float t_hit, uint32_t inst, uint32_t) {
     HitRec o = h;
+    o.t = t_hit;                                                      // the engine's record carries b0 in .t (trace_engine.cuh)
     o.slot = h.slot == kMiss ? kMiss : (inst != kNoInst ? instances[inst].prim_number : info[h.slot].x);   // slot -> prim_number (bvh/mod.rs:92)
     hits[r] = o;
   }
@@ -148,7 +149,7 @@ struct BatchAnyPolicy {
     const float4 a = rays[2 * (size_t)r], b = rays[2 * (size_t)r + 1];
     ray = make_ray(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w);
   }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t, uint32_t) { occluded[r] = h.slot != kMiss ? 1 : 0; }
+  RT_DEV void commit(uint32_t, const HitRec& h, float, uint32_t, uint32_t) { occluded[r] = h.slot != kMiss ? 1 : 0; }
 };
 template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_closest_batch_engine(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ perm, uint32_t n,

@@ -46,8 +46,8 @@ k_shade_path(RenderParams p, int parity) {
       uint32_t bounces = ps.y & 0xffu; bool specular_bounce = (ps.z & 1u) != 0;
       const uint2 sinf = p.w.sinfo[sample];
       SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = ps.w & 0xffffu; ss.d2 = ps.w >> 16; ss.da = 0;
-      SurfHit si; float t_hit;
-      hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
+      SurfHit si;
+      hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si);
       const uint4 info = p.sc.info[h.slot];
       Spec l_add = spec(0.0f);
       if ((bounces == 0 || specular_bounce) && info.z != kNoLight) l_add = beta * area_L(p.sc.lights[info.z], si.n, -ray.d);   // path.rs:127-131

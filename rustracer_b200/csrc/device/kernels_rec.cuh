@@ -42,9 +42,9 @@ __global__ void __launch_bounds__(RT_REC_THREADS, RT_REC_MIN_BLOCKS * 128 / RT_R
     if (h.slot == kMiss) {                                              // whitted.rs:91-94: every light's le(ray)
       for (uint32_t j = 0; j < p.sc.n_lights; j++) colour = colour + light_le(p.sc, p.sc.lights[j], ray.d);
     } else {
-      SurfHit si; float t_hit;
+      SurfHit si;
       SurfTex st; RayDiff rd; rtgpu_lobe hit_lobes[TEX ? rtml::kMaxLobes : 1];
-      hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[i] : kNoInst, ray, t_hit, si, TEX ? &st : nullptr);
+      hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[i] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si, TEX ? &st : nullptr);
       const uint4 info = p.sc.info[h.slot];
       const uint32_t mtype = info.y < p.sc.n_materials ? p.sc.materials[info.y].type : (uint32_t)RTGPU_MAT_NONE;
       const V3 n_before = si.ns;                                        // whitted.rs:53: shading normal BEFORE the scattering functions (bump map)
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(128) k_shade_ao(RenderParams p) {
     if (h.slot == kMiss) continue;
     Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
     ray.t_max = inf_f();
-    SurfHit si; float t_hit;
-    hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
+    SurfHit si;
+    hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si);
     const Inter it = inter_of(si);
     const uint32_t sample = p.w.pstate[slot].x;
     const uint2 sinf = p.w.sinfo[sample];

@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(RT_TEX_THREADS, 1024 / RT_TEX_THREADS) k_eval_
     if ((ps.y & 0xffu) >= max_depth) continue;                        // path.rs:139-141: no scattering functions past the last bounce
     Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
     ray.t_max = inf_f();
-    SurfHit si; SurfTex st; float t_hit;
-    hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si, &st);
+    SurfHit si; SurfTex st;
+    hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si, &st);
     RayDiff rd = no_diff();
     if (ps.z & 2u) {                                                  // still the ray k_raygen made: it has a differential (renderer.rs:110-111)
       const uint32_t sample = ps.x;

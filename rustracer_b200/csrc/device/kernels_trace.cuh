@@ -171,7 +171,9 @@ struct ClosestPolicy {
   const float4* ray_o; const float4* ray_d; const uint32_t* list; HitRec* hits; uint32_t* hit_inst; uint8_t* hit_class; uint32_t slot;
   RT_DEV ClosestPolicy(const float4* o, const float4* d, const uint32_t* l, HitRec* h, uint32_t* hi, uint8_t* hc) : ray_o(o), ray_d(d), list(l), hits(h), hit_inst(hi), hit_class(hc), slot(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
-  RT_DEV void commit(uint32_t, const HitRec& h, uint32_t inst, uint32_t cls) { hits[slot] = h; hit_class[slot] = (uint8_t)cls; if (INST) hit_inst[slot] = inst; }
+  // the record keeps the three barycentrics {b0, slot, b1, b2} (RenderParams::hit_t_is_b0): the shade kernels rebuild the surface from them instead of
+  // repeating the watertight test, and nothing downstream reads the distance
+  RT_DEV void commit(uint32_t, const HitRec& h, float, uint32_t inst, uint32_t cls) { hits[slot] = h; hit_class[slot] = (uint8_t)cls; if (INST) hit_inst[slot] = inst; }
 };
 template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -342,7 +344,7 @@ struct ShadowPolicy {
   const RenderParams& p; AnyQueue aq; uint32_t sample;
   RT_DEV ShadowPolicy(const RenderParams& p_, const AnyQueue& a) : p(p_), aq(a), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t, uint32_t) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, float, uint32_t, uint32_t) {
     if (h.slot != kMiss) return;
     const float4 c = aq.c[idx];
     float4* L = &p.w.L[sample];
@@ -362,7 +364,7 @@ struct MisPolicy {
   const RenderParams& p; uint32_t sample;
   RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
-  RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst, uint32_t) {
+  RT_DEV void commit(uint32_t idx, const HitRec& h, float, uint32_t inst, uint32_t) {
     const float4 c = p.w.mi_c[idx];
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];
@@ -459,8 +461,8 @@ __global__ void __launch_bounds__(256) k_lightgrid_mark(RenderParams p, const ui
     if (h.slot == kMiss) continue;
     Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
     ray.t_max = inf_f();
-    SurfHit si; float t_hit;
-    hit_surface(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, t_hit, si);
+    SurfHit si;
+    hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si);
     const size_t voxel = grid_voxel(p.sc, p.grid, si.p);
     if (p.grid.slots[voxel] != -1) continue;
     if (atomicCAS(&p.grid.slots[voxel], -1, -2) != -1) continue;      // somebody else claims it

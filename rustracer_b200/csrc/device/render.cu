@@ -327,6 +327,7 @@ static int run_render(rtgpu_ctx* ctx, const rtgpu_render_desc* rd, const int32_t
   bool has_infinite = false;
   for (const rtgpu_light& l : ctx->h_lights) has_infinite |= l.kind == RTGPU_LIGHT_INFINITE;
   const int tstats = ctx->count_traversal ? TRACE_COUNTING : (ctx->simple_traversal ? TRACE_SIMPLE : TRACE_ENGINE);
+  p.hit_t_is_b0 = tstats == TRACE_ENGINE ? 1 : 0;                     // what the closest-hit records of this render carry in .t (wave.cuh)
   size_t ev_used = 0;
   auto next_event = [&]() -> cudaEvent_t {
     if (ev_used == ctx->event_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->event_pool.push_back(e); }

@@ -422,4 +422,26 @@ RT_DEV bool hit_surface(const DScene& sc, uint32_t slot, uint32_t inst, const Ra
   return true;
 }
 
+// The same record for a hit whose barycentrics the traversal engine kept (HitRec {b0, slot, b1, b2}, trace_engine.cuh): a triangle's surface follows from
+// them directly — they are the values the watertight test produced (mesh.rs:321-329), so nothing is tested twice; a quadric, or a record written by the
+// reference walker (have_bary == false), takes the full intersection above.
+RT_DEV bool hit_surface_bary(const DScene& sc, uint32_t slot, uint32_t inst, const Ray& ray, bool have_bary, float b0, float b1, float b2, SurfHit& si, SurfTex* ex = nullptr) {
+  const float4 g0 = sc.geom[(size_t)slot * 3];
+  const uint32_t kind_bits = __float_as_uint(g0.w);
+  const bool instanced = inst != kNoInst;
+  Ray r = ray;
+  if (instanced) r = instance_ray(sc.instances[inst], ray);
+  SurfHit o;
+  SurfHit& dst = instanced ? o : si;
+  float t;
+  if ((kind_bits & 3u) == RTGPU_PRIM_TRIANGLE) {
+    const float4 g1 = sc.geom[(size_t)slot * 3 + 1], g2 = sc.geom[(size_t)slot * 3 + 2];
+    const V3 p0 = v3(g0), p1 = v3(g1), p2 = v3(g2);
+    if (!have_bary && !tri_hit_test(p0, p1, p2, r, b0, b1, b2, t)) return false;
+    tri_surface(sc, slot, sc.info[slot].w, p0, p1, p2, b0, b1, b2, r.d, dst, ex);
+  } else if (!quadric_intersect(sc.quadrics[kind_bits >> 2], r, t, true, &dst, ex)) return false;
+  if (instanced) instance_surface(sc.instances[inst], o, si, ex);
+  return true;
+}
+
 }  // namespace rt

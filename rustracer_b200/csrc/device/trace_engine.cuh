@@ -94,7 +94,10 @@ RT_DEV bool slab_interval_bf(float4 lo, float4 hi, V3 o, V3 inv_dir, bool nx, bo
 }
 
 // Policy: RT_DEV void load(uint32_t idx, Ray& ray)                            — fetch queue entry idx (lane-private bookkeeping inside)
-//         RT_DEV void commit(uint32_t idx, const HitRec& h, uint32_t inst)    — called by the lanes holding a finished ray (divergent);
+//         RT_DEV void commit(uint32_t idx, const HitRec& h, float t_hit, uint32_t inst, uint32_t cls)
+//                                                                             — called by the lanes holding a finished ray (divergent);
+//                                                                               h.t holds the FIRST barycentric of a triangle hit (the distance is t_hit:
+//                                                                               during a closest-hit walk it is ray.t_max, one register instead of two),
 //                                                                               inst = instance row of the hit or kNoInst
 // INST: the scene holds object instances (TransformedPrimitive, primitive.rs:79-118).  A leaf primitive flagged as an
 // instance suspends the leaf: an exit marker with the resume point goes on the stack, the ray moves to object space
@@ -112,7 +115,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
   Ray ray = make_ray(v3(0, 0, 0), v3(0, 0, 1), 0.0f);
   V3 inv_dir = v3(0, 0, 0); bool nx = false, ny = false, nz = false;
   TriRay tr; tr.o = v3(0, 0, 0); tr.kx = 0; tr.ky = 1; tr.kz = 2; tr.sx = tr.sy = tr.sz = 0.0f;
-  HitRec hit; hit.t = inf_f(); hit.slot = kMiss; hit.b1 = hit.b2 = 0.0f;
+  HitRec hit; hit.t = 0.0f; hit.slot = kMiss; hit.b1 = hit.b2 = 0.0f;   // hit.t: barycentric b0 of the best hit (see Policy::commit)
   // Traversal stack (64 entries, bvh/mod.rs:372): the bottom RT_ENGINE_SMEM_DEPTH entries of every lane live in shared
   // memory as [entry][thread] (conflict-free, ~25-cycle pops, no L1 traffic: profiles/r01c-v2a showed more local-memory
   // sectors than global ones and 19 % of the stall samples on the pop), the rarely used rest in local memory.
@@ -174,7 +177,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
       if (pending) {
         HitRec hc = hit; uint32_t cls = (uint32_t)Q_MISS_CLASS;
         if (hit.slot != kMiss) { cls = hit.slot >> kHitSlotBits; hc.slot = hit.slot & kHitSlotMask; }
-        pol.commit(idx, hc, hit_inst, cls);
+        pol.commit(idx, hc, hit.slot != kMiss ? ray.t_max : inf_f(), hit_inst, cls);   // (an any-hit policy ignores the distance)
         pending = false;
       }
       if (queue_empty) break;                                          // busy == 0 and nothing left to fetch
@@ -188,7 +191,7 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
         if (idx < n) {
           pol.load(idx, ray);
           RT_ENGINE_SET_RAY(ray);
-          hit.t = inf_f(); hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
+          hit.t = 0.0f; hit.slot = kMiss; hit.b1 = 0.0f; hit.b2 = 0.0f;
           sp = 0;
           if (INST) { inst = kNoInst; hit_inst = kNoInst; }
           // root: the reference tests the root's own bounds first
@@ -332,14 +335,14 @@ RT_DEV void trace_engine(const DScene& sc, uint32_t* cursor, uint32_t n, Policy&
           const float4 g2 = __ldg(&geom[3 * (size_t)slot + 2]);
           ok = tri_hit_test_pre(tr, ray.t_max, v3(g0), v3(g1), v3(g2), b0, b1, b2, t);
         } else {
-          b1 = 0.0f; b2 = 0.0f;
+          b0 = 0.0f; b1 = 0.0f; b2 = 0.0f;
           Ray rq; pol.load(idx, rq);                                   // the direction is not kept in registers across the walk:
           if (INST && inst != kNoInst) rq = instance_ray(sc.instances[inst], rq);
           rq.t_max = ray.t_max;                                        // re-read it for the (rare) quadric test
           ok = quadric_intersect(sc.quadrics[kind_bits >> 2], rq, t, false, nullptr);
         }
         if (ok) {
-          hit.t = t; hit.slot = slot | (((__float_as_uint(g1.w) >> kGeomClassShift) & 7u) << kHitSlotBits); hit.b1 = b1; hit.b2 = b2;
+          hit.t = b0; hit.slot = slot | (((__float_as_uint(g1.w) >> kGeomClassShift) & 7u) << kHitSlotBits); hit.b1 = b1; hit.b2 = b2;
           if (INST) hit_inst = inst;
           if (ANY) { done = true; break; }
           ray.t_max = t;

@@ -74,6 +74,7 @@ struct RenderParams {
   // wave decomposition: my tiles [tile_first, tile_first + n_tiles) x samples [sample_first, sample_first + n_samples)
   int tiles_x, tile_rank, tile_world, tile_first, n_tiles, sample_first, n_samples;
   const int32_t* explicit_pixels;      // li_samples mode: {x, y, sample} triples, else null
+  int hit_t_is_b0;                     // 1: w.hit[].t holds the first barycentric of the hit (records written by the traversal engine), 0: the distance (reference walker)
   uint32_t n_items;
 };
 
