@@ -2,6 +2,10 @@
 // (include/rtgpu.h).  Hand-written CUDA for sm_100a; compiled with -fmad=false.
 #define RT_QUADRIC_INLINE 1   // shapes.cuh: quadric tests inlined (hot on sphere / disk / cylinder scenes)
 #include <atomic>
+#include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include "context.hpp"
 #include "trace_engine.cuh"
@@ -331,9 +335,21 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if (s->n_nodes > 0 && (!s->node_lo || !s->node_hi)) return fail(ctx, RTGPU_ERR_ARG, "node arrays missing");
   if (s->n_prims > 0 && (!s->prim_geom || !s->prim_info)) return fail(ctx, RTGPU_ERR_ARG, "primitive arrays missing");
   DScene& d = ctx->scene;
+  // RT_UPLOAD_TIMING=1: wall time of each staging step on stderr (tools/upload_probe.py)
+  const bool timing = std::getenv("RT_UPLOAD_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[upload] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
   // interleave node_lo / node_hi into one 32-byte record per node (one DRAM sector per node visit)
   {
-    std::vector<float> inter((size_t)s->n_nodes * 8);
+    // staging arrays are left uninitialised (new float[n]) and first touched by the threads that fill them: value-initialising 0.6 GB vectors on one
+    // thread was half of the upload time of a 10 M-triangle scene (profiles/r02t_upload_probe_c4.log)
+    std::unique_ptr<float[]> inter(new float[(size_t)s->n_nodes * 8]);
     parallel_for(s->n_nodes, [&](size_t i0, size_t i1) {
       for (size_t i = i0; i < i1; i++) {
         std::memcpy(&inter[i * 8], &s->node_lo[i * 4], 16);
@@ -341,10 +357,11 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
       }
     });
     const float* p = nullptr;
-    int rc = upload(ctx, inter.data(), inter.size(), &p); if (rc) return rc;
+    int rc = upload(ctx, inter.get(), (size_t)s->n_nodes * 8, &p); if (rc) return rc;
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `inter` dies at scope end
     d.nodes = (const float4*)p;
   }
+  lap("nodes interleave + copy");
   int rc;
   const float* pf = nullptr; const uint32_t* pu = nullptr;
   // wide nodes for the traversal engine (trace_engine.cuh) + "last primitive of the leaf" marks in the geometry copy
@@ -356,39 +373,81 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     // Collapsed nodes (trace_engine.cuh): one record per interior node at EVEN depth below the root of its tree — the scene's tree and
     // every object definition's — numbered in pre-order; it holds the children's children (a leaf child stands for itself).
     auto is_leaf = [&](size_t i) { return (bits(s->node_hi[i * 4 + 3]) >> 2) != 0; };
-    std::vector<uint32_t> interior_index(nn, 0xffffffffu);
+    // Pre-order of the collapsed tree == array order of the nodes that get a record (the array is the binary tree's pre-order), so the numbering is
+    // a mark pass (which interior nodes sit at even depth: disjoint subtrees walked by all host threads) and a prefix count over the array.
+    // One thread walking a 10 M-triangle tree took 120 ms (profiles/r02v_upload_probe_c4.log).
+    constexpr uint32_t kUnmarked = 0xffffffffu, kMarked = 0xfffffffeu;
+    std::unique_ptr<uint32_t[]> interior_index(new uint32_t[nn ? nn : 1]);
+    parallel_for(nn, [&](size_t i0, size_t i1) { for (size_t i = i0; i < i1; i++) interior_index[i] = kUnmarked; });
     uint32_t n_interior = 0;
-    std::vector<size_t> roots;
-    if (nn > 0) roots.push_back(0);
-    for (uint32_t k = 0; k < s->n_instances && s->instances; k++) if (s->instances[k].root_node != 0xffffffffu && s->instances[k].root_node < nn) roots.push_back(s->instances[k].root_node);
     {
-      std::vector<size_t> todo;
-      for (size_t r : roots) {
-        if (is_leaf(r) || interior_index[r] != 0xffffffffu) continue;
-        todo.push_back(r);
-        while (!todo.empty()) {
-          const size_t i = todo.back(); todo.pop_back();
-          if (interior_index[i] != 0xffffffffu) continue;
-          interior_index[i] = n_interior++;
-          const size_t kids[2] = {i + 1, (size_t)bits(s->node_lo[i * 4 + 3])};
-          size_t grand[4]; int ng = 0;
-          for (size_t c : kids) {
-            if (c >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
-            if (is_leaf(c)) continue;
-            const size_t g0 = c + 1, g1 = bits(s->node_lo[c * 4 + 3]);
-            if (g0 >= nn || g1 >= nn) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
-            grand[ng++] = g0; grand[ng++] = g1;
-          }
-          for (int k = ng - 1; k >= 0; k--) if (!is_leaf(grand[k])) todo.push_back(grand[k]);   // pre-order: the first grandchild's subtree follows its parent
+      std::vector<size_t> roots;
+      if (nn > 0) roots.push_back(0);
+      for (uint32_t k = 0; k < s->n_instances && s->instances; k++) if (s->instances[k].root_node != 0xffffffffu && s->instances[k].root_node < nn) roots.push_back(s->instances[k].root_node);
+      std::sort(roots.begin(), roots.end());
+      roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
+      std::atomic<int> bad_child{0};
+      // marks node i and lists its interior grandchildren (the roots of the next collapsed level)
+      auto visit = [&](size_t i, std::vector<size_t>& out) {
+        if (interior_index[i] != kUnmarked) return;
+        interior_index[i] = kMarked;
+        const size_t kids[2] = {i + 1, (size_t)bits(s->node_lo[i * 4 + 3])};
+        for (size_t c : kids) {
+          if (c >= nn) { bad_child = 1; return; }
+          if (is_leaf(c)) continue;
+          const size_t g[2] = {c + 1, (size_t)bits(s->node_lo[c * 4 + 3])};
+          for (size_t q : g) { if (q >= nn) { bad_child = 1; return; } if (!is_leaf(q)) out.push_back(q); }
         }
+      };
+      const size_t n_threads = std::max<size_t>(1, std::thread::hardware_concurrency());
+      std::vector<size_t> frontier, next;
+      for (size_t r : roots) if (!is_leaf(r)) frontier.push_back(r);
+      while (!frontier.empty() && frontier.size() < 64 * n_threads && !bad_child) {   // the top levels, until there is a subtree per thread and then some
+        next.clear();
+        for (size_t i : frontier) visit(i, next);
+        frontier.swap(next);
       }
+      std::atomic<size_t> cursor{0};
+      auto worker = [&]() {
+        std::vector<size_t> todo, kids;
+        while (true) {
+          const size_t t = cursor.fetch_add(1);
+          if (t >= frontier.size() || bad_child) return;
+          todo.assign(1, frontier[t]);
+          while (!todo.empty()) { const size_t i = todo.back(); todo.pop_back(); kids.clear(); visit(i, kids); todo.insert(todo.end(), kids.begin(), kids.end()); }
+        }
+      };
+      {
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < n_threads && t < frontier.size(); t++) pool.emplace_back(worker);
+        worker();
+        for (auto& t : pool) t.join();
+      }
+      if (bad_child) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
+      // prefix count of the marked nodes in array order
+      const size_t chunk = (nn + n_threads - 1) / n_threads;
+      std::vector<uint32_t> counts(n_threads + 1, 0);
+      auto span = [&](size_t t, size_t& a, size_t& b) { a = std::min(nn, t * chunk); b = std::min(nn, a + chunk); };
+      auto for_chunks = [&](auto body) {
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < n_threads; t++) pool.emplace_back(body, t);
+        body((size_t)0);
+        for (auto& t : pool) t.join();
+      };
+      for_chunks([&](size_t t) { size_t a, b; span(t, a, b); uint32_t c = 0; for (size_t i = a; i < b; i++) c += interior_index[i] == kMarked; counts[t + 1] = c; });
+      for (size_t t = 0; t < n_threads; t++) counts[t + 1] += counts[t];
+      n_interior = counts[n_threads];
+      for_chunks([&](size_t t) { size_t a, b; span(t, a, b); uint32_t c = counts[t]; for (size_t i = a; i < b; i++) if (interior_index[i] == kMarked) interior_index[i] = c++; });
       d.n_top = 0;
     }
     auto ref_of = [&](size_t i) -> uint32_t {
       const uint32_t n_prims = bits(s->node_hi[i * 4 + 3]) >> 2;
       return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];
     };
-    std::vector<float> wide((size_t)n_interior * 32, 0.0f);
+    lap("collapsed numbering (DFS)");
+    const size_t wide_floats = (size_t)n_interior * 32;
+    std::unique_ptr<float[]> wide(new float[wide_floats]);          // every record is written in full below
+    lap("wide alloc");
 #else
     // compact interior numbering: the top levels of the scene's tree first, breadth-first (the engine can stage them in shared
     // memory, RT_ENGINE_TOP_NODES), then every other interior node in array (pre-order) order
@@ -415,19 +474,23 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
       const uint32_t n_prims = bits(s->node_hi[i * 4 + 3]) >> 2;
       return n_prims > 0 ? (0x80000000u | bits(s->node_lo[i * 4 + 3])) : interior_index[i];
     };
-    std::vector<float> wide((size_t)n_interior * 16, 0.0f);
+    const size_t wide_floats = (size_t)n_interior * 16;
+    std::unique_ptr<float[]> wide(new float[wide_floats]());
 #endif
-    std::vector<float> geom(s->prim_geom, s->prim_geom + (size_t)s->n_prims * 12);
+    const size_t geom_floats = (size_t)s->n_prims * 12;
+    std::unique_ptr<float[]> geom(new float[geom_floats]);
     // shade-queue id of every slot's material in bits 2..4 of the second float4's w: the engine has that word in a register
     // when it records a hit, so classification needs no second look-up (hit slots are packed into 29 bits next to it)
     if (s->n_prims >= (1u << kHitSlotBits)) return fail(ctx, RTGPU_ERR_ARG, "more than 2^29 primitive slots");
     parallel_for(s->n_prims, [&](size_t s0, size_t s1) {
+      std::memcpy(&geom[s0 * 12], &s->prim_geom[s0 * 12], (s1 - s0) * 12 * sizeof(float));
       for (size_t slot = s0; slot < s1; slot++) {
         const uint32_t mrow = s->prim_info[slot * 4 + 1];
         const uint32_t type = (mrow < s->n_materials && s->materials) ? s->materials[mrow].type : (uint32_t)RTGPU_MAT_NONE;
         geom[slot * 12 + 7] = fbits(bits(geom[slot * 12 + 7]) | ((uint32_t)material_queue(type) << kGeomClassShift));
       }
     });
+    lap("geom copy + class bits");
     std::atomic<int> bad_nodes{0};                                    // every node writes its own wide record / its own leaf's last slot
     parallel_for(nn, [&](size_t n0, size_t n1) {
       for (size_t i = n0; i < n1; i++) {
@@ -440,6 +503,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
 #if RT_ENGINE_WIDE4
         if (interior_index[i] == 0xffffffffu) continue;                // an interior node of odd depth: absorbed by its parent's record
         float* w = &wide[(size_t)interior_index[i] * 32];
+        std::memset(w, 0, 32 * sizeof(float));
         const size_t kids[2] = {i + 1, (size_t)off};
         uint32_t axes = meta & 3u, refs[4];
         for (int c = 0; c < 2; c++) {
@@ -467,6 +531,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
 #endif
       }
     });
+    lap("wide records + last bits");
     if (bad_nodes == 1) return fail(ctx, RTGPU_ERR_ARG, "leaf primitive range outside the primitive arrays");
     if (bad_nodes == 2) return fail(ctx, RTGPU_ERR_ARG, "interior node child index outside the node arrays");
     d.root_ref = nn > 0 ? ref_of(0) : 0xffffffffu;
@@ -484,10 +549,12 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
     }
     if ((rc = upload(ctx, inst.data(), inst.size(), &d.instances))) return rc;
     d.n_instances = s->n_instances;
-    if ((rc = upload(ctx, wide.data(), wide.size(), &pf))) return rc; d.wide = (const float4*)pf;
-    if ((rc = upload(ctx, geom.data(), geom.size(), &pf))) return rc; d.geom = (const float4*)pf;
+    if ((rc = upload(ctx, wide.get(), wide_floats, &pf))) return rc; d.wide = (const float4*)pf;
+    if ((rc = upload(ctx, geom.get(), geom_floats, &pf))) return rc; d.geom = (const float4*)pf;
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die at scope end
+    lap("wide + geom copy");
   }
+  lap("staging vectors freed");
   if ((rc = upload(ctx, s->prim_info, (size_t)s->n_prims * 4, &pu))) return rc; d.info = (const uint4*)pu;
   if ((rc = upload(ctx, s->tri_n, s->tri_n ? (size_t)s->n_prims * 9 : 0, &d.tri_n))) return rc;
   if ((rc = upload(ctx, s->tri_s, s->tri_s ? (size_t)s->n_prims * 9 : 0, &d.tri_s))) return rc;
@@ -515,6 +582,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   if (s->n_lights) ctx->h_lights.assign(s->lights, s->lights + s->n_lights);
   if (s->n_materials) ctx->h_materials.assign(s->materials, s->materials + s->n_materials);
   RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  lap("info + tables copy");
   ctx->has_scene = true;
   return RTGPU_OK;
 }

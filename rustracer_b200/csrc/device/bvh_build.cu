@@ -13,6 +13,9 @@
 //   * nodes of at most 32 primitives are handled by one thread each with the sequential code;
 //   * the linear pre-order layout comes from subtree sizes (bottom-up over the levels) and offsets (top-down).
 // `splitmethod "middle"` and the per-definition trees of object instances stay on the host builder.
+#include <cstdlib>
+#include <cstdio>
+#include <chrono>
 #include <cfloat>
 #include <cstring>
 #include <vector>
@@ -427,11 +430,22 @@ extern "C" int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_
   if (n_prims == 0 || n_prims >= (1ull << 30)) return fail(ctx, RTGPU_ERR_ARG, "rtgpu_build_bvh: primitive count must be in [1, 2^30)");
   RT_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t N = (uint32_t)n_prims, cap = 2 * N;
-  std::vector<void*> allocs;
-  auto release = [&]() { for (void* p : allocs) cudaFree(p); };
+  const bool timing = std::getenv("RT_UPLOAD_TIMING") != nullptr;     // wall time of the steps around the build on stderr (tools/upload_probe.py)
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[build_bvh] %-25s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
+  // one arena for the ~35 work arrays: a cudaMalloc / cudaFree pair per array was 90 ms of a 26 ms build (profiles/r02v_upload_probe_c4.log)
+  struct Req { void** p; size_t bytes; };
+  std::vector<Req> reqs;
+  char* arena = nullptr;
+  auto release = [&]() { if (arena) cudaFree(arena); arena = nullptr; };
   int rc = 0;
-  auto dmalloc = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e != cudaSuccess) { rc = check_cuda(ctx, e, "cudaMalloc (rtgpu_build_bvh)"); return false; } allocs.push_back(*p); return true; };
-#define DA(ptr, count) if (!dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count))) { release(); return rc; }
+#define DA(ptr, count) reqs.push_back(Req{(void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)})
   Nodes nd{}; Work w{};
   DA(nd.start, cap); DA(nd.end, cap); DA(nd.base, cap); DA(nd.left, cap); DA(nd.right, cap); DA(nd.mid, cap); DA(nd.bslot, cap); DA(nd.size, cap); DA(nd.off, cap);
   DA(nd.state, cap); DA(nd.axis, cap); DA(nd.best, cap); DA(nd.box, (size_t)cap * 6); DA(nd.cbox, (size_t)cap * 6);
@@ -439,11 +453,21 @@ extern "C" int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_
   const uint32_t max_large = N / (kSmall + 1) + 1, n_tiles = (N + 1 + kScanTile - 1) / kScanTile;
   DA(d_bounds, (size_t)N * 6); DA(w.perm, N); DA(w.node_of, N); DA(w.flags, (size_t)N + 1); DA(w.flist, N); DA(w.tlist, N); DA(w.ordered, N);
   DA(w.bcount, (size_t)max_large * NB); DA(w.bbox, (size_t)max_large * NB * 6); DA(w.counters, 4); DA(tile_sums, n_tiles); DA(d_lo, cap); DA(d_hi, cap);
+  {
+    size_t total_bytes = 0;
+    for (const Req& r : reqs) total_bytes += (r.bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc((void**)&arena, total_bytes ? total_bytes : 256);
+    if (e != cudaSuccess) { arena = nullptr; return check_cuda(ctx, e, "cudaMalloc (rtgpu_build_bvh)"); }
+    size_t at = 0;
+    for (const Req& r : reqs) { *r.p = arena + at; at += (r.bytes + 255) & ~(size_t)255; }
+  }
 #undef DA
+  lap("device allocations");
   w.bounds = d_bounds; w.n = N; w.max_prims = (uint32_t)(max_prims_per_node < 0 ? 0 : max_prims_per_node);
   cudaStream_t s = ctx->stream;
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = check_cuda(ctx, _e, #call); release(); return rc; } } while (0)
   CK(cudaMemcpyAsync(d_bounds, prim_bounds, sizeof(float) * 6 * (size_t)N, cudaMemcpyHostToDevice, s));
+  lap("bounds to the device");
   CK(cudaEventRecord(ctx->ev0, s));
   const unsigned pos_blocks = (N + 255) / 256, pos1_blocks = (N + 1 + 255) / 256;
   k_init<<<pos_blocks, 256, 0, s>>>(nd, w); ctx->launches++;
@@ -484,6 +508,7 @@ extern "C" int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_
   for (size_t l = 0; l < levels.size(); l++) { k_offsets<<<(levels[l].second + 255) / 256, 256, 0, s>>>(nd, levels[l].first, levels[l].second); ctx->launches++; }
   k_emit<<<(total + 255) / 256, 256, 0, s>>>(nd, total, d_lo, d_hi); ctx->launches++;
   CK(cudaEventRecord(ctx->ev1, s));
+  lap("build kernels");
   CK(cudaMemcpyAsync(node_lo, d_lo, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(node_hi, d_hi, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(ordered, w.ordered, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
@@ -491,7 +516,9 @@ extern "C" int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_
   CK(cudaGetLastError());
   if (build_ms) CK(cudaEventElapsedTime(build_ms, ctx->ev0, ctx->ev1));
 #undef CK
+  lap("nodes + order to the host");
   *n_nodes_out = total;
   release();
+  lap("device frees");
   return RTGPU_OK;
 }

@@ -17,12 +17,12 @@ struct Builder {
   const std::vector<Box3>& bounds;
   std::vector<float> cx, cy, cz;          // centroids by prim id
   std::vector<uint32_t> perm;             // working permutation of prim ids (the reference permutes `primitive_info`)
-  std::vector<uint32_t>& ordered;
+  uvec<uint32_t>& ordered;
   std::vector<BuildNode> pool; std::atomic<uint32_t> pool_next{0};
   size_t max_prims; int split_method;
   std::atomic<int> spare_threads{0};
 
-  Builder(const std::vector<Box3>& b, std::vector<uint32_t>& ord) : bounds(b), ordered(ord) {}
+  Builder(const std::vector<Box3>& b, uvec<uint32_t>& ord) : bounds(b), ordered(ord) {}
   const std::vector<float>& cen(int d) const { return d == 0 ? cx : (d == 1 ? cy : cz); }
   uint32_t alloc() { return pool_next.fetch_add(1); }
 

@@ -12,8 +12,8 @@
 namespace rth {
 
 struct FlatBvh {
-  std::vector<float> node_lo, node_hi;   // float4 per node (see include/rtgpu.h)
-  std::vector<uint32_t> ordered;         // slot -> prim_number
+  uvec<float> node_lo, node_hi;          // float4 per node (see include/rtgpu.h)
+  uvec<uint32_t> ordered;                // slot -> prim_number
   uint32_t n_nodes = 0, n_leaves = 0, max_leaf_prims = 0;
   double build_seconds = 0;
 };

@@ -1,5 +1,9 @@
 // See scene_build.hpp.  Reference line numbers are relative to /root/reference/rustracer-core/src/.
 #include "scene_build.hpp"
+#include <chrono>
+#include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include "../common/material_lobes.hpp"
 #include <stdexcept>
 #include <thread>
@@ -181,6 +185,15 @@ void make_render_desc(const rt_scene& in, rtgpu_render_desc& rd) {
 }
 
 void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhBuilder external_builder, void* builder_user) {
+  // RT_UPLOAD_TIMING=1: wall time of each step on stderr (tools/upload_probe.py)
+  const bool timing = std::getenv("RT_UPLOAD_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[flatten] %-27s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
   // 1. primitives in Shape-directive order with world-space geometry and bounds
   // Shapes of an object definition (api.rs:951-957) form their own primitive list; an ObjectInstance is one primitive of
   // the scene's list, at the directive's place.
@@ -248,6 +261,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
       P_.push_back(Prim{si, 0}); B_.push_back(b);
     }
   }
+  lap("world vertices + bounds");
   // 2a. object definitions: the aggregate `ObjectInstance` builds when a definition holds more than one primitive
   //     (api.rs:1071-1080, same accelerator parameters), else the primitive itself
   std::vector<FlatBvh> dbvh(in.n_objects);
@@ -275,22 +289,38 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
   // 2b. same SAH BVH as the reference over the scene's primitive list
   if (external_builder && in.accel.split_method == RT_SPLIT_SAH && !bounds.empty()) {
     const size_t nb = bounds.size();
-    std::vector<float> pb(nb * 6);
+    uvec<float> pb(nb * 6);
     parallel_for(nb, threads, [&](size_t i0, size_t i1) {
       for (size_t i = i0; i < i1; i++) { pb[i * 6] = bounds[i].lo.x; pb[i * 6 + 1] = bounds[i].lo.y; pb[i * 6 + 2] = bounds[i].lo.z; pb[i * 6 + 3] = bounds[i].hi.x; pb[i * 6 + 4] = bounds[i].hi.y; pb[i * 6 + 5] = bounds[i].hi.z; }
     });
+    lap("primitive bounds packed");
     out.bvh = FlatBvh();
     out.bvh.node_lo.resize(nb * 8); out.bvh.node_hi.resize(nb * 8); out.bvh.ordered.resize(nb);
+    // first touch of the builder's output pages by all threads: a device-to-host copy into untouched pageable memory faults them in one by one
+    // (317 ms for the 680 MB of a 10 M-triangle tree against ~70 ms into resident pages, profiles/r02v_upload_probe_c4.log)
+    parallel_for(nb, threads, [&](size_t i0, size_t i1) {
+      std::memset(&out.bvh.node_lo[i0 * 8], 0, (i1 - i0) * 8 * sizeof(float)); std::memset(&out.bvh.node_hi[i0 * 8], 0, (i1 - i0) * 8 * sizeof(float));
+      std::memset(&out.bvh.ordered[i0], 0, (i1 - i0) * sizeof(uint32_t));
+    });
+    lap("builder output pages touched");
     uint32_t n_nodes = 0; float ms = 0.0f;
     const int rc = external_builder(builder_user, pb.data(), nb, std::max(0, (int)in.accel.max_node_prims), out.bvh.node_lo.data(), out.bvh.node_hi.data(), out.bvh.ordered.data(), &n_nodes, &ms);
+    lap("external builder call");
     if (rc != 0) throw std::runtime_error("external BVH builder failed (code " + std::to_string(rc) + ")");
     out.bvh.n_nodes = n_nodes; out.bvh.node_lo.resize((size_t)n_nodes * 4); out.bvh.node_hi.resize((size_t)n_nodes * 4);
     out.bvh.build_seconds = ms * 1e-3;
-    for (uint32_t i = 0; i < n_nodes; i++) {
-      uint32_t meta; std::memcpy(&meta, &out.bvh.node_hi[(size_t)i * 4 + 3], 4);
-      if (meta >> 2) { out.bvh.n_leaves++; out.bvh.max_leaf_prims = std::max(out.bvh.max_leaf_prims, meta >> 2); }
-    }
+    std::mutex tally;
+    parallel_for(n_nodes, threads, [&](size_t i0, size_t i1) {
+      uint32_t leaves = 0, widest = 0;
+      for (size_t i = i0; i < i1; i++) {
+        uint32_t meta; std::memcpy(&meta, &out.bvh.node_hi[i * 4 + 3], 4);
+        if (meta >> 2) { leaves++; widest = std::max(widest, meta >> 2); }
+      }
+      std::lock_guard<std::mutex> g(tally);
+      out.bvh.n_leaves += leaves; out.bvh.max_leaf_prims = std::max(out.bvh.max_leaf_prims, widest);
+    });
   } else build_bvh(bounds, in.accel.max_node_prims, in.accel.split_method, threads, out.bvh);
+  lap("BVH build (incl. builder I/O)");
   const size_t N0 = prims.size();
   // 2c. append the definitions' trees and slots to the same arrays with absolute indices
   std::vector<uint32_t> def_root_node(in.n_objects, 0xffffffffu), def_first_slot(in.n_objects, 0), def_first_pn(in.n_objects, 0);
@@ -327,8 +357,9 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
   std::vector<uint32_t> first_prim(in.n_shapes + 1, 0);
   for (uint32_t si = 0; si < in.n_shapes; si++)
     first_prim[si + 1] = first_prim[si] + (in.shapes[si].object_def >= 0 ? 0 : (in.shapes[si].kind == RT_SHAPE_TRIMESH ? in.shapes[si].n_indices / 3 : 1));
-  out.slot_of_prim.assign(N, 0);
-  for (size_t slot = 0; slot < N; slot++) out.slot_of_prim[out.bvh.ordered[slot]] = (uint32_t)slot;
+  out.slot_of_prim.resize(N);                                          // `ordered` is a permutation: every entry is written
+  parallel_for(N, threads, [&](size_t s0, size_t s1) { for (size_t slot = s0; slot < s1; slot++) out.slot_of_prim[out.bvh.ordered[slot]] = (uint32_t)slot; });
+  lap("definitions + slot_of_prim");
   std::vector<int32_t> light_of_prim(N, -1);
   Vec3 wc = v3(0, 0, 0); float world_radius = 0.0f;
   if (out.bvh.n_nodes > 0) {                                          // Bounds3::bounding_sphere (bounds.rs:197-211)
@@ -432,11 +463,13 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     out.lights.push_back(g);
   }
   // 4. per-slot arrays in ordered_prims order
-  out.prim_geom.assign(N * 12, 0.0f);
-  out.prim_info.assign(N * 4, 0u);
-  if (any_n) out.tri_n.assign(N * 9, 0.0f);
-  if (any_s) out.tri_s.assign(N * 9, 0.0f);
-  if (any_uv) out.tri_uv.assign(N * 6, 0.0f);
+  // uninitialised (hmath.hpp uvec): the loop below writes every word of every row it owns, starting from zeros
+  out.prim_geom.resize(N * 12);
+  out.prim_info.resize(N * 4);
+  if (any_n) out.tri_n.resize(N * 9);
+  if (any_s) out.tri_s.resize(N * 9);
+  if (any_uv) out.tri_uv.resize(N * 6);
+  lap("lights + output allocation");
   std::vector<uint32_t> mesh_flags(in.n_shapes, 0);                   // per mesh: orientation flags (interaction.rs:119-122)
   bool any_instance = false;
   for (uint32_t si = 0; si < in.n_shapes; si++) {
@@ -454,6 +487,10 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     const Prim& pr = prim_of(pn);
     const rt_shape& s = in.shapes[pr.shape];
     float* g = &out.prim_geom[slot * 12];
+    std::memset(g, 0, 12 * sizeof(float));
+    if (any_n) std::memset(&out.tri_n[slot * 9], 0, 9 * sizeof(float));
+    if (any_s) std::memset(&out.tri_s[slot * 9], 0, 9 * sizeof(float));
+    if (any_uv) std::memset(&out.tri_uv[slot * 6], 0, 6 * sizeof(float));
     uint32_t flags = 0;
     if (s.kind == RT_SHAPE_INSTANCE) {                                // a degenerate triangle for walkers that do not know instances
       const uint32_t d = (uint32_t)s.instance_of;
@@ -481,6 +518,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
     info[0] = pn; info[1] = s.material >= 0 ? (uint32_t)s.material : 0xffffffffu; info[2] = (uint32_t)light_of_prim[pn]; info[3] = flags;
   }
   });
+  lap("geometry + info rows");
   for (uint32_t d = 0; d < in.n_objects; d++)                         // a one-primitive definition has no leaf node to mark its last slot
     if (dprims[d].size() == 1) { uint32_t u; std::memcpy(&u, &out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], 4); put_bits(&out.prim_geom[(size_t)def_first_slot[d] * 12 + 7], u | 1u); }
   bool any_textured = false;
@@ -521,6 +559,7 @@ void flatten_scene(const rt_scene& in, int threads, FlatScene& out, ExternalBvhB
   d.n_lights = (uint32_t)out.lights.size(); d.lights = out.lights.data();
   d.n_env_floats = (uint32_t)out.env_data.size(); d.env_data = out.env_data.data();
   make_render_desc(in, out.render);
+  lap("materials + descriptor");
 }
 
 }  // namespace rth

@@ -12,9 +12,9 @@ namespace rth {
 
 struct FlatScene {
   FlatBvh bvh;
-  std::vector<float> prim_geom;          // 12 floats per slot
-  std::vector<uint32_t> prim_info;       // 4 per slot
-  std::vector<float> tri_n, tri_s, tri_uv;
+  uvec<float> prim_geom;                 // 12 floats per slot
+  uvec<uint32_t> prim_info;              // 4 per slot
+  uvec<float> tri_n, tri_s, tri_uv;
   std::vector<rtgpu_quadric> quadrics;
   std::vector<rtgpu_material> materials;
   std::vector<rtgpu_lobe> lobes;         // lobe lists of the RTGPU_MAT_LOBES materials
@@ -23,7 +23,7 @@ struct FlatScene {
   std::vector<float> tex_data;
   std::vector<rtgpu_light> lights;
   std::vector<float> env_data;
-  std::vector<uint32_t> slot_of_prim;    // prim_number -> slot
+  uvec<uint32_t> slot_of_prim;           // prim_number -> slot
   rtgpu_scene_desc desc{};
   rtgpu_render_desc render{};
   size_t n_triangles = 0;
