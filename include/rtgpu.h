@@ -243,6 +243,8 @@ int rtgpu_build_bvh(rtgpu_ctx* ctx, const float* prim_bounds, uint64_t n_prims, 
  *   the closest-hit launch of bounce b + 1; 2 = also the closest-hit MIS rays beside the any-hit MIS rays; default 2; results identical),
  * "waves_in_flight" (path integrator: 2 = two waves at a time on two stream groups with two sets of wave buffers, so the first bounces of one
  *   wave run under the short late-bounce launches of the other; 1 = one after the other; default 2; samples identical),
+ * "engine_carveout" (shared memory the traversal-engine kernels ask for, in per cent of the SM maximum; the rest of the 256 KB is L1; -1 = the
+ *   driver's choice; default 33 = the 100 KB configuration that holds their 8 x 9 KB of traversal stacks),
  * "profile" (1 = rtgpu_render times every launch with CUDA events and fills rtgpu_stats.ms_closest/anyhit/shade/other),
  * "count_traversal" (1 = rtgpu_render also fills rtgpu_stats.nodes_* / prims_*). */
 int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value);

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <thread>
 #include "context.hpp"
+namespace rt { int configure_trace_engines(int carveout_percent); }   // tu_trace.cu
 #include "trace_engine.cuh"
 #include <cstring>
 #include <algorithm>
@@ -242,6 +243,15 @@ static void free_scene(rtgpu_ctx* ctx) {
   rt::free_lightgrid(ctx);
 }
 
+static void apply_engine_carveout(int pct) {
+  if (pct < 0) return;
+  rt::configure_trace_engines(pct);
+  cudaFuncSetAttribute(k_closest_batch_engine<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_closest_batch_engine<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_anyhit_batch_engine<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_anyhit_batch_engine<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 extern "C" {
 
 int rtgpu_create(int device, rtgpu_ctx** out) {
@@ -267,6 +277,9 @@ int rtgpu_create(int device, rtgpu_ctx** out) {
     delete ctx; return RTGPU_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // L1 / shared-memory split of the traversal engines (tu_trace.cu configure_trace_engines); RT_ENGINE_CARVEOUT overrides for sweeps (-1: driver's choice)
+  if (const char* e = std::getenv("RT_ENGINE_CARVEOUT")) ctx->engine_carveout = std::atoi(e);
+  apply_engine_carveout(ctx->engine_carveout);
   // traversal stacks live in local memory; prefer L1 over shared memory for the traversal kernels
   *out = ctx;
   return RTGPU_OK;
@@ -317,6 +330,10 @@ int rtgpu_set_option(rtgpu_ctx* ctx, const char* name, int value) {
   if (std::strcmp(name, "node_threshold") == 0) {
     if (value < 0 || value > 32) return fail(ctx, RTGPU_ERR_ARG, "node_threshold must be in [0, 32]");
     ctx->node_threshold = value; ctx->scene.tune_node_threshold = value; return RTGPU_OK;
+  }
+  if (std::strcmp(name, "engine_carveout") == 0) {            // per cent of the SM's shared memory the traversal engines ask for (the rest is L1)
+    if (value < -1 || value > 100) return fail(ctx, RTGPU_ERR_ARG, "engine_carveout must be in [-1, 100]");
+    ctx->engine_carveout = value; cudaSetDevice(ctx->device); apply_engine_carveout(value); return RTGPU_OK;
   }
   if (std::strcmp(name, "refill_threshold") == 0) {           // <= 0 would enter the refill branch with no idle lane and spin
     if (value < 1 || value > 32) return fail(ctx, RTGPU_ERR_ARG, "refill_threshold must be in [1, 32]");

@@ -42,6 +42,7 @@ struct rtgpu_ctx {
   // host-buffer batches (api.cu host_batch): two persistent device slots {rays, results} and their {copied-in, traced, copied-out} events
   void* batch_rays[2] = {nullptr, nullptr}; void* batch_out[2] = {nullptr, nullptr}; size_t batch_cap = 0;
   cudaEvent_t batch_ev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  int engine_carveout = 33;   // shared-memory carve-out of the traversal engines in per cent of the SM maximum (-1: the driver's choice, 132 KB; 33 -> the 100 KB configuration, 156 KB of L1: C5 +0.8 %, profiles/r03b)
   int sort_min_rays = 32768;  // batch API: batches below this are traced in the caller's order
   int profile = 0;            // rtgpu_render: time every launch with CUDA events, per kernel class (rtgpu_stats.ms_*)
   int count_traversal = 0;    // rtgpu_render: count BVH nodes visited / primitives tested (rtgpu_stats.nodes_* / prims_*)

@@ -13,6 +13,8 @@ void launch_trace_closest(int mode, const RenderParams& p, const float4* ray_o, 
 void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx, const HitRec* hits, bool from_hit_class, unsigned blocks, cudaStream_t s);
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s);
 void launch_trace_mis(bool atomic, int mode, const RenderParams& p, unsigned blocks, cudaStream_t s);
+// shared-memory carve-out (per cent of the SM's maximum) of the traversal-engine kernels on the current device; < 0 leaves the driver's choice
+int configure_trace_engines(int carveout_percent);
 void launch_material_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* hist, uint32_t n_bins, uint32_t* out, unsigned blocks, cudaStream_t s);
 uint32_t ray_sort_bins();
 void launch_ray_sort(const RenderParams& p, const uint32_t* list, int count_idx, uint32_t* keys, uint32_t* hist, uint32_t* out, unsigned blocks, cudaStream_t s);

@@ -23,6 +23,19 @@ void launch_classify(const RenderParams& p, const uint32_t* list, int count_idx,
   if (from_hit_class) k_classify<true><<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
   else k_classify<false><<<blocks, 256, 0, s>>>(p, list, count_idx, hits);
 }
+// The engine kernels keep 8 KB of traversal stacks per block in shared memory and run 8 blocks per SM (74 KB with the per-block reserve).  Left alone the
+// driver configured 132 KB of shared memory for them (it sizes for the 14 blocks shared memory alone would admit; registers admit 8), which leaves 121 KB
+// of the SM's 256 KB as L1 for a kernel whose every node fetch goes through it (profiles/r02m: launch__shared_mem_config_size 135 KB, L1 hit rate 37 - 62 %).
+int configure_trace_engines(int pct) {
+  if (pct < 0) return 0;
+  int bad = 0;
+#define RT_CARVE(k) bad |= cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess
+  RT_CARVE(k_trace_closest_engine<false>); RT_CARVE(k_trace_closest_engine<true>);
+  RT_CARVE((k_trace_shadow_engine<false, false>)); RT_CARVE((k_trace_shadow_engine<false, true>)); RT_CARVE((k_trace_shadow_engine<true, false>)); RT_CARVE((k_trace_shadow_engine<true, true>));
+  RT_CARVE((k_trace_mis_engine<false, false>)); RT_CARVE((k_trace_mis_engine<false, true>)); RT_CARVE((k_trace_mis_engine<true, false>)); RT_CARVE((k_trace_mis_engine<true, true>));
+#undef RT_CARVE
+  return bad;
+}
 // q: 0 = NEE shadow queue, 1 = queue of the MIS rays towards infinite lights (both any-hit)
 void launch_trace_shadow(bool atomic, int mode, const RenderParams& p, int q, unsigned blocks, cudaStream_t s) {
   if (mode == TRACE_COUNTING) { if (atomic) k_trace_shadow<true, true><<<blocks, 128, 0, s>>>(p, q); else k_trace_shadow<false, true><<<blocks, 128, 0, s>>>(p, q); }
