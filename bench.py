@@ -508,6 +508,8 @@ def run_ours(a):
         dev.comm_init(ident[0], rank, world)
     rd = sc.render_desc()
     rd.seed = 1
+    if os.environ.get("RT_WAVE_PATHS"):                                 # A/B runs: paths per wave (0 = the library's default)
+        rd.wave_paths = int(os.environ["RT_WAVE_PATHS"])
     spp, job_spp = a.spp_per_step, rd.spp
     rd.tile_rank, rd.tile_world = rank, world
 
