@@ -5,6 +5,8 @@
 // be a list named `vertex_indices` with int32/uint32 items; quads are split (0,1,2)+(3,0,2); faces with any
 // other vertex count are ignored; only `vertex` and `face` elements are allowed.
 #include "pbrt_frontend.hpp"
+#include <thread>
+#include <atomic>
 #include <cstdio>
 #include <sstream>
 
@@ -59,10 +61,21 @@ struct Reader {
 
 }  // namespace
 
+// static split of [0, n) over the host threads
+template <class F> static void parallel_chunks(size_t n, F body) {
+  const size_t threads = std::max<size_t>(1, std::thread::hardware_concurrency());
+  if (threads == 1 || n < ((size_t)1 << 16)) { body((size_t)0, n); return; }
+  const size_t chunk = (n + threads - 1) / threads;
+  std::vector<std::thread> pool;
+  for (size_t b = chunk; b < n; b += chunk) pool.emplace_back([=, &body]() { body(b, std::min(n, b + chunk)); });
+  body((size_t)0, std::min(n, chunk));
+  for (auto& t : pool) t.join();
+}
+
 void read_ply(const std::string& filename, PlyMesh& out) {
   FILE* f = std::fopen(filename.c_str(), "rb");
   if (!f) throw ParseError("PLY file \"" + filename + "\": cannot open");   // plymesh.rs:26 `File::open(..).unwrap()`
-  std::vector<unsigned char> data;
+  uvec<unsigned char> data;                                         // uninitialised: fread fills it (hmath.hpp)
   std::fseek(f, 0, SEEK_END); long sz = std::ftell(f); std::fseek(f, 0, SEEK_SET);
   data.resize((size_t)std::max(0L, sz));
   if (sz > 0 && std::fread(data.data(), 1, (size_t)sz, f) != (size_t)sz) { std::fclose(f); throw ParseError("PLY: short read"); }
@@ -161,6 +174,20 @@ void read_ply(const std::string& filename, PlyMesh& out) {
       for (size_t k = 0; k < e.props.size(); k++)
         takes[k] = e.props[k].is_list && e.props[k].name == "vertex_indices" && (e.props[k].type == S_I32 || e.props[k].type == S_U32);   // ListInt / ListUInt only (plymesh.rs:233-240)
       if (r.fmt == 1 && e.props.size() == 1 && takes[0] && e.props[0].count_type == S_U8) {   // fast path: `list uchar int vertex_indices`, little-endian
+        // all triangles (13-byte records): checked and copied by all host threads
+        if ((size_t)(r.end - r.p) >= 13 * e.count && e.count >= (1u << 16)) {
+          const unsigned char* base = r.p;
+          std::atomic<int> other{0};
+          parallel_chunks(e.count, [&](size_t i0, size_t i1) { for (size_t i = i0; i < i1; i++) if (base[13 * i] != 3) { other = 1; return; } });
+          if (!other) {
+            const size_t first = out.indices.size();
+            out.indices.resize(first + 3 * e.count);
+            int32_t* dst = out.indices.data() + first;
+            parallel_chunks(e.count, [&](size_t i0, size_t i1) { for (size_t i = i0; i < i1; i++) std::memcpy(dst + 3 * i, base + 13 * i + 1, 12); });
+            r.p += 13 * e.count;
+            continue;
+          }
+        }
         for (size_t i = 0; i < e.count; i++) {
           if (r.p >= r.end) throw ParseError("PLY: unexpected end of data");
           const size_t n = *r.p++;

@@ -211,3 +211,26 @@ def test_ply_round_trip(native_libs, tmp_path):
     got = np.ctypeslib.as_array(s.P, shape=(s.n_vertices, 3))
     assert np.array_equal(got, v.astype(np.float32))
     assert np.array_equal(np.ctypeslib.as_array(s.indices, shape=(len(f), 3)), f)
+
+
+def test_ply_large_mesh_fast_paths(native_libs, tmp_path):
+    """The all-triangles record copy of large face lists (ply_reader.cpp, taken from 65,536 faces on) against numpy, and the same file with its
+    last face turned into a quad, which must take the per-face loop and fan into two triangles (plymesh.rs:107-127)."""
+    v, f = scenes.icosphere(6)                                           # 81,920 faces
+    assert len(f) >= 1 << 16
+    scenes.write_ply(tmp_path / "big.ply", v, f)
+    txt = scenes.header(16, 16, 1, 'Integrator "path"', 40, ([0, 0, -5], [0, 0, 0], [0, 1, 0])) + 'WorldBegin\nShape "plymesh" "string filename" "big.ply"\nWorldEnd\n'
+    sc = Scene.from_string(txt, search_dir=tmp_path)
+    s = sc.ir.shapes[0]
+    assert s.n_indices == 3 * len(f) and s.n_vertices == len(v)
+    assert np.array_equal(np.ctypeslib.as_array(s.indices, shape=(len(f), 3)), f)
+    assert np.array_equal(np.ctypeslib.as_array(s.P, shape=(s.n_vertices, 3)), v.astype(np.float32))
+    # same mesh, last record a quad (a, b, c, d) -> triangles (a, b, c) and (d, a, c)
+    raw = open(tmp_path / "big.ply", "rb").read()
+    quad = np.array([f[-1][0], f[-1][1], f[-1][2], f[0][0]], "<i4")
+    open(tmp_path / "quad.ply", "wb").write(raw[:-13] + bytes([4]) + quad.tobytes())
+    sc2 = Scene.from_string(txt.replace("big.ply", "quad.ply"), search_dir=tmp_path)
+    s2 = sc2.ir.shapes[0]
+    assert s2.n_indices == 3 * (len(f) + 1)
+    got = np.ctypeslib.as_array(s2.indices, shape=(len(f) + 1, 3))
+    assert np.array_equal(got[:-2], f[:-1]) and list(got[-2]) == list(quad[:3]) and list(got[-1]) == [quad[3], quad[0], quad[2]]
