@@ -35,16 +35,17 @@ k_shade_path(RenderParams p, int parity) {
     bool alive = false;
     uint32_t slot = 0;
     if (i < n) {
-      slot = p.w.matq[MAT][i];
+      slot = ld_stream(&p.w.matq[MAT][i]);
       Ray ray = load_ray(p.w.ray_o, p.w.ray_d, slot, nullptr);
       ray.t_max = inf_f();
-      const HitRec h = p.w.hit[slot];
-      const float4 bt = p.w.beta[slot];
+      const float4 hv = ld_stream((const float4*)&p.w.hit[slot]);
+      HitRec h; h.t = hv.x; h.slot = __float_as_uint(hv.y); h.b1 = hv.z; h.b2 = hv.w;
+      const float4 bt = ld_stream(&p.w.beta[slot]);
       Spec beta = spec(bt.x, bt.y, bt.z); float eta_scale = bt.w;
-      uint4 ps = p.w.pstate[slot];
+      uint4 ps = ld_stream(&p.w.pstate[slot]);
       const uint32_t sample = ps.x;
       uint32_t bounces = ps.y & 0xffu; bool specular_bounce = (ps.z & 1u) != 0;
-      const uint2 sinf = p.w.sinfo[sample];
+      const uint2 sinf = ld_stream(&p.w.sinfo[sample]);
       SamplerState ss; ss.ph = sinf.x; ss.s = sinf.y; ss.d1 = ps.w & 0xffffu; ss.d2 = ps.w >> 16; ss.da = 0;
       SurfHit si;
       hit_surface_bary(p.sc, h.slot, p.w.hit_inst ? p.w.hit_inst[slot] : kNoInst, ray, p.hit_t_is_b0 != 0, h.t, h.b1, h.b2, si);
@@ -102,14 +103,14 @@ k_shade_path(RenderParams p, int parity) {
           }
         }
         if (alive) {
-          p.w.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
-          p.w.pstate[slot] = make_uint4(sample, bounces, specular_bounce ? 1u : 0u, (ss.d1 & 0xffffu) | (ss.d2 << 16));
+          st_stream(&p.w.beta[slot], make_float4(beta.r, beta.g, beta.b, eta_scale));
+          st_stream(&p.w.pstate[slot], make_uint4(sample, bounces, specular_bounce ? 1u : 0u, (ss.d1 & 0xffffu) | (ss.d2 << 16)));
         }
       }
       if (!is_black(l_add)) { float4 L = p.w.L[sample]; L.x += l_add.r; L.y += l_add.g; L.z += l_add.b; p.w.L[sample] = L; }
     }
     const uint32_t pos = warp_append(out_count, alive);
-    if (alive) out_list[pos] = slot;
+    if (alive) st_stream(&out_list[pos], slot);
   }
 }
 

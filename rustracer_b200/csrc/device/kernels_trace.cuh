@@ -50,15 +50,15 @@ __global__ void __launch_bounds__(256) k_raygen(RenderParams p) {
     (void)ss.get_1d(p.scfg);                                          // time: drawn, unused by the camera
     P2 p_lens = ss.get_2d(p.scfg);
     p.w.L[i] = make_float4(0.0f, 0.0f, 0.0f, valid ? 1.0f : 0.0f);
-    p.w.pfilm[i] = make_float2(p_film.x, p_film.y);
-    p.w.sinfo[i] = make_uint2(ss.ph, s);
+    st_stream(&p.w.pfilm[i], make_float2(p_film.x, p_film.y));
+    st_stream(&p.w.sinfo[i], make_uint2(ss.ph, s));
     if (valid) {                                                      // items are compacted: item slot = queue position
       Ray ray = camera_ray(p.r2c, p.c2w, p.lens_radius, p.focal_distance, p_film, p_lens);
       store_ray(p.w.ray_o, p.w.ray_d, pos, ray, 0);
-      p.w.beta[pos] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+      st_stream(&p.w.beta[pos], make_float4(1.0f, 1.0f, 1.0f, 1.0f));
       // path: z bit 1 = "camera ray" (carries the ray differential); recursive: z = depth, w != 0 = camera ray
       p.w.pstate[pos] = make_uint4(i, p.integrator == RTGPU_INTEGRATOR_PATH ? 0u : 1u, p.integrator == RTGPU_INTEGRATOR_PATH ? 2u : 0u, ss.d1 | (ss.d2 << 16));
-      p.w.list[0][pos] = pos;
+      st_stream(&p.w.list[0][pos], pos);
     }
   }
 }
@@ -173,7 +173,7 @@ struct ClosestPolicy {
   RT_DEV void load(uint32_t idx, Ray& ray) { slot = list ? list[idx] : idx; ray = load_ray(ray_o, ray_d, slot, nullptr); }
   // the record keeps the three barycentrics {b0, slot, b1, b2} (RenderParams::hit_t_is_b0): the shade kernels rebuild the surface from them instead of
   // repeating the watertight test, and nothing downstream reads the distance
-  RT_DEV void commit(uint32_t, const HitRec& h, float, uint32_t inst, uint32_t cls) { hits[slot] = h; hit_class[slot] = (uint8_t)cls; if (INST) hit_inst[slot] = inst; }
+  RT_DEV void commit(uint32_t, const HitRec& h, float, uint32_t inst, uint32_t cls) { st_stream((float4*)&hits[slot], make_float4(h.t, __uint_as_float(h.slot), h.b1, h.b2)); hit_class[slot] = (uint8_t)cls; if (INST) hit_inst[slot] = inst; }
 };
 template <bool INST>
 __global__ void __launch_bounds__(128, RT_ENGINE_MIN_BLOCKS) k_trace_closest_engine(RenderParams p, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t
       const uint32_t i = base + (uint32_t)k * 256u + threadIdx.x;
       q[k] = -1; slot[k] = 0; off[k] = 0;
       if (i < n) {
-        slot[k] = list ? list[i] : i;
-        if (FROM_CLASS) q[k] = (int)p.w.hit_class[slot[k]];
+        slot[k] = list ? ld_stream(&list[i]) : i;
+        if (FROM_CLASS) q[k] = (int)ld_stream(&p.w.hit_class[slot[k]]);
         else {
           const uint32_t hslot = hits[slot[k]].slot;
           if (hslot == kMiss) q[k] = Q_MISS;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) k_classify(RenderParams p, const uint32_t
     if (threadIdx.x < Q_COUNT && s_count[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&p.w.counters[C_MATQ0 + threadIdx.x], s_count[threadIdx.x]);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kClassifyPerThread; k++) if (q[k] >= 0) p.w.matq[q[k]][s_base[q[k]] + off[k]] = slot[k];
+    for (int k = 0; k < kClassifyPerThread; k++) if (q[k] >= 0) st_stream(&p.w.matq[q[k]][s_base[q[k]] + off[k]], slot[k]);
     __syncthreads();
   }
 }
@@ -346,7 +346,7 @@ struct ShadowPolicy {
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(aq.o, aq.d, idx, &sample); }
   RT_DEV void commit(uint32_t idx, const HitRec& h, float, uint32_t, uint32_t) {
     if (h.slot != kMiss) return;
-    const float4 c = aq.c[idx];
+    const float4 c = ld_stream(&aq.c[idx]);
     float4* L = &p.w.L[sample];
     if (ATOMIC) { atomicAdd(&L->x, c.x); atomicAdd(&L->y, c.y); atomicAdd(&L->z, c.z); }
     else { float4 v = *L; v.x += c.x; v.y += c.y; v.z += c.z; *L = v; }
@@ -365,7 +365,7 @@ struct MisPolicy {
   RT_DEV MisPolicy(const RenderParams& p_) : p(p_), sample(0) {}
   RT_DEV void load(uint32_t idx, Ray& ray) { ray = load_ray(p.w.mi_o, p.w.mi_d, idx, &sample); }
   RT_DEV void commit(uint32_t idx, const HitRec& h, float, uint32_t inst, uint32_t) {
-    const float4 c = p.w.mi_c[idx];
+    const float4 c = ld_stream(&p.w.mi_c[idx]);
     const uint32_t light_row = __float_as_uint(c.w);
     const rtgpu_light& light = p.sc.lights[light_row];
     const Ray ray0 = load_ray(p.w.mi_o, p.w.mi_d, idx, nullptr);

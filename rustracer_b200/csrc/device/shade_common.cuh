@@ -56,12 +56,12 @@ RT_DEV Inter inter_of(const SurfHit& si) { Inter it; it.p = si.p; it.p_error = s
 
 RT_DEV void push_shadow(const RenderParams& p, const Ray& ray, uint32_t sample, Spec c) {
   const uint32_t pos = warp_append(&p.w.counters[C_SHADOW], true);
-  if (pos < p.w.cap_shadow) { store_ray(p.w.sh_o, p.w.sh_d, pos, ray, sample); p.w.sh_c[pos] = make_float4(c.r, c.g, c.b, 0.0f); }
+  if (pos < p.w.cap_shadow) { store_ray(p.w.sh_o, p.w.sh_d, pos, ray, sample); st_stream(&p.w.sh_c[pos], make_float4(c.r, c.g, c.b, 0.0f)); }
   else p.w.counters[C_OVERFLOW] = 1;
 }
 RT_DEV void push_mis(const RenderParams& p, const Ray& ray, uint32_t sample, Spec c, uint32_t light_row) {
   const uint32_t pos = warp_append(&p.w.counters[C_MIS], true);
-  if (pos < p.w.cap_mis) { store_ray(p.w.mi_o, p.w.mi_d, pos, ray, sample); p.w.mi_c[pos] = make_float4(c.r, c.g, c.b, __uint_as_float(light_row)); }
+  if (pos < p.w.cap_mis) { store_ray(p.w.mi_o, p.w.mi_d, pos, ray, sample); st_stream(&p.w.mi_c[pos], make_float4(c.r, c.g, c.b, __uint_as_float(light_row))); }
   else p.w.counters[C_OVERFLOW] = 1;
 }
 
@@ -107,7 +107,7 @@ RT_DEV void estimate_direct(const RenderParams& p, const SurfHit& si, const Bsdf
           const uint32_t pos = warp_append(&p.w.counters[C_MIS_ANY], true);
           if (pos < p.w.cap_mis) {
             store_ray(p.w.ma_o, p.w.ma_d, pos, spawn_ray(it, wi2), sample);
-            p.w.ma_c[pos] = make_float4(w.r * le.r, w.g * le.g, w.b * le.b, 0.0f);
+            st_stream(&p.w.ma_c[pos], make_float4(w.r * le.r, w.g * le.g, w.b * le.b, 0.0f));
           } else p.w.counters[C_OVERFLOW] = 1;
         } else warp_append(&p.w.counters[C_MIS_SKIPPED], true);       // traced by the reference, contributes nothing
       } else push_mis(p, spawn_ray(it, wi2), sample, w, light_row);
