@@ -23,6 +23,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import resource
 import subprocess
 import sys
 import tempfile
@@ -185,8 +186,12 @@ def oracle_rate(o, a, seconds=15.0, threads=0):
     rate = st.camera_rays / max(st.seconds_tiles, 1e-6)
     want_tiles = max(8 * int(st.threads), int(rate * seconds / (256.0 * job_spp)))
     stride = max(1, n_tiles // want_tiles)
+    ru0 = resource.getrusage(resource.RUSAGE_SELF)
     _, _, st = o.render(sampler=samp, sampler_kind=0, threads=threads, tile_stride=stride)
+    ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    cpu_user, cpu_sys = ru1.ru_utime - ru0.ru_utime, ru1.ru_stime - ru0.ru_stime
     return {"value": st.camera_rays / st.seconds_tiles, "unit": UNIT, "cores": int(st.threads), "kind": "port",
+            "sys_frac": cpu_sys / max(cpu_user + cpu_sys, 1e-9),
             "sample": f"every {stride}-th 16x16 tile of the {a.xres}x{a.yres} frame at the job's {job_spp} spp (the reference's loop order: all samples of a tile, then the "
                       f"next tile): {st.camera_rays} camera paths in {st.seconds_tiles:.2f} s (C++ restatement of rustracer's renderer, -O3 -march=native, ZeroTwoSequence "
                       f"sampler; the Rust binary cannot be built here)",
@@ -214,15 +219,36 @@ def run_reference(a):
             vals.append(r)
         last = r
     rates = [r["value"] for r in vals] if vals else [last["value"]]
-    v = float(np.mean(rates))
-    secs = float(np.mean([r["seconds"] for r in vals])) if vals else last["seconds"]
+    # value = the BEST of the K bounded samples (spread alongside): the CPU arm is the denominator of the speed-up, so its fastest run is the
+    # conservative one.  Until round 2 the restated SpatialLightDistribution took a mutex on every lookup where the reference's hash is lock-free;
+    # with 16 threads that lock made the same sample run at 2.3 M or at 5.5 M samples/s from one process to the next, the slow ones with most of
+    # their CPU time in the kernel (profiles/r03i_bench.json).  The lookup is lock-free now (oracle/orc_render.hpp); as a safety net a measurement
+    # whose kernel share of the CPU time is above 15 % is still repeated once in a fresh process and the better one kept.
+    v = float(np.max(rates))
+    best = (vals or [last])[int(np.argmax(rates))]
+    secs = best["seconds"]
+    sys_frac = float(np.median([r["sys_frac"] for r in (vals or [last])]))
+    retried = None
+    if sys_frac > 0.15 and not os.environ.get("RT_CPU_ARM_RETRY"):
+        cmd = [sys.executable, os.path.abspath(__file__)] + sys.argv[1:]
+        env = dict(os.environ, RT_CPU_ARM_RETRY="1")
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env).stdout.strip().splitlines()[-1]
+            retried = json.loads(out)
+        except Exception as e:
+            log("retry of the disturbed CPU arm failed:", e)
+        if retried and retried.get("value", 0.0) > v:
+            retried["cpu_baseline"]["first_attempt"] = {"value": v, "sys_frac": sys_frac}
+            emit(retried)
+            return
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, sc),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"],
-                             "spread": {"min": float(np.min(rates)), "max": float(np.max(rates)), "n": len(rates)}},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": best["sample"] + "; value = best of the K samples",
+                             "spread": {"min": float(np.min(rates)), "max": float(np.max(rates)), "mean": float(np.mean(rates)), "n": len(rates)},
+                             "sys_frac": sys_frac, "retried": retried is not None},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "mrays_per_s": float(np.mean([r["mrays_per_s"] for r in vals])) if vals else last["mrays_per_s"], "gpu_launches": 0,
+            "mrays_per_s": best["mrays_per_s"], "gpu_launches": 0,
             "scene_build_seconds": t_build}
     emit(line)
 
@@ -230,7 +256,7 @@ def run_reference(a):
 def cpu_baseline_subprocess(a, workload, timeout=900):
     """The CPU arm in a fresh process: measured inside this one (CUDA context, torch thread pools, the clock sampler) the same CPU sample
     ran 2x slower (profiles/r01h).  One untimed pass first: a cold first pass was 2x slower once (profiles/r01zc_bench.json)."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "1", "--level", str(a.level),
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "2", "--warmup", "1", "--level", str(a.level),
            "--cpu-seconds", str(a.cpu_seconds)]
     if workload == a.workload:
         cmd += ["--xres", str(a.xres), "--yres", str(a.yres), "--spp-per-step", str(a.spp_per_step)]

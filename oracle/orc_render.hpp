@@ -187,14 +187,20 @@ struct UniformLightDistribution : LightDistribution {            // :37-54
   explicit UniformLightDistribution(const Scene& s) { d = Distribution1D(std::vector<float>(s.lights.size(), 1.0f)); }
   const Distribution1D* lookup(V3) override { return &d; }
 };
-struct SpatialLightDistribution : LightDistribution {            // :59-296 (hash table -> mutex-guarded map: same values per voxel)
+struct SpatialLightDistribution : LightDistribution {            // :59-296
+  // The reference's table is a lock-free hash (atomics, lightdistrib.rs:201-296); here one atomic pointer per voxel (at most 64^3), filled on first use:
+  // same values per voxel, and like the reference no lock on the read path (a mutex around every lookup made the 16-thread CPU arm contend on it:
+  // samples/s varied 2x between processes with the kernel's share of the CPU time, profiles/r03i_bench.json).
   const Scene* scene; uint32_t n_voxels[3];
-  std::unordered_map<uint64_t, std::unique_ptr<Distribution1D>> table; std::mutex mu;
+  std::vector<std::atomic<const Distribution1D*>> table;
+  ~SpatialLightDistribution() override { for (auto& e : table) delete e.load(); }
   SpatialLightDistribution(const Scene* s, uint32_t max_voxels) : scene(s) {   // :67-99
     Bounds3 b = s->world_bounds();
     V3 diag = b.diagonal();
     float b_max = diag[b.maximum_extent()];
     for (int i = 0; i < 3; i++) n_voxels[i] = std::max<uint32_t>(1u, f2u32(std::round(diag[i] / b_max * (float)max_voxels)));
+    table = std::vector<std::atomic<const Distribution1D*>>((size_t)n_voxels[0] * n_voxels[1] * n_voxels[2]);
+    for (auto& e : table) e.store(nullptr, std::memory_order_relaxed);
   }
   Distribution1D compute_distribution(const int32_t pi[3]) const {   // :101-179
     Bounds3 wb = scene->world_bounds();
@@ -225,14 +231,14 @@ struct SpatialLightDistribution : LightDistribution {            // :59-296 (has
   }
   const Distribution1D* lookup(V3 p) override {
     int32_t pi[3]; voxel_of(p, pi);
-    uint64_t packed = ((uint64_t)pi[0] << 40) | ((uint64_t)pi[1] << 20) | (uint64_t)pi[2];   // :201
-    std::lock_guard<std::mutex> g(mu);
-    auto it = table.find(packed);
-    if (it != table.end()) return it->second.get();
-    auto d = std::unique_ptr<Distribution1D>(new Distribution1D(compute_distribution(pi)));
-    const Distribution1D* r = d.get();
-    table.emplace(packed, std::move(d));
-    return r;
+    std::atomic<const Distribution1D*>& slot = table[((size_t)pi[0] * n_voxels[1] + (size_t)pi[1]) * n_voxels[2] + (size_t)pi[2]];
+    const Distribution1D* d = slot.load(std::memory_order_acquire);
+    if (d) return d;
+    const Distribution1D* mine = new Distribution1D(compute_distribution(pi));   // two threads may both compute a new voxel: same values, one copy kept
+    const Distribution1D* expected = nullptr;
+    if (slot.compare_exchange_strong(expected, mine, std::memory_order_acq_rel, std::memory_order_acquire)) return mine;
+    delete mine;
+    return expected;
   }
 };
 
