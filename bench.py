@@ -173,8 +173,7 @@ def count_triangles(sc):
 def oracle_rate(o, a, seconds=15.0, threads=0):
     """The oracle renderer (ZeroTwoSequence sampler, 16x16 tiles from a shared counter, all host threads) on a bounded sample of the
     workload: every `stride`-th tile of the frame, each rendered the way renderer::render does it (renderer.rs:83-130) — ALL of the job's
-    samples of a pixel before the next pixel, one film merge under the mutex per tile.  (A sample of many tiles at few samples each made
-    the per-tile mutex traffic dominate on some runs: 2.6 M against 4.7-5.2 M samples/s, profiles/r02b_bench.json.)
+    samples of a pixel before the next pixel, one film merge under the mutex per tile.
     o: the OracleScene (its SAH BVH is built once)."""
     from rustracer_b200 import _abi as A
     job_spp = workload_config(a)["job_spp"]
