@@ -1,4 +1,4 @@
-"""profiles/roofline_traffic.json from the raw pages of the round-2 `ncu --set full` captures (tools/ncu_round2.sh):
+"""profiles/roofline_traffic.json from the raw pages of the round-2 `ncu --set full` captures (tools/ncu_round3.sh; round-2 mid-point captures: tools/ncu_round2.sh, profiles/r02f_*):
 
     python tools/roofline_traffic.py
 
@@ -55,19 +55,19 @@ LIM = "L1 data pipe (l1tex__data_pipe_lsu_wavefronts: scattered per-lane node fe
 def main():
     P = lambda f: os.path.join(ROOT, "profiles", f)
     out = {}
-    c5 = load(P("r02f_ncu_full_closest_c5_raw.csv"))
-    out["c5_path_closest"] = summarise(c5, "profiles/r02f_ncu_full_closest_c5_raw.csv (ncu --set full --clock-control none; the 96 closest-hit launches of one c5_path step, 32 spp)",
+    c5 = load(P("r03k_ncu_full_closest_c5_raw.csv"))
+    out["c5_path_closest"] = summarise(c5, "profiles/r03k_ncu_full_closest_c5_raw.csv (ncu --set full --clock-control none; the 96 closest-hit launches of one c5_path step, 32 spp)",
                                        "k_trace_closest_engine + k_trace_mis_engine", "the 5 M-triangle scene (640 MB of collapsed nodes + geometry) does not fit the L2: DRAM serves part of "
                                        "the tree besides the ray / hit records; the kernel is bound by the L1 data pipe (l1_frac) and instruction issue, not by DRAM", LIM)
-    c3 = load(P("r02f_ncu_full_closest_c3_raw.csv"))
-    out["c3_path_closest"] = summarise(c3, "profiles/r02f_ncu_full_closest_c3_raw.csv (the 12 closest-hit launches of one c3_path step, 8 spp)", "k_trace_closest_engine + k_trace_mis_engine",
+    c3 = load(P("r03k_ncu_full_closest_c3_raw.csv"))
+    out["c3_path_closest"] = summarise(c3, "profiles/r03k_ncu_full_closest_c3_raw.csv (the 12 closest-hit launches of one c3_path step, 8 spp)", "k_trace_closest_engine + k_trace_mis_engine",
                                        "the 1 M-triangle scene (130 MB) is mostly L2-resident: DRAM moves the ray / hit records and the first touch of the tree", LIM)
-    c4 = load(P("r02f_ncu_full_c4_raw.csv"))
+    c4 = load(P("r03k_ncu_full_c4_raw.csv"))
     closest = [l for l in c4 if "closest" in str(l["Kernel Name"])][-1:]
     anyhit = [l for l in c4 if "anyhit" in str(l["Kernel Name"])][-1:]
-    out["c4_closest"] = summarise(closest, "profiles/r02f_ncu_full_c4_raw.csv (second 16 Mi-ray launch of k_closest_batch_engine against 10,014,720 triangles)", "k_closest_batch_engine",
+    out["c4_closest"] = summarise(closest, "profiles/r03k_ncu_full_c4_raw.csv (second 16 Mi-ray launch of k_closest_batch_engine against 10,014,720 triangles)", "k_closest_batch_engine",
                                   "HBM-resident config: 1.3 GB of nodes + geometry; rays binned by origin cell and direction octant before the launch", LIM)
-    out["c4_anyhit"] = summarise(anyhit, "profiles/r02f_ncu_full_c4_raw.csv (second 16 Mi-ray launch of k_anyhit_batch_engine)", "k_anyhit_batch_engine", "as c4_closest", LIM)
+    out["c4_anyhit"] = summarise(anyhit, "profiles/r03k_ncu_full_c4_raw.csv (second 16 Mi-ray launch of k_anyhit_batch_engine)", "k_anyhit_batch_engine", "as c4_closest", LIM)
     json.dump(out, open(P("roofline_traffic.json"), "w"), indent=1)
     for k, v in out.items():
         print(f"{k:18s} dram {v['dram_bytes_per_launch'] / 1e6:9.1f} MB/launch  l2 {v['l2_bytes_per_launch'] / 1e6:9.1f} MB/launch  l2_frac {v['l2_frac']:.2f} l1_frac {v['l1_frac']:.2f} "
