@@ -284,6 +284,8 @@ int rtgpu_reduce_film(rtgpu_ctx** ctxs, int n, int root);
  *   rank 0:      rtgpu_comm_unique_id(id)  -> ship the RTGPU_COMM_ID_BYTES to the other ranks by any means (file, socket, MPI, torch store)
  *   every rank:  rtgpu_comm_init(ctx, id, rank, world);  rtgpu_render(... tile_rank = rank, tile_world = world ...);
  *                rtgpu_reduce_film_nccl(ctx, root, NULL); then on the root: rtgpu_read_film / rtgpu_resolve_film
+ *   every rank:  rtgpu_comm_destroy(ctx) (or rtgpu_destroy, which calls it) at the SAME point of the job: ncclCommDestroy may wait for the peers, so a rank
+ *                must not block on another rank's exit (waitpid, join) while its own communicator is still open
  * NCCL is opened at run time (dlopen "libnccl.so.2"), so the library has no link-time dependency on it; RTGPU_ERR_UNSUPPORTED when absent. */
 #define RTGPU_COMM_ID_BYTES 128
 int rtgpu_comm_unique_id(void* id_out);
