@@ -71,3 +71,20 @@ def test_counter_and_reference_samplers_agree_statistically(native_libs):
     ta = a.reshape(4, 8, 4, 8, 3).mean((1, 3, 4))
     tb = b.reshape(4, 8, 4, 8, 3).mean((1, 3, 4))
     assert np.abs(ta - tb).max() / ta.mean() < 0.15
+
+
+def test_spatial_light_distribution_is_thread_count_independent(native_libs, tmp_path):
+    """SpatialLightDistribution::lookup (lightdistrib.rs:183-296) fills its voxel table on first use from whichever thread gets there first; the
+    oracle's lock-free table (one atomic pointer per voxel, a losing thread drops its copy) must give every voxel the same distribution whoever
+    builds it: the film rendered by 1 thread and by 8 threads contending on fresh tables is identical, sample for sample (tiles own their pixels
+    under the box filter, so the merge order does not matter either)."""
+    from oracle import binding as ob
+    from rustracer_b200 import Scene, scenes
+    sc = Scene.from_string(scenes.c3_scene(str(tmp_path), level=2, xres=96, yres=64, spp=4), search_dir=tmp_path)
+    films = []
+    for threads in (1, 8, 8):
+        o = ob.OracleScene(sc.ir_ptr)                      # a fresh scene = empty voxel tables
+        film, _, st = o.render(sampler_kind=0, threads=threads)
+        assert st.threads == threads
+        films.append(film)
+    assert np.array_equal(films[0], films[1]) and np.array_equal(films[1], films[2])
