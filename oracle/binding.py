@@ -19,10 +19,31 @@ class orc_stats(C.Structure):
                 ("seconds_total", C.c_double), ("threads", C.c_int32)]
 
 
+def _cpu_stamp():
+    """Model name + feature flags of this host: what `-march=native` specialises the native build for."""
+    import hashlib
+    try:
+        info = open("/proc/cpuinfo").read().split("\n\n")[0]
+        keep = [l for l in info.splitlines() if l.split(":")[0].strip() in ("model name", "flags")]
+        return hashlib.sha1("\n".join(keep).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(native=False, quiet=True):
-    """Compile the oracle with g++ (no FMA contraction).  native=True adds -march=native (GPU-box baseline)."""
+    """Compile the oracle with g++ (no FMA contraction).  native=True adds -march=native (GPU-box baseline); a native library that was built
+    on another kind of CPU (it travels with the repository snapshot) is rebuilt for the host it is about to run on."""
     target = "native" if native else "all"
-    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL if quiet else None)
+    cmd = ["make", "-C", _HERE, target]
+    stamp = os.path.join(_HERE, "_build", "native.cpu")
+    if native:
+        have = open(stamp).read().strip() if os.path.exists(stamp) else None
+        if have != _cpu_stamp():
+            cmd.insert(1, "-B")
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL if quiet else None)
+    if native:
+        with open(stamp, "w") as f:
+            f.write(_cpu_stamp() + "\n")
     return os.path.join(_HERE, "_build", "liboracle_native.so" if native else "liboracle.so")
 
 
@@ -31,8 +52,8 @@ def lib(native=False):
     if _lib is not None and not native:
         return _lib
     path = os.path.join(_HERE, "_build", "liboracle_native.so" if native else "liboracle.so")
-    if not os.path.exists(path):
-        build(native=native)
+    if native or not os.path.exists(path):
+        build(native=native)                 # native: no-op when up to date and built for this CPU
     l = C.CDLL(path)
     PF = C.POINTER(C.c_float)
     l.orc_scene_create.restype = C.c_void_p
