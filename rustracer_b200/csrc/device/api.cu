@@ -365,7 +365,7 @@ int rtgpu_upload_scene(rtgpu_ctx* ctx, const rtgpu_scene_desc* s) {
   // interleave node_lo / node_hi into one 32-byte record per node (one DRAM sector per node visit)
   {
     // staging arrays are left uninitialised (new float[n]) and first touched by the threads that fill them: value-initialising 0.6 GB vectors on one
-    // thread was half of the upload time of a 10 M-triangle scene (profiles/r02t_upload_probe_c4.log)
+    // thread was half of the upload time of a 10 M-triangle scene (profiles/r02t_upload_probe_c4_before.log)
     std::unique_ptr<float[]> inter(new float[(size_t)s->n_nodes * 8]);
     parallel_for(s->n_nodes, [&](size_t i0, size_t i1) {
       for (size_t i = i0; i < i1; i++) {
